@@ -1,0 +1,196 @@
+// gs_device.cuh -- device-side primitives of the read-matching path (sm_100a).
+// Reference semantics cited as C/ = core/src/main/java/org/metagene/genestrip/ (pfeiferd/genestrip v3.0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define GS_LABEL_END 0xFFFFFFFFu      // terminator lane (past the last k-mer position)
+#define GS_LABEL_MISS 0xFFFFFFFEu     // taxIdNode == null
+#define GS_LABEL_INVALID 0xFFFFFFFDu  // INVALID_NODE (C/match/FastqKMerMatcher.java:63)
+#define GS_VAL_NONODE 0xFFFFu         // stored value whose tax id has no tree node -> null (C/store/Database.java:136-143)
+
+#define GS_WARPS_PER_BLOCK 8
+#define GS_TILE_POS 1024                   // k-mer positions per tile
+#define GS_TILE_BASES (GS_TILE_POS + 32)   // bases staged per tile (positions + k-1 <= +30, padded to 16)
+#define GS_TILE_GROUPS (GS_TILE_BASES / 16)
+#define GS_CODE_WORDS (GS_TILE_BASES / 32 + 1)
+#define GS_VALID_WORDS (GS_TILE_BASES / 32 + 1)
+#define GS_TABLE_CAP 128                   // distinct taxa per read tracked by the fast path
+#define GS_MAX_PATHS 128                   // maxClassificationPaths upper bound (C/GSConfigKey.java:350)
+#define GS_MAXCONTIG_SHIFT 40
+#define GS_ORDINAL_MASK ((1ULL << GS_MAXCONTIG_SHIFT) - 1)
+
+// Device view of the database (one per device).
+struct GsDbView {
+    const u64* keys;        // sorted ascending, storage position == index (KMerSortedArray)
+    const uint16_t* vals;   // value index per position (Java short - Short.MIN_VALUE), GS_VAL_NONODE if no node
+    u64 n;
+    const u32* bstart;      // bucket index over the top `bbits` key bits: [bstart[b], bstart[b+1])
+    int bshift;             // key >> bshift = bucket
+    u64 nBuckets;
+    int k;
+    const u64* bloom;       // BlockedKMerBloomFilter words (buckets + 17)
+    u64 bloomBuckets, bloomMagic;
+    long long bloomSeed;
+    int hasBloom;
+    const int* parent;      // by value index, -1 root / none
+    const int* depth;
+    const int* pre;         // DFS interval labels: a is ancestor-or-self of b  <=>  pre[a] <= pre[b] <= last[a]
+    const int* last;
+    int nValues;
+};
+
+// |v| mod d for the Java idiom Math.abs(v % d) (C/bloom/BlockedKMerBloomFilter.java:248-249,
+// C/bloom/AbstractKMerBloomFilter.java:265-267): abs(v % d) == |v| mod d, and |Long.MIN_VALUE| = 2^63 as unsigned.
+// magic = floor((2^64-1)/d): q = mulhi(a, magic) is floor(a/d) or one less, so one conditional subtract suffices.
+__device__ __forceinline__ u64 gs_absmod(long long v, u64 d, u64 magic) {
+    u64 a = v < 0 ? (u64)0 - (u64)v : (u64)v;
+    u64 q = __umul64hi(a, magic);
+    u64 r = a - q * d;
+    return r >= d ? r - d : r;
+}
+
+__device__ __forceinline__ u64 gs_rotl64(u64 x, int s) { return (x << s) | (x >> (64 - s)); }
+
+// 4 ASCII bases (little-endian word, first base in the low byte) -> 8 bits of 2-bit codes, first base in the
+// top pair, C=0 G=1 A=2 T=3 (C/util/CGAT.java:66-69), and a 4-bit validity mask (bit i = base i is one of the
+// upper-case letters CGAT; everything else, incl. lower case and N, is invalid: CGAT.java:60-69).
+__device__ __forceinline__ void gs_conv4(u32 w, u32& code8, u32& valid4) {
+    u32 x = (w >> 1) & 0x03030303u;                                    // A=0 C=1 G=3 T=2
+    u32 c = (((~x) & 0x01010101u) << 1) | ((x >> 1) & 0x01010101u);    // C=0 G=1 A=2 T=3
+    code8 = (c * 0x40100401u) >> 24;
+    u32 eq = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);
+    valid4 = (((eq & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+}
+
+// forward k-mer of the window starting at tile-relative position p from the packed big-endian 2-bit stream
+__device__ __forceinline__ u64 gs_extract(const u64* cw, int p, int k) {
+    int w = p >> 5, o = (p & 31) * 2;
+    u64 hi = cw[w], lo = cw[w + 1];
+    u64 x = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+    return x >> (64 - 2 * k);
+}
+
+// reverse complement in 2-bit space: complement = code ^ 1 (C<->G, A<->T; CGAT.java:71-74), order reversed
+// (kMerToLongReverse, CGAT.java:245-265)
+__device__ __forceinline__ u64 gs_revcomp(u64 fwd, int k) {
+    u64 x = fwd ^ 0x5555555555555555ULL;
+    u64 r = __brevll(x);
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    return r >> (64 - 2 * k);
+}
+
+// standardKMer (CGAT.java:145-147): the larger of the two encodings (both < 2^62, so unsigned == signed order)
+__device__ __forceinline__ u64 gs_canonical(u64 fwd, int k) {
+    u64 rc = gs_revcomp(fwd, k);
+    return fwd > rc ? fwd : rc;
+}
+
+// BlockedKMerBloomFilter.containsLong (C/bloom/BlockedKMerBloomFilter.java:181-198).  The second word is only
+// loaded when the first one passes (same answer; ~0.89 of the misses stop after one 8-byte load).
+__device__ __forceinline__ bool gs_bloom_blocked(const u64* __restrict__ words, u64 buckets, u64 magic, long long seed, u64 key) {
+    long long h = seed ^ (long long)key;
+    u64 start = gs_absmod(h, buckets, magic);
+    u64 h2 = (u64)h ^ gs_rotl64((u64)h, 32);
+    u64 a = __ldg(words + start);
+    u64 m1 = (1ULL << (h2 & 63)) | (1ULL << ((h2 >> 6) & 63));
+    if ((a & m1) != m1) return false;
+    u64 b = __ldg(words + start + 1 + (h2 >> 60));
+    u64 m2 = (1ULL << ((h2 >> 12) & 63)) | (1ULL << ((h2 >> 18) & 63));
+    return (b & m2) == m2;
+}
+
+// MurmurHash3DropIn.hash64 (C/util/MurmurHash3DropIn.java:60-87)
+__device__ __forceinline__ u64 gs_murmur64(u64 data, u64 seed) {
+    u64 hash = seed;
+    u64 k = ((data & 0x00ff00ff00ff00ffULL) << 8) | ((data >> 8) & 0x00ff00ff00ff00ffULL);
+    k = (k << 48) | ((k & 0xffff0000ULL) << 16) | ((k >> 16) & 0xffff0000ULL) | (k >> 48);
+    k *= 0x87c37b91114253d5ULL;
+    k = gs_rotl64(k, 31);
+    k *= 0x4cf5ad432745937fULL;
+    hash ^= k;
+    hash = gs_rotl64(hash, 27) * 5 + 0x52dce729ULL;
+    hash ^= 8;
+    hash ^= hash >> 33;
+    hash *= 0xff51afd7ed558ccdULL;
+    hash ^= hash >> 33;
+    hash *= 0xc4ceb9fe1a85ec53ULL;
+    hash ^= hash >> 33;
+    return hash ^ data;
+}
+
+// KMerSortedArray.getLong (C/store/KMerSortedArray.java:298-349): prefilter, then the position of `key` in the
+// sorted array.  The binary search runs inside the bucket of the key's top bits instead of over [0, n): same
+// position because keys are distinct and sorted.  Returns the label (value index / MISS) and the position.
+__device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBloom, u64& pos) {
+    if (useBloom && !gs_bloom_blocked(db.bloom, db.bloomBuckets, db.bloomMagic, db.bloomSeed, key)) return GS_LABEL_MISS;
+    u64 b = key >> db.bshift;
+    if (b >= db.nBuckets) return GS_LABEL_MISS;  // not a 2k-bit value (only reachable through gs_db_lookup)
+    u32 lo = __ldg(db.bstart + b), hi = __ldg(db.bstart + b + 1);
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        u64 kv = __ldg(db.keys + mid);
+        if (kv < key) lo = mid + 1; else hi = mid;
+    }
+    if ((u64)lo >= db.n || __ldg(db.keys + lo) != key) return GS_LABEL_MISS;
+    pos = lo;
+    uint16_t v = __ldg(db.vals + lo);
+    return v == GS_VAL_NONODE ? GS_LABEL_MISS : (u32)v;
+}
+
+__device__ __forceinline__ bool gs_anc_or_self(const GsDbView& db, int a, int b) {
+    int pb = __ldg(db.pre + b);
+    return __ldg(db.pre + a) <= pb && pb <= __ldg(db.last + a);
+}
+
+// Stage one tile of a read into shared memory: packed 2-bit codes (big-endian u64 stream) and a validity bit
+// per base.  `src` = first base of the tile, nb = number of real bases in the tile (bases beyond are invalid).
+// Adds this lane's number of invalid bases with tile-relative index < lowLimit to badLow, and sets badTail if it
+// saw an invalid base with index >= lowLimit (for the INVALID-iteration count, see gs_match.cu); only bases with
+// tile-relative index < countLimit are counted.
+__device__ __forceinline__ void gs_stage_tile(const uint8_t* __restrict__ src, int nb, int lane, u32* code32, uint16_t* valid16,
+                                              int lowLimit, int countLimit, int& badLow, int& badTail) {
+    const int groups = (nb + 15) >> 4;
+    const int sh = (int)((uintptr_t)src & 15);
+    const uint4* ap = (const uint4*)(src - sh);
+    for (int j = lane; j < GS_TILE_GROUPS; j += 32) {
+        u32 code = 0, valid = 0;
+        if (j < groups) {
+            uint4 A = __ldg(ap + j);
+            u32 r0, r1, r2, r3;
+            if (sh == 0) { r0 = A.x; r1 = A.y; r2 = A.z; r3 = A.w; }
+            else {
+                uint4 B = __ldg(ap + j + 1);
+                const int bs = (sh & 3) * 8;
+                u32 w0, w1, w2, w3, w4;
+                switch (sh >> 2) {
+                    case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; break;
+                    case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; break;
+                    case 2: w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; break;
+                    default: w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; break;
+                }
+                r0 = __funnelshift_r(w0, w1, bs); r1 = __funnelshift_r(w1, w2, bs);
+                r2 = __funnelshift_r(w2, w3, bs); r3 = __funnelshift_r(w3, w4, bs);
+            }
+            u32 c0, c1, c2, c3, v0, v1, v2, v3;
+            gs_conv4(r0, c0, v0); gs_conv4(r1, c1, v1); gs_conv4(r2, c2, v2); gs_conv4(r3, c3, v3);
+            code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+            valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+            const int rem = nb - j * 16;                       // real bases in this group
+            const u32 inRange = rem >= 16 ? 0xFFFFu : ((1u << rem) - 1u);
+            valid &= inRange;
+            const int cntRem = countLimit - j * 16;            // tiles overlap by 32 bases: count each base once
+            const u32 cntMask = cntRem >= 16 ? 0xFFFFu : (cntRem <= 0 ? 0u : ((1u << cntRem) - 1u));
+            u32 bad = (~valid) & inRange & cntMask;
+            const int lowRem = lowLimit - j * 16;              // bases of this group below lowLimit
+            const u32 lowMask = lowRem >= 16 ? 0xFFFFu : (lowRem <= 0 ? 0u : ((1u << lowRem) - 1u));
+            badLow += __popc(bad & lowMask);
+            badTail |= (bad & ~lowMask) != 0;
+        }
+        code32[j ^ 1] = code;      // u64 word w = (code32 group 2w << 32) | group 2w+1
+        valid16[j] = (uint16_t)valid;
+    }
+}

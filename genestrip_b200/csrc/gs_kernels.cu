@@ -1,0 +1,503 @@
+// gs_kernels.cu -- hand-written sm_100a kernels of the Genestrip read-matching path.
+//
+// One warp owns one read.  A read is staged tile-wise into shared memory as a packed 2-bit code stream plus a
+// validity bit per base (128-bit global loads, ASCII -> 2 bit with SIMD-in-register arithmetic); then every lane
+// takes one k-mer position of a 32-position chunk: window validity, forward/reverse-complement k-mer from the
+// packed stream (registers only), blocked Bloom probe, bucketed binary search of the sorted k-mer array.  The 32
+// labels of a chunk sit in the 32 lanes, so the reference's sequential contig logic
+// (C/match/FastqKMerMatcher.java:327-535) becomes ballot/shuffle run-length detection; per-taxon statistics go
+// out as atomics at run ends, unique k-mers as test-then-atomicOr on the position bitset, and the per-read
+// vote table (distinct taxa in first-occurrence order + counts) feeds the classification at the end of the read.
+//
+// Why the decomposition is exact (derivation in DESIGN.md "matchRead as a per-position labelling"):
+//  * a position is INVALID iff its window holds a non-CGAT byte; consecutive loop iterations of the reference
+//    cover exactly these positions, so contigs are maximal runs of equal per-position labels;
+//  * the tax-error counter adds one per miss position and one per INVALID *iteration* = one per bad base b with
+//    b <= max-1, plus one if there is a bad base in [max, L-1] and base max-1 is fine;
+//  * the error gate is monotone, so "gate closed at any time" == "final count exceeds the bound", and a closed
+//    gate discards all votes (:474), hence votes are only needed for reads whose gate stays open;
+//  * mergeReadTaxidPath (:568-586) is idempotent per node, so only first occurrences of distinct taxa matter.
+#include "gs_kernels.cuh"
+
+#define FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ bool gs_is_cgat(uint8_t c) { return c == 'C' || c == 'G' || c == 'A' || c == 'T'; }
+
+// ---------------------------------------------------------------------------------------------------------
+// match
+// ---------------------------------------------------------------------------------------------------------
+struct WarpTable {
+    u32* vi;
+    u32* cnt;
+    int cap;
+};
+
+// add `len` votes for taxon `v`; new taxa are appended in first-occurrence order.  Returns false on overflow.
+// `countR1From`: entries with index >= countR1From bump reads1KMer (FastqKMerMatcher.java:434-439).
+__device__ __forceinline__ bool gs_table_add(const WarpTable& T, int& nTab, u32 v, u32 len, int lane, long long* r1k, int countR1From) {
+    int hit = -1;
+    for (int j = lane; j < nTab; j += 32) if (T.vi[j] == v) hit = j;
+    bool ok = true;
+    if (__ballot_sync(FULL, hit >= 0)) {
+        if (hit >= 0) T.cnt[hit] += len;
+    } else if (nTab < T.cap) {
+        if (lane == 0) {
+            T.vi[nTab] = v;
+            T.cnt[nTab] = len;
+            if (nTab >= countR1From) atomicAdd((u64*)(r1k + v), 1ULL);
+        }
+        nTab++;
+    } else {
+        ok = false;
+    }
+    __syncwarp();
+    return ok;
+}
+
+__device__ __forceinline__ int gs_table_count(const WarpTable& T, int nTab, int node, int lane) {
+    int c = 0;
+    for (int j = lane; j < nTab; j += 32) if ((int)T.vi[j] == node) c = (int)T.cnt[j];
+    return __reduce_add_sync(FULL, c);
+}
+
+// sumCounts (C/tax/SmallTaxTree.java:184-193): votes of node and all its ancestors
+__device__ __forceinline__ int gs_sum_counts(const GsDbView& db, const WarpTable& T, int nTab, int node, int lane) {
+    int pc = __ldg(db.pre + node);
+    int part = 0;
+    for (int j = lane; j < nTab; j += 32) {
+        int e = (int)T.vi[j];
+        if (__ldg(db.pre + e) <= pc && pc <= __ldg(db.last + e)) part += (int)T.cnt[j];
+    }
+    return __reduce_add_sync(FULL, part);
+}
+
+// getLowestCommonAncestor (C/tax/SmallTaxTree.java:263-289); -1 = null
+__device__ __forceinline__ int gs_lca(const GsDbView& db, int a, int b) {
+    if (a == b) return a;
+    if (a < 0 || b < 0) return -1;
+    int da = __ldg(db.depth + a), dbb = __ldg(db.depth + b);
+    while (da > dbb) { a = __ldg(db.parent + a); da--; }
+    while (dbb > da) { b = __ldg(db.parent + b); dbb--; }
+    while (a != b) {
+        a = __ldg(db.parent + a); b = __ldg(db.parent + b);
+        if (a < 0 || b < 0) return -1;
+    }
+    return a;
+}
+
+// MODE 0: fast path (table in shared memory).  MODE 1: slow path for reads that overflowed the fast table
+// (table in global scratch sized nValues; contig statistics and unique bits were already applied by the fast
+// path, only reads1KMer beyond the first GS_TABLE_CAP taxa and the classification are done here).
+// DUMP: additionally write the per-position labels / positions (parity tests).
+template <int MODE, bool DUMP>
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const GsMatchParams P) {
+    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_CODE_WORDS];
+    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_VALID_WORDS];
+    __shared__ u32 s_tabVi[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
+    __shared__ u32 s_tabCnt[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
+    __shared__ u32 s_cand[GS_WARPS_PER_BLOCK][GS_MAX_PATHS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 gw = blockIdx.x * GS_WARPS_PER_BLOCK + warp, nw = gridDim.x * GS_WARPS_PER_BLOCK;
+    const GsDbView& db = P.db;
+    const int k = db.k;
+    const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    const int V = db.nValues;
+    const bool useBloom = P.useBloom && db.hasBloom;
+    u64* cw = s_code[warp];
+    u32* vw = s_valid[warp];
+    u32* cand = s_cand[warp];
+    WarpTable T;
+    if (MODE == 0) { T.vi = s_tabVi[warp]; T.cnt = s_tabCnt[warp]; T.cap = GS_TABLE_CAP; }
+    else { T.vi = P.slowTable + (size_t)gw * 2 * (size_t)V; T.cnt = T.vi + V; T.cap = V; }
+    const u32 nItems = MODE == 0 ? P.nReads : *P.overflowCount;
+
+    for (u32 item = gw; item < nItems; item += nw) {
+        const u32 r = MODE == 0 ? item : P.overflowList[item];
+        const u64 start = P.offsets[r];
+        const int L = (int)(P.offsets[r + 1] - start);
+        const int max = L - k + 1;
+        const u64 ordinal = P.firstReadNo + r;
+        int classV = -1;
+        u32 readKmers = 0, flags = 0, taxErr = P.classify ? 0u : 0xFFFFFFFFu;
+        if (max <= 0) {
+            if (lane == 0 && MODE == 0) P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
+            continue;
+        }
+        const uint8_t* rb = P.bases + start;
+        int nTab = 0, misses = 0, badLow = 0, badTail = 0, carryLen = 0;
+        bool overflow = false;
+        u32 carryLabel = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
+        u64 runCursor = 0;               // want_runs: next free slot of this read's run list
+
+        for (int t0 = 0; t0 <= max; t0 += GS_TILE_POS) {
+            const int nb = min(L - t0, GS_TILE_BASES);
+            const bool lastTile = t0 + GS_TILE_POS > max;
+            __syncwarp();
+            gs_stage_tile(rb + t0, nb, lane, (u32*)cw, (uint16_t*)vw, max - t0, lastTile ? GS_TILE_BASES : GS_TILE_POS, badLow, badTail);
+            __syncwarp();
+            const int lim = max - t0;  // tile-relative index of the terminator position
+            const int nchunks = (min(lim, GS_TILE_POS - 1) >> 5) + 1;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; c++) {
+                const int prel = c * 32 + lane;
+                u32 lab = GS_LABEL_END;
+                u64 pos = 0;
+                if (prel < lim) {
+                    u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
+                    if ((vbits & kmask) != kmask) lab = GS_LABEL_INVALID;
+                    else lab = gs_lookup(db, gs_canonical(gs_extract(cw, prel, k), k), useBloom, pos);
+                    if (DUMP) {
+                        u64 o = P.kmerOffsets[r] + (u64)(t0 + prel);
+                        P.dumpLabels[o] = lab == GS_LABEL_INVALID ? -2 : (lab == GS_LABEL_MISS ? -1 : (int)lab);
+                        P.dumpPos[o] = lab < GS_LABEL_INVALID ? (long long)pos : -1LL;
+                    }
+                }
+                const bool isTax = lab < GS_LABEL_INVALID;
+                if (P.classify) misses += __popc(__ballot_sync(FULL, lab == GS_LABEL_MISS));
+                if (MODE == 0 && isTax && P.bitset) {  // KMerUniqueCounterBits.putInlined (C/store/KMerUniqueCounterBits.java:117-143)
+                    u64 bit = 1ULL << (pos & 63);
+                    u64* wp = P.bitset + (pos >> 6);
+                    if (!(*(volatile u64*)wp & bit)) atomicOr(wp, bit);
+                    if (P.hitCounts) {  // Java short ++ with wrap-around, two counters per 32-bit word
+                        u32* hp = (u32*)P.hitCounts + (pos >> 1);
+                        const int sh = (int)(pos & 1) * 16;
+                        u32 old = *hp, assumed;
+                        do {
+                            assumed = old;
+                            u32 nv = (assumed & ~(0xFFFFu << sh)) | ((((assumed >> sh) + 1u) & 0xFFFFu) << sh);
+                            old = atomicCAS(hp, assumed, nv);
+                        } while (old != assumed);
+                    }
+                }
+                // ---- contigs = maximal runs of equal labels (FastqKMerMatcher.java:370, 390-421)
+                u32 prev = __shfl_up_sync(FULL, lab, 1);
+                if (lane == 0) prev = carryLabel;
+                const bool isStart = lab != prev;
+                const u32 S = __ballot_sync(FULL, isStart);
+                const u32 below = S & ((1u << lane) - 1u);
+                int runLen;  // length of the run that ends right before this lane (meaningful if isStart)
+                if (lane == 0) runLen = carryLen;
+                else if (below) runLen = lane - (31 - __clz(below));
+                else runLen = carryLen + lane;
+                const bool flushTax = isStart && prev < GS_LABEL_INVALID && runLen > 0;
+                if (MODE == 0 && flushTax) {  // :396-410 (contig boundary) and :458-471 (final contig)
+                    atomicAdd((u64*)(P.counters + 0 * (size_t)V + prev), (u64)runLen);
+                    atomicAdd((u64*)(P.counters + 1 * (size_t)V + prev), 1ULL);
+                    atomicAdd((u64*)(P.counters + 2 * (size_t)V + prev), (u64)runLen * (u64)runLen);
+                    atomicMax(P.maxcontig + prev, ((u64)runLen << GS_MAXCONTIG_SHIFT) | (GS_ORDINAL_MASK - (ordinal & GS_ORDINAL_MASK)));
+                }
+                if (MODE == 0 && P.runs) {  // printKrakenStyleOut (:597-611): every finished run incl. '0' and 'A'
+                    const bool flushAny = isStart && runLen > 0;
+                    const u32 FA = __ballot_sync(FULL, flushAny);
+                    if (flushAny) {
+                        u64 slot = P.runOffsets[r] + runCursor + (u64)__popc(FA & ((1u << lane) - 1u));
+                        if (slot < P.runsCap) P.runs[slot] = gs_run{prev, (u32)runLen};
+                    }
+                    runCursor += (u64)__popc(FA);
+                }
+                u32 F = __ballot_sync(FULL, flushTax);
+                while (F) {
+                    const int src = __ffs(F) - 1;
+                    F &= F - 1;
+                    const u32 v = __shfl_sync(FULL, prev, src);
+                    const u32 n = (u32)__shfl_sync(FULL, runLen, src);
+                    if (!overflow) {
+                        if (!gs_table_add(T, nTab, v, n, lane, P.counters + 3 * (size_t)V, MODE == 0 ? 0 : GS_TABLE_CAP)) overflow = true;
+                    }
+                }
+                if (S) carryLen = 32 - (31 - __clz(S)); else carryLen += 32;
+                carryLabel = __shfl_sync(FULL, lab, 31);
+            }
+        }
+        if (MODE == 0 && P.runs && lane == 0) P.runCounts[r] = (u32)runCursor;
+
+        bool found = nTab > 0;
+        if (MODE == 0 && overflow) {
+            flags |= GS_READ_SLOWPATH;
+            if (lane == 0) { u32 slot = atomicAdd(P.overflowCount, 1u); P.overflowList[slot] = r; }
+        }
+        if (P.classify) {
+            // INVALID iterations (:346-363, 372-373): see file header
+            const int bl = __reduce_add_sync(FULL, badLow);
+            const bool bt = __any_sync(FULL, badTail);
+            const int inv = bl + ((bt && gs_is_cgat(rb[max - 1])) ? 1 : 0);
+            const int E = inv + misses;
+            const double mte = P.maxTaxErr;
+            const bool closed = mte >= 0 && ((mte >= 1 && (double)E > mte) || ((double)E > mte * (double)max));  // :374-379
+            taxErr = closed ? 0xFFFFFFFFu : (u32)E;
+            if (found && !closed && !overflow) {
+                // ---- mergeReadTaxidPath over the distinct taxa in first-occurrence order (:568-586)
+                int used = 0;
+                for (int j = 0; j < nTab; j++) {
+                    const int n = (int)T.vi[j];
+                    const int pn = __ldg(db.pre + n), ln = __ldg(db.last + n);
+                    int hit = -1;
+                    bool repl = false;
+                    for (int base = 0; base < used && hit < 0; base += 32) {
+                        const int i = base + lane;
+                        bool r1 = false, r2 = false;
+                        if (i < used) {
+                            const int cnode = (int)cand[i];
+                            const int pc = __ldg(db.pre + cnode), lc = __ldg(db.last + cnode);
+                            r1 = pc <= pn && pn <= lc;  // candidate is ancestor-or-self of node -> replace by node
+                            r2 = pn <= pc && pc <= ln;  // node is ancestor-or-self of candidate  -> keep
+                        }
+                        const u32 bm = __ballot_sync(FULL, r1 || r2);
+                        if (bm) { const int f = __ffs(bm) - 1; hit = base + f; repl = __shfl_sync(FULL, (int)r1, f) != 0; }
+                    }
+                    if (hit >= 0) { if (repl && lane == 0) cand[hit] = (u32)n; }
+                    else if (used < P.maxPaths) { if (lane == 0) cand[used] = (u32)n; used++; }
+                    __syncwarp();
+                }
+                // ---- score candidates, keep maxima and ties in order (:474-487)
+                int best = 0, ties = 0;
+                for (int i = 0; i < used; i++) {
+                    const int cnode = (int)cand[i];
+                    const int sum = gs_sum_counts(db, T, nTab, cnode, lane);
+                    __syncwarp();
+                    if (sum > best) { best = sum; if (lane == 0) cand[0] = (u32)cnode; ties = 0; }
+                    else if (sum == best) { ties++; if (lane == 0) cand[ties] = (u32)cnode; }
+                    __syncwarp();
+                }
+                // ---- lowestNodeWhereSumAboveThreshold (:488-492, C/tax/SmallTaxTree.java:208-221)
+                if (P.threshold > 1) {
+                    for (int i = 0; i <= ties; i++) {
+                        int node = (int)cand[i], res = 0, outn = -1;
+                        while (node >= 0) {
+                            const int cnt = gs_table_count(T, nTab, node, lane);
+                            if (cnt > 0) { res += cnt; if (res >= P.threshold) { outn = node; break; } }
+                            node = __ldg(db.parent + node);
+                        }
+                        __syncwarp();
+                        if (lane == 0) cand[i] = (u32)outn;
+                        __syncwarp();
+                    }
+                }
+                // ---- LCA of the ties (:493-497)
+                int node = (int)cand[0];
+                for (int i = 1; i <= ties; i++) node = gs_lca(db, node, (int)cand[i]);
+                classV = node;
+                if (node < 0) {
+                    found = false;  // `return false` (:498-500)
+                } else {
+                    const int rk = (ties > 0 || P.threshold > 1) ? gs_sum_counts(db, T, nTab, (int)cand[0], lane) : best;  // :506-507
+                    readKmers = (u32)rk;
+                    const int classErrC = max - rk;
+                    const double mce = P.maxClassErr;
+                    if (mce < 0 || (mce >= 1 && (double)classErrC <= mce) || ((double)classErrC <= mce * (double)max)) {  // :509-510
+                        flags |= GS_READ_ACCEPTED;
+                        if (lane == 0) {  // :518-520 (the four double sums are done by the host in read order)
+                            atomicAdd((u64*)(P.counters + 4 * (size_t)V + node), 1ULL);
+                            atomicAdd((u64*)(P.counters + 5 * (size_t)V + node), (u64)rk);
+                            atomicAdd((u64*)(P.counters + 6 * (size_t)V + node), (u64)L);
+                        }
+                    }
+                }
+            }
+        }
+        if (found) flags |= GS_READ_FOUND;
+        if (lane == 0 && !(MODE == 0 && overflow)) {
+            if (MODE == 1) flags |= GS_READ_SLOWPATH;
+            P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
+        } else if (lane == 0) {
+            P.out[r] = gs_read_result{-1, 0u, taxErr, flags | GS_READ_FOUND};
+        }
+    }
+}
+
+void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
+    const int threads = GS_WARPS_PER_BLOCK * 32;
+    if (mode == 0) {
+        if (dump) gs_match_kernel<0, true><<<blocks, threads, 0, st>>>(P);
+        else gs_match_kernel<0, false><<<blocks, threads, 0, st>>>(P);
+    } else {
+        gs_match_kernel<1, false><<<blocks, threads, 0, st>>>(P);
+    }
+}
+
+// New per-taxon maximum contig lengths set by reads of [firstReadNo, firstReadNo + nReads) (:402-409).
+__global__ void gs_maxcontig_events_kernel(const u64* __restrict__ maxcontig, int V, u64 firstReadNo, u32 nReads,
+                                           gs_maxcontig_event* ev, u32* nEv) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    u64 cur = maxcontig[v];
+    if (!cur) return;
+    u64 ord = GS_ORDINAL_MASK - (cur & GS_ORDINAL_MASK);
+    if (ord >= firstReadNo && ord < firstReadNo + nReads) {
+        u32 slot = atomicAdd(nEv, 1u);
+        ev[slot] = gs_maxcontig_event{(u32)v, (u32)(cur >> GS_MAXCONTIG_SHIFT), ord};
+    }
+}
+void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st) {
+    gs_maxcontig_events_kernel<<<(V + 255) / 256, 256, 0, st>>>(maxcontig, V, firstReadNo, nReads, ev, nEv);
+}
+
+// KMerUniqueCounterBits.getUniqueKmerCounts (C/store/KMerUniqueCounterBits.java:146-163): per value index, the
+// number of set bits among its storage positions.  One thread per 64-bit bitset word; equal value indices of a
+// warp's current bits are pre-aggregated with match_any before the atomic.
+__global__ void gs_unique_popcount_kernel(const u64* __restrict__ bits, u64 wordBegin, u64 wordEnd, const uint16_t* __restrict__ vals,
+                                          u64 n, long long* unique) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w0 = wordBegin + (u64)blockIdx.x * blockDim.x; w0 < wordEnd; w0 += stride) {  // warp-uniform trip count
+        const u64 w = w0 + threadIdx.x;
+        u64 word = w < wordEnd ? __ldg(bits + w) : 0ULL;
+        while (__any_sync(FULL, word != 0)) {
+            int v = -1;
+            if (word) {
+                const int b = __ffsll((long long)word) - 1;
+                word &= word - 1;
+                const u64 pos = w * 64 + (u64)b;
+                if (pos < n) { uint16_t vv = __ldg(vals + pos); if (vv != GS_VAL_NONODE) v = vv; }
+            }
+            const u32 peers = __match_any_sync(FULL, v);
+            if (v >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd((u64*)(unique + v), (u64)__popc(peers));
+        }
+    }
+}
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const uint16_t* vals, u64 n, long long* unique, int blocks, cudaStream_t st) {
+    if (wordEnd > wordBegin) gs_unique_popcount_kernel<<<blocks, 256, 0, st>>>(bits, wordBegin, wordEnd, vals, n, unique);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// database build helpers
+// ---------------------------------------------------------------------------------------------------------
+// bucket index: bstart[b] = first position whose key has top bits >= b; bstart[nb] = n
+__global__ void gs_bucket_index_kernel(const u64* __restrict__ keys, u64 n, int bshift, u64 nb, u32* bstart) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const u64 cur = i < n ? (keys[i] >> bshift) : nb;
+        const u64 from = i == 0 ? 0 : (keys[i - 1] >> bshift) + 1;
+        for (u64 b = from; b <= cur && b <= nb; b++) bstart[b] = (u32)i;
+    }
+}
+void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st) {
+    gs_bucket_index_kernel<<<148 * 8, 256, 0, st>>>(keys, n, bshift, nb, bstart);
+}
+
+// BlockedKMerBloomFilter.putLong (C/bloom/BlockedKMerBloomFilter.java:108-124) for every stored key
+__global__ void gs_bloom_build_kernel(const u64* __restrict__ keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long h = seed ^ (long long)keys[i];
+        u64 start = gs_absmod(h, buckets, magic);
+        u64 h2 = (u64)h ^ gs_rotl64((u64)h, 32);
+        u64 m1 = (1ULL << (h2 & 63)) | (1ULL << ((h2 >> 6) & 63));
+        u64 m2 = (1ULL << ((h2 >> 12) & 63)) | (1ULL << ((h2 >> 18) & 63));
+        atomicOr(words + start, m1);
+        atomicOr(words + start + 1 + (h2 >> 60), m2);
+    }
+}
+void gs_launch_bloom_build(const u64* keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed, cudaStream_t st) {
+    gs_bloom_build_kernel<<<148 * 8, 256, 0, st>>>(keys, n, words, buckets, magic, seed);
+}
+
+__global__ void gs_convert_values_kernel(const int16_t* __restrict__ raw, const int* __restrict__ hasNode, u64 n, int V, uint16_t* vals, u32* bad) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int idx = (int)raw[i] + 32768;  // index - Short.MIN_VALUE (C/store/KMerSortedArray.java:348)
+        if (idx >= V) { atomicAdd(bad, 1u); vals[i] = GS_VAL_NONODE; }
+        else vals[i] = (hasNode && !hasNode[idx]) ? GS_VAL_NONODE : (uint16_t)idx;
+    }
+}
+void gs_launch_convert_values(const int16_t* raw, const int* hasNode, u64 n, int V, uint16_t* vals, u32* bad, cudaStream_t st) {
+    gs_convert_values_kernel<<<148 * 8, 256, 0, st>>>(raw, hasNode, n, V, vals, bad);
+}
+
+__global__ void gs_check_sorted_kernel(const u64* __restrict__ keys, u64 n, int k, u32* bad) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (keys[i] >> (2 * k)) atomicAdd(bad, 1u);
+        if (i + 1 < n && keys[i] >= keys[i + 1]) atomicAdd(bad, 1u);
+    }
+}
+void gs_launch_check_sorted(const u64* keys, u64 n, int k, u32* bad, cudaStream_t st) { gs_check_sorted_kernel<<<148 * 8, 256, 0, st>>>(keys, n, k, bad); }
+
+// KMerStore.getLong probe (tests)
+__global__ void gs_lookup_kernel(GsDbView db, const u64* __restrict__ kmers, u64 n, int useBloom, int* vidx, long long* pos) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 p = 0;
+        u32 lab = gs_lookup(db, kmers[i], useBloom && db.hasBloom, p);
+        vidx[i] = lab == GS_LABEL_MISS ? -1 : (int)lab;
+        pos[i] = lab == GS_LABEL_MISS ? -1LL : (long long)p;
+    }
+}
+void gs_launch_lookup(const GsDbView& db, const u64* kmers, u64 n, int useBloom, int* vidx, long long* pos, cudaStream_t st) {
+    gs_lookup_kernel<<<148 * 4, 256, 0, st>>>(db, kmers, n, useBloom, vidx, pos);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// filter
+// ---------------------------------------------------------------------------------------------------------
+// KMerProbFilter.containsLong for the three filter kinds
+__device__ __forceinline__ bool gs_filter_contains(const GsFilterView& f, u64 key) {
+    if (f.kind == GS_BLOOM_BLOCKED) return gs_bloom_blocked(f.words, (u64)f.p1, f.magic, f.p0, key);
+    // AbstractKMerBloomFilter.containsLong (C/bloom/AbstractKMerBloomFilter.java:209-216): stop at the first 0 bit
+    for (int i = 0; i < (int)f.p1; i++) {
+        const u64 fac = (u64)__ldg(f.factors + i);
+        const long long h = f.kind == GS_BLOOM_XOR ? (long long)(fac ^ key) : (long long)gs_murmur64(key, fac);
+        const u64 idx = gs_absmod(h, (u64)f.p0, f.magic);
+        if (!((__ldg(f.words + (idx >> 6)) >> (idx & 63)) & 1ULL)) return false;
+    }
+    return true;
+}
+
+__global__ void gs_filter_contains_kernel(GsFilterView f, const u64* __restrict__ kmers, u64 n, uint8_t* out) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = gs_filter_contains(f, kmers[i]) ? 1 : 0;
+}
+void gs_launch_filter_contains(const GsFilterView& f, const u64* kmers, u64 n, uint8_t* out, cudaStream_t st) {
+    gs_filter_contains_kernel<<<148 * 4, 256, 0, st>>>(f, kmers, n, out);
+}
+
+// FastqBloomFilter.isAcceptRead (C/bloom/FastqBloomFilter.java:120-161).  The two early exits are mutually
+// exclusive (hits + misses <= max), so the decision is  hits_total >= max(1, posThreshold); the scan stops as soon
+// as that many hits were seen (warp-wide, chunk granularity).
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_filter_kernel(const GsFilterParams P) {
+    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_CODE_WORDS];
+    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_VALID_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 gw = blockIdx.x * GS_WARPS_PER_BLOCK + warp, nw = gridDim.x * GS_WARPS_PER_BLOCK;
+    const int k = P.k;
+    const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    u64* cw = s_code[warp];
+    u32* vw = s_valid[warp];
+    for (u32 r = gw; r < P.nReads; r += nw) {
+        const u64 start = P.offsets[r];
+        const int L = (int)(P.offsets[r + 1] - start);
+        const int max = L - k + 1;
+        int posThreshold = P.minPosCount > 0 ? P.minPosCount : (int)((double)max * P.posRatio);  // :122
+        const int need = posThreshold < 1 ? 1 : posThreshold;
+        int hits = 0;
+        for (int t0 = 0; t0 < max && hits < need; t0 += GS_TILE_POS) {
+            const int nb = min(L - t0, GS_TILE_BASES);
+            int d0 = 0, d1 = 0;
+            __syncwarp();
+            gs_stage_tile(P.bases + start + t0, nb, lane, (u32*)cw, (uint16_t*)vw, 0, 0, d0, d1);
+            __syncwarp();
+            const int lim = min(max - t0, GS_TILE_POS);
+            for (int c = 0; c * 32 < lim && hits < need; c++) {
+                const int prel = c * 32 + lane;
+                bool hit = false;
+                if (prel < lim) {
+                    u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
+                    if ((vbits & kmask) == kmask) hit = gs_filter_contains(P.f, gs_canonical(gs_extract(cw, prel, k), k));
+                }
+                hits += __popc(__ballot_sync(FULL, hit));
+            }
+        }
+        if (lane == 0) P.accept[r] = hits >= need ? 1 : 0;
+    }
+}
+void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st) {
+    gs_filter_kernel<<<blocks, GS_WARPS_PER_BLOCK * 32, 0, st>>>(P);
+}
+
+int gs_match_kernel_occupancy(int mode) {
+    int nb = 0;
+    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_match_kernel<0, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_match_kernel<1, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
+    return nb;
+}

@@ -1,0 +1,56 @@
+// gs_kernels.cuh -- kernel parameter blocks and launchers shared by gs_kernels.cu and gs_capi.cu
+#pragma once
+#include "../../include/genestrip_b200.h"
+#include "gs_device.cuh"
+
+struct GsMatchParams {
+    GsDbView db;
+    const uint8_t* bases;   // reads back to back, ASCII
+    const u64* offsets;     // [nReads + 1]
+    u32 nReads;
+    u64 firstReadNo;
+    gs_read_result* out;    // [nReads]
+    long long* counters;    // [7][nValues]: kmers, contigs, contigLenSquaredSum, reads1KMer, reads, readsKmers, readsBPs
+    u64* maxcontig;         // [nValues] (maxContigLen << 40) | (2^40-1 - read ordinal)
+    u64* bitset;            // unique k-mer bits by storage position, or NULL
+    uint16_t* hitCounts;    // per-position hit counters (maxKMerResCounts > 0), or NULL
+    int classify, useBloom, maxPaths, threshold;
+    double maxTaxErr, maxClassErr;
+    u32* overflowList;      // reads with more than GS_TABLE_CAP distinct taxa
+    u32* overflowCount;
+    u32* slowTable;         // MODE 1: per-warp vote tables in global memory, 2 * nValues u32 each
+    // kraken-style runs (want_runs)
+    gs_run* runs; const u64* runOffsets; u64 runsCap; u32* runCounts;
+    // label dump (parity tests)
+    const u64* kmerOffsets; int* dumpLabels; long long* dumpPos;
+};
+
+struct GsFilterView {
+    int kind;
+    long long p0, p1;        // blocked: seed, buckets; hashed: bits, hashes
+    u64 magic;               // floor((2^64-1)/modulus)
+    const long long* factors;
+    const u64* words;
+};
+
+struct GsFilterParams {
+    GsFilterView f;
+    const uint8_t* bases;
+    const u64* offsets;
+    u32 nReads;
+    int k, minPosCount;
+    double posRatio;
+    uint8_t* accept;
+};
+
+void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
+void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const uint16_t* vals, u64 n, long long* unique, int blocks, cudaStream_t st);
+void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);
+void gs_launch_bloom_build(const u64* keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed, cudaStream_t st);
+void gs_launch_convert_values(const int16_t* raw, const int* hasNode, u64 n, int V, uint16_t* vals, u32* bad, cudaStream_t st);
+void gs_launch_check_sorted(const u64* keys, u64 n, int k, u32* bad, cudaStream_t st);
+void gs_launch_lookup(const GsDbView& db, const u64* kmers, u64 n, int useBloom, int* vidx, long long* pos, cudaStream_t st);
+void gs_launch_filter_contains(const GsFilterView& f, const u64* kmers, u64 n, uint8_t* out, cudaStream_t st);
+void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st);
+int gs_match_kernel_occupancy(int mode);

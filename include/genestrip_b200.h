@@ -1,0 +1,206 @@
+/* genestrip_b200.h -- C ABI of the B200-native Genestrip read-matching hot path.
+ *
+ * This is the drop-in boundary (DESIGN.md "Boundary").  The reference (pfeiferd/genestrip v3.0) is pure
+ * Java and has no FFI for this path; its seams are Java override points.  Each entry point below names
+ * the reference interface it replaces, with
+ *   C/ = core/src/main/java/org/metagene/genestrip/
+ * A JNI shim (integration/jni/gs_jni.cpp, shown in INTEGRATION.md) binds exactly these symbols.
+ *
+ * Conventions: plain pointers and sizes only; every function returning int returns 0 on success and a
+ * negative gs_status on failure (text via gs_last_error(), thread-local); nothing throws or calls back
+ * into the host.  There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * GS_ERR_CUDA.
+ */
+#ifndef GENESTRIP_B200_H
+#define GENESTRIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+typedef enum gs_status {
+    GS_OK = 0,
+    GS_ERR_ARG = -1,     /* bad argument / call order */
+    GS_ERR_CUDA = -2,    /* CUDA runtime error (incl. no device) */
+    GS_ERR_STATE = -3,   /* object not finalized / ticket not pending */
+    GS_ERR_LIMIT = -4    /* a documented size limit was exceeded */
+} gs_status;
+
+typedef struct gs_ctx gs_ctx;       /* one per process: the set of GPUs used */
+typedef struct gs_db gs_db;         /* device-resident database: k-mer store + tax tree + Bloom prefilter */
+typedef struct gs_sess gs_sess;     /* one `match` run over one fastq key (FastqKMerMatcher.runMatcher) */
+typedef struct gs_filter gs_filter; /* device-resident `filter` goal index (KMerProbFilter) */
+typedef struct gs_fsess gs_fsess;   /* one `filter` run (FastqBloomFilter.runFilter) */
+typedef uint64_t gs_ticket;
+
+int gs_abi_version(void);
+const char* gs_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces: ExecutionContext / thread pool sizing (C/DefaultExecutionContext.java:78) -- the unit of
+ * parallelism is a GPU instead of a consumer thread.  device_ordinals == NULL, n == 0 => device 0. */
+gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices);
+void gs_ctx_destroy(gs_ctx*);
+int gs_ctx_n_devices(const gs_ctx*);
+
+/* Pinned host memory for read batches (replaces the ReadEntry pool, C/fastq/AbstractFastqReader.java:85-104). */
+void* gs_alloc_pinned(size_t bytes);
+void gs_free_pinned(void*);
+
+/* ---- database -----------------------------------------------------------------------------------
+ * Replaces: Database.load + convertKMerStore (C/store/Database.java:136-143, 265-314) as the data source,
+ * KMerSortedArray's arrays (C/store/KMerSortedArray.java:63-66) as the layout that is uploaded.
+ * keys: sorted ascending, distinct, < 2^62, storage position == array index (KMerSortedArray.getLong :298-349).
+ * vidx_raw: the Java short as stored (value index + Short.MIN_VALUE).  Segments may be streamed in any order. */
+gs_db* gs_db_create(gs_ctx*, int k, uint64_t n_kmers, int n_values);
+int gs_db_put_keys(gs_db*, uint64_t offset, const int64_t* keys, uint64_t n);
+int gs_db_put_values(gs_db*, uint64_t offset, const int16_t* vidx_raw, uint64_t n);
+/* RadixKMerStore source (C/store/RadixKMerStore.java:369-412, 714-730): entries of one bucket, packed as
+ * (valueIndex << (62 - radix_bits)) | (kmer >>> radix_bits), sorted by the remaining bits.  The library
+ * rebuilds full keys and merges them into its own sorted layout (results are identical by
+ * T/match/RadixKMerStoreBenchmarkTest.java:186-229).  Call once per non-empty bucket, then finalize. */
+int gs_db_put_radix_bucket(gs_db*, int radix_bits, uint32_t radix, const int64_t* entries, uint32_t n);
+/* SmallTaxTree flattened by value index (C/tax/SmallTaxTree.java; storeIndex == value index, Database.java:107-128).
+ * parent_by_vidx[v] = value index of the parent node, -1 for the root.  has_node[v] == 0 marks a stored value
+ * whose tax id has no tree node: such k-mers convert to null (Database.java:136-143) and count as misses.
+ * has_node may be NULL (all present). */
+int gs_db_set_tree(gs_db*, const int32_t* parent_by_vidx, const int32_t* has_node, int n_values);
+/* BlockedKMerBloomFilter as deserialized from bloom.ser (C/bloom/BlockedKMerBloomFilter.java:181-198):
+ * seed, buckets, data[buckets+17]. */
+int gs_db_set_bloom_blocked(gs_db*, int64_t seed, uint64_t buckets, const int64_t* words, uint64_t n_words);
+/* Build the store's optimized filter on the device exactly as KMerSortedArray.optimize does
+ * (C/store/KMerSortedArray.java:409-422 with AbstractKMerStore.createOptimizedFilter :271-285, 10 bits/key,
+ * seed = new Random(42).nextLong()).  Needs all keys uploaded.  words_out (may be NULL) receives the
+ * buckets+17 words for comparison with a host-built filter. */
+int gs_db_build_bloom_blocked(gs_db*, int64_t* words_out, uint64_t n_words_out);
+int gs_db_finalize(gs_db*); /* builds the bucket index, replicates to every device of the context */
+void gs_db_destroy(gs_db*);
+uint64_t gs_db_device_bytes(const gs_db*);
+/* Lookup probe for tests (KMerStore.getLong, C/store/KMerStore.java:157): vidx_out[i] = value index or -1
+ * (miss / value without node), pos_out[i] = storage position or -1.  use_bloom follows useBloomFilterForMatch. */
+int gs_db_lookup(gs_db*, const int64_t* kmers, uint64_t n, int use_bloom, int32_t* vidx_out, int64_t* pos_out);
+
+/* ---- match --------------------------------------------------------------------------------------
+ * Replaces: MatchResultGoal.createMatcher (C/goals/MatchResultGoal.java:174-197) -> FastqKMerMatcher
+ * (C/match/FastqKMerMatcher.java:127-147) and its config keys (C/GSConfigKey.java:302-350). */
+typedef struct gs_match_cfg {
+    int classify_reads;                /* classifyReads && !matchlr  (taxTree != null)          */
+    int count_unique_kmers;            /* countUniqueKMers                                       */
+    int max_kmer_res_counts;           /* maxKMerResCounts (>0: per-k-mer hit counters)          */
+    int use_bloom_filter;              /* useBloomFilterForMatch                                 */
+    int max_classification_paths;      /* maxClassificationPaths, 1..128                         */
+    int min_kmers_for_class;           /* minKMersForClass (threshold)                           */
+    double max_read_tax_error_count;   /* maxReadTaxErrorCount                                   */
+    double max_read_class_error_count; /* maxReadClassErrorCount                                 */
+    int want_runs;                     /* writeKrakenStyleOut: return per-read contig runs       */
+    int reserved;
+} gs_match_cfg;
+void gs_match_cfg_default(gs_match_cfg*);
+
+/* Per-read result, 16 bytes (what FastqKMerMatcher.matchRead leaves in MatcherReadEntry, :327-535). */
+typedef struct gs_read_result {
+    int32_t class_vidx;   /* entry.classNode's value index, -1 = null                                  */
+    uint32_t read_kmers;  /* readKmers (:506-507); 0 if unclassified                                   */
+    uint32_t tax_err;     /* readTaxErrorCount at the end of the loop; 0xFFFFFFFF = -1 (gate closed/off) */
+    uint32_t flags;       /* GS_READ_* */
+} gs_read_result;
+#define GS_READ_FOUND 1u      /* matchRead's return value (drives the filtered FASTQ, :304-307)        */
+#define GS_READ_ACCEPTED 2u   /* the classified-read statistics were updated (:509-526)                 */
+#define GS_READ_SLOWPATH 4u   /* more distinct taxa than the fast path tracks; resolved by the slow path */
+
+/* One contig run of a read for the kraken-style line (printKrakenStyleOut, :597-611). */
+typedef struct gs_run {
+    uint32_t label; /* value index, GS_RUN_MISS ('0') or GS_RUN_INVALID ('A') */
+    uint32_t len;
+} gs_run;
+#define GS_RUN_MISS 0xFFFFFFFEu
+#define GS_RUN_INVALID 0xFFFFFFFDu
+
+/* A new per-taxon maximum contig length was set by a read of this batch (:402-409); the host copies the
+ * read's descriptor while it still has the batch. */
+typedef struct gs_maxcontig_event {
+    uint32_t vidx;
+    uint32_t contig_len;
+    uint64_t read_no;
+} gs_maxcontig_event;
+
+/* Per value index: the integer fields of CountsPerTaxid (C/match/CountsPerTaxid.java:127-159). */
+typedef struct gs_taxon_counts {
+    int64_t kmers, contigs, contig_len_squared_sum, reads_1kmer, reads, reads_kmers, reads_bps, unique_kmers;
+    int32_t max_contig_len;
+    int32_t touched;             /* statsIndex[vi] != null (a row exists even if all counters are 0) */
+    uint64_t max_contig_read_no; /* first read (lowest ordinal) that reached max_contig_len */
+} gs_taxon_counts;
+
+gs_sess* gs_match_open(gs_db*, const gs_match_cfg*);
+/* Submit one batch of reads: bases = the reads' sequence bytes back to back (ASCII, exactly as parsed:
+ * no upper-casing), offsets[n_reads+1] byte offsets into bases, first_read_no =
+ * global ordinal of read 0 (file order; used for the maxContigDescriptor tie-break).  Host buffers must stay
+ * valid until the ticket is collected.  Up to GS_MAX_INFLIGHT tickets may be pending. */
+#define GS_MAX_INFLIGHT 2
+int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                    uint64_t first_read_no, gs_ticket* ticket);
+/* Wait for a ticket.  out[n_reads]; events[ev_cap] / n_events may be NULL.  If want_runs: run_offsets
+ * [n_reads+1] and runs[runs_cap] receive the contig runs (GS_ERR_LIMIT if runs_cap is too small). */
+int gs_match_collect(gs_sess*, gs_ticket, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
+                     uint32_t* n_events, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap);
+/* End of run: merges all devices, runs the unique-k-mer count (KMerUniqueCounterBits.getUniqueKmerCounts,
+ * C/store/KMerUniqueCounterBits.java:146-163) and returns per-value-index counts[n_values].
+ * top_counts (may be NULL): (n_values+1) x max_kmer_res_counts Java shorts, row n_values = total
+ * (getMaxCountsCounts :173-199). */
+int gs_match_finish(gs_sess*, gs_taxon_counts* counts, int16_t* top_counts);
+void gs_match_close(gs_sess*);
+
+/* Device-resident variants (inputs already in HBM; used by bench.py's kernel-only number and by a host that
+ * decodes on the GPU).  d_bases must be 16-byte aligned and readable 32 bytes past the last base.  Runs on the
+ * session's device 0, asynchronously on the session's stream; gs_match_sync waits. */
+int gs_match_run_device(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                        uint64_t first_read_no, gs_read_result* d_out);
+int gs_match_sync(gs_sess*);
+/* Raw device state for cross-process reduction over NCCL (one process per GPU, DESIGN.md "Multi-GPU"):
+ * counters = int64[7][n_values] (kmers, contigs, sqsum, reads1, reads, readsKmers, readsBPs),
+ * maxcontig = uint64[n_values] packed (len << 40 | ~ordinal), bitset = uint64[ceil(n_kmers/64)] or NULL. */
+int gs_match_device_state(gs_sess*, int64_t** counters, uint64_t** maxcontig, uint64_t** bitset,
+                          uint64_t* bitset_words);
+/* Per-taxon popcount of bitset words [word_begin, word_end) into d_unique (int64[n_values], device, added to). */
+int gs_match_unique_popcount(gs_sess*, const uint64_t* d_bitset, uint64_t word_begin, uint64_t word_end,
+                             int64_t* d_unique);
+/* CUDA stream (cudaStream_t) the device-resident calls are issued on; kernels launched since open. */
+void* gs_match_stream(gs_sess*);
+uint64_t gs_match_kernel_launches(const gs_sess*);
+/* Debug/parity: per-position labels of a device-resident batch: labels[i] = value index, -1 miss, -2 invalid;
+ * pos[i] = storage position or -1; kmer_offsets[n_reads+1] = prefix sums of max(0, L-k+1). All device pointers. */
+int gs_match_dump_labels(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                         const uint64_t* d_kmer_offsets, int32_t* d_labels, int64_t* d_pos);
+
+/* ---- filter -------------------------------------------------------------------------------------
+ * Replaces: LoadIndexGoal's KMerProbFilter (C/goals/LoadIndexGoal.java:92-104) and FastqBloomFilter
+ * (C/bloom/FastqBloomFilter.java:62-161) built in FilterGoal.makeFile (C/goals/FilterGoal.java:80-108). */
+#define GS_BLOOM_BLOCKED 0
+#define GS_BLOOM_XOR 1
+#define GS_BLOOM_MURMUR 2
+/* blocked: p0 = seed, p1 = buckets, factors = NULL;  xor/murmur: p0 = bits (the modulus), p1 = hashes,
+ * factors[hashes] = hashFactors (C/bloom/AbstractKMerBloomFilter.java:104-110). */
+gs_filter* gs_filter_create(gs_ctx*, int kind, int64_t p0, int64_t p1, const int64_t* factors,
+                            const int64_t* words, uint64_t n_words);
+void gs_filter_destroy(gs_filter*);
+/* KMerProbFilter.containsLong (C/bloom/KMerProbFilter.java:66) for tests. */
+int gs_filter_contains(gs_filter*, const int64_t* kmers, uint64_t n, uint8_t* out);
+gs_fsess* gs_filter_open(gs_filter*, int k, int min_pos_count, double pos_ratio);
+int gs_filter_submit(gs_fsess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, gs_ticket*);
+/* accept[n_reads]: 1 = isAcceptRead (C/bloom/FastqBloomFilter.java:120-161). */
+int gs_filter_collect(gs_fsess*, gs_ticket, uint8_t* accept);
+int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                         uint8_t* d_accept);
+int gs_filter_sync(gs_fsess*);
+void gs_filter_close(gs_fsess*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENESTRIP_B200_H */
