@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- `match` goal throughput (k-mers/s, reads/s) of the B200-native Genestrip hot path.
+
+Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl reference]; for N > 1 launched by torchrun,
+one rank per GPU.  A step = one pass of the hot path (encode -> Bloom -> store lookup -> per-taxon counting ->
+per-read classification) over one batch of synthetic 150 bp reads against the viral-scale synthetic database
+(BASELINE.json configs[1]).  Rank 0 prints ONE JSON line.
+
+  value      k-mers/s, inputs resident in HBM when the timed region starts (device-resident C-ABI entry point)
+  e2e        the same metric through gs_match_submit/gs_match_collect with pinned HOST buffers (H2D + D2H inside)
+  roofline   HBM-bound: algorithmic bytes per k-mer (DESIGN.md "Roofline") x k-mers per launch / launch duration
+  cpu_baseline  the CPU oracle (restated reference algorithm, all host threads) on a bounded sample, rank 0, N=1
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+READ_LEN = 150
+WORKLOADS = {
+    # name: (levels, fanout, db k-mers, reads per step, fraction of reads from the DB, substitution rate)
+    "viral": dict(levels=4, fanout=10, n_kmers=100_000_000, reads_per_step=4_000_000, frac_db=0.5, sub_rate=0.01,
+                  desc="viral-scale synthetic db (~10k leaf taxa, 1e8 31-mers), match on 150 bp Illumina-like reads (BASELINE.json configs[1])"),
+    "tiny": dict(levels=2, fanout=3, n_kmers=2_000_000, reads_per_step=200_000, frac_db=0.7, sub_rate=0.01,
+                 desc="tiny synthetic db (9 leaf taxa, 2e6 31-mers), smoke-size"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# synthetic project on the GPU (torch is plumbing here: random numbers, sort, device memory)
+# --------------------------------------------------------------------------------------------------------------
+def make_database(torch, dev, wl, seed):
+    """Genomes for every leaf of a fan-out tree; 1 % of every genome is copied from its next sibling so that LCA != leaf
+    occurs.  Returns sorted distinct canonical 31-mers, raw Java-short value indices, the parent array, the genomes."""
+    from genestrip_b200 import synth
+    parent, level_start = synth.parent_array_fanout(wl["levels"], wl["fanout"])
+    V = len(parent)
+    leaf0 = level_start[-1]
+    n_leaves = V - leaf0
+    glen = int(math.ceil(wl["n_kmers"] / n_leaves * 1.004)) + K - 1
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    codes = torch.randint(0, 4, (n_leaves, glen), generator=g, device=dev, dtype=torch.int8)  # C0 G1 A2 T3
+    nsh = max(K, glen // 100)
+    sib = (torch.arange(n_leaves, device=dev) + 1) % wl["fanout"] + (torch.arange(n_leaves, device=dev) // wl["fanout"]) * wl["fanout"]
+    codes[:, glen // 2: glen // 2 + nsh] = codes[sib, glen // 3: glen // 3 + nsh]
+    # canonical k-mers of every window (CGAT.java:145-265 semantics: fwd big-endian 2-bit, rc = reversed complement, max)
+    nwin = glen - K + 1
+    fwd = torch.zeros((n_leaves, nwin), dtype=torch.int64, device=dev)
+    rc = torch.zeros((n_leaves, nwin), dtype=torch.int64, device=dev)
+    for i in range(K):
+        c = codes[:, i:i + nwin].to(torch.int64)
+        fwd = (fwd << 2) | c
+        rc = rc | ((c ^ 1) << (2 * i))
+    canon = torch.maximum(fwd, rc).reshape(-1)
+    del fwd, rc
+    leaf = (torch.arange(n_leaves, device=dev, dtype=torch.int64).repeat_interleave(nwin))
+    keys, order = torch.sort(canon)
+    leaf = leaf[order]
+    del canon, order
+    uniq, inv, cnt = torch.unique_consecutive(keys, return_inverse=True, return_counts=True)
+    # value of a k-mer = LCA of all leaves holding it: longest common prefix of the leaf's base-`fanout` digits
+    n_u = uniq.numel()
+    lo = torch.full((n_u,), n_leaves, dtype=torch.int64, device=dev).scatter_reduce(0, inv, leaf, reduce="amin")
+    hi = torch.zeros((n_u,), dtype=torch.int64, device=dev).scatter_reduce(0, inv, leaf, reduce="amax")
+    vidx = torch.zeros((n_u,), dtype=torch.int64, device=dev)          # root
+    found = torch.zeros((n_u,), dtype=torch.bool, device=dev)
+    for lvl in range(wl["levels"], 0, -1):                               # deepest level where all holders agree
+        div = wl["fanout"] ** (wl["levels"] - lvl)
+        same = (lo // div == hi // div) & ~found
+        vidx = torch.where(same, level_start[lvl] + lo // div, vidx)
+        found |= same
+    vals_raw = (vidx - 32768).to(torch.int16)
+    return uniq, vals_raw, parent, codes
+
+
+def make_reads(torch, dev, wl, codes, n_reads, seed):
+    """n_reads x READ_LEN ASCII bases on the device (+64 bytes of slack), offsets uint64[n+1]."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n_leaves, glen = codes.shape
+    gi = torch.randint(0, n_leaves, (n_reads,), generator=g, device=dev)
+    st = torch.randint(0, glen - READ_LEN + 1, (n_reads,), generator=g, device=dev)
+    strand = torch.rand((n_reads,), generator=g, device=dev) < 0.5
+    from_db = torch.rand((n_reads,), generator=g, device=dev) < wl["frac_db"]
+    ar = torch.arange(READ_LEN, device=dev)
+    col = torch.where(strand[:, None], st[:, None] + (READ_LEN - 1 - ar)[None, :], st[:, None] + ar[None, :])
+    c = codes[gi[:, None], col]
+    c = torch.where(strand[:, None], c ^ 1, c)
+    rnd = torch.randint(0, 4, (n_reads, READ_LEN), generator=g, device=dev, dtype=torch.int8)
+    c = torch.where(from_db[:, None], c, rnd)
+    sub = torch.rand((n_reads, READ_LEN), generator=g, device=dev) < wl["sub_rate"]
+    c = torch.where(sub, rnd, c)
+    lut = torch.tensor(list(b"CGAT"), dtype=torch.uint8, device=dev)
+    bases = torch.zeros(n_reads * READ_LEN + 64, dtype=torch.uint8, device=dev)
+    bases[: n_reads * READ_LEN] = lut[c.to(torch.int64)].reshape(-1)
+    offsets = (torch.arange(n_reads + 1, device=dev, dtype=torch.int64) * READ_LEN)
+    return bases, offsets
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (NVML; B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log("clock sampling unavailable:", e)
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {getattr(nv, n): n for n in dir(nv) if n.startswith("nvmlClocksThrottleReason") or n.startswith("nvmlClocksEventReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and bit & (bit - 1) == 0:
+                        self.reasons.add(nm.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        rs = sorted(x for x in self.reasons if x not in ("GpuIdle", "None", "All"))
+        norm = {"SwPowerCap": "sw_power_cap", "HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                "SwThermalSlowdown": "sw_thermal_slowdown", "HwPowerBrakeSlowdown": "hw_power_brake_slowdown",
+                "ApplicationsClocksSetting": "applications_clocks_setting", "SyncBoost": "sync_boost",
+                "UserDefinedClocks": "applications_clocks_setting", "DisplayClockSetting": "display_clock_setting"}
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(set(norm.get(r, r) for r in rs)), "samples": len(self.samples)}
+
+
+def algorithmic_bytes_per_kmer(n_db, h, use_bloom=True, count_unique=True, f=0.01):
+    """SURVEY.md §8(d) / DESIGN.md "Roofline": ASCII base stream + two Bloom words + binary-search keys and the short value
+    for the k-mers that reach the search + the unique-bitset RMW for hits."""
+    s = h + (1.0 - h) * (f if use_bloom else 1.0)
+    return (READ_LEN / (READ_LEN - K + 1)) + (16.0 if use_bloom else 0.0) + s * (8.0 * math.ceil(math.log2(max(n_db, 2))) + 2.0) + (8.0 * h if count_unique else 0.0)
+
+
+def cpu_reference(gs_oracle, keys_h, vals_h, V, parent, bases_h, offsets_h, threads, target_s, steps=1):
+    """Times the CPU oracle (restated reference algorithm, reference threading model) on a bounded sample."""
+    odb = gs_oracle.OracleDb.from_arrays(K, keys_h, vals_h, V, parent, build_bloom=True)
+    cfg = gs_oracle.match_cfg(k=K)
+    n_all = len(offsets_h) - 1
+    probe = min(n_all, 20000)
+    t0 = time.perf_counter()
+    odb.match_reads_mt(cfg, bases_h, offsets_h[: probe + 1], threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(n_all, max(probe, probe * target_s / dt)))
+    times, kmers, per = [], 0, None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        kmers, per = odb.match_reads_mt(cfg, bases_h, offsets_h[: n + 1], threads)
+        times.append(time.perf_counter() - t0)
+    odb.free()
+    return n, kmers, per, times
+
+
+def as_tensor(torch, ptr, nbytes, dev):
+    """Wrap a raw device pointer (owned by the C library) as a uint8 torch tensor (no copy)."""
+    class _Raw:
+        pass
+    r = _Raw()
+    r.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(r, device=dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GS_BENCH_WORKLOAD", "viral"), choices=sorted(WORKLOADS))
+    ap.add_argument("--reads-per-step", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    wl = dict(WORKLOADS[args.workload])
+    if args.reads_per_step:
+        wl["reads_per_step"] = args.reads_per_step
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1 and args.impl == "native":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    threads = os.cpu_count() or 1
+
+    # ---------------- synthetic project (same DB on every rank, different reads per rank)
+    t0 = time.perf_counter()
+    keys, vals_raw, parent, codes = make_database(torch, dev, wl, seed=43)
+    V = len(parent)
+    n_db = keys.numel()
+    R = wl["reads_per_step"]
+    n_batches = 2  # alternate between two resident batches (each far larger than the 126 MB L2)
+    batches = [make_reads(torch, dev, wl, codes, R, seed=4343 + 1000 * rank + b) for b in range(n_batches)]
+    torch.cuda.synchronize()
+    log("rank %d: synthetic project: %d db k-mers, %d tree nodes, %d reads/step (%.1f s)" % (rank, n_db, V, R, time.perf_counter() - t0))
+    kmers_per_step = R * (READ_LEN - K + 1)
+    config = {"workload": "%s: %s" % (args.workload, wl["desc"]), "k": K, "db_kmers": int(n_db), "tree_nodes": int(V), "read_len": READ_LEN,
+              "reads_per_step": R, "kmers_per_step": kmers_per_step, "frac_reads_from_db": wl["frac_db"], "substitution_rate": wl["sub_rate"],
+              "count_unique_kmers": True, "classify_reads": True, "use_bloom_filter": True,
+              "l2_policy": "inputs larger than L2: %.0f MB of bases per step, %.0f MB database, alternating batches" % (R * READ_LEN / 1e6, n_db * 10 / 1e6),
+              "parallelism": "reads sharded over %d GPU(s), database replicated" % world}
+
+    keys_h = keys.cpu().numpy()
+    vals_h = vals_raw.cpu().numpy()
+    b0_h = batches[0][0][: R * READ_LEN].cpu().numpy()
+    off_h = batches[0][1].cpu().numpy().astype(np.uint64)
+
+    if args.impl == "reference":
+        import gs_oracle
+        n, kmers, per, times = cpu_reference(gs_oracle, keys_h, vals_h, V, parent, b0_h, off_h, threads, args.cpu_seconds, steps=max(1, args.steps + args.warmup))
+        times = times[args.warmup:] if len(times) > args.warmup else times
+        dt = float(np.mean(times))
+        val = kmers / dt
+        line = {"impl": "reference", "metric": "match k-mers/s", "value": val, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "reads_per_s": n / dt, "config": config,
+                "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "port",
+                                 "sample": "%d of the %d reads of one step per timed step; C++ restatement of FastqKMerMatcher.matchRead with the reference's threading model (no JDK on this image)" % (n, R)},
+                "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- native arm
+    from genestrip_b200 import capi
+    ctx = capi.Context([local])
+    db = capi.Database(ctx, K, keys_h, vals_h, V, parent_by_vidx=parent, build_bloom=True)
+    del keys, vals_raw
+    log("rank %d: database on device: %.2f GB" % (rank, db.device_bytes / 1e9))
+    cfg = capi.default_match_cfg()
+    sess = capi.MatchSession(db, cfg)
+    stream = torch.cuda.ExternalStream(sess.stream, device=dev)
+    d_out = torch.zeros(R * 16, dtype=torch.uint8, device=dev)
+
+    def device_step(i):
+        bases, offsets = batches[i % n_batches]
+        sess.run_device(bases.data_ptr(), offsets.data_ptr(), R, i * R, d_out.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        device_step(i)
+    sess.sync()
+    launches0 = sess.kernel_launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            device_step(args.warmup + i)
+            ev[i + 1].record(stream)
+    sess.sync()
+    barrier()
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.result()
+    launches = sess.kernel_launches - launches0
+
+    # ---------------- end-to-end: pinned host buffers through submit/collect (H2D + kernels + D2H per step)
+    nb = R * READ_LEN
+    pinned = [capi.PinnedBuffer(nb + 64) for _ in range(n_batches)]
+    pin_off = capi.PinnedBuffer((R + 1) * 8)
+    for b in range(n_batches):
+        pinned[b].array[:nb] = batches[b][0][:nb].cpu().numpy()
+    offs = pin_off.view(np.uint64, R + 1)
+    offs[:] = off_h
+    sess2 = capi.MatchSession(db, cfg)
+
+    def e2e_run(n_steps, first):
+        pend = []
+        for i in range(n_steps):
+            pend.append(sess2.submit(pinned[(first + i) % n_batches].array, offs, (first + i) * R))
+            if len(pend) == capi.GS_MAX_INFLIGHT:
+                sess2.collect(pend.pop(0), want_events=False)
+        while pend:
+            sess2.collect(pend.pop(0), want_events=False)
+
+    e2e_run(args.warmup, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps, args.warmup)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---------------- end of job: merge the per-rank state (only exchange step of the path)
+    red_ms = 0.0
+    counts, _ = None, None
+    if dist:
+        c_ptr, m_ptr, b_ptr, b_words = sess.device_state()
+        t_c = as_tensor(torch, c_ptr, 7 * V * 8, dev).view(torch.int64)
+        t_m = as_tensor(torch, m_ptr, V * 8, dev).view(torch.int64)
+        t_b = as_tensor(torch, b_ptr, b_words * 8, dev).view(torch.int64)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        dist.all_reduce(t_c, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t_m, op=dist.ReduceOp.MAX)   # packed (len << 40 | ~ordinal) keys are < 2^63: signed max == unsigned max
+        # unique bitset: all-to-all of 1/world slices, local OR, per-taxon popcount of the own slice, sum of the counts
+        per = (b_words + world - 1) // world
+        padded = torch.zeros(per * world, dtype=torch.int64, device=dev)
+        padded[:b_words] = t_b
+        recv = torch.empty_like(padded)
+        dist.all_to_all_single(recv, padded)
+        mine = recv.view(world, per)[0].clone()
+        for r in range(1, world):
+            mine |= recv.view(world, per)[r]
+        uniq = torch.zeros(V, dtype=torch.int64, device=dev)
+        lo_w = rank * per
+        hi_w = min(b_words, lo_w + per)
+        # popcount kernel indexes words absolutely: place the merged slice at its position of a scratch bitset
+        t_b.zero_()
+        if hi_w > lo_w:
+            t_b[lo_w:hi_w] = mine[: hi_w - lo_w]
+        torch.cuda.synchronize()
+        sess.unique_popcount(b_ptr, lo_w, hi_w, uniq.data_ptr())
+        sess.sync()
+        dist.all_reduce(uniq, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize()
+        red_ms = e0.elapsed_time(e1)
+        total_hits = int(t_c[:V].sum().item())
+        unique_total = int(uniq.sum().item())
+    else:
+        counts, _ = sess.finish()
+        total_hits = int(counts["kmers"].sum())
+        unique_total = int(counts["unique_kmers"].sum())
+
+    # max over ranks of the timed region
+    tt = torch.tensor([total_ms + red_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    steps_done = args.warmup + args.steps
+    h = total_hits / float(steps_done * kmers_per_step * world) if dist else total_hits / float(steps_done * kmers_per_step)
+    value = world * args.steps * kmers_per_step / (total_ms_max / 1e3)
+    e2e_value = world * args.steps * kmers_per_step / (e2e_ms_max / 1e3)
+
+    line = None
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bpk = algorithmic_bytes_per_kmer(n_db, h)
+        kernel_ms = float(np.mean(step_ms))
+        achieved = bpk * kmers_per_step / (kernel_ms / 1e3) / 1e9
+        line = {"metric": "match k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+                "data": "synthetic", "reads_per_s": value / (READ_LEN - K + 1), "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R * 16 + 4 + V * 16,
+                        "reads_per_s": e2e_value / (READ_LEN - K + 1)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "gs_match_kernel<0,false>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk,
+                             "hit_fraction": h, "peak_source": peak_src},
+                "end_of_job_reduce_ms": red_ms, "hits_total": total_hits, "unique_kmers_total": unique_total}
+
+    # ---------------- CPU baseline + bench-scale parity spot check (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import gs_oracle
+        n, kmers, per, times = cpu_reference(gs_oracle, keys_h, vals_h, V, parent, b0_h, off_h, threads, args.cpu_seconds)
+        sess3 = capi.MatchSession(db, cfg)
+        t = sess3.submit(b0_h, off_h[: n + 1].copy(), 0)
+        sess3.collect(t)
+        c3, _ = sess3.finish()
+        sess3.close()
+        parity = bool(np.array_equal(c3["kmers"], per))
+        line["cpu_baseline"] = {"value": kmers / times[0], "unit": "k-mers/s", "cores": threads, "kind": "port",
+                                "sample": "first %d reads of one step (%.1f s of CPU work); C++ restatement of FastqKMerMatcher.matchRead, %d matcher threads" % (n, times[0], threads),
+                                "parity_kmers_per_taxon_equal": parity}
+        if not parity:
+            log("PARITY FAILURE on the bench sample")
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sess.close()
+    sess2.close()
+    for p in pinned:
+        p.free()
+    pin_off.free()
+    db.close()
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,379 @@
+"""ctypes binding of the C ABI in include/genestrip_b200.h (the same symbols the JNI shim binds).
+
+Thin and typed: numpy arrays in, numpy arrays out; every error code becomes GenestripError with the
+library's message.  There is no CPU fallback -- a missing extension or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+
+GS_ABI_VERSION = 1
+GS_MAX_INFLIGHT = 2
+GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
+GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
+GS_BLOOM_BLOCKED, GS_BLOOM_XOR, GS_BLOOM_MURMUR = 0, 1, 2
+
+
+class GenestripError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("genestrip_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class MatchCfg(C.Structure):
+    """gs_match_cfg (include/genestrip_b200.h); defaults = C/GSConfigKey.java:302-350."""
+    _fields_ = [("classify_reads", C.c_int), ("count_unique_kmers", C.c_int), ("max_kmer_res_counts", C.c_int),
+                ("use_bloom_filter", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
+                ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
+                ("want_runs", C.c_int), ("reserved", C.c_int)]
+
+
+READ_RESULT_DTYPE = np.dtype([("class_vidx", "<i4"), ("read_kmers", "<u4"), ("tax_err", "<u4"), ("flags", "<u4")])
+RUN_DTYPE = np.dtype([("label", "<u4"), ("len", "<u4")])
+EVENT_DTYPE = np.dtype([("vidx", "<u4"), ("contig_len", "<u4"), ("read_no", "<u8")])
+TAXON_COUNTS_DTYPE = np.dtype([("kmers", "<i8"), ("contigs", "<i8"), ("contig_len_squared_sum", "<i8"), ("reads_1kmer", "<i8"),
+                               ("reads", "<i8"), ("reads_kmers", "<i8"), ("reads_bps", "<i8"), ("unique_kmers", "<i8"),
+                               ("max_contig_len", "<i4"), ("touched", "<i4"), ("max_contig_read_no", "<u8")])
+assert READ_RESULT_DTYPE.itemsize == 16 and TAXON_COUNTS_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 16
+
+_lib = None
+
+_P = C.c_void_p
+_SIGS = {
+    "gs_abi_version": (C.c_int, []),
+    "gs_last_error": (C.c_char_p, []),
+    "gs_ctx_create": (_P, [_P, C.c_int]),
+    "gs_ctx_destroy": (None, [_P]),
+    "gs_ctx_n_devices": (C.c_int, [_P]),
+    "gs_alloc_pinned": (_P, [C.c_size_t]),
+    "gs_free_pinned": (None, [_P]),
+    "gs_db_create": (_P, [_P, C.c_int, C.c_uint64, C.c_int]),
+    "gs_db_put_keys": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "gs_db_put_values": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "gs_db_put_radix_bucket": (C.c_int, [_P, C.c_int, C.c_uint32, _P, C.c_uint32]),
+    "gs_db_set_tree": (C.c_int, [_P, _P, _P, C.c_int]),
+    "gs_db_set_bloom_blocked": (C.c_int, [_P, C.c_int64, C.c_uint64, _P, C.c_uint64]),
+    "gs_db_build_bloom_blocked": (C.c_int, [_P, _P, C.c_uint64]),
+    "gs_db_finalize": (C.c_int, [_P]),
+    "gs_db_destroy": (None, [_P]),
+    "gs_db_device_bytes": (C.c_uint64, [_P]),
+    "gs_db_lookup": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
+    "gs_match_cfg_default": (None, [C.POINTER(MatchCfg)]),
+    "gs_match_open": (_P, [_P, C.POINTER(MatchCfg)]),
+    "gs_match_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "gs_match_collect": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, _P, C.c_uint64]),
+    "gs_match_finish": (C.c_int, [_P, _P, _P]),
+    "gs_match_close": (None, [_P]),
+    "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _P]),
+    "gs_match_sync": (C.c_int, [_P]),
+    "gs_match_device_state": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "gs_match_unique_popcount": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
+    "gs_match_stream": (_P, [_P]),
+    "gs_match_kernel_launches": (C.c_uint64, [_P]),
+    "gs_match_dump_labels": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
+    "gs_filter_create": (_P, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_uint64]),
+    "gs_filter_destroy": (None, [_P]),
+    "gs_filter_contains": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "gs_filter_open": (_P, [_P, C.c_int, C.c_int, C.c_double]),
+    "gs_filter_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "gs_filter_collect": (C.c_int, [_P, C.c_uint64, _P]),
+    "gs_filter_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
+    "gs_filter_sync": (C.c_int, [_P]),
+    "gs_filter_stream": (_P, [_P]),
+    "gs_filter_close": (None, [_P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Load the CUDA extension; fails loudly when it is missing (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GenestripError(-2, "CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.gs_abi_version() != GS_ABI_VERSION:
+            raise GenestripError(-1, "ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GenestripError(rc, lib().gs_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def _arr(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Context:
+    """gs_ctx: the GPUs used by this process (replaces the consumer-thread pool, C/DefaultExecutionContext.java:78)."""
+
+    def __init__(self, devices=None):
+        L = lib()
+        if devices:
+            d = (C.c_int * len(devices))(*devices)
+            self.h = L.gs_ctx_create(C.cast(d, _P), len(devices))
+        else:
+            self.h = L.gs_ctx_create(None, 0)
+        if not self.h:
+            raise GenestripError(-2, L.gs_last_error().decode())
+
+    @property
+    def n_devices(self):
+        return lib().gs_ctx_n_devices(self.h)
+
+    def close(self):
+        if self.h:
+            lib().gs_ctx_destroy(self.h)
+            self.h = None
+
+
+class PinnedBuffer:
+    """gs_alloc_pinned as a numpy uint8 view (the pinned, double-buffered host batches of the parser)."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().gs_alloc_pinned(nbytes)
+        if not self.ptr:
+            raise GenestripError(-2, lib().gs_last_error().decode())
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def view(self, dtype, count, offset=0):
+        return self.array[offset:offset + count * np.dtype(dtype).itemsize].view(dtype)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().gs_free_pinned(self.ptr)
+            self.ptr = None
+
+
+class Database:
+    """gs_db: sorted k-mer store + value indices + tax tree + blocked Bloom prefilter, device resident."""
+
+    def __init__(self, ctx, k, keys, vidx_raw, n_values, parent_by_vidx=None, has_node=None, bloom=None, build_bloom=False,
+                 radix=None):
+        L = lib()
+        self.ctx = ctx
+        self.k = k
+        self.n_values = int(n_values)
+        if radix is None:
+            keys = _arr(keys, np.int64)
+            vidx_raw = _arr(vidx_raw, np.int16)
+            self.n_kmers = int(keys.shape[0])
+        else:
+            self.n_kmers = int(sum(len(e) for _, e in radix[1]))
+        self.h = L.gs_db_create(ctx.h, k, self.n_kmers, self.n_values)
+        if not self.h:
+            raise GenestripError(-1, L.gs_last_error().decode())
+        try:
+            if radix is None:
+                seg = 1 << 24  # streamed in segments like the reference's BigArrays (2^27) -- smaller here to exercise offsets
+                for off in range(0, self.n_kmers, seg):
+                    n = min(seg, self.n_kmers - off)
+                    _check(L.gs_db_put_keys(self.h, off, _ptr(keys[off:off + n]), n))
+                    _check(L.gs_db_put_values(self.h, off, _ptr(vidx_raw[off:off + n]), n))
+            else:
+                radix_bits, buckets = radix
+                for r, entries in buckets:
+                    e = _arr(entries, np.int64)
+                    _check(L.gs_db_put_radix_bucket(self.h, radix_bits, int(r), _ptr(e), len(e)))
+            if parent_by_vidx is not None:
+                p = _arr(parent_by_vidx, np.int32)
+                hn = None if has_node is None else _arr(has_node, np.int32)
+                _check(L.gs_db_set_tree(self.h, _ptr(p), _ptr(hn), self.n_values))
+            self.bloom_words = None
+            if bloom is not None:
+                seed, buckets, words = bloom
+                words = _arr(words, np.int64)
+                _check(L.gs_db_set_bloom_blocked(self.h, int(seed), int(buckets), _ptr(words), len(words)))
+            elif build_bloom:
+                nb = (max(1, self.n_kmers) * 10 + 63) // 64
+                out = np.zeros(nb + 17, dtype=np.int64) if build_bloom == "return" else None
+                _check(L.gs_db_build_bloom_blocked(self.h, _ptr(out), 0 if out is None else len(out)))
+                self.bloom_words = out
+            _check(L.gs_db_finalize(self.h))
+        except Exception:
+            L.gs_db_destroy(self.h)
+            self.h = None
+            raise
+
+    @property
+    def device_bytes(self):
+        return lib().gs_db_device_bytes(self.h)
+
+    def lookup(self, kmers, use_bloom=True):
+        kmers = _arr(kmers, np.int64)
+        v = np.empty(len(kmers), dtype=np.int32)
+        p = np.empty(len(kmers), dtype=np.int64)
+        _check(lib().gs_db_lookup(self.h, _ptr(kmers), len(kmers), 1 if use_bloom else 0, _ptr(v), _ptr(p)))
+        return v, p
+
+    def close(self):
+        if self.h:
+            lib().gs_db_destroy(self.h)
+            self.h = None
+
+
+def default_match_cfg(**over):
+    cfg = MatchCfg()
+    lib().gs_match_cfg_default(C.byref(cfg))
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class MatchSession:
+    """gs_sess: one FastqKMerMatcher.runMatcher run (C/match/FastqKMerMatcher.java:181-235)."""
+
+    def __init__(self, db, cfg=None):
+        self.db = db
+        self.cfg = cfg if cfg is not None else default_match_cfg()
+        self.h = lib().gs_match_open(db.h, C.byref(self.cfg))
+        if not self.h:
+            raise GenestripError(-1, lib().gs_last_error().decode())
+        self._keep = {}
+
+    def submit(self, bases, offsets, first_read_no):
+        """bases: uint8 array (host, ideally pinned); offsets: uint64[n+1].  Returns a ticket."""
+        n = len(offsets) - 1
+        t = C.c_uint64(0)
+        _check(lib().gs_match_submit(self.h, _ptr(bases), _ptr(offsets), n, int(first_read_no), C.byref(t)))
+        self._keep[t.value] = (bases, offsets, n)
+        return t.value
+
+    def collect(self, ticket, want_events=True):
+        bases, offsets, n = self._keep.pop(ticket)
+        out = np.empty(n, dtype=READ_RESULT_DTYPE)
+        ev = np.empty(max(self.db.n_values, 1), dtype=EVENT_DTYPE)
+        nev = C.c_uint32(0)
+        runs = run_off = None
+        if self.cfg.want_runs:
+            k = self.db.k
+            lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+            cap = int(np.maximum(lens - k + 1, 0).sum())
+            run_off = np.zeros(n + 1, dtype=np.uint64)
+            runs = np.empty(max(cap, 1), dtype=RUN_DTYPE)
+            _check(lib().gs_match_collect(self.h, ticket, _ptr(out), _ptr(ev), len(ev), C.byref(nev), _ptr(run_off), _ptr(runs), cap))
+            runs = runs[:int(run_off[n])]
+        else:
+            _check(lib().gs_match_collect(self.h, ticket, _ptr(out), _ptr(ev), len(ev), C.byref(nev), None, None, 0))
+        return out, ev[:nev.value].copy(), run_off, runs
+
+    def finish(self):
+        V = self.db.n_values
+        counts = np.zeros(max(V, 1), dtype=TAXON_COUNTS_DTYPE)
+        top = None
+        if self.cfg.count_unique_kmers and self.cfg.max_kmer_res_counts > 0:
+            top = np.zeros((V + 1, self.cfg.max_kmer_res_counts), dtype=np.int16)
+        _check(lib().gs_match_finish(self.h, _ptr(counts), _ptr(top)))
+        return counts[:V], top
+
+    # ---- device-resident variants (bench kernel-only number, NCCL reduction of raw state)
+    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, first_read_no, d_out_ptr):
+        _check(lib().gs_match_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, int(first_read_no), d_out_ptr))
+
+    def sync(self):
+        _check(lib().gs_match_sync(self.h))
+
+    def device_state(self):
+        c, m, b = _P(), _P(), _P()
+        w = C.c_uint64(0)
+        _check(lib().gs_match_device_state(self.h, C.byref(c), C.byref(m), C.byref(b), C.byref(w)))
+        return c.value, m.value, b.value, w.value
+
+    def unique_popcount(self, d_bitset_ptr, word_begin, word_end, d_unique_ptr):
+        _check(lib().gs_match_unique_popcount(self.h, d_bitset_ptr, word_begin, word_end, d_unique_ptr))
+
+    def dump_labels(self, d_bases_ptr, d_offsets_ptr, n_reads, d_kmer_offsets_ptr, d_labels_ptr, d_pos_ptr):
+        _check(lib().gs_match_dump_labels(self.h, d_bases_ptr, d_offsets_ptr, n_reads, d_kmer_offsets_ptr, d_labels_ptr, d_pos_ptr))
+
+    @property
+    def stream(self):
+        return lib().gs_match_stream(self.h)
+
+    @property
+    def kernel_launches(self):
+        return lib().gs_match_kernel_launches(self.h)
+
+    def close(self):
+        if self.h:
+            lib().gs_match_close(self.h)
+            self.h = None
+
+
+class Filter:
+    """gs_filter: the `filter` goal's KMerProbFilter index, device resident (C/goals/LoadIndexGoal.java:92-104)."""
+
+    def __init__(self, ctx, kind, p0, p1, factors, words):
+        words = _arr(words, np.int64)
+        f = None if factors is None else _arr(factors, np.int64)
+        self.h = lib().gs_filter_create(ctx.h, kind, int(p0), int(p1), _ptr(f), _ptr(words), len(words))
+        if not self.h:
+            raise GenestripError(-1, lib().gs_last_error().decode())
+
+    def contains(self, kmers):
+        kmers = _arr(kmers, np.int64)
+        out = np.empty(len(kmers), dtype=np.uint8)
+        _check(lib().gs_filter_contains(self.h, _ptr(kmers), len(kmers), _ptr(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().gs_filter_destroy(self.h)
+            self.h = None
+
+
+class FilterSession:
+    """gs_fsess: one FastqBloomFilter.runFilter run (C/bloom/FastqBloomFilter.java:80-161)."""
+
+    def __init__(self, flt, k, min_pos_count=1, pos_ratio=0.2):
+        self.h = lib().gs_filter_open(flt.h, k, min_pos_count, pos_ratio)
+        if not self.h:
+            raise GenestripError(-1, lib().gs_last_error().decode())
+        self._keep = {}
+
+    def submit(self, bases, offsets):
+        n = len(offsets) - 1
+        t = C.c_uint64(0)
+        _check(lib().gs_filter_submit(self.h, _ptr(bases), _ptr(offsets), n, C.byref(t)))
+        self._keep[t.value] = (bases, offsets, n)
+        return t.value
+
+    def collect(self, ticket):
+        _, _, n = self._keep.pop(ticket)
+        out = np.empty(n, dtype=np.uint8)
+        _check(lib().gs_filter_collect(self.h, ticket, _ptr(out)))
+        return out
+
+    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr):
+        _check(lib().gs_filter_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr))
+
+    def sync(self):
+        _check(lib().gs_filter_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().gs_filter_stream(self.h)
+
+    def close(self):
+        if self.h:
+            lib().gs_filter_close(self.h)
+            self.h = None

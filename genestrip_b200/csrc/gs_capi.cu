@@ -1,0 +1,1087 @@
+// gs_capi.cu -- the C ABI of include/genestrip_b200.h: device-resident database, match / filter sessions with
+// double-buffered batches on side streams, end-of-run merge.  No CPU fallback: every compute entry point needs a
+// CUDA device and fails with GS_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gs_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int gs_fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return gs_fail(GS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CUP(call)                                                                                             \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            gs_fail(GS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return nullptr;                                                                                   \
+        }                                                                                                     \
+    } while (0)
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t count) {
+    *p = nullptr;
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// grow a device buffer (contents are not preserved); the caller guarantees no kernel still uses it
+template <typename T>
+static cudaError_t dgrow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return cudaSuccess;
+    if (*p) { cudaError_t e = cudaFree(*p); if (e != cudaSuccess) return e; *p = nullptr; }
+    size_t ncap = need + need / 4 + 64;
+    cudaError_t e = cudaMalloc((void**)p, ncap * sizeof(T));
+    if (e == cudaSuccess) *cap = ncap;
+    return e;
+}
+template <typename T>
+static cudaError_t hgrow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return cudaSuccess;
+    if (*p) { cudaError_t e = cudaFreeHost(*p); if (e != cudaSuccess) return e; *p = nullptr; }
+    size_t ncap = need + need / 4 + 64;
+    cudaError_t e = cudaMallocHost((void**)p, ncap * sizeof(T));
+    if (e == cudaSuccess) *cap = ncap;
+    return e;
+}
+
+static u64 magic_for(u64 d) { return d ? (~0ULL) / d : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+struct gs_ctx {
+    std::vector<int> devs;
+    std::vector<int> sms;
+};
+
+extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
+extern "C" const char* gs_last_error(void) { return g_err.c_str(); }
+
+extern "C" gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        gs_fail(GS_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    gs_ctx* c = new gs_ctx();
+    if (!device_ordinals || n_devices <= 0) c->devs.push_back(0);
+    else c->devs.assign(device_ordinals, device_ordinals + n_devices);
+    for (int d : c->devs) {
+        if (d < 0 || d >= count) { gs_fail(GS_ERR_ARG, "device ordinal %d out of range [0,%d)", d, count); delete c; return nullptr; }
+        int sm = 0;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, d);
+        c->sms.push_back(sm > 0 ? sm : 148);
+    }
+    // peer access between the devices of the context (database replication, end-of-run merge)
+    for (size_t i = 0; i < c->devs.size(); i++)
+        for (size_t j = 0; j < c->devs.size(); j++) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->devs[i], c->devs[j]);
+            if (can) { cudaSetDevice(c->devs[i]); cudaDeviceEnablePeerAccess(c->devs[j], 0); cudaGetLastError(); }
+        }
+    cudaSetDevice(c->devs[0]);
+    return c;
+}
+extern "C" void gs_ctx_destroy(gs_ctx* c) { delete c; }
+extern "C" int gs_ctx_n_devices(const gs_ctx* c) { return c ? (int)c->devs.size() : 0; }
+
+extern "C" void* gs_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, std::max<size_t>(bytes, 1));
+    if (e != cudaSuccess) { gs_fail(GS_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+extern "C" void gs_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// database
+// ---------------------------------------------------------------------------------------------------------
+struct DevDb {
+    int dev = 0;
+    u64* keys = nullptr;
+    uint16_t* vals = nullptr;
+    u32* bstart = nullptr;
+    u64* bloom = nullptr;
+    int *parent = nullptr, *depth = nullptr, *pre = nullptr, *last = nullptr;
+    GsDbView view;
+};
+
+struct gs_db {
+    gs_ctx* ctx = nullptr;
+    int k = 0;
+    u64 n = 0;
+    int V = 0;
+    bool finalized = false;
+    std::vector<DevDb> d;
+    int16_t* rawVals = nullptr;  // device 0 staging of the Java shorts
+    std::vector<int> hParent, hHasNode, hDepth, hPre, hLast;
+    bool hasTree = false;
+    // bloom
+    bool hasBloom = false;
+    long long bloomSeed = 0;
+    u64 bloomBuckets = 0, bloomWords = 0;
+    // bucket index
+    int bbits = 0, bshift = 0;
+    u64 nBuckets = 0;
+    // radix source staging
+    std::vector<std::pair<u64, int16_t>> radixItems;
+    u64 bytes = 0;
+};
+
+extern "C" gs_db* gs_db_create(gs_ctx* ctx, int k, uint64_t n_kmers, int n_values) {
+    if (!ctx) { gs_fail(GS_ERR_ARG, "null context"); return nullptr; }
+    if (k < 1 || k > 31) { gs_fail(GS_ERR_ARG, "k=%d out of range [1,31]", k); return nullptr; }
+    if (n_values < 0 || n_values > 65535) { gs_fail(GS_ERR_LIMIT, "n_values=%d exceeds 65535 (KMerSortedArray.MAX_VALUES)", n_values); return nullptr; }
+    if (n_kmers >= 0xFFFFFFF0ULL) { gs_fail(GS_ERR_LIMIT, "n_kmers=%llu exceeds the 32-bit position limit of this build", (unsigned long long)n_kmers); return nullptr; }
+    gs_db* db = new gs_db();
+    db->ctx = ctx; db->k = k; db->n = n_kmers; db->V = n_values;
+    db->d.resize(ctx->devs.size());
+    for (size_t i = 0; i < ctx->devs.size(); i++) db->d[i].dev = ctx->devs[i];
+    CUP(cudaSetDevice(ctx->devs[0]));
+    CUP(dmalloc(&db->d[0].keys, n_kmers + 1));
+    CUP(dmalloc(&db->rawVals, n_kmers));
+    CUP(cudaMemset(db->d[0].keys, 0, (n_kmers + 1) * sizeof(u64)));
+    CUP(cudaMemset(db->rawVals, 0x80, std::max<u64>(n_kmers, 1) * sizeof(int16_t)));  // 0x8080 -> index 128; overwritten by put_values
+    return db;
+}
+
+extern "C" int gs_db_put_keys(gs_db* db, uint64_t offset, const int64_t* keys, uint64_t n) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "key segment [%llu,%llu) exceeds n_kmers=%llu", (unsigned long long)offset, (unsigned long long)(offset + n), (unsigned long long)db->n);
+    CU(cudaSetDevice(db->d[0].dev));
+    CU(cudaMemcpy(db->d[0].keys + offset, keys, n * sizeof(u64), cudaMemcpyHostToDevice));
+    return GS_OK;
+}
+
+extern "C" int gs_db_put_values(gs_db* db, uint64_t offset, const int16_t* vidx_raw, uint64_t n) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "value segment exceeds n_kmers");
+    CU(cudaSetDevice(db->d[0].dev));
+    CU(cudaMemcpy(db->rawVals + offset, vidx_raw, n * sizeof(int16_t), cudaMemcpyHostToDevice));
+    return GS_OK;
+}
+
+extern "C" int gs_db_put_radix_bucket(gs_db* db, int radix_bits, uint32_t radix, const int64_t* entries, uint32_t n) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    if (radix_bits < 16 || radix_bits > 30) return gs_fail(GS_ERR_ARG, "radix_bits=%d out of range [16,30]", radix_bits);
+    if (radix >= (1u << radix_bits)) return gs_fail(GS_ERR_ARG, "radix %u out of range", radix);
+    const int remainingBits = 62 - radix_bits;  // RadixKMerStore.java:165-168
+    const u64 remainingMask = (1ULL << remainingBits) - 1;
+    for (uint32_t i = 0; i < n; i++) {
+        const u64 e = (u64)entries[i];
+        const u64 kmer = ((e & remainingMask) << radix_bits) | (u64)radix;  // RadixKMerStore.visit :714-730
+        const int vi = (int)(e >> remainingBits);
+        if (vi >= db->V) return gs_fail(GS_ERR_ARG, "radix entry value index %d >= n_values", vi);
+        db->radixItems.emplace_back(kmer, (int16_t)(vi - 32768));
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_db_set_tree(gs_db* db, const int32_t* parent_by_vidx, const int32_t* has_node, int n_values) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    if (n_values != db->V) return gs_fail(GS_ERR_ARG, "n_values mismatch (%d vs %d)", n_values, db->V);
+    const int V = db->V;
+    db->hParent.assign(parent_by_vidx, parent_by_vidx + V);
+    if (has_node) db->hHasNode.assign(has_node, has_node + V); else db->hHasNode.assign(V, 1);
+    for (int v = 0; v < V; v++) {
+        if (!db->hHasNode[v]) { db->hParent[v] = -1; continue; }
+        int p = db->hParent[v];
+        if (p < -1 || p >= V || p == v) return gs_fail(GS_ERR_ARG, "parent of value index %d is %d", v, p);
+        if (p >= 0 && !db->hHasNode[p]) return gs_fail(GS_ERR_ARG, "parent %d of value index %d has no node", p, v);
+    }
+    // depth + DFS interval labels (a is ancestor-or-self of b <=> pre[a] <= pre[b] <= last[a])
+    std::vector<std::vector<int>> kids(V);
+    std::vector<int> roots;
+    for (int v = 0; v < V; v++) {
+        if (!db->hHasNode[v]) continue;
+        if (db->hParent[v] < 0) roots.push_back(v); else kids[db->hParent[v]].push_back(v);
+    }
+    db->hDepth.assign(V, 0); db->hPre.assign(V, -1); db->hLast.assign(V, -1);
+    int counter = 0, visited = 0, nodes = 0;
+    for (int v = 0; v < V; v++) nodes += db->hHasNode[v] ? 1 : 0;
+    std::vector<std::pair<int, size_t>> stack;
+    for (int r : roots) {
+        stack.emplace_back(r, 0);
+        db->hPre[r] = counter++; db->hDepth[r] = 0; visited++;
+        while (!stack.empty()) {
+            auto& top = stack.back();
+            if (top.second < kids[top.first].size()) {
+                int c = kids[top.first][top.second++];
+                db->hPre[c] = counter++; db->hDepth[c] = db->hDepth[stack.back().first] + 1; visited++;
+                stack.emplace_back(c, 0);
+            } else {
+                db->hLast[top.first] = counter - 1;
+                stack.pop_back();
+            }
+        }
+    }
+    if (visited != nodes) return gs_fail(GS_ERR_ARG, "tax tree has a cycle (%d of %d nodes reachable from roots)", visited, nodes);
+    // nodes without a tree node never appear as labels; give them an empty interval
+    for (int v = 0; v < V; v++) if (!db->hHasNode[v]) { db->hPre[v] = counter; db->hLast[v] = counter - 1; }
+    db->hasTree = true;
+    return GS_OK;
+}
+
+extern "C" int gs_db_set_bloom_blocked(gs_db* db, int64_t seed, uint64_t buckets, const int64_t* words, uint64_t n_words) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    if (buckets == 0 || n_words < buckets + 17) return gs_fail(GS_ERR_ARG, "blocked Bloom filter needs buckets+17 words (buckets=%llu, n_words=%llu)", (unsigned long long)buckets, (unsigned long long)n_words);
+    CU(cudaSetDevice(db->d[0].dev));
+    if (db->d[0].bloom) { CU(cudaFree(db->d[0].bloom)); db->d[0].bloom = nullptr; }
+    CU(dmalloc(&db->d[0].bloom, buckets + 17));
+    CU(cudaMemcpy(db->d[0].bloom, words, (buckets + 17) * sizeof(u64), cudaMemcpyHostToDevice));
+    db->hasBloom = true; db->bloomSeed = seed; db->bloomBuckets = buckets; db->bloomWords = buckets + 17;
+    return GS_OK;
+}
+
+static int upload_radix_items(gs_db* db) {
+    if (db->radixItems.empty()) return GS_OK;
+    if (db->radixItems.size() != db->n) return gs_fail(GS_ERR_ARG, "radix buckets hold %zu entries, n_kmers=%llu", db->radixItems.size(), (unsigned long long)db->n);
+    std::sort(db->radixItems.begin(), db->radixItems.end());
+    std::vector<u64> keys(db->n);
+    std::vector<int16_t> vals(db->n);
+    for (size_t i = 0; i < db->radixItems.size(); i++) { keys[i] = db->radixItems[i].first; vals[i] = db->radixItems[i].second; }
+    db->radixItems.clear(); db->radixItems.shrink_to_fit();
+    CU(cudaMemcpy(db->d[0].keys, keys.data(), db->n * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->rawVals, vals.data(), db->n * sizeof(int16_t), cudaMemcpyHostToDevice));
+    return GS_OK;
+}
+
+extern "C" int gs_db_build_bloom_blocked(gs_db* db, int64_t* words_out, uint64_t n_words_out) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    CU(cudaSetDevice(db->d[0].dev));
+    int rc = upload_radix_items(db);
+    if (rc) return rc;
+    // BlockedKMerBloomFilter.ensureExpectedSize (C/bloom/BlockedKMerBloomFilter.java:201-219) with bitsPerKey = 10
+    const u64 entries = std::max<u64>(1, db->n);
+    const u64 buckets = (entries * 10 + 63) / 64;
+    const long long seed = -5025562857975149833LL;  // new Random(42).nextLong() (:91-93)
+    if (db->d[0].bloom) { CU(cudaFree(db->d[0].bloom)); db->d[0].bloom = nullptr; }
+    CU(dmalloc(&db->d[0].bloom, buckets + 17));
+    CU(cudaMemset(db->d[0].bloom, 0, (buckets + 17) * sizeof(u64)));
+    gs_launch_bloom_build(db->d[0].keys, db->n, db->d[0].bloom, buckets, magic_for(buckets), seed, 0);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    db->hasBloom = true; db->bloomSeed = seed; db->bloomBuckets = buckets; db->bloomWords = buckets + 17;
+    if (words_out) {
+        if (n_words_out < buckets + 17) return gs_fail(GS_ERR_ARG, "words_out too small: %llu < %llu", (unsigned long long)n_words_out, (unsigned long long)(buckets + 17));
+        CU(cudaMemcpy(words_out, db->d[0].bloom, (buckets + 17) * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_db_finalize(gs_db* db) {
+    if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
+    DevDb& d0 = db->d[0];
+    CU(cudaSetDevice(d0.dev));
+    int rc = upload_radix_items(db);
+    if (rc) return rc;
+    if (!db->hasTree) {  // no tree given: every value index is its own root (classification off / tests without tree)
+        std::vector<int> parent(db->V, -1);
+        rc = gs_db_set_tree(db, parent.data(), nullptr, db->V);
+        if (rc) return rc;
+    }
+    const int V = db->V;
+    u32* dBad = nullptr;
+    CU(dmalloc(&dBad, 1));
+    CU(cudaMemset(dBad, 0, sizeof(u32)));
+    gs_launch_check_sorted(d0.keys, db->n, db->k, dBad, 0);
+    CU(cudaGetLastError());
+    u32 bad = 0;
+    CU(cudaMemcpy(&bad, dBad, sizeof(u32), cudaMemcpyDeviceToHost));
+    if (bad) { cudaFree(dBad); return gs_fail(GS_ERR_ARG, "keys are not strictly ascending 2k-bit values (%u violations)", bad); }
+    // values: Java short -> value index, GS_VAL_NONODE for values without a tree node
+    int* dHas = nullptr;
+    CU(dmalloc(&dHas, (size_t)V));
+    CU(cudaMemcpy(dHas, db->hHasNode.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    CU(dmalloc(&d0.vals, db->n));
+    gs_launch_convert_values(db->rawVals, dHas, db->n, V, d0.vals, dBad, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(&bad, dBad, sizeof(u32), cudaMemcpyDeviceToHost));
+    CU(cudaFree(dHas));
+    CU(cudaFree(dBad));
+    if (bad) return gs_fail(GS_ERR_ARG, "%u stored values have an index >= n_values", bad);
+    CU(cudaFree(db->rawVals)); db->rawVals = nullptr;
+    // bucket index over the top key bits: ~4 keys per bucket on average
+    int lg = 0;
+    while ((1ULL << (lg + 1)) <= std::max<u64>(db->n, 1)) lg++;
+    db->bbits = std::max(0, std::min(std::min(2 * db->k, 30), lg - 1));
+    db->bshift = 2 * db->k - db->bbits;
+    db->nBuckets = 1ULL << db->bbits;
+    CU(dmalloc(&d0.bstart, db->nBuckets + 1));
+    gs_launch_bucket_index(d0.keys, db->n, db->bshift, db->nBuckets, d0.bstart, 0);
+    CU(cudaGetLastError());
+    // tree
+    CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));
+    CU(cudaMemcpy(d0.parent, db->hParent.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d0.depth, db->hDepth.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d0.pre, db->hPre.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d0.last, db->hLast.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    // replicate to the other devices of the context
+    for (size_t i = 1; i < db->d.size(); i++) {
+        DevDb& di = db->d[i];
+        CU(cudaSetDevice(di.dev));
+        CU(dmalloc(&di.keys, db->n + 1)); CU(dmalloc(&di.vals, db->n)); CU(dmalloc(&di.bstart, db->nBuckets + 1));
+        CU(dmalloc(&di.parent, (size_t)V)); CU(dmalloc(&di.depth, (size_t)V)); CU(dmalloc(&di.pre, (size_t)V)); CU(dmalloc(&di.last, (size_t)V));
+        CU(cudaMemcpyPeer(di.keys, di.dev, d0.keys, d0.dev, (db->n + 1) * sizeof(u64)));
+        CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
+        CU(cudaMemcpyPeer(di.bstart, di.dev, d0.bstart, d0.dev, (db->nBuckets + 1) * sizeof(u32)));
+        CU(cudaMemcpyPeer(di.parent, di.dev, d0.parent, d0.dev, (size_t)V * sizeof(int)));
+        CU(cudaMemcpyPeer(di.depth, di.dev, d0.depth, d0.dev, (size_t)V * sizeof(int)));
+        CU(cudaMemcpyPeer(di.pre, di.dev, d0.pre, d0.dev, (size_t)V * sizeof(int)));
+        CU(cudaMemcpyPeer(di.last, di.dev, d0.last, d0.dev, (size_t)V * sizeof(int)));
+        if (db->hasBloom) {
+            CU(dmalloc(&di.bloom, db->bloomWords));
+            CU(cudaMemcpyPeer(di.bloom, di.dev, d0.bloom, d0.dev, db->bloomWords * sizeof(u64)));
+        }
+        CU(cudaDeviceSynchronize());
+    }
+    for (DevDb& d : db->d) {
+        GsDbView& v = d.view;
+        v.keys = d.keys; v.vals = d.vals; v.n = db->n; v.bstart = d.bstart; v.bshift = db->bshift; v.nBuckets = db->nBuckets;
+        v.k = db->k; v.bloom = d.bloom; v.bloomBuckets = db->bloomBuckets; v.bloomMagic = magic_for(db->bloomBuckets);
+        v.bloomSeed = db->bloomSeed; v.hasBloom = db->hasBloom ? 1 : 0;
+        v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
+    }
+    db->bytes = (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
+    CU(cudaSetDevice(d0.dev));
+    db->finalized = true;
+    return GS_OK;
+}
+
+extern "C" void gs_db_destroy(gs_db* db) {
+    if (!db) return;
+    for (DevDb& d : db->d) {
+        cudaSetDevice(d.dev);
+        cudaFree(d.keys); cudaFree(d.vals); cudaFree(d.bstart); cudaFree(d.bloom);
+        cudaFree(d.parent); cudaFree(d.depth); cudaFree(d.pre); cudaFree(d.last);
+    }
+    if (db->rawVals) { cudaSetDevice(db->d[0].dev); cudaFree(db->rawVals); }
+    delete db;
+}
+
+extern "C" uint64_t gs_db_device_bytes(const gs_db* db) { return db ? db->bytes : 0; }
+
+extern "C" int gs_db_lookup(gs_db* db, const int64_t* kmers, uint64_t n, int use_bloom, int32_t* vidx_out, int64_t* pos_out) {
+    if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
+    CU(cudaSetDevice(db->d[0].dev));
+    u64* dK = nullptr; int* dV = nullptr; long long* dP = nullptr;
+    CU(dmalloc(&dK, n)); CU(dmalloc(&dV, n)); CU(dmalloc(&dP, n));
+    CU(cudaMemcpy(dK, kmers, n * sizeof(u64), cudaMemcpyHostToDevice));
+    if (n) gs_launch_lookup(db->d[0].view, dK, n, use_bloom, dV, dP, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(vidx_out, dV, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pos_out, dP, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaFree(dK)); CU(cudaFree(dV)); CU(cudaFree(dP));
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// match sessions
+// ---------------------------------------------------------------------------------------------------------
+struct MatchSlot {
+    bool pending = false;
+    gs_ticket ticket = 0;
+    u32 nReads = 0;
+    u64 firstReadNo = 0;
+    u64 totalKmers = 0;
+    uint8_t* dBases = nullptr; size_t basesCap = 0;
+    u64* dOffsets = nullptr; size_t offCap = 0;
+    gs_read_result* dOut = nullptr; size_t outCap = 0;
+    gs_read_result* hOut = nullptr; size_t hOutCap = 0;
+    gs_maxcontig_event* dEv = nullptr; gs_maxcontig_event* hEv = nullptr; u32* dNEv = nullptr; u32* hNEv = nullptr;
+    // want_runs
+    u64* dKmerOff = nullptr; size_t kmerOffCap = 0;
+    u64* hKmerOff = nullptr; size_t hKmerOffCap = 0;
+    gs_run* dRuns = nullptr; size_t runsCap = 0;
+    u32* dRunCounts = nullptr; size_t runCountsCap = 0;
+    u32* hRunCounts = nullptr; size_t hRunCountsCap = 0;
+    cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
+};
+
+struct DevSess {
+    int dev = 0, devIndex = 0, sms = 148;
+    cudaStream_t sCopyIn = nullptr, sCompute = nullptr, sCopyOut = nullptr;
+    long long* counters = nullptr;  // [7][V]
+    u64* maxcontig = nullptr;       // [V]
+    u64* bitset = nullptr; u64 bitsetWords = 0;
+    uint16_t* hitCounts = nullptr;
+    long long* unique = nullptr;    // [V]
+    u32* overflowList = nullptr; size_t ovCap = 0;
+    u32* overflowCount = nullptr;
+    u32* slowTable = nullptr;
+    int fastBlocks = 0, slowBlocks = 0;
+    MatchSlot slots[GS_MAX_INFLIGHT];
+};
+
+struct gs_sess {
+    gs_db* db = nullptr;
+    gs_match_cfg cfg;
+    std::vector<DevSess> devs;
+    u64 nextTicket = 1;
+    u64 launches = 0;
+    bool finished = false;
+};
+
+extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->classify_reads = 1;              // C/GSConfigKey.java:302
+    c->count_unique_kmers = 1;          // :305
+    c->max_kmer_res_counts = 0;         // :344
+    c->use_bloom_filter = 1;            // :320
+    c->max_classification_paths = 10;   // :350
+    c->min_kmers_for_class = 1;         // :341
+    c->max_read_tax_error_count = -1;   // :328
+    c->max_read_class_error_count = -1; // :337
+    c->want_runs = 0;
+}
+
+static int sess_alloc_dev(gs_sess* s, DevSess& D) {
+    const int V = s->db->V;
+    CU(cudaSetDevice(D.dev));
+    CU(cudaStreamCreateWithFlags(&D.sCopyIn, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&D.sCompute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&D.sCopyOut, cudaStreamNonBlocking));
+    CU(dmalloc(&D.counters, (size_t)7 * V));
+    CU(cudaMemset(D.counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
+    CU(dmalloc(&D.maxcontig, (size_t)V));
+    CU(cudaMemset(D.maxcontig, 0, std::max<size_t>(V, 1) * sizeof(u64)));
+    CU(dmalloc(&D.unique, (size_t)V));
+    if (s->cfg.count_unique_kmers) {
+        D.bitsetWords = (s->db->n + 63) / 64;
+        CU(dmalloc(&D.bitset, D.bitsetWords));
+        CU(cudaMemset(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64)));
+        if (s->cfg.max_kmer_res_counts > 0) {
+            CU(dmalloc(&D.hitCounts, s->db->n + 2));
+            CU(cudaMemset(D.hitCounts, 0, (s->db->n + 2) * sizeof(uint16_t)));
+        }
+    }
+    CU(dmalloc(&D.overflowCount, 1));
+    const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
+    D.fastBlocks = D.sms * occ0;
+    D.slowBlocks = std::max(1, D.sms / 4);
+    CU(dmalloc(&D.slowTable, (size_t)D.slowBlocks * GS_WARPS_PER_BLOCK * 2 * std::max(V, 1)));
+    for (MatchSlot& sl : D.slots) {
+        CU(cudaEventCreateWithFlags(&sl.evH2D, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming));
+        CU(dmalloc(&sl.dEv, (size_t)std::max(V, 1)));
+        CU(dmalloc(&sl.dNEv, 1));
+        CU(cudaMallocHost((void**)&sl.hEv, std::max<size_t>(V, 1) * sizeof(gs_maxcontig_event)));
+        CU(cudaMallocHost((void**)&sl.hNEv, sizeof(u32)));
+    }
+    return GS_OK;
+}
+
+extern "C" void gs_match_close(gs_sess* s) {
+    if (!s) return;
+    for (DevSess& D : s->devs) {
+        cudaSetDevice(D.dev);
+        cudaDeviceSynchronize();
+        for (MatchSlot& sl : D.slots) {
+            cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dOut); cudaFree(sl.dEv); cudaFree(sl.dNEv);
+            cudaFree(sl.dKmerOff); cudaFree(sl.dRuns); cudaFree(sl.dRunCounts);
+            if (sl.hOut) cudaFreeHost(sl.hOut);
+            if (sl.hEv) cudaFreeHost(sl.hEv);
+            if (sl.hNEv) cudaFreeHost(sl.hNEv);
+            if (sl.hKmerOff) cudaFreeHost(sl.hKmerOff);
+            if (sl.hRunCounts) cudaFreeHost(sl.hRunCounts);
+            if (sl.evH2D) cudaEventDestroy(sl.evH2D);
+            if (sl.evCompute) cudaEventDestroy(sl.evCompute);
+            if (sl.evDone) cudaEventDestroy(sl.evDone);
+        }
+        cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
+        cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
+        if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
+        if (D.sCompute) cudaStreamDestroy(D.sCompute);
+        if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
+    }
+    delete s;
+}
+
+extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
+    if (!db || !db->finalized) { gs_fail(GS_ERR_STATE, "database not finalized"); return nullptr; }
+    gs_match_cfg c;
+    if (cfg) c = *cfg; else gs_match_cfg_default(&c);
+    if (c.max_classification_paths < 1 || c.max_classification_paths > GS_MAX_PATHS) {
+        gs_fail(GS_ERR_ARG, "max_classification_paths=%d out of range [1,%d]", c.max_classification_paths, GS_MAX_PATHS);
+        return nullptr;
+    }
+    if (c.use_bloom_filter && !db->hasBloom) c.use_bloom_filter = 0;  // store without filter: KMerSortedArray.getLong :299 skips it
+    gs_sess* s = new gs_sess();
+    s->db = db; s->cfg = c;
+    s->devs.resize(db->d.size());
+    for (size_t i = 0; i < db->d.size(); i++) {
+        s->devs[i].dev = db->d[i].dev; s->devs[i].devIndex = (int)i; s->devs[i].sms = db->ctx->sms[i];
+        if (sess_alloc_dev(s, s->devs[i]) != GS_OK) { gs_match_close(s); return nullptr; }
+    }
+    cudaSetDevice(db->d[0].dev);
+    return s;
+}
+
+static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
+    memset(&P, 0, sizeof(P));
+    P.db = s->db->d[D.devIndex].view;
+    P.counters = D.counters; P.maxcontig = D.maxcontig; P.bitset = D.bitset; P.hitCounts = D.hitCounts;
+    P.classify = s->cfg.classify_reads ? 1 : 0;
+    P.useBloom = s->cfg.use_bloom_filter ? 1 : 0;
+    P.maxPaths = s->cfg.max_classification_paths;
+    P.threshold = s->cfg.min_kmers_for_class;
+    P.maxTaxErr = s->cfg.max_read_tax_error_count;
+    P.maxClassErr = s->cfg.max_read_class_error_count;
+    P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.slowTable = D.slowTable;
+}
+
+// kernels of one batch on the compute stream: fast path, slow path over the overflow list, max-contig events
+static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv) {
+    if (P.nReads > D.ovCap || !D.overflowList) {
+        CU(cudaStreamSynchronize(D.sCompute));
+        CU(dgrow(&D.overflowList, &D.ovCap, (size_t)P.nReads));
+    }
+    P.overflowList = D.overflowList;
+    CU(cudaMemsetAsync(D.overflowCount, 0, sizeof(u32), D.sCompute));
+    if (dNEv) CU(cudaMemsetAsync(dNEv, 0, sizeof(u32), D.sCompute));
+    if (P.nReads == 0) return GS_OK;
+    const int fastBlocks = (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
+    gs_launch_match(P, 0, false, fastBlocks, D.sCompute);
+    CU(cudaGetLastError());
+    gs_launch_match(P, 1, false, D.slowBlocks, D.sCompute);
+    CU(cudaGetLastError());
+    s->launches += 2;
+    if (dEv) {
+        gs_launch_maxcontig_events(D.maxcontig, s->db->V, P.firstReadNo, P.nReads, dEv, dNEv, D.sCompute);
+        CU(cudaGetLastError());
+        s->launches += 1;
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                               uint64_t first_read_no, gs_ticket* ticket) {
+    if (!s || s->finished) return gs_fail(GS_ERR_STATE, "session missing or finished");
+    if (!ticket || !offsets || (!bases && n_reads && offsets[n_reads] > offsets[0])) return gs_fail(GS_ERR_ARG, "null argument");
+    if (first_read_no + n_reads > GS_ORDINAL_MASK) return gs_fail(GS_ERR_LIMIT, "read ordinal exceeds 2^40");
+    const gs_ticket t = s->nextTicket;
+    const size_t nDev = s->devs.size();
+    DevSess& D = s->devs[(t - 1) % nDev];
+    MatchSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
+    const u64 base0 = offsets[0];
+    const u64 nBytes = offsets[n_reads] - base0;
+    const int k = s->db->k;
+    u64 totalKmers = 0;
+    for (u32 i = 0; i < n_reads; i++) {
+        if (offsets[i + 1] < offsets[i]) return gs_fail(GS_ERR_ARG, "offsets not ascending at read %u", i);
+        const u64 L = offsets[i + 1] - offsets[i];
+        if (L > 0x7FFFFFF0ULL) return gs_fail(GS_ERR_LIMIT, "read %u longer than 2^31 bases", i);
+        if (s->cfg.want_runs && L >= (u64)k) totalKmers += L - k + 1;
+    }
+    CU(cudaSetDevice(D.dev));
+    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
+    CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
+    CU(dgrow(&sl.dOut, &sl.outCap, (size_t)n_reads));
+    CU(hgrow(&sl.hOut, &sl.hOutCap, (size_t)n_reads));
+    // inputs: host -> device on the copy-in stream (cudaMemcpyAsync; truly asynchronous for pinned buffers)
+    if (nBytes) CU(cudaMemcpyAsync(sl.dBases, bases + base0, nBytes, cudaMemcpyHostToDevice, D.sCopyIn));
+    CU(cudaMemcpyAsync(sl.dOffsets, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
+    GsMatchParams P;
+    fill_params(s, D, P);
+    if (s->cfg.want_runs) {
+        CU(hgrow(&sl.hKmerOff, &sl.hKmerOffCap, (size_t)n_reads + 1));
+        u64 acc = 0;
+        for (u32 i = 0; i < n_reads; i++) {
+            sl.hKmerOff[i] = acc;
+            const u64 L = offsets[i + 1] - offsets[i];
+            if (L >= (u64)k) acc += L - k + 1;
+        }
+        sl.hKmerOff[n_reads] = acc;
+        CU(dgrow(&sl.dKmerOff, &sl.kmerOffCap, (size_t)n_reads + 1));
+        CU(dgrow(&sl.dRuns, &sl.runsCap, (size_t)totalKmers));
+        CU(dgrow(&sl.dRunCounts, &sl.runCountsCap, (size_t)n_reads));
+        CU(hgrow(&sl.hRunCounts, &sl.hRunCountsCap, (size_t)n_reads));
+        CU(cudaMemcpyAsync(sl.dKmerOff, sl.hKmerOff, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
+        CU(cudaMemsetAsync(sl.dRunCounts, 0, std::max<size_t>(n_reads, 1) * sizeof(u32), D.sCopyIn));
+        P.runs = sl.dRuns; P.runOffsets = sl.dKmerOff; P.runsCap = totalKmers; P.runCounts = sl.dRunCounts;
+    }
+    CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
+    CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
+    P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
+    // offsets are relative to bases + offsets[0] on the device: the kernel subtracts nothing, so rebase here
+    // (the device copy of the base stream starts at host offset base0)
+    P.bases = sl.dBases - base0;
+    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv);
+    if (rc) return rc;
+    CU(cudaEventRecord(sl.evCompute, D.sCompute));
+    // results: device -> pinned host on the copy-out stream
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
+    if (n_reads) CU(cudaMemcpyAsync(sl.hOut, sl.dOut, (size_t)n_reads * sizeof(gs_read_result), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hEv, sl.dEv, std::max<size_t>(s->db->V, 1) * sizeof(gs_maxcontig_event), cudaMemcpyDeviceToHost, D.sCopyOut));
+    if (s->cfg.want_runs && n_reads) CU(cudaMemcpyAsync(sl.hRunCounts, sl.dRunCounts, (size_t)n_reads * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaEventRecord(sl.evDone, D.sCopyOut));
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.firstReadNo = first_read_no; sl.totalKmers = totalKmers;
+    s->nextTicket++;
+    *ticket = t;
+    return GS_OK;
+}
+
+extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
+                                uint32_t* n_events, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (t == 0 || t >= s->nextTicket) return gs_fail(GS_ERR_STATE, "unknown ticket %llu", (unsigned long long)t);
+    const size_t nDev = s->devs.size();
+    DevSess& D = s->devs[(t - 1) % nDev];
+    MatchSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (!sl.pending || sl.ticket != t) return gs_fail(GS_ERR_STATE, "ticket %llu is not pending", (unsigned long long)t);
+    CU(cudaSetDevice(D.dev));
+    CU(cudaEventSynchronize(sl.evDone));
+    sl.pending = false;
+    if (out && sl.nReads) memcpy(out, sl.hOut, (size_t)sl.nReads * sizeof(gs_read_result));
+    if (n_events) {
+        const u32 ne = *sl.hNEv;
+        if (events) {
+            if (ne > ev_cap) return gs_fail(GS_ERR_LIMIT, "%u max-contig events, capacity %u", ne, ev_cap);
+            memcpy(events, sl.hEv, (size_t)ne * sizeof(gs_maxcontig_event));
+        }
+        *n_events = ne;
+    }
+    if (s->cfg.want_runs && run_offsets) {
+        u64 acc = 0;
+        for (u32 i = 0; i < sl.nReads; i++) { run_offsets[i] = acc; acc += sl.hRunCounts[i]; }
+        run_offsets[sl.nReads] = acc;
+        if (runs) {
+            if (acc > runs_cap) return gs_fail(GS_ERR_LIMIT, "%llu contig runs, capacity %llu", (unsigned long long)acc, (unsigned long long)runs_cap);
+            // runs of read i sit at dRuns[kmerOff[i] .. + count): copy the dense prefix region back, then compact
+            std::vector<gs_run> tmp((size_t)sl.totalKmers);
+            if (sl.totalKmers) CU(cudaMemcpy(tmp.data(), sl.dRuns, (size_t)sl.totalKmers * sizeof(gs_run), cudaMemcpyDeviceToHost));
+            for (u32 i = 0; i < sl.nReads; i++)
+                if (sl.hRunCounts[i]) memcpy(runs + run_offsets[i], tmp.data() + sl.hKmerOff[i], (size_t)sl.hRunCounts[i] * sizeof(gs_run));
+        }
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_match_run_device(gs_sess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                                   uint64_t first_read_no, gs_read_result* d_out) {
+    if (!s || s->finished) return gs_fail(GS_ERR_STATE, "session missing or finished");
+    if (((uintptr_t)d_bases & 15) != 0) return gs_fail(GS_ERR_ARG, "d_bases must be 16-byte aligned");
+    DevSess& D = s->devs[0];
+    CU(cudaSetDevice(D.dev));
+    GsMatchParams P;
+    fill_params(s, D, P);
+    P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = d_out;
+    return launch_batch(s, D, P, nullptr, nullptr);
+}
+
+extern "C" int gs_match_sync(gs_sess* s) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    for (DevSess& D : s->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaStreamSynchronize(D.sCopyIn));
+        CU(cudaStreamSynchronize(D.sCompute));
+        CU(cudaStreamSynchronize(D.sCopyOut));
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_match_device_state(gs_sess* s, int64_t** counters, uint64_t** maxcontig, uint64_t** bitset, uint64_t* bitset_words) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    DevSess& D = s->devs[0];
+    if (counters) *counters = (int64_t*)D.counters;
+    if (maxcontig) *maxcontig = (uint64_t*)D.maxcontig;
+    if (bitset) *bitset = (uint64_t*)D.bitset;
+    if (bitset_words) *bitset_words = D.bitsetWords;
+    return GS_OK;
+}
+
+extern "C" int gs_match_unique_popcount(gs_sess* s, const uint64_t* d_bitset, uint64_t word_begin, uint64_t word_end, int64_t* d_unique) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    DevSess& D = s->devs[0];
+    CU(cudaSetDevice(D.dev));
+    gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].vals, s->db->n, (long long*)d_unique, D.sms * 8, D.sCompute);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    return GS_OK;
+}
+
+extern "C" void* gs_match_stream(gs_sess* s) { return s ? (void*)s->devs[0].sCompute : nullptr; }
+extern "C" uint64_t gs_match_kernel_launches(const gs_sess* s) { return s ? s->launches : 0; }
+
+extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                                    const uint64_t* d_kmer_offsets, int32_t* d_labels, int64_t* d_pos) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    DevSess& D = s->devs[0];
+    CU(cudaSetDevice(D.dev));
+    // side-effect free apart from the dump: private scratch accumulators
+    const int V = s->db->V;
+    long long* counters = nullptr; u64* maxcontig = nullptr; gs_read_result* out = nullptr; u32* ovList = nullptr; u32* ovCount = nullptr;
+    CU(dmalloc(&counters, (size_t)7 * V)); CU(dmalloc(&maxcontig, (size_t)V)); CU(dmalloc(&out, (size_t)n_reads));
+    CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 1));
+    CU(cudaMemset(counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
+    CU(cudaMemset(maxcontig, 0, std::max<size_t>(V, 1) * sizeof(u64)));
+    CU(cudaMemset(ovCount, 0, sizeof(u32)));
+    GsMatchParams P;
+    fill_params(s, D, P);
+    P.counters = counters; P.maxcontig = maxcontig; P.bitset = nullptr; P.hitCounts = nullptr;
+    P.overflowList = ovList; P.overflowCount = ovCount;
+    P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
+    P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
+    CU(cudaStreamSynchronize(D.sCompute));
+    if (n_reads) gs_launch_match(P, 0, true, D.fastBlocks, D.sCompute);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.sCompute));
+    CU(cudaFree(counters)); CU(cudaFree(maxcontig)); CU(cudaFree(out)); CU(cudaFree(ovList)); CU(cudaFree(ovCount));
+    return GS_OK;
+}
+
+// getMaxCountsCounts (C/store/KMerUniqueCounterBits.java:173-211): per value index the n largest per-position hit
+// counters (Java shorts, signed compare, rows start as zeros) among the positions whose bit is set.
+static void update_max_counts(int16_t count, int16_t* target, int n) {
+    for (int j = 0; j < n; j++) {
+        if (count > target[j]) {
+            for (int q = n - 1; q > j; q--) target[q] = target[q - 1];
+            target[j] = count;
+            return;
+        }
+    }
+}
+
+extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top_counts) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    for (DevSess& D : s->devs)
+        for (MatchSlot& sl : D.slots)
+            if (sl.pending) return gs_fail(GS_ERR_STATE, "ticket %llu still pending", (unsigned long long)sl.ticket);
+    int rc = gs_match_sync(s);
+    if (rc) return rc;
+    const int V = s->db->V;
+    const u64 n = s->db->n;
+    DevSess& D0 = s->devs[0];
+    std::vector<long long> acc((size_t)7 * V, 0), tmp((size_t)7 * V);
+    std::vector<u64> mc((size_t)V, 0), mtmp((size_t)V);
+    // per-device accumulators -> host sums / maxima; bitsets and hit counters are merged into device 0
+    for (DevSess& D : s->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaMemcpy(tmp.data(), D.counters, (size_t)7 * V * sizeof(long long), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(mtmp.data(), D.maxcontig, (size_t)V * sizeof(u64), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < acc.size(); i++) acc[i] += tmp[i];
+        for (int v = 0; v < V; v++) mc[v] = std::max(mc[v], mtmp[v]);
+    }
+    std::vector<long long> uniq((size_t)V, 0);
+    if (D0.bitset) {
+        CU(cudaSetDevice(D0.dev));
+        if (s->devs.size() > 1 && !s->finished) {
+            u64* peerBits = nullptr; uint16_t* peerCnt = nullptr;
+            CU(dmalloc(&peerBits, D0.bitsetWords));
+            if (D0.hitCounts) CU(dmalloc(&peerCnt, n + 2));
+            for (size_t i = 1; i < s->devs.size(); i++) {
+                CU(cudaMemcpyPeer(peerBits, D0.dev, s->devs[i].bitset, s->devs[i].dev, D0.bitsetWords * sizeof(u64)));
+                gs_launch_or_words(D0.bitset, peerBits, D0.bitsetWords, D0.sCompute);
+                CU(cudaGetLastError());
+                if (D0.hitCounts) {
+                    CU(cudaMemcpyPeer(peerCnt, D0.dev, s->devs[i].hitCounts, s->devs[i].dev, (n + 2) * sizeof(uint16_t)));
+                    gs_launch_add_u16(D0.hitCounts, peerCnt, n, D0.sCompute);
+                    CU(cudaGetLastError());
+                }
+                CU(cudaStreamSynchronize(D0.sCompute));
+                s->launches += D0.hitCounts ? 2 : 1;
+            }
+            CU(cudaFree(peerBits));
+            if (peerCnt) CU(cudaFree(peerCnt));
+        }
+        CU(cudaMemsetAsync(D0.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D0.sCompute));
+        gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].vals, n, D0.unique, D0.sms * 8, D0.sCompute);
+        CU(cudaGetLastError());
+        s->launches += 1;
+        CU(cudaStreamSynchronize(D0.sCompute));
+        CU(cudaMemcpy(uniq.data(), D0.unique, (size_t)V * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    s->finished = true;
+    if (counts) {
+        for (int v = 0; v < V; v++) {
+            gs_taxon_counts& c = counts[v];
+            c.kmers = acc[0 * (size_t)V + v]; c.contigs = acc[1 * (size_t)V + v]; c.contig_len_squared_sum = acc[2 * (size_t)V + v];
+            c.reads_1kmer = acc[3 * (size_t)V + v]; c.reads = acc[4 * (size_t)V + v]; c.reads_kmers = acc[5 * (size_t)V + v];
+            c.reads_bps = acc[6 * (size_t)V + v];
+            c.unique_kmers = D0.bitset ? uniq[v] : -1;  // FastqKMerMatcher.java:224-229
+            c.max_contig_len = (int32_t)(mc[v] >> GS_MAXCONTIG_SHIFT);
+            c.max_contig_read_no = mc[v] ? GS_ORDINAL_MASK - (mc[v] & GS_ORDINAL_MASK) : 0;
+            c.touched = (c.reads_1kmer > 0 || c.reads > 0) ? 1 : 0;  // getCountsPerTaxid was called (:545-556)
+        }
+    }
+    if (top_counts && D0.hitCounts && s->cfg.max_kmer_res_counts > 0) {
+        const int nTop = s->cfg.max_kmer_res_counts;
+        memset(top_counts, 0, (size_t)(V + 1) * nTop * sizeof(int16_t));
+        std::vector<u64> bits(D0.bitsetWords);
+        std::vector<uint16_t> hc(n), vals(n);
+        CU(cudaMemcpy(bits.data(), D0.bitset, D0.bitsetWords * sizeof(u64), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hc.data(), D0.hitCounts, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(vals.data(), s->db->d[0].vals, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        for (u64 w = 0; w < D0.bitsetWords; w++) {
+            u64 word = bits[w];
+            while (word) {
+                const int b = __builtin_ctzll(word);
+                word &= word - 1;
+                const u64 pos = w * 64 + (u64)b;
+                if (pos >= n || vals[pos] == GS_VAL_NONODE) continue;
+                update_max_counts((int16_t)hc[pos], top_counts + (size_t)vals[pos] * nTop, nTop);
+                update_max_counts((int16_t)hc[pos], top_counts + (size_t)V * nTop, nTop);
+            }
+        }
+    }
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// filter
+// ---------------------------------------------------------------------------------------------------------
+struct DevFilter {
+    int dev = 0;
+    u64* words = nullptr;
+    long long* factors = nullptr;
+    GsFilterView view;
+};
+struct gs_filter {
+    gs_ctx* ctx = nullptr;
+    std::vector<DevFilter> d;
+};
+
+extern "C" void gs_filter_destroy(gs_filter* f) {
+    if (!f) return;
+    for (DevFilter& d : f->d) { cudaSetDevice(d.dev); cudaFree(d.words); cudaFree(d.factors); }
+    delete f;
+}
+
+extern "C" gs_filter* gs_filter_create(gs_ctx* ctx, int kind, int64_t p0, int64_t p1, const int64_t* factors,
+                                       const int64_t* words, uint64_t n_words) {
+    if (!ctx) { gs_fail(GS_ERR_ARG, "null context"); return nullptr; }
+    if (!words) { gs_fail(GS_ERR_ARG, "null words"); return nullptr; }
+    u64 modulus = 0;
+    if (kind == GS_BLOOM_BLOCKED) {
+        if (p1 <= 0 || n_words < (u64)p1 + 17) { gs_fail(GS_ERR_ARG, "blocked filter: buckets=%lld needs buckets+17 words, got %llu", (long long)p1, (unsigned long long)n_words); return nullptr; }
+        modulus = (u64)p1;
+    } else if (kind == GS_BLOOM_XOR || kind == GS_BLOOM_MURMUR) {
+        if (p0 <= 0 || p1 <= 0 || !factors || n_words * 64 < (u64)p0) { gs_fail(GS_ERR_ARG, "hashed filter: bits=%lld hashes=%lld words=%llu", (long long)p0, (long long)p1, (unsigned long long)n_words); return nullptr; }
+        modulus = (u64)p0;
+    } else { gs_fail(GS_ERR_ARG, "unknown filter kind %d", kind); return nullptr; }
+    gs_filter* f = new gs_filter();
+    f->ctx = ctx;
+    f->d.resize(ctx->devs.size());
+    for (size_t i = 0; i < ctx->devs.size(); i++) {
+        DevFilter& d = f->d[i];
+        d.dev = ctx->devs[i];
+        if (cudaSetDevice(d.dev) != cudaSuccess || dmalloc(&d.words, n_words) != cudaSuccess ||
+            cudaMemcpy(d.words, words, n_words * sizeof(u64), cudaMemcpyHostToDevice) != cudaSuccess) {
+            gs_fail(GS_ERR_CUDA, "filter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            gs_filter_destroy(f); return nullptr;
+        }
+        if (kind != GS_BLOOM_BLOCKED) {
+            if (dmalloc(&d.factors, (size_t)p1) != cudaSuccess ||
+                cudaMemcpy(d.factors, factors, (size_t)p1 * sizeof(long long), cudaMemcpyHostToDevice) != cudaSuccess) {
+                gs_fail(GS_ERR_CUDA, "filter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                gs_filter_destroy(f); return nullptr;
+            }
+        }
+        d.view.kind = kind; d.view.p0 = p0; d.view.p1 = p1; d.view.magic = magic_for(modulus);
+        d.view.factors = d.factors; d.view.words = d.words;
+    }
+    cudaSetDevice(ctx->devs[0]);
+    return f;
+}
+
+extern "C" int gs_filter_contains(gs_filter* f, const int64_t* kmers, uint64_t n, uint8_t* out) {
+    if (!f) return gs_fail(GS_ERR_STATE, "null filter");
+    CU(cudaSetDevice(f->d[0].dev));
+    u64* dK = nullptr; uint8_t* dO = nullptr;
+    CU(dmalloc(&dK, n)); CU(dmalloc(&dO, n));
+    CU(cudaMemcpy(dK, kmers, n * sizeof(u64), cudaMemcpyHostToDevice));
+    if (n) gs_launch_filter_contains(f->d[0].view, dK, n, dO, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dO, n, cudaMemcpyDeviceToHost));
+    CU(cudaFree(dK)); CU(cudaFree(dO));
+    return GS_OK;
+}
+
+struct FilterSlot {
+    bool pending = false;
+    gs_ticket ticket = 0;
+    u32 nReads = 0;
+    uint8_t* dBases = nullptr; size_t basesCap = 0;
+    u64* dOffsets = nullptr; size_t offCap = 0;
+    uint8_t* dAccept = nullptr; size_t accCap = 0;
+    uint8_t* hAccept = nullptr; size_t hAccCap = 0;
+    cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
+};
+struct DevFsess {
+    int dev = 0, devIndex = 0, blocks = 0;
+    cudaStream_t sCopyIn = nullptr, sCompute = nullptr, sCopyOut = nullptr;
+    FilterSlot slots[GS_MAX_INFLIGHT];
+};
+struct gs_fsess {
+    gs_filter* f = nullptr;
+    int k = 31, minPosCount = 1;
+    double posRatio = 0.2;
+    std::vector<DevFsess> devs;
+    u64 nextTicket = 1;
+};
+
+extern "C" void gs_filter_close(gs_fsess* s) {
+    if (!s) return;
+    for (DevFsess& D : s->devs) {
+        cudaSetDevice(D.dev);
+        cudaDeviceSynchronize();
+        for (FilterSlot& sl : D.slots) {
+            cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dAccept);
+            if (sl.hAccept) cudaFreeHost(sl.hAccept);
+            if (sl.evH2D) cudaEventDestroy(sl.evH2D);
+            if (sl.evCompute) cudaEventDestroy(sl.evCompute);
+            if (sl.evDone) cudaEventDestroy(sl.evDone);
+        }
+        if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
+        if (D.sCompute) cudaStreamDestroy(D.sCompute);
+        if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
+    }
+    delete s;
+}
+
+extern "C" gs_fsess* gs_filter_open(gs_filter* f, int k, int min_pos_count, double pos_ratio) {
+    if (!f) { gs_fail(GS_ERR_ARG, "null filter"); return nullptr; }
+    if (k < 1 || k > 31) { gs_fail(GS_ERR_ARG, "k=%d out of range [1,31]", k); return nullptr; }
+    gs_fsess* s = new gs_fsess();
+    s->f = f; s->k = k; s->minPosCount = min_pos_count; s->posRatio = pos_ratio;
+    s->devs.resize(f->d.size());
+    for (size_t i = 0; i < f->d.size(); i++) {
+        DevFsess& D = s->devs[i];
+        D.dev = f->d[i].dev; D.devIndex = (int)i;
+        bool ok = cudaSetDevice(D.dev) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&D.sCopyIn, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&D.sCompute, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&D.sCopyOut, cudaStreamNonBlocking) == cudaSuccess;
+        for (FilterSlot& sl : D.slots)
+            ok = ok && cudaEventCreateWithFlags(&sl.evH2D, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { gs_fail(GS_ERR_CUDA, "filter session setup failed: %s", cudaGetErrorString(cudaGetLastError())); gs_filter_close(s); return nullptr; }
+        D.blocks = f->ctx->sms[i] * std::max(1, gs_match_kernel_occupancy(2));
+    }
+    cudaSetDevice(f->d[0].dev);
+    return s;
+}
+
+static void fill_fparams(gs_fsess* s, DevFsess& D, GsFilterParams& P) {
+    P.f = s->f->d[D.devIndex].view;
+    P.k = s->k; P.minPosCount = s->minPosCount; P.posRatio = s->posRatio;
+}
+
+extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, gs_ticket* ticket) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (!ticket || !offsets) return gs_fail(GS_ERR_ARG, "null argument");
+    const gs_ticket t = s->nextTicket;
+    const size_t nDev = s->devs.size();
+    DevFsess& D = s->devs[(t - 1) % nDev];
+    FilterSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
+    for (u32 i = 0; i < n_reads; i++) {
+        if (offsets[i + 1] < offsets[i]) return gs_fail(GS_ERR_ARG, "offsets not ascending at read %u", i);
+        if (offsets[i + 1] - offsets[i] > 0x7FFFFFF0ULL) return gs_fail(GS_ERR_LIMIT, "read %u longer than 2^31 bases", i);
+    }
+    const u64 base0 = offsets[0];
+    const u64 nBytes = offsets[n_reads] - base0;
+    CU(cudaSetDevice(D.dev));
+    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
+    CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
+    CU(dgrow(&sl.dAccept, &sl.accCap, (size_t)n_reads));
+    CU(hgrow(&sl.hAccept, &sl.hAccCap, (size_t)n_reads));
+    if (nBytes) CU(cudaMemcpyAsync(sl.dBases, bases + base0, nBytes, cudaMemcpyHostToDevice, D.sCopyIn));
+    CU(cudaMemcpyAsync(sl.dOffsets, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
+    CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
+    CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
+    GsFilterParams P;
+    fill_fparams(s, D, P);
+    P.bases = sl.dBases - base0; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept;
+    if (n_reads) {
+        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
+        gs_launch_filter(P, blocks, D.sCompute);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(sl.evCompute, D.sCompute));
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
+    if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaEventRecord(sl.evDone, D.sCopyOut));
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads;
+    s->nextTicket++;
+    *ticket = t;
+    return GS_OK;
+}
+
+extern "C" int gs_filter_collect(gs_fsess* s, gs_ticket t, uint8_t* accept) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (t == 0 || t >= s->nextTicket) return gs_fail(GS_ERR_STATE, "unknown ticket %llu", (unsigned long long)t);
+    const size_t nDev = s->devs.size();
+    DevFsess& D = s->devs[(t - 1) % nDev];
+    FilterSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (!sl.pending || sl.ticket != t) return gs_fail(GS_ERR_STATE, "ticket %llu is not pending", (unsigned long long)t);
+    CU(cudaSetDevice(D.dev));
+    CU(cudaEventSynchronize(sl.evDone));
+    sl.pending = false;
+    if (accept && sl.nReads) memcpy(accept, sl.hAccept, sl.nReads);
+    return GS_OK;
+}
+
+extern "C" int gs_filter_run_device(gs_fsess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint8_t* d_accept) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (((uintptr_t)d_bases & 15) != 0) return gs_fail(GS_ERR_ARG, "d_bases must be 16-byte aligned");
+    DevFsess& D = s->devs[0];
+    CU(cudaSetDevice(D.dev));
+    GsFilterParams P;
+    fill_fparams(s, D, P);
+    P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.accept = d_accept;
+    if (n_reads) {
+        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
+        gs_launch_filter(P, blocks, D.sCompute);
+        CU(cudaGetLastError());
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_filter_sync(gs_fsess* s) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    for (DevFsess& D : s->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaStreamSynchronize(D.sCopyIn));
+        CU(cudaStreamSynchronize(D.sCompute));
+        CU(cudaStreamSynchronize(D.sCopyOut));
+    }
+    return GS_OK;
+}
+
+extern "C" void* gs_filter_stream(gs_fsess* s) { return s ? (void*)s->devs[0].sCompute : nullptr; }

@@ -359,6 +359,18 @@ void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, cons
     if (wordEnd > wordBegin) gs_unique_popcount_kernel<<<blocks, 256, 0, st>>>(bits, wordBegin, wordEnd, vals, n, unique);
 }
 
+// end-of-run merge of per-device unique-k-mer state (one process driving several GPUs): dst |= src, dst += src
+__global__ void gs_or_words_kernel(u64* __restrict__ dst, const u64* __restrict__ src, u64 n) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] |= src[i];
+}
+void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st) { gs_or_words_kernel<<<148 * 8, 256, 0, st>>>(dst, src, n); }
+__global__ void gs_add_u16_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src, u64 n) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (uint16_t)(dst[i] + src[i]);  // Java short wrap-around
+}
+void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st) { gs_add_u16_kernel<<<148 * 8, 256, 0, st>>>(dst, src, n); }
+
 // ---------------------------------------------------------------------------------------------------------
 // database build helpers
 // ---------------------------------------------------------------------------------------------------------

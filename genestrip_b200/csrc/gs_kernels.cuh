@@ -46,6 +46,8 @@ struct GsFilterParams {
 void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
 void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const uint16_t* vals, u64 n, long long* unique, int blocks, cudaStream_t st);
+void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
+void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);
 void gs_launch_bloom_build(const u64* keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed, cudaStream_t st);
 void gs_launch_convert_values(const int16_t* raw, const int* hasNode, u64 n, int V, uint16_t* vals, u32* bad, cudaStream_t st);

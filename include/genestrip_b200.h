@@ -141,7 +141,8 @@ gs_sess* gs_match_open(gs_db*, const gs_match_cfg*);
 /* Submit one batch of reads: bases = the reads' sequence bytes back to back (ASCII, exactly as parsed:
  * no upper-casing), offsets[n_reads+1] byte offsets into bases, first_read_no =
  * global ordinal of read 0 (file order; used for the maxContigDescriptor tie-break).  Host buffers must stay
- * valid until the ticket is collected.  Up to GS_MAX_INFLIGHT tickets may be pending. */
+ * valid until the ticket is collected.  Batches are dealt round-robin to the devices of the context; up to
+ * GS_MAX_INFLIGHT tickets may be pending per device (collect in submission order). */
 #define GS_MAX_INFLIGHT 2
 int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                     uint64_t first_read_no, gs_ticket* ticket);
@@ -198,6 +199,7 @@ int gs_filter_collect(gs_fsess*, gs_ticket, uint8_t* accept);
 int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                          uint8_t* d_accept);
 int gs_filter_sync(gs_fsess*);
+void* gs_filter_stream(gs_fsess*);
 void gs_filter_close(gs_fsess*);
 
 #ifdef __cplusplus

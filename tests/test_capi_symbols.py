@@ -1,0 +1,56 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol include/genestrip_b200.h
+declares, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "genestrip_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(native):
+    lib = ctypes.CDLL(native.LIB_PATH if hasattr(native, "LIB_PATH") else None) if False else native.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
+    assert set(native.EXPORTED_SYMBOLS) == set(declared)
+    assert lib.gs_abi_version() == 1
+
+
+def test_struct_layouts(native):
+    assert ctypes.sizeof(native.MatchCfg) == 48
+    assert native.READ_RESULT_DTYPE.itemsize == 16
+    assert native.RUN_DTYPE.itemsize == 8
+    assert native.EVENT_DTYPE.itemsize == 16
+    assert native.TAXON_COUNTS_DTYPE.itemsize == 80
+    cfg = native.default_match_cfg()
+    # defaults of C/GSConfigKey.java:302-350
+    assert (cfg.classify_reads, cfg.count_unique_kmers, cfg.max_kmer_res_counts, cfg.use_bloom_filter) == (1, 1, 0, 1)
+    assert (cfg.max_classification_paths, cfg.min_kmers_for_class) == (10, 1)
+    assert cfg.max_read_tax_error_count == -1 and cfg.max_read_class_error_count == -1
+
+
+def test_no_cpu_fallback(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(native.GenestripError) as e:
+        native.Context()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "genestrip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "gs_oracle" not in text and "oracle/" not in text, "%s references the oracle" % f
