@@ -182,7 +182,9 @@ def _edge_reads(genomes, rng):
         for p in rng.integers(0, L, size=max(1, L // 300)):
             r[int(p)] = ord("CGAT"[int(rng.integers(0, 4))])
         reads.append(bytes(r))
-        r2 = bytearray(r); r2[1024 + 29] = ord("N") if L > 1054 else r2[0]; reads.append(bytes(r2))
+        r2 = bytearray(r)
+        r2[min(1024 + 29, L - 1)] = ord("N")
+        reads.append(bytes(r2))
     return reads
 
 

@@ -68,7 +68,7 @@ def assert_match_parity(native, orun, res, counts, top=None, check_unique=True):
     assert len(res) == n
     o = orun.reads
     np.testing.assert_array_equal(res["class_vidx"], o["class_vidx"], err_msg="class node")
-    np.testing.assert_array_equal(res["tax_err"].astype(np.int64), np.where(o["tax_err"] < 0, 0xFFFFFFFF, o["tax_err"]).astype(np.int64), err_msg="readTaxErrorCount")
+    np.testing.assert_array_equal(res["tax_err"].astype(np.int64), np.where(o["tax_err"] < 0, 0xFFFFFFFF, o["tax_err"].astype(np.int64)), err_msg="readTaxErrorCount")
     acc = (res["flags"] & native.GS_READ_ACCEPTED) != 0
     np.testing.assert_array_equal(acc, o["accepted"] != 0, err_msg="accepted")
     np.testing.assert_array_equal(res["read_kmers"][acc].astype(np.int64), o["read_kmers"][o["accepted"] != 0].astype(np.int64), err_msg="readKmers")
