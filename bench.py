@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="table", choices=["table", "classic"],
+                    help="device index: 128-byte probe table (default) or the reference's Bloom filter + sorted-array search")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     wl = dict(WORKLOADS[args.workload])
@@ -267,7 +269,8 @@ def main():
     db = capi.Database(ctx, K, keys_h, vals_h, V, parent_by_vidx=parent, build_bloom=True)
     del keys, vals_raw
     log("rank %d: database on device: %.2f GB" % (rank, db.device_bytes / 1e9))
-    cfg = capi.default_match_cfg()
+    cfg = capi.default_match_cfg(layout=capi.GS_LAYOUT_CLASSIC if args.layout == "classic" else capi.GS_LAYOUT_TABLE)
+    config["layout"] = args.layout
     sess = capi.MatchSession(db, cfg)
     stream = torch.cuda.ExternalStream(sess.stream, device=dev)
     d_out = torch.zeros(R * 16, dtype=torch.uint8, device=dev)

@@ -15,6 +15,7 @@ GS_MAX_INFLIGHT = 2
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
 GS_BLOOM_BLOCKED, GS_BLOOM_XOR, GS_BLOOM_MURMUR = 0, 1, 2
+GS_LAYOUT_TABLE, GS_LAYOUT_CLASSIC = 0, 1
 
 
 class GenestripError(RuntimeError):
@@ -28,7 +29,7 @@ class MatchCfg(C.Structure):
     _fields_ = [("classify_reads", C.c_int), ("count_unique_kmers", C.c_int), ("max_kmer_res_counts", C.c_int),
                 ("use_bloom_filter", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
                 ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
-                ("want_runs", C.c_int), ("reserved", C.c_int)]
+                ("want_runs", C.c_int), ("layout", C.c_int)]
 
 
 READ_RESULT_DTYPE = np.dtype([("class_vidx", "<i4"), ("read_kmers", "<u4"), ("tax_err", "<u4"), ("flags", "<u4")])

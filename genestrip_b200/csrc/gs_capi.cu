@@ -141,6 +141,7 @@ struct DevDb {
     uint16_t* vals = nullptr;
     u32* bstart = nullptr;
     u64* bloom = nullptr;
+    uint4* tab = nullptr;
     int *parent = nullptr, *depth = nullptr, *pre = nullptr, *last = nullptr;
     GsDbView view;
 };
@@ -162,6 +163,8 @@ struct gs_db {
     // bucket index
     int bbits = 0, bshift = 0;
     u64 nBuckets = 0;
+    // probe table
+    int tbits = 0, rbits = 0;
     // radix source staging
     std::vector<std::pair<u64, int16_t>> radixItems;
     u64 bytes = 0;
@@ -349,6 +352,22 @@ extern "C" int gs_db_finalize(gs_db* db) {
     CU(dmalloc(&d0.bstart, db->nBuckets + 1));
     gs_launch_bucket_index(d0.keys, db->n, db->bshift, db->nBuckets, d0.bstart, 0);
     CU(cudaGetLastError());
+    // probe table: ~4..8 keys per 14-slot line
+    {
+        int tb = GS_TAB_MIN_BITS;
+        while ((8ULL << tb) < db->n) tb++;
+        db->tbits = tb; db->rbits = 62 - tb;
+        const u64 nB = 1ULL << tb;
+        u32* counts = nullptr;
+        CU(dmalloc(&d0.tab, nB * 8));
+        CU(dmalloc(&counts, nB));
+        CU(cudaMemset(d0.tab, 0, nB * 128));
+        CU(cudaMemset(counts, 0, nB * sizeof(u32)));
+        gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, db->tbits, db->rbits, 0);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(counts));
+    }
     // tree
     CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));
     CU(cudaMemcpy(d0.parent, db->hParent.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
@@ -365,6 +384,8 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaMemcpyPeer(di.keys, di.dev, d0.keys, d0.dev, (db->n + 1) * sizeof(u64)));
         CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
         CU(cudaMemcpyPeer(di.bstart, di.dev, d0.bstart, d0.dev, (db->nBuckets + 1) * sizeof(u32)));
+        CU(dmalloc(&di.tab, (8ULL << db->tbits)));
+        CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (128ULL << db->tbits)));
         CU(cudaMemcpyPeer(di.parent, di.dev, d0.parent, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.depth, di.dev, d0.depth, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.pre, di.dev, d0.pre, d0.dev, (size_t)V * sizeof(int)));
@@ -380,9 +401,10 @@ extern "C" int gs_db_finalize(gs_db* db) {
         v.keys = d.keys; v.vals = d.vals; v.n = db->n; v.bstart = d.bstart; v.bshift = db->bshift; v.nBuckets = db->nBuckets;
         v.k = db->k; v.bloom = d.bloom; v.bloomBuckets = db->bloomBuckets; v.bloomMagic = magic_for(db->bloomBuckets);
         v.bloomSeed = db->bloomSeed; v.hasBloom = db->hasBloom ? 1 : 0;
+        v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits;
         v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
     }
-    db->bytes = (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
+    db->bytes = (128ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
     CU(cudaSetDevice(d0.dev));
     db->finalized = true;
     return GS_OK;
@@ -392,7 +414,7 @@ extern "C" void gs_db_destroy(gs_db* db) {
     if (!db) return;
     for (DevDb& d : db->d) {
         cudaSetDevice(d.dev);
-        cudaFree(d.keys); cudaFree(d.vals); cudaFree(d.bstart); cudaFree(d.bloom);
+        cudaFree(d.keys); cudaFree(d.vals); cudaFree(d.bstart); cudaFree(d.bloom); cudaFree(d.tab);
         cudaFree(d.parent); cudaFree(d.depth); cudaFree(d.pre); cudaFree(d.last);
     }
     if (db->rawVals) { cudaSetDevice(db->d[0].dev); cudaFree(db->rawVals); }
@@ -460,6 +482,8 @@ struct gs_sess {
     u64 nextTicket = 1;
     u64 launches = 0;
     bool finished = false;
+    int layout = GS_LAYOUT_TABLE;
+    u64 nPos = 0;  // "storage positions" addressed by the unique-k-mer bitset: table slot ids or sorted-array indices
 };
 
 extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
@@ -488,12 +512,12 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
     CU(cudaMemset(D.maxcontig, 0, std::max<size_t>(V, 1) * sizeof(u64)));
     CU(dmalloc(&D.unique, (size_t)V));
     if (s->cfg.count_unique_kmers) {
-        D.bitsetWords = (s->db->n + 63) / 64;
+        D.bitsetWords = (s->nPos + 63) / 64;
         CU(dmalloc(&D.bitset, D.bitsetWords));
         CU(cudaMemset(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64)));
         if (s->cfg.max_kmer_res_counts > 0) {
-            CU(dmalloc(&D.hitCounts, s->db->n + 2));
-            CU(cudaMemset(D.hitCounts, 0, (s->db->n + 2) * sizeof(uint16_t)));
+            CU(dmalloc(&D.hitCounts, s->nPos + 2));
+            CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
         }
     }
     CU(dmalloc(&D.overflowCount, 1));
@@ -548,8 +572,11 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
         return nullptr;
     }
     if (c.use_bloom_filter && !db->hasBloom) c.use_bloom_filter = 0;  // store without filter: KMerSortedArray.getLong :299 skips it
+    if (c.layout != GS_LAYOUT_TABLE && c.layout != GS_LAYOUT_CLASSIC) { gs_fail(GS_ERR_ARG, "unknown layout %d", c.layout); return nullptr; }
     gs_sess* s = new gs_sess();
     s->db = db; s->cfg = c;
+    s->layout = c.layout;
+    s->nPos = c.layout == GS_LAYOUT_TABLE ? ((u64)GS_TAB_SLOT_STRIDE << db->tbits) : db->n;
     s->devs.resize(db->d.size());
     for (size_t i = 0; i < db->d.size(); i++) {
         s->devs[i].dev = db->d[i].dev; s->devs[i].devIndex = (int)i; s->devs[i].sms = db->ctx->sms[i];
@@ -567,6 +594,7 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     P.useBloom = s->cfg.use_bloom_filter ? 1 : 0;
     P.maxPaths = s->cfg.max_classification_paths;
     P.threshold = s->cfg.min_kmers_for_class;
+    P.layout = s->layout;
     P.maxTaxErr = s->cfg.max_read_tax_error_count;
     P.maxClassErr = s->cfg.max_read_class_error_count;
     P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.slowTable = D.slowTable;
@@ -738,7 +766,7 @@ extern "C" int gs_match_unique_popcount(gs_sess* s, const uint64_t* d_bitset, ui
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     DevSess& D = s->devs[0];
     CU(cudaSetDevice(D.dev));
-    gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].vals, s->db->n, (long long*)d_unique, D.sms * 8, D.sCompute);
+    gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].view, s->layout, (long long*)d_unique, D.sms * 8, D.sCompute);
     CU(cudaGetLastError());
     s->launches += 1;
     return GS_OK;
@@ -794,7 +822,7 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
     int rc = gs_match_sync(s);
     if (rc) return rc;
     const int V = s->db->V;
-    const u64 n = s->db->n;
+    const u64 n = s->nPos;
     DevSess& D0 = s->devs[0];
     std::vector<long long> acc((size_t)7 * V, 0), tmp((size_t)7 * V);
     std::vector<u64> mc((size_t)V, 0), mtmp((size_t)V);
@@ -829,7 +857,7 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
             if (peerCnt) CU(cudaFree(peerCnt));
         }
         CU(cudaMemsetAsync(D0.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D0.sCompute));
-        gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].vals, n, D0.unique, D0.sms * 8, D0.sCompute);
+        gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].view, s->layout, D0.unique, D0.sms * 8, D0.sCompute);
         CU(cudaGetLastError());
         s->launches += 1;
         CU(cudaStreamSynchronize(D0.sCompute));
@@ -851,21 +879,24 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
     if (top_counts && D0.hitCounts && s->cfg.max_kmer_res_counts > 0) {
         const int nTop = s->cfg.max_kmer_res_counts;
         memset(top_counts, 0, (size_t)(V + 1) * nTop * sizeof(int16_t));
-        std::vector<u64> bits(D0.bitsetWords);
-        std::vector<uint16_t> hc(n), vals(n);
-        CU(cudaMemcpy(bits.data(), D0.bitset, D0.bitsetWords * sizeof(u64), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(hc.data(), D0.hitCounts, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(vals.data(), s->db->d[0].vals, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-        for (u64 w = 0; w < D0.bitsetWords; w++) {
-            u64 word = bits[w];
-            while (word) {
-                const int b = __builtin_ctzll(word);
-                word &= word - 1;
-                const u64 pos = w * 64 + (u64)b;
-                if (pos >= n || vals[pos] == GS_VAL_NONODE) continue;
-                update_max_counts((int16_t)hc[pos], top_counts + (size_t)vals[pos] * nTop, nTop);
-                update_max_counts((int16_t)hc[pos], top_counts + (size_t)V * nTop, nTop);
-            }
+        u64 total = 0;
+        for (int v = 0; v < V; v++) total += (u64)uniq[v];
+        u32* dHits = nullptr; unsigned long long* dN = nullptr;
+        CU(dmalloc(&dHits, (size_t)total)); CU(dmalloc(&dN, 1));
+        CU(cudaMemsetAsync(dN, 0, sizeof(unsigned long long), D0.sCompute));
+        gs_launch_collect_hits(D0.bitset, D0.bitsetWords, D0.hitCounts, s->db->d[0].view, s->layout, dHits, dN, total, D0.sCompute);
+        CU(cudaGetLastError());
+        s->launches += 1;
+        CU(cudaStreamSynchronize(D0.sCompute));
+        unsigned long long got = 0;
+        CU(cudaMemcpy(&got, dN, sizeof(got), cudaMemcpyDeviceToHost));
+        if (got != total) return gs_fail(GS_ERR_STATE, "hit list holds %llu entries, expected %llu", got, (unsigned long long)total);
+        std::vector<u32> hits((size_t)total);
+        if (total) CU(cudaMemcpy(hits.data(), dHits, (size_t)total * sizeof(u32), cudaMemcpyDeviceToHost));
+        CU(cudaFree(dHits)); CU(cudaFree(dN));
+        for (u32 hcv : hits) {  // the n largest counters per row: independent of the visiting order
+            update_max_counts((int16_t)(hcv & 0xFFFF), top_counts + (size_t)(hcv >> 16) * nTop, nTop);
+            update_max_counts((int16_t)(hcv & 0xFFFF), top_counts + (size_t)V * nTop, nTop);
         }
     }
     return GS_OK;

@@ -10,6 +10,8 @@ typedef unsigned int u32;
 #define GS_LABEL_END 0xFFFFFFFFu      // terminator lane (past the last k-mer position)
 #define GS_LABEL_MISS 0xFFFFFFFEu     // taxIdNode == null
 #define GS_LABEL_INVALID 0xFFFFFFFDu  // INVALID_NODE (C/match/FastqKMerMatcher.java:63)
+#define GS_LAYOUT_TABLE 0             // default device index: 128-byte probe table (one DRAM line touch per k-mer)
+#define GS_LAYOUT_CLASSIC 1           // the reference's structures: blocked Bloom filter + (bucketed) binary search
 #define GS_VAL_NONODE 0xFFFFu         // stored value whose tax id has no tree node -> null (C/store/Database.java:136-143)
 
 #define GS_WARPS_PER_BLOCK 8
@@ -36,6 +38,10 @@ struct GsDbView {
     u64 bloomBuckets, bloomMagic;
     long long bloomSeed;
     int hasBloom;
+    // probe table (GS_LAYOUT_TABLE): 2^tbits lines of 128 bytes; line = 14 fingerprint bytes, fill count, overflow flag,
+    // then 14 entries (remainder << 16 | value).  One DRAM line touch answers hit/miss and yields the value.
+    const uint4* tab;
+    int tbits, rbits;       // bucket = mix62(key) >> rbits, remainder = low rbits bits, rbits = 62 - tbits
     const int* parent;      // by value index, -1 root / none
     const int* depth;
     const int* pre;         // DFS interval labels: a is ancestor-or-self of b  <=>  pre[a] <= pre[b] <= last[a]
@@ -139,6 +145,73 @@ __device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBl
     pos = lo;
     uint16_t v = __ldg(db.vals + lo);
     return v == GS_VAL_NONODE ? GS_LABEL_MISS : (u32)v;
+}
+
+// ---- probe table -------------------------------------------------------------------------------------------
+// Measured on B200 (profiles/microbench/randload.cu): a random 8-byte probe into a multi-GB array costs one DRAM line
+// touch (~39.5 G touches/s for the whole GPU) whatever its size up to 128 bytes.  The reference's structures need
+// Bloom word(s) + bucket index + keys + value = 2.2 touches per k-mer at the viral-scale mix; this table needs one.
+#define GS_TAB_SLOTS 14
+#define GS_TAB_SLOT_STRIDE 16   // slot id = bucket * 16 + j: the "storage position" used by the unique-k-mer bitset
+#define GS_TAB_MIN_BITS 14      // rbits + 16 value bits must fit 64 bits
+#define GS_M62 ((1ULL << 62) - 1)
+
+// bijection on [0, 2^62) (xor-shifts and odd multiplications mod 2^62): equal hashes <=> equal keys, so the bucket
+// number plus the remainder identify the key exactly and only the remainder has to be stored.
+__host__ __device__ __forceinline__ u64 gs_mix62(u64 x) {
+    x ^= x >> 31;
+    x = (x * 0x7FB5D329728EA185ULL) & GS_M62;
+    x ^= x >> 27;
+    x = (x * 0x81DADEF4BC2DD44DULL) & GS_M62;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ u32 gs_fp_of(u64 rem) { return (u32)((rem >> 3) & 0xFF); }
+
+// Returns the label (value index / MISS); pos = slot id of the match.
+__device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {
+    if (key > GS_M62) return GS_LABEL_MISS;
+    const u64 h = gs_mix62(key);
+    u64 b = h >> db.rbits;
+    const u64 rem = h & ((1ULL << db.rbits) - 1);
+    const u32 fp4 = gs_fp_of(rem) * 0x01010101u;
+    const u64 bmask = (1ULL << db.tbits) - 1;
+    for (;;) {
+        const uint4* line = db.tab + b * 8;
+        const uint4 hd = __ldg(line);
+        const u32 cnt = (hd.w >> 16) & 0xFF;
+        // fingerprint match mask over the 14 slots (bytes 0..13 of the header)
+        u32 m = (((__vcmpeq4(hd.x, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+        m |= ((((__vcmpeq4(hd.y, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4;
+        m |= ((((__vcmpeq4(hd.z, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 8;
+        m |= ((((__vcmpeq4(hd.w, fp4) & 0x00000101u) * 0x01020408u) >> 24) & 3u) << 12;
+        m &= (1u << cnt) - 1u;
+        const u64* ent = (const u64*)(line + 1);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 e = __ldg(ent + j);
+            if ((e >> 16) == rem) {
+                pos = b * GS_TAB_SLOT_STRIDE + (u64)j;
+                const u32 v = (u32)(e & 0xFFFF);
+                return v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
+            }
+        }
+        if (!(hd.w >> 24)) return GS_LABEL_MISS;  // nothing spilled past this bucket
+        b = (b + 1) & bmask;
+    }
+}
+
+// value stored at a "storage position" of the unique-k-mer bitset: sorted-array index (classic) or table slot id
+__device__ __forceinline__ u32 gs_value_at(const GsDbView& db, int layout, u64 pos) {
+    if (layout == GS_LAYOUT_TABLE) {
+        const u64 b = pos / GS_TAB_SLOT_STRIDE;
+        const u32 j = (u32)(pos % GS_TAB_SLOT_STRIDE);
+        if (b >> db.tbits || j >= GS_TAB_SLOTS) return GS_VAL_NONODE;
+        return (u32)(__ldg((const u64*)(db.tab + b * 8 + 1) + j) & 0xFFFF);
+    }
+    return pos < db.n ? (u32)__ldg(db.vals + pos) : GS_VAL_NONODE;
 }
 
 __device__ __forceinline__ bool gs_anc_or_self(const GsDbView& db, int a, int b) {

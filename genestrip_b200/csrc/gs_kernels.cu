@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const
                 if (prel < lim) {
                     u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
                     if ((vbits & kmask) != kmask) lab = GS_LABEL_INVALID;
-                    else lab = gs_lookup(db, gs_canonical(gs_extract(cw, prel, k), k), useBloom, pos);
+                    else {
+                        const u64 key = gs_canonical(gs_extract(cw, prel, k), k);
+                        lab = P.layout == GS_LAYOUT_TABLE ? gs_lookup_table(db, key, pos) : gs_lookup(db, key, useBloom, pos);
+                    }
                     if (DUMP) {
                         u64 o = P.kmerOffsets[r] + (u64)(t0 + prel);
                         P.dumpLabels[o] = lab == GS_LABEL_INVALID ? -2 : (lab == GS_LABEL_MISS ? -1 : (int)lab);
@@ -336,8 +339,7 @@ void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u3
 // KMerUniqueCounterBits.getUniqueKmerCounts (C/store/KMerUniqueCounterBits.java:146-163): per value index, the
 // number of set bits among its storage positions.  One thread per 64-bit bitset word; equal value indices of a
 // warp's current bits are pre-aggregated with match_any before the atomic.
-__global__ void gs_unique_popcount_kernel(const u64* __restrict__ bits, u64 wordBegin, u64 wordEnd, const uint16_t* __restrict__ vals,
-                                          u64 n, long long* unique) {
+__global__ void gs_unique_popcount_kernel(const u64* __restrict__ bits, u64 wordBegin, u64 wordEnd, GsDbView db, int layout, long long* unique) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 w0 = wordBegin + (u64)blockIdx.x * blockDim.x; w0 < wordEnd; w0 += stride) {  // warp-uniform trip count
         const u64 w = w0 + threadIdx.x;
@@ -348,15 +350,72 @@ __global__ void gs_unique_popcount_kernel(const u64* __restrict__ bits, u64 word
                 const int b = __ffsll((long long)word) - 1;
                 word &= word - 1;
                 const u64 pos = w * 64 + (u64)b;
-                if (pos < n) { uint16_t vv = __ldg(vals + pos); if (vv != GS_VAL_NONODE) v = vv; }
+                const u32 vv = gs_value_at(db, layout, pos);
+                if (vv != GS_VAL_NONODE) v = (int)vv;
             }
             const u32 peers = __match_any_sync(FULL, v);
             if (v >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd((u64*)(unique + v), (u64)__popc(peers));
         }
     }
 }
-void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const uint16_t* vals, u64 n, long long* unique, int blocks, cudaStream_t st) {
-    if (wordEnd > wordBegin) gs_unique_popcount_kernel<<<blocks, 256, 0, st>>>(bits, wordBegin, wordEnd, vals, n, unique);
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st) {
+    if (wordEnd > wordBegin) gs_unique_popcount_kernel<<<blocks, 256, 0, st>>>(bits, wordBegin, wordEnd, db, layout, unique);
+}
+
+// (value index, hit counter) of every set position, for getMaxCountsCounts (C/store/KMerUniqueCounterBits.java:173-199)
+__global__ void gs_collect_hits_kernel(const u64* __restrict__ bits, u64 nWords, const uint16_t* __restrict__ hitCounts, GsDbView db, int layout,
+                                       u32* out, unsigned long long* nOut, u64 cap) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nWords; w += stride) {
+        u64 word = bits[w];
+        while (word) {
+            const int b = __ffsll((long long)word) - 1;
+            word &= word - 1;
+            const u64 pos = w * 64 + (u64)b;
+            const u32 vv = gs_value_at(db, layout, pos);
+            if (vv == GS_VAL_NONODE) continue;
+            const u64 slot = atomicAdd(nOut, 1ULL);
+            if (slot < cap) out[slot] = (vv << 16) | (u32)hitCounts[pos];
+        }
+    }
+}
+void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st) {
+    gs_collect_hits_kernel<<<148 * 8, 256, 0, st>>>(bits, nWords, hitCounts, db, layout, out, nOut, cap);
+}
+
+// ---- probe table build: every key claims a slot of its home bucket; full buckets spill to the next one and are flagged
+__global__ void gs_table_insert_kernel(const u64* __restrict__ keys, const uint16_t* __restrict__ vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 bmask = (1ULL << tbits) - 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 h = gs_mix62(keys[i]);
+        u64 b = h >> rbits;
+        const u64 rem = h & ((1ULL << rbits) - 1);
+        const u64 entry = (rem << 16) | (u64)vals[i];
+        const uint8_t fp = (uint8_t)gs_fp_of(rem);
+        for (;;) {
+            uint8_t* line = (uint8_t*)(tab + b * 8);
+            const u32 idx = atomicAdd(counts + b, 1u);
+            if (idx < GS_TAB_SLOTS) {
+                ((u64*)(line + 16))[idx] = entry;
+                line[idx] = fp;
+                break;
+            }
+            line[15] = 1;  // something spilled past this bucket
+            b = (b + 1) & bmask;
+        }
+    }
+}
+__global__ void gs_table_finalize_kernel(uint4* tab, const u32* __restrict__ counts, u64 nBuckets) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride) {
+        const u32 c = counts[b];
+        ((uint8_t*)(tab + b * 8))[14] = (uint8_t)(c < GS_TAB_SLOTS ? c : GS_TAB_SLOTS);
+    }
+}
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
+    gs_table_insert_kernel<<<148 * 8, 256, 0, st>>>(keys, vals, n, tab, counts, tbits, rbits);
+    gs_table_finalize_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, 1ULL << tbits);
 }
 
 // end-of-run merge of per-device unique-k-mer state (one process driving several GPUs): dst |= src, dst += src
@@ -431,6 +490,9 @@ __global__ void gs_lookup_kernel(GsDbView db, const u64* __restrict__ kmers, u64
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         u64 p = 0;
         u32 lab = gs_lookup(db, kmers[i], useBloom && db.hasBloom, p);
+        // the probe table must agree with the reference structures on every query
+        u64 p2 = 0;
+        if (db.tab && gs_lookup_table(db, kmers[i], p2) != lab) lab = 0x7FFFFFFFu;
         vidx[i] = lab == GS_LABEL_MISS ? -1 : (int)lab;
         pos[i] = lab == GS_LABEL_MISS ? -1LL : (long long)p;
     }

@@ -15,6 +15,7 @@ struct GsMatchParams {
     u64* bitset;            // unique k-mer bits by storage position, or NULL
     uint16_t* hitCounts;    // per-position hit counters (maxKMerResCounts > 0), or NULL
     int classify, useBloom, maxPaths, threshold;
+    int layout;             // GS_LAYOUT_TABLE / GS_LAYOUT_CLASSIC
     double maxTaxErr, maxClassErr;
     u32* overflowList;      // reads with more than GS_TABLE_CAP distinct taxa
     u32* overflowCount;
@@ -45,7 +46,9 @@ struct GsFilterParams {
 
 void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
-void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const uint16_t* vals, u64 n, long long* unique, int blocks, cudaStream_t st);
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st);
+void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
 void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
 void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);

@@ -98,8 +98,10 @@ typedef struct gs_match_cfg {
     double max_read_tax_error_count;   /* maxReadTaxErrorCount                                   */
     double max_read_class_error_count; /* maxReadClassErrorCount                                 */
     int want_runs;                     /* writeKrakenStyleOut: return per-read contig runs       */
-    int reserved;
+    int layout;                        /* device index: GS_LAYOUT_TABLE (default) or GS_LAYOUT_CLASSIC; same results  */
 } gs_match_cfg;
+#define GS_LAYOUT_TABLE 0   /* 128-byte probe table built from the store's arrays: one DRAM line touch per k-mer      */
+#define GS_LAYOUT_CLASSIC 1 /* the reference's own structures: blocked Bloom filter + binary search of the sorted array */
 void gs_match_cfg_default(gs_match_cfg*);
 
 /* Per-read result, 16 bytes (what FastqKMerMatcher.matchRead leaves in MatcherReadEntry, :327-535). */
@@ -165,7 +167,8 @@ int gs_match_run_device(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offs
 int gs_match_sync(gs_sess*);
 /* Raw device state for cross-process reduction over NCCL (one process per GPU, DESIGN.md "Multi-GPU"):
  * counters = int64[7][n_values] (kmers, contigs, sqsum, reads1, reads, readsKmers, readsBPs),
- * maxcontig = uint64[n_values] packed (len << 40 | ~ordinal), bitset = uint64[ceil(n_kmers/64)] or NULL. */
+ * maxcontig = uint64[n_values] packed (len << 40 | ~ordinal), bitset = uint64[bitset_words] or NULL, one bit per
+ * storage position of the session's layout (table slot id or sorted-array index). */
 int gs_match_device_state(gs_sess*, int64_t** counters, uint64_t** maxcontig, uint64_t** bitset,
                           uint64_t* bitset_words);
 /* Per-taxon popcount of bitset words [word_begin, word_end) into d_unique (int64[n_values], device, added to). */

@@ -77,14 +77,24 @@ def test_labels_per_position(project, reads, oracle, native):
     total = int(kofs[-1])
     d_lab = torch.full((total,), -9, dtype=torch.int32, device=dev)
     d_pos = torch.full((total,), -9, dtype=torch.int64, device=dev)
-    sess = native.MatchSession(gdb)
-    try:
-        sess.dump_labels(d_bases.data_ptr(), d_off.data_ptr(), len(offsets) - 1, d_kofs.data_ptr(), d_lab.data_ptr(), d_pos.data_ptr())
-        torch.cuda.synchronize()
-    finally:
-        sess.close()
-    np.testing.assert_array_equal(d_lab.cpu().numpy(), orun.labels)
-    np.testing.assert_array_equal(d_pos.cpu().numpy(), orun.label_pos)
+    for layout in (native.GS_LAYOUT_TABLE, native.GS_LAYOUT_CLASSIC):
+        sess = native.MatchSession(gdb, native.default_match_cfg(layout=layout))
+        try:
+            sess.dump_labels(d_bases.data_ptr(), d_off.data_ptr(), len(offsets) - 1, d_kofs.data_ptr(), d_lab.data_ptr(), d_pos.data_ptr())
+            torch.cuda.synchronize()
+        finally:
+            sess.close()
+        np.testing.assert_array_equal(d_lab.cpu().numpy(), orun.labels)
+        pos = d_pos.cpu().numpy()
+        if layout == native.GS_LAYOUT_CLASSIC:
+            # storage positions of the reference's sorted array (KMerSortedArray.getLong posStore, :298-349)
+            np.testing.assert_array_equal(pos, orun.label_pos)
+        else:
+            # probe-table slot ids: a bijection of the reference positions (same k-mer <=> same slot)
+            hit = orun.label_pos >= 0
+            assert (pos[~hit] == -1).all()
+            pairs = np.unique(np.stack([orun.label_pos[hit], pos[hit]]), axis=1)
+            assert len(np.unique(pairs[0])) == pairs.shape[1] == len(np.unique(pairs[1]))
 
 
 CONFIGS = [
@@ -102,6 +112,9 @@ CONFIGS = [
     dict(max_classification_paths=1),
     dict(max_classification_paths=2, min_kmers_for_class=3),
     dict(max_kmer_res_counts=4),
+    dict(layout=1),
+    dict(layout=1, use_bloom_filter=0),
+    dict(layout=1, max_kmer_res_counts=4),
 ]
 
 
@@ -199,8 +212,8 @@ def _fastq(reads):
     return b"".join(b"@r%d x\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
 
 
-@pytest.mark.parametrize("cfg", [dict(), dict(max_read_tax_error_count=0.5), dict(want_runs=1), dict(min_kmers_for_class=3)],
-                         ids=["default", "taxerr", "runs", "threshold"])
+@pytest.mark.parametrize("cfg", [dict(), dict(max_read_tax_error_count=0.5), dict(want_runs=1), dict(min_kmers_for_class=3), dict(layout=1)],
+                         ids=["default", "taxerr", "runs", "threshold", "classic"])
 def test_edge_case_reads(project, oracle, native, cfg):
     odb, gdb, genomes = project
     rng = np.random.default_rng(99)
