@@ -32,20 +32,21 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force=False, verbose=False):
-    """Compile every CUDA/C++ source of the package into one shared library."""
-    if not force and not needs_build():
+def build_native(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA/C++ source of the package into one shared library (`defines`/`out`: tuning variants)."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-o", LIB_PATH + ".tmp"] + srcs + ["-lz"]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-o", out + ".tmp"] + srcs + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(out + ".tmp", out)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -66,6 +66,7 @@ _SIGS = {
     "gs_match_open": (_P, [_P, C.POINTER(MatchCfg)]),
     "gs_match_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
     "gs_match_collect": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, _P, C.c_uint64]),
+    "gs_match_collect_view": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(C.c_uint32)]),
     "gs_match_finish": (C.c_int, [_P, _P, _P]),
     "gs_match_close": (None, [_P]),
     "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _P]),
@@ -93,10 +94,11 @@ def lib():
     """Load the CUDA extension; fails loudly when it is missing (no CPU fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("GS_LIB_VARIANT") or LIB_PATH  # tuning variants built by build_native(defines=..., out=...)
+        if not os.path.exists(path):
             raise GenestripError(-2, "CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                                 "(there is no CPU fallback)" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+                                 "(there is no CPU fallback)" % path)
+        L = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)
             fn.restype = res
@@ -277,6 +279,16 @@ class MatchSession:
         else:
             _check(lib().gs_match_collect(self.h, ticket, _ptr(out), _ptr(ev), len(ev), C.byref(nev), None, None, 0))
         return out, ev[:nev.value].copy(), run_off, runs
+
+    def collect_view(self, ticket):
+        """Zero-copy collect: numpy views of the session's pinned result / event staging (valid until the slot is reused)."""
+        self._keep.pop(ticket)
+        out, ev = _P(), _P()
+        n, nev = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().gs_match_collect_view(self.h, ticket, C.byref(out), C.byref(n), C.byref(ev), C.byref(nev)))
+        res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value * 16,)).view(READ_RESULT_DTYPE) if n.value else np.zeros(0, READ_RESULT_DTYPE)
+        evs = np.ctypeslib.as_array(C.cast(ev, C.POINTER(C.c_uint8)), shape=(nev.value * 16,)).view(EVENT_DTYPE) if nev.value else np.zeros(0, EVENT_DTYPE)
+        return res, evs
 
     def finish(self):
         V = self.db.n_values

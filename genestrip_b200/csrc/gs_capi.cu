@@ -141,7 +141,7 @@ struct DevDb {
     uint16_t* vals = nullptr;
     u32* bstart = nullptr;
     u64* bloom = nullptr;
-    uint4* tab = nullptr;
+    u64* tab = nullptr;
     int *parent = nullptr, *depth = nullptr, *pre = nullptr, *last = nullptr;
     GsDbView view;
 };
@@ -165,6 +165,7 @@ struct gs_db {
     u64 nBuckets = 0;
     // probe table
     int tbits = 0, rbits = 0;
+    bool seenLeased = false;  // the table's in-line seen bits belong to at most one unique-counting session at a time
     // radix source staging
     std::vector<std::pair<u64, int16_t>> radixItems;
     u64 bytes = 0;
@@ -352,16 +353,16 @@ extern "C" int gs_db_finalize(gs_db* db) {
     CU(dmalloc(&d0.bstart, db->nBuckets + 1));
     gs_launch_bucket_index(d0.keys, db->n, db->bshift, db->nBuckets, d0.bstart, 0);
     CU(cudaGetLastError());
-    // probe table: ~4..8 keys per 14-slot line
+    // probe table: 1..2 keys per 4-slot bucket
     {
         int tb = GS_TAB_MIN_BITS;
-        while ((8ULL << tb) < db->n) tb++;
+        while ((2ULL << tb) < db->n) tb++;
         db->tbits = tb; db->rbits = 62 - tb;
         const u64 nB = 1ULL << tb;
         u32* counts = nullptr;
-        CU(dmalloc(&d0.tab, nB * 8));
+        CU(dmalloc(&d0.tab, nB * 4));
         CU(dmalloc(&counts, nB));
-        CU(cudaMemset(d0.tab, 0, nB * 128));
+        CU(cudaMemset(d0.tab, 0, nB * 32));
         CU(cudaMemset(counts, 0, nB * sizeof(u32)));
         gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, db->tbits, db->rbits, 0);
         CU(cudaGetLastError());
@@ -384,8 +385,8 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaMemcpyPeer(di.keys, di.dev, d0.keys, d0.dev, (db->n + 1) * sizeof(u64)));
         CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
         CU(cudaMemcpyPeer(di.bstart, di.dev, d0.bstart, d0.dev, (db->nBuckets + 1) * sizeof(u32)));
-        CU(dmalloc(&di.tab, (8ULL << db->tbits)));
-        CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (128ULL << db->tbits)));
+        CU(dmalloc(&di.tab, (4ULL << db->tbits)));
+        CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (32ULL << db->tbits)));
         CU(cudaMemcpyPeer(di.parent, di.dev, d0.parent, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.depth, di.dev, d0.depth, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.pre, di.dev, d0.pre, d0.dev, (size_t)V * sizeof(int)));
@@ -404,7 +405,7 @@ extern "C" int gs_db_finalize(gs_db* db) {
         v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits;
         v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
     }
-    db->bytes = (128ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
+    db->bytes = (32ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
     CU(cudaSetDevice(d0.dev));
     db->finalized = true;
     return GS_OK;
@@ -450,7 +451,8 @@ struct MatchSlot {
     u64* dOffsets = nullptr; size_t offCap = 0;
     gs_read_result* dOut = nullptr; size_t outCap = 0;
     gs_read_result* hOut = nullptr; size_t hOutCap = 0;
-    gs_maxcontig_event* dEv = nullptr; gs_maxcontig_event* hEv = nullptr; u32* dNEv = nullptr; u32* hNEv = nullptr;
+    gs_maxcontig_event* dEv = nullptr; gs_maxcontig_event* hEv = nullptr;
+    u32* dNEv = nullptr; u32* hNEv = nullptr;  // [0] = number of events, [1] = malformed-offsets flag
     // want_runs
     u64* dKmerOff = nullptr; size_t kmerOffCap = 0;
     u64* hKmerOff = nullptr; size_t hKmerOffCap = 0;
@@ -483,6 +485,7 @@ struct gs_sess {
     u64 launches = 0;
     bool finished = false;
     int layout = GS_LAYOUT_TABLE;
+    bool inlineSeen = false;  // unique k-mer bits are kept in the probe-table lines (leased from the database)
     u64 nPos = 0;  // "storage positions" addressed by the unique-k-mer bitset: table slot ids or sorted-array indices
 };
 
@@ -513,8 +516,14 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
     CU(dmalloc(&D.unique, (size_t)V));
     if (s->cfg.count_unique_kmers) {
         D.bitsetWords = (s->nPos + 63) / 64;
-        CU(dmalloc(&D.bitset, D.bitsetWords));
-        CU(cudaMemset(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64)));
+        if (s->inlineSeen) {
+            gs_launch_table_clear_seen(s->db->d[D.devIndex].tab, s->nPos, 0);
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+        } else {
+            CU(dmalloc(&D.bitset, D.bitsetWords));
+            CU(cudaMemset(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64)));
+        }
         if (s->cfg.max_kmer_res_counts > 0) {
             CU(dmalloc(&D.hitCounts, s->nPos + 2));
             CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
@@ -530,9 +539,9 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
         CU(cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming));
         CU(dmalloc(&sl.dEv, (size_t)std::max(V, 1)));
-        CU(dmalloc(&sl.dNEv, 1));
+        CU(dmalloc(&sl.dNEv, 2));
         CU(cudaMallocHost((void**)&sl.hEv, std::max<size_t>(V, 1) * sizeof(gs_maxcontig_event)));
-        CU(cudaMallocHost((void**)&sl.hNEv, sizeof(u32)));
+        CU(cudaMallocHost((void**)&sl.hNEv, 2 * sizeof(u32)));
     }
     return GS_OK;
 }
@@ -560,6 +569,7 @@ extern "C" void gs_match_close(gs_sess* s) {
         if (D.sCompute) cudaStreamDestroy(D.sCompute);
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
     }
+    if (s->inlineSeen) s->db->seenLeased = false;
     delete s;
 }
 
@@ -577,6 +587,7 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
     s->db = db; s->cfg = c;
     s->layout = c.layout;
     s->nPos = c.layout == GS_LAYOUT_TABLE ? ((u64)GS_TAB_SLOT_STRIDE << db->tbits) : db->n;
+    if (c.layout == GS_LAYOUT_TABLE && c.count_unique_kmers && !db->seenLeased) { s->inlineSeen = true; db->seenLeased = true; }
     s->devs.resize(db->d.size());
     for (size_t i = 0; i < db->d.size(); i++) {
         s->devs[i].dev = db->d[i].dev; s->devs[i].devIndex = (int)i; s->devs[i].sms = db->ctx->sms[i];
@@ -589,7 +600,9 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
 static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     memset(&P, 0, sizeof(P));
     P.db = s->db->d[D.devIndex].view;
-    P.counters = D.counters; P.maxcontig = D.maxcontig; P.bitset = D.bitset; P.hitCounts = D.hitCounts;
+    P.counters = D.counters; P.maxcontig = D.maxcontig; P.hitCounts = D.hitCounts;
+    if (s->inlineSeen) { P.bitset = nullptr; P.seenTab = (u32*)s->db->d[D.devIndex].tab; }
+    else { P.bitset = D.bitset; P.seenTab = nullptr; }
     P.classify = s->cfg.classify_reads ? 1 : 0;
     P.useBloom = s->cfg.use_bloom_filter ? 1 : 0;
     P.maxPaths = s->cfg.max_classification_paths;
@@ -608,7 +621,8 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     }
     P.overflowList = D.overflowList;
     CU(cudaMemsetAsync(D.overflowCount, 0, sizeof(u32), D.sCompute));
-    if (dNEv) CU(cudaMemsetAsync(dNEv, 0, sizeof(u32), D.sCompute));
+    if (dNEv) CU(cudaMemsetAsync(dNEv, 0, 2 * sizeof(u32), D.sCompute));
+    P.errFlag = dNEv ? dNEv + 1 : nullptr;
     if (P.nReads == 0) return GS_OK;
     const int fastBlocks = (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
     gs_launch_match(P, 0, false, fastBlocks, D.sCompute);
@@ -637,13 +651,14 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     const u64 base0 = offsets[0];
     const u64 nBytes = offsets[n_reads] - base0;
     const int k = s->db->k;
-    u64 totalKmers = 0;
-    for (u32 i = 0; i < n_reads; i++) {
-        if (offsets[i + 1] < offsets[i]) return gs_fail(GS_ERR_ARG, "offsets not ascending at read %u", i);
-        const u64 L = offsets[i + 1] - offsets[i];
-        if (L > 0x7FFFFFF0ULL) return gs_fail(GS_ERR_LIMIT, "read %u longer than 2^31 bases", i);
-        if (s->cfg.want_runs && L >= (u64)k) totalKmers += L - k + 1;
-    }
+    if (offsets[n_reads] < base0) return gs_fail(GS_ERR_ARG, "offsets not ascending");
+    u64 totalKmers = 0;  // per-read offsets are validated on the device (errFlag); only want_runs needs a host pass
+    if (s->cfg.want_runs)
+        for (u32 i = 0; i < n_reads; i++) {
+            if (offsets[i + 1] < offsets[i]) return gs_fail(GS_ERR_ARG, "offsets not ascending at read %u", i);
+            const u64 L = offsets[i + 1] - offsets[i];
+            if (L >= (u64)k) totalKmers += L - k + 1;
+        }
     CU(cudaSetDevice(D.dev));
     CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
     CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
@@ -683,7 +698,7 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     // results: device -> pinned host on the copy-out stream
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hOut, sl.dOut, (size_t)n_reads * sizeof(gs_read_result), cudaMemcpyDeviceToHost, D.sCopyOut));
-    CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, 2 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaMemcpyAsync(sl.hEv, sl.dEv, std::max<size_t>(s->db->V, 1) * sizeof(gs_maxcontig_event), cudaMemcpyDeviceToHost, D.sCopyOut));
     if (s->cfg.want_runs && n_reads) CU(cudaMemcpyAsync(sl.hRunCounts, sl.dRunCounts, (size_t)n_reads * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaEventRecord(sl.evDone, D.sCopyOut));
@@ -693,8 +708,7 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     return GS_OK;
 }
 
-extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
-                                uint32_t* n_events, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap) {
+static int wait_ticket(gs_sess* s, gs_ticket t, DevSess** Dout, MatchSlot** slOut) {
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     if (t == 0 || t >= s->nextTicket) return gs_fail(GS_ERR_STATE, "unknown ticket %llu", (unsigned long long)t);
     const size_t nDev = s->devs.size();
@@ -704,9 +718,32 @@ extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs
     CU(cudaSetDevice(D.dev));
     CU(cudaEventSynchronize(sl.evDone));
     sl.pending = false;
+    *Dout = &D; *slOut = &sl;
+    if (sl.hNEv[1]) return gs_fail(GS_ERR_ARG, "batch of ticket %llu holds malformed read offsets (descending, or a read longer than 2^31 bases)", (unsigned long long)t);
+    return GS_OK;
+}
+
+extern "C" int gs_match_collect_view(gs_sess* s, gs_ticket t, const gs_read_result** out, uint32_t* n_reads,
+                                     const gs_maxcontig_event** events, uint32_t* n_events) {
+    DevSess* D; MatchSlot* sl;
+    int rc = wait_ticket(s, t, &D, &sl);
+    if (rc) return rc;
+    if (out) *out = sl->hOut;
+    if (n_reads) *n_reads = sl->nReads;
+    if (events) *events = sl->hEv;
+    if (n_events) *n_events = sl->hNEv[0];
+    return GS_OK;
+}
+
+extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
+                                uint32_t* n_events, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap) {
+    DevSess* Dp; MatchSlot* slp;
+    int rc = wait_ticket(s, t, &Dp, &slp);
+    if (rc) return rc;
+    MatchSlot& sl = *slp;
     if (out && sl.nReads) memcpy(out, sl.hOut, (size_t)sl.nReads * sizeof(gs_read_result));
     if (n_events) {
-        const u32 ne = *sl.hNEv;
+        const u32 ne = sl.hNEv[0];
         if (events) {
             if (ne > ev_cap) return gs_fail(GS_ERR_LIMIT, "%u max-contig events, capacity %u", ne, ev_cap);
             memcpy(events, sl.hEv, (size_t)ne * sizeof(gs_maxcontig_event));
@@ -752,9 +789,27 @@ extern "C" int gs_match_sync(gs_sess* s) {
     return GS_OK;
 }
 
+// In-line seen bits -> the session's compact bitset (same addressing as the external one: slot id = bucket * 16 + j)
+static int materialize_bitset(gs_sess* s, DevSess& D) {
+    if (!s->inlineSeen) return GS_OK;
+    CU(cudaSetDevice(D.dev));
+    if (!D.bitset) CU(dmalloc(&D.bitset, D.bitsetWords));
+    gs_launch_table_extract_seen(s->db->d[D.devIndex].tab, s->nPos, D.bitset, D.sCompute);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.sCompute));
+    s->launches += 1;
+    return GS_OK;
+}
+
 extern "C" int gs_match_device_state(gs_sess* s, int64_t** counters, uint64_t** maxcontig, uint64_t** bitset, uint64_t* bitset_words) {
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     DevSess& D = s->devs[0];
+    if (bitset && s->cfg.count_unique_kmers) {
+        int rc = gs_match_sync(s);
+        if (rc) return rc;
+        rc = materialize_bitset(s, D);
+        if (rc) return rc;
+    }
     if (counters) *counters = (int64_t*)D.counters;
     if (maxcontig) *maxcontig = (uint64_t*)D.maxcontig;
     if (bitset) *bitset = (uint64_t*)D.bitset;
@@ -790,7 +845,7 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     CU(cudaMemset(ovCount, 0, sizeof(u32)));
     GsMatchParams P;
     fill_params(s, D, P);
-    P.counters = counters; P.maxcontig = maxcontig; P.bitset = nullptr; P.hitCounts = nullptr;
+    P.counters = counters; P.maxcontig = maxcontig; P.bitset = nullptr; P.seenTab = nullptr; P.hitCounts = nullptr;
     P.overflowList = ovList; P.overflowCount = ovCount;
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
     P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
@@ -835,6 +890,8 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
         for (int v = 0; v < V; v++) mc[v] = std::max(mc[v], mtmp[v]);
     }
     std::vector<long long> uniq((size_t)V, 0);
+    if (s->cfg.count_unique_kmers)
+        for (DevSess& D : s->devs) { rc = materialize_bitset(s, D); if (rc) return rc; }
     if (D0.bitset) {
         CU(cudaSetDevice(D0.dev));
         if (s->devs.size() > 1 && !s->finished) {
@@ -980,6 +1037,7 @@ struct FilterSlot {
     u64* dOffsets = nullptr; size_t offCap = 0;
     uint8_t* dAccept = nullptr; size_t accCap = 0;
     uint8_t* hAccept = nullptr; size_t hAccCap = 0;
+    u32* dErr = nullptr; u32* hErr = nullptr;
     cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
 };
 struct DevFsess {
@@ -1001,8 +1059,9 @@ extern "C" void gs_filter_close(gs_fsess* s) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
         for (FilterSlot& sl : D.slots) {
-            cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dAccept);
+            cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dAccept); cudaFree(sl.dErr);
             if (sl.hAccept) cudaFreeHost(sl.hAccept);
+            if (sl.hErr) cudaFreeHost(sl.hErr);
             if (sl.evH2D) cudaEventDestroy(sl.evH2D);
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
@@ -1030,7 +1089,8 @@ extern "C" gs_fsess* gs_filter_open(gs_filter* f, int k, int min_pos_count, doub
         for (FilterSlot& sl : D.slots)
             ok = ok && cudaEventCreateWithFlags(&sl.evH2D, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming) == cudaSuccess;
+                 cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming) == cudaSuccess &&
+                 dmalloc(&sl.dErr, 1) == cudaSuccess && cudaMallocHost((void**)&sl.hErr, sizeof(u32)) == cudaSuccess;
         if (!ok) { gs_fail(GS_ERR_CUDA, "filter session setup failed: %s", cudaGetErrorString(cudaGetLastError())); gs_filter_close(s); return nullptr; }
         D.blocks = f->ctx->sms[i] * std::max(1, gs_match_kernel_occupancy(2));
     }
@@ -1051,10 +1111,7 @@ extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_
     DevFsess& D = s->devs[(t - 1) % nDev];
     FilterSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
     if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
-    for (u32 i = 0; i < n_reads; i++) {
-        if (offsets[i + 1] < offsets[i]) return gs_fail(GS_ERR_ARG, "offsets not ascending at read %u", i);
-        if (offsets[i + 1] - offsets[i] > 0x7FFFFFF0ULL) return gs_fail(GS_ERR_LIMIT, "read %u longer than 2^31 bases", i);
-    }
+    if (offsets[n_reads] < offsets[0]) return gs_fail(GS_ERR_ARG, "offsets not ascending");
     const u64 base0 = offsets[0];
     const u64 nBytes = offsets[n_reads] - base0;
     CU(cudaSetDevice(D.dev));
@@ -1068,7 +1125,8 @@ extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_
     CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
     GsFilterParams P;
     fill_fparams(s, D, P);
-    P.bases = sl.dBases - base0; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept;
+    P.bases = sl.dBases - base0; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept; P.errFlag = sl.dErr;
+    CU(cudaMemsetAsync(sl.dErr, 0, sizeof(u32), D.sCompute));
     if (n_reads) {
         const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
         gs_launch_filter(P, blocks, D.sCompute);
@@ -1077,6 +1135,7 @@ extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hErr, sl.dErr, sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaEventRecord(sl.evDone, D.sCopyOut));
     sl.pending = true; sl.ticket = t; sl.nReads = n_reads;
     s->nextTicket++;
@@ -1094,6 +1153,7 @@ extern "C" int gs_filter_collect(gs_fsess* s, gs_ticket t, uint8_t* accept) {
     CU(cudaSetDevice(D.dev));
     CU(cudaEventSynchronize(sl.evDone));
     sl.pending = false;
+    if (*sl.hErr) return gs_fail(GS_ERR_ARG, "batch of ticket %llu holds malformed read offsets", (unsigned long long)t);
     if (accept && sl.nReads) memcpy(accept, sl.hAccept, sl.nReads);
     return GS_OK;
 }
@@ -1105,7 +1165,7 @@ extern "C" int gs_filter_run_device(gs_fsess* s, const uint8_t* d_bases, const u
     CU(cudaSetDevice(D.dev));
     GsFilterParams P;
     fill_fparams(s, D, P);
-    P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.accept = d_accept;
+    P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.accept = d_accept; P.errFlag = nullptr;
     if (n_reads) {
         const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
         gs_launch_filter(P, blocks, D.sCompute);

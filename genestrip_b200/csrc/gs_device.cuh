@@ -9,6 +9,13 @@ typedef unsigned int u32;
 
 #define GS_LABEL_END 0xFFFFFFFFu      // terminator lane (past the last k-mer position)
 #define GS_LABEL_MISS 0xFFFFFFFEu     // taxIdNode == null
+#define GS_LABEL_PENDING 0xFFFFFFFCu  // kernel-internal: table header load issued, not resolved yet
+#ifndef GS_GROUP
+#define GS_GROUP 4                    // chunks (of 32 positions) whose probe-table loads are in flight together
+#endif
+#ifndef GS_MIN_BLOCKS
+#define GS_MIN_BLOCKS 3               // resident CTAs per SM the match kernel is compiled for (register budget)
+#endif
 #define GS_LABEL_INVALID 0xFFFFFFFDu  // INVALID_NODE (C/match/FastqKMerMatcher.java:63)
 #define GS_LAYOUT_TABLE 0             // default device index: 128-byte probe table (one DRAM line touch per k-mer)
 #define GS_LAYOUT_CLASSIC 1           // the reference's structures: blocked Bloom filter + (bucketed) binary search
@@ -38,9 +45,9 @@ struct GsDbView {
     u64 bloomBuckets, bloomMagic;
     long long bloomSeed;
     int hasBloom;
-    // probe table (GS_LAYOUT_TABLE): 2^tbits lines of 128 bytes; line = 14 fingerprint bytes, fill count, overflow flag,
-    // then 14 entries (remainder << 16 | value).  One DRAM line touch answers hit/miss and yields the value.
-    const uint4* tab;
+    // probe table (GS_LAYOUT_TABLE): 2^tbits buckets of one 32-byte sector = four 8-byte entries; one 256-bit load
+    // answers hit/miss and yields the value and the position's seen bit (see "probe table" below)
+    const u64* tab;
     int tbits, rbits;       // bucket = mix62(key) >> rbits, remainder = low rbits bits, rbits = 62 - tbits
     const int* parent;      // by value index, -1 root / none
     const int* depth;
@@ -148,16 +155,25 @@ __device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBl
 }
 
 // ---- probe table -------------------------------------------------------------------------------------------
-// Measured on B200 (profiles/microbench/randload.cu): a random 8-byte probe into a multi-GB array costs one DRAM line
-// touch (~39.5 G touches/s for the whole GPU) whatever its size up to 128 bytes.  The reference's structures need
-// Bloom word(s) + bucket index + keys + value = 2.2 touches per k-mer at the viral-scale mix; this table needs one.
-#define GS_TAB_SLOTS 14
-#define GS_TAB_SLOT_STRIDE 16   // slot id = bucket * 16 + j: the "storage position" used by the unique-k-mer bitset
-#define GS_TAB_MIN_BITS 14      // rbits + 16 value bits must fit 64 bits
+// Measured on B200 (profiles/microbench/randwide.cu, randline.cu): fully divergent loads are capped at ~39.4 G requests/s
+// for the whole GPU whatever their width (8, 16 or 32 bytes per lane) and whether DRAM moves 64 or 128 bytes for them.
+// The reference's structures need Bloom word(s) + bucket index + keys + value = 3-5 requests per k-mer; this table
+// needs one: a bucket is one 32-byte sector of four 8-byte entries, fetched with a single 256-bit load (LDG.E.256).
+//   entry = remainder << 19 | value << 3 | spill << 2 | occupied << 1 | seen
+// bucket = mix62(key) >> rbits, remainder = low rbits bits (mix62 is a bijection, so bucket + remainder identify the key);
+// `spill` (slot 0 only) = a key of this bucket was pushed to a following bucket; `seen` = unique-k-mer bit of the session
+// that leases it (KMerUniqueCounterBits), so counting a k-mer as seen needs no second memory request.
+#define GS_TAB_SLOTS 4
+#define GS_TAB_SLOT_STRIDE 4    // slot id = bucket * 4 + j: the "storage position" used for unique k-mer counting
+#define GS_TAB_MIN_BITS 17      // rbits <= 45 so that remainder + value + 3 flag bits fit 64 bits
+#define GS_TAB_SEEN 1ULL
+#define GS_TAB_OCC 2ULL
+#define GS_TAB_SPILL 4ULL
+#define GS_TAB_VAL_SHIFT 3
+#define GS_TAB_REM_SHIFT 19
 #define GS_M62 ((1ULL << 62) - 1)
 
-// bijection on [0, 2^62) (xor-shifts and odd multiplications mod 2^62): equal hashes <=> equal keys, so the bucket
-// number plus the remainder identify the key exactly and only the remainder has to be stored.
+// bijection on [0, 2^62) (xor-shifts and odd multiplications mod 2^62): equal hashes <=> equal keys
 __host__ __device__ __forceinline__ u64 gs_mix62(u64 x) {
     x ^= x >> 31;
     x = (x * 0x7FB5D329728EA185ULL) & GS_M62;
@@ -167,49 +183,50 @@ __host__ __device__ __forceinline__ u64 gs_mix62(u64 x) {
     return x;
 }
 
-__device__ __forceinline__ u32 gs_fp_of(u64 rem) { return (u32)((rem >> 3) & 0xFF); }
+struct GsBucket { u64 e[4]; };
 
-// Returns the label (value index / MISS); pos = slot id of the match.
-__device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {
-    if (key > GS_M62) return GS_LABEL_MISS;
-    const u64 h = gs_mix62(key);
+// one 256-bit load of a bucket; .cg: served by L2 so that seen bits set by other SMs are visible
+__device__ __forceinline__ GsBucket gs_load_bucket(const u64* tab, u64 b) {
+    GsBucket r;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.e[0]), "=l"(r.e[1]), "=l"(r.e[2]), "=l"(r.e[3]) : "l"(tab + b * 4));
+    return r;
+}
+
+// Resolve a lookup whose home bucket is already loaded.  Returns the label (value index / MISS);
+// pos = slot id of the match, seen = the slot's seen bit as loaded.
+__device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBucket bk, u64& pos, bool& seen) {
     u64 b = h >> db.rbits;
-    const u64 rem = h & ((1ULL << db.rbits) - 1);
-    const u32 fp4 = gs_fp_of(rem) * 0x01010101u;
-    const u64 bmask = (1ULL << db.tbits) - 1;
+    const u64 want = ((h & ((1ULL << db.rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;
+    const u64 cmpMask = ~((1ULL << GS_TAB_REM_SHIFT) - 1) | GS_TAB_OCC;
     for (;;) {
-        const uint4* line = db.tab + b * 8;
-        const uint4 hd = __ldg(line);
-        const u32 cnt = (hd.w >> 16) & 0xFF;
-        // fingerprint match mask over the 14 slots (bytes 0..13 of the header)
-        u32 m = (((__vcmpeq4(hd.x, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-        m |= ((((__vcmpeq4(hd.y, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4;
-        m |= ((((__vcmpeq4(hd.z, fp4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 8;
-        m |= ((((__vcmpeq4(hd.w, fp4) & 0x00000101u) * 0x01020408u) >> 24) & 3u) << 12;
-        m &= (1u << cnt) - 1u;
-        const u64* ent = (const u64*)(line + 1);
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const u64 e = __ldg(ent + j);
-            if ((e >> 16) == rem) {
+#pragma unroll
+        for (int j = 0; j < GS_TAB_SLOTS; j++) {
+            if ((bk.e[j] & cmpMask) == want) {
                 pos = b * GS_TAB_SLOT_STRIDE + (u64)j;
-                const u32 v = (u32)(e & 0xFFFF);
+                seen = bk.e[j] & GS_TAB_SEEN;
+                const u32 v = (u32)(bk.e[j] >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
                 return v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
             }
         }
-        if (!(hd.w >> 24)) return GS_LABEL_MISS;  // nothing spilled past this bucket
-        b = (b + 1) & bmask;
+        if (!(bk.e[0] & GS_TAB_SPILL)) return GS_LABEL_MISS;  // nothing spilled past this bucket
+        b = (b + 1) & ((1ULL << db.tbits) - 1);
+        bk = gs_load_bucket(db.tab, b);
     }
+}
+
+__device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {
+    if (key > GS_M62) return GS_LABEL_MISS;
+    const u64 h = gs_mix62(key);
+    bool seen;
+    return gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
 }
 
 // value stored at a "storage position" of the unique-k-mer bitset: sorted-array index (classic) or table slot id
 __device__ __forceinline__ u32 gs_value_at(const GsDbView& db, int layout, u64 pos) {
     if (layout == GS_LAYOUT_TABLE) {
-        const u64 b = pos / GS_TAB_SLOT_STRIDE;
-        const u32 j = (u32)(pos % GS_TAB_SLOT_STRIDE);
-        if (b >> db.tbits || j >= GS_TAB_SLOTS) return GS_VAL_NONODE;
-        return (u32)(__ldg((const u64*)(db.tab + b * 8 + 1) + j) & 0xFFFF);
+        if ((pos / GS_TAB_SLOT_STRIDE) >> db.tbits) return GS_VAL_NONODE;
+        const u64 e = __ldcg(db.tab + pos);
+        return (e & GS_TAB_OCC) ? (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu : GS_VAL_NONODE;
     }
     return pos < db.n ? (u32)__ldg(db.vals + pos) : GS_VAL_NONODE;
 }

@@ -85,12 +85,24 @@ __device__ __forceinline__ int gs_lca(const GsDbView& db, int a, int b) {
     return a;
 }
 
+// Java short ++ with wrap-around, two counters per 32-bit word (KMerUniqueCounterBits.putInlined :134-140)
+__device__ __forceinline__ void gs_hit_count_inc(uint16_t* hitCounts, u64 pos) {
+    u32* hp = (u32*)hitCounts + (pos >> 1);
+    const int sh = (int)(pos & 1) * 16;
+    u32 old = *hp, assumed;
+    do {
+        assumed = old;
+        u32 nv = (assumed & ~(0xFFFFu << sh)) | ((((assumed >> sh) + 1u) & 0xFFFFu) << sh);
+        old = atomicCAS(hp, assumed, nv);
+    } while (old != assumed);
+}
+
 // MODE 0: fast path (table in shared memory).  MODE 1: slow path for reads that overflowed the fast table
 // (table in global scratch sized nValues; contig statistics and unique bits were already applied by the fast
 // path, only reads1KMer beyond the first GS_TABLE_CAP taxa and the classification are done here).
 // DUMP: additionally write the per-position labels / positions (parity tests).
 template <int MODE, bool DUMP>
-__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const GsMatchParams P) {
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_match_kernel(const GsMatchParams P) {
     __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_CODE_WORDS];
     __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_VALID_WORDS];
     __shared__ u32 s_tabVi[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
@@ -115,7 +127,12 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const
     for (u32 item = gw; item < nItems; item += nw) {
         const u32 r = MODE == 0 ? item : P.overflowList[item];
         const u64 start = P.offsets[r];
-        const int L = (int)(P.offsets[r + 1] - start);
+        const u64 end = P.offsets[r + 1];
+        int L = (int)(end - start);
+        if (end < start || end - start > 0x7FFFFFF0ULL) {  // malformed offsets: reported by gs_match_collect
+            if (lane == 0 && P.errFlag) atomicOr(P.errFlag, 1u);
+            L = 0;
+        }
         const int max = L - k + 1;
         const u64 ordinal = P.firstReadNo + r;
         int classV = -1;
@@ -139,40 +156,80 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const
             const int lim = max - t0;  // tile-relative index of the terminator position
             const int nchunks = (min(lim, GS_TILE_POS - 1) >> 5) + 1;
 #pragma unroll 1
-            for (int c = 0; c < nchunks; c++) {
-                const int prel = c * 32 + lane;
-                u32 lab = GS_LABEL_END;
-                u64 pos = 0;
-                if (prel < lim) {
-                    u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
-                    if ((vbits & kmask) != kmask) lab = GS_LABEL_INVALID;
-                    else {
-                        const u64 key = gs_canonical(gs_extract(cw, prel, k), k);
-                        lab = P.layout == GS_LAYOUT_TABLE ? gs_lookup_table(db, key, pos) : gs_lookup(db, key, useBloom, pos);
-                    }
-                    if (DUMP) {
+            for (int c0 = 0; c0 < nchunks; c0 += GS_GROUP) {
+              // ---- phase A/B: labels of GS_GROUP chunks; with the probe table all header loads of the group are
+              // issued before the first one is consumed (memory-level parallelism: GS_GROUP line touches in flight per lane)
+              u32 labs[GS_GROUP];
+              u64 poss[GS_GROUP];
+              bool seens[GS_GROUP];
+              if (P.layout == GS_LAYOUT_TABLE) {
+                  u64 hs[GS_GROUP];
+                  GsBucket hds[GS_GROUP];
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++) {
+                      const int prel = (c0 + g) * 32 + lane;
+                      labs[g] = GS_LABEL_END; poss[g] = 0; seens[g] = true; hs[g] = 0; hds[g] = GsBucket{{0, 0, 0, 0}};
+                      if (c0 + g < nchunks && prel < lim) {
+                          const u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
+                          if ((vbits & kmask) != kmask) labs[g] = GS_LABEL_INVALID;
+                          else {
+                              hs[g] = gs_mix62(gs_canonical(gs_extract(cw, prel, k), k));
+                              hds[g] = gs_load_bucket(db.tab, hs[g] >> db.rbits);
+                              labs[g] = GS_LABEL_PENDING;
+                          }
+                      }
+                  }
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++)
+                      if (labs[g] == GS_LABEL_PENDING) labs[g] = gs_table_resolve(db, hs[g], hds[g], poss[g], seens[g]);
+              } else {
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++) {
+                      const int prel = (c0 + g) * 32 + lane;
+                      labs[g] = GS_LABEL_END; poss[g] = 0;
+                      if (c0 + g < nchunks && prel < lim) {
+                          const u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
+                          if ((vbits & kmask) != kmask) labs[g] = GS_LABEL_INVALID;
+                          else labs[g] = gs_lookup(db, gs_canonical(gs_extract(cw, prel, k), k), useBloom, poss[g]);
+                      }
+                  }
+              }
+              // ---- phase C: unique k-mer bits (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143):
+              // all test loads of the group first, then the atomics of the bits that were still clear
+              if (MODE == 0 && P.seenTab) {  // seen bits live in the probe-table line that was just fetched: no extra load
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++) {
+                      if (labs[g] >= GS_LABEL_INVALID) continue;
+                      if (!seens[g]) atomicOr(P.seenTab + poss[g] * 2, (u32)GS_TAB_SEEN);  // low word of the slot's entry
+                      if (P.hitCounts) gs_hit_count_inc(P.hitCounts, poss[g]);
+                  }
+              } else if (MODE == 0 && P.bitset) {
+                  u64 seen[GS_GROUP];
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++)
+                      seen[g] = labs[g] < GS_LABEL_INVALID ? *(volatile u64*)(P.bitset + (poss[g] >> 6)) : ~0ULL;
+#pragma unroll
+                  for (int g = 0; g < GS_GROUP; g++) {
+                      if (labs[g] >= GS_LABEL_INVALID) continue;
+                      const u64 bit = 1ULL << (poss[g] & 63);
+                      if (!(seen[g] & bit)) atomicOr(P.bitset + (poss[g] >> 6), bit);
+                      if (P.hitCounts) gs_hit_count_inc(P.hitCounts, poss[g]);
+                  }
+              }
+              // ---- phase D: the reference's sequential contig logic, chunk by chunk
+#pragma unroll
+              for (int g = 0; g < GS_GROUP; g++) {
+                if (c0 + g >= nchunks) break;
+                const u32 lab = labs[g];
+                if (DUMP) {
+                    const int prel = (c0 + g) * 32 + lane;
+                    if (prel < lim) {
                         u64 o = P.kmerOffsets[r] + (u64)(t0 + prel);
                         P.dumpLabels[o] = lab == GS_LABEL_INVALID ? -2 : (lab == GS_LABEL_MISS ? -1 : (int)lab);
-                        P.dumpPos[o] = lab < GS_LABEL_INVALID ? (long long)pos : -1LL;
+                        P.dumpPos[o] = lab < GS_LABEL_INVALID ? (long long)poss[g] : -1LL;
                     }
                 }
-                const bool isTax = lab < GS_LABEL_INVALID;
                 if (P.classify) misses += __popc(__ballot_sync(FULL, lab == GS_LABEL_MISS));
-                if (MODE == 0 && isTax && P.bitset) {  // KMerUniqueCounterBits.putInlined (C/store/KMerUniqueCounterBits.java:117-143)
-                    u64 bit = 1ULL << (pos & 63);
-                    u64* wp = P.bitset + (pos >> 6);
-                    if (!(*(volatile u64*)wp & bit)) atomicOr(wp, bit);
-                    if (P.hitCounts) {  // Java short ++ with wrap-around, two counters per 32-bit word
-                        u32* hp = (u32*)P.hitCounts + (pos >> 1);
-                        const int sh = (int)(pos & 1) * 16;
-                        u32 old = *hp, assumed;
-                        do {
-                            assumed = old;
-                            u32 nv = (assumed & ~(0xFFFFu << sh)) | ((((assumed >> sh) + 1u) & 0xFFFFu) << sh);
-                            old = atomicCAS(hp, assumed, nv);
-                        } while (old != assumed);
-                    }
-                }
                 // ---- contigs = maximal runs of equal labels (FastqKMerMatcher.java:370, 390-421)
                 u32 prev = __shfl_up_sync(FULL, lab, 1);
                 if (lane == 0) prev = carryLabel;
@@ -211,6 +268,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_match_kernel(const
                 }
                 if (S) carryLen = 32 - (31 - __clz(S)); else carryLen += 32;
                 carryLabel = __shfl_sync(FULL, lab, 31);
+              }
             }
         }
         if (MODE == 0 && P.runs && lane == 0) P.runCounts[r] = (u32)runCursor;
@@ -383,37 +441,50 @@ void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCoun
     gs_collect_hits_kernel<<<148 * 8, 256, 0, st>>>(bits, nWords, hitCounts, db, layout, out, nOut, cap);
 }
 
-// ---- probe table build: every key claims a slot of its home bucket; full buckets spill to the next one and are flagged
-__global__ void gs_table_insert_kernel(const u64* __restrict__ keys, const uint16_t* __restrict__ vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits) {
+// ---- probe table build: every key claims a slot of its home bucket; keys of full buckets go to the next bucket with
+// room and the buckets they pass are flagged (phase 2, after all entries are in place)
+__global__ void gs_table_insert_kernel(const u64* __restrict__ keys, const uint16_t* __restrict__ vals, u64 n, u64* tab, u32* counts, int tbits, int rbits) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 bmask = (1ULL << tbits) - 1;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const u64 h = gs_mix62(keys[i]);
         u64 b = h >> rbits;
-        const u64 rem = h & ((1ULL << rbits) - 1);
-        const u64 entry = (rem << 16) | (u64)vals[i];
-        const uint8_t fp = (uint8_t)gs_fp_of(rem);
+        const u64 entry = ((h & ((1ULL << rbits) - 1)) << GS_TAB_REM_SHIFT) | ((u64)vals[i] << GS_TAB_VAL_SHIFT) | GS_TAB_OCC;
         for (;;) {
-            uint8_t* line = (uint8_t*)(tab + b * 8);
-            const u32 idx = atomicAdd(counts + b, 1u);
-            if (idx < GS_TAB_SLOTS) {
-                ((u64*)(line + 16))[idx] = entry;
-                line[idx] = fp;
-                break;
-            }
-            line[15] = 1;  // something spilled past this bucket
+            const u32 idx = atomicAdd(counts + b, 1u) & 0x7FFFFFFFu;
+            if (idx < GS_TAB_SLOTS) { tab[b * 4 + idx] = entry; break; }
+            atomicOr(counts + b, 0x80000000u);  // something spilled past this bucket
             b = (b + 1) & bmask;
         }
     }
 }
-__global__ void gs_table_finalize_kernel(uint4* tab, const u32* __restrict__ counts, u64 nBuckets) {
+__global__ void gs_table_finalize_kernel(u64* tab, const u32* __restrict__ counts, u64 nBuckets) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride) {
-        const u32 c = counts[b];
-        ((uint8_t*)(tab + b * 8))[14] = (uint8_t)(c < GS_TAB_SLOTS ? c : GS_TAB_SLOTS);
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride)
+        if (counts[b] & 0x80000000u) tab[b * 4] |= GS_TAB_SPILL;
+}
+// seen bits of all entries -> 0 (a session leases them), and seen bits -> compact bitset (bit = slot id)
+__global__ void gs_table_clear_seen_kernel(u64* tab, u64 nSlots) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride) {
+        const u64 e = tab[i];
+        if (e & GS_TAB_SEEN) tab[i] = e & ~GS_TAB_SEEN;
     }
 }
-void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
+__global__ void gs_table_extract_seen_kernel(const u64* __restrict__ tab, u64 nSlots, u64* out) {
+    // one warp gathers 32 x 2 entries into one u64 word of the bitset with two ballots
+    const u64 warpsTotal = ((u64)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 64 < nSlots; w += warpsTotal) {
+        const u64 i0 = w * 64 + lane, i1 = i0 + 32;
+        const u32 lo = __ballot_sync(FULL, i0 < nSlots && (__ldcg(tab + i0) & GS_TAB_SEEN));
+        const u32 hi = __ballot_sync(FULL, i1 < nSlots && (__ldcg(tab + i1) & GS_TAB_SEEN));
+        if (lane == 0) out[w] = ((u64)hi << 32) | lo;
+    }
+}
+void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st) { gs_table_clear_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots); }
+void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st) { gs_table_extract_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots, out); }
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
     gs_table_insert_kernel<<<148 * 8, 256, 0, st>>>(keys, vals, n, tab, counts, tbits, rbits);
     gs_table_finalize_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, 1ULL << tbits);
 }
@@ -539,7 +610,12 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_filter_kernel(cons
     u32* vw = s_valid[warp];
     for (u32 r = gw; r < P.nReads; r += nw) {
         const u64 start = P.offsets[r];
-        const int L = (int)(P.offsets[r + 1] - start);
+        const u64 end = P.offsets[r + 1];
+        int L = (int)(end - start);
+        if (end < start || end - start > 0x7FFFFFF0ULL) {
+            if (lane == 0 && P.errFlag) atomicOr(P.errFlag, 1u);
+            L = 0;
+        }
         const int max = L - k + 1;
         int posThreshold = P.minPosCount > 0 ? P.minPosCount : (int)((double)max * P.posRatio);  // :122
         const int need = posThreshold < 1 ? 1 : posThreshold;

@@ -13,12 +13,14 @@ struct GsMatchParams {
     long long* counters;    // [7][nValues]: kmers, contigs, contigLenSquaredSum, reads1KMer, reads, readsKmers, readsBPs
     u64* maxcontig;         // [nValues] (maxContigLen << 40) | (2^40-1 - read ordinal)
     u64* bitset;            // unique k-mer bits by storage position, or NULL
+    u32* seenTab;           // probe table as u32 words when the session leases its in-entry seen bits (then bitset == NULL)
     uint16_t* hitCounts;    // per-position hit counters (maxKMerResCounts > 0), or NULL
     int classify, useBloom, maxPaths, threshold;
     int layout;             // GS_LAYOUT_TABLE / GS_LAYOUT_CLASSIC
     double maxTaxErr, maxClassErr;
     u32* overflowList;      // reads with more than GS_TABLE_CAP distinct taxa
     u32* overflowCount;
+    u32* errFlag;           // set when a read's offsets are malformed (descending / longer than 2^31)
     u32* slowTable;         // MODE 1: per-warp vote tables in global memory, 2 * nValues u32 each
     // kraken-style runs (want_runs)
     gs_run* runs; const u64* runOffsets; u64 runsCap; u32* runCounts;
@@ -42,13 +44,16 @@ struct GsFilterParams {
     int k, minPosCount;
     double posRatio;
     uint8_t* accept;
+    u32* errFlag;
 };
 
 void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
 void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st);
 void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
-void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, uint4* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
+void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st);
+void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st);
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
 void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
 void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);

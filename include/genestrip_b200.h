@@ -152,6 +152,10 @@ int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uin
  * [n_reads+1] and runs[runs_cap] receive the contig runs (GS_ERR_LIMIT if runs_cap is too small). */
 int gs_match_collect(gs_sess*, gs_ticket, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
                      uint32_t* n_events, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap);
+/* Zero-copy variant: *out / *events point into the session's pinned staging buffers (a JNI shim wraps them with
+ * NewDirectByteBuffer); valid until GS_MAX_INFLIGHT further batches were submitted to the same device. */
+int gs_match_collect_view(gs_sess*, gs_ticket, const gs_read_result** out, uint32_t* n_reads,
+                          const gs_maxcontig_event** events, uint32_t* n_events);
 /* End of run: merges all devices, runs the unique-k-mer count (KMerUniqueCounterBits.getUniqueKmerCounts,
  * C/store/KMerUniqueCounterBits.java:146-163) and returns per-value-index counts[n_values].
  * top_counts (may be NULL): (n_values+1) x max_kmer_res_counts Java shorts, row n_values = total

@@ -354,3 +354,29 @@ def test_reference_match_read_kat(oracle, native, gpu_ctx):
     finally:
         gdb.close()
         odb.free()
+
+
+def test_two_sessions_share_one_database(project, reads, oracle, native):
+    """The probe table's in-line seen bits are leased by the first unique-counting session; a second concurrent session
+    falls back to its own bitset.  Both must give the reference's unique counts, also after the lease is released."""
+    odb, gdb, _ = project
+    bases, offsets, _, fq = reads
+    n = 2000
+    off = np.ascontiguousarray(offsets[: n + 1])
+    orun = odb.match_files(util.oracle_cfg(oracle, K), [synth.fastq_bytes(bases, off, None)])
+    a = native.MatchSession(gdb)
+    b = native.MatchSession(gdb)
+    try:
+        ta = a.submit(bases, off, 0)
+        tb = b.submit(bases, off, 0)
+        ra, _, _, _ = a.collect(ta)
+        rb, _, _, _ = b.collect(tb)
+        ca, _ = a.finish()
+        cb, _ = b.finish()
+    finally:
+        a.close()
+        b.close()
+    util.assert_match_parity(native, orun, ra, ca)
+    util.assert_match_parity(native, orun, rb, cb)
+    res, _, counts, _, _, _ = util.gpu_match(native, gdb, bases, off)   # new lease: bits were cleared
+    util.assert_match_parity(native, orun, res, counts)
