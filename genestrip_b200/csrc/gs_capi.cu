@@ -529,7 +529,7 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
             CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
         }
     }
-    CU(dmalloc(&D.overflowCount, 1));
+    CU(dmalloc(&D.overflowCount, 2));  // [0] overflow list length, [1] work counter
     const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
     D.fastBlocks = D.sms * occ0;
     D.slowBlocks = std::max(1, D.sms / 4);
@@ -610,7 +610,7 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     P.layout = s->layout;
     P.maxTaxErr = s->cfg.max_read_tax_error_count;
     P.maxClassErr = s->cfg.max_read_class_error_count;
-    P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.slowTable = D.slowTable;
+    P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.workCounter = D.overflowCount + 1; P.slowTable = D.slowTable;
 }
 
 // kernels of one batch on the compute stream: fast path, slow path over the overflow list, max-contig events
@@ -620,7 +620,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
         CU(dgrow(&D.overflowList, &D.ovCap, (size_t)P.nReads));
     }
     P.overflowList = D.overflowList;
-    CU(cudaMemsetAsync(D.overflowCount, 0, sizeof(u32), D.sCompute));
+    CU(cudaMemsetAsync(D.overflowCount, 0, 2 * sizeof(u32), D.sCompute));
     if (dNEv) CU(cudaMemsetAsync(dNEv, 0, 2 * sizeof(u32), D.sCompute));
     P.errFlag = dNEv ? dNEv + 1 : nullptr;
     if (P.nReads == 0) return GS_OK;
@@ -839,14 +839,14 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     const int V = s->db->V;
     long long* counters = nullptr; u64* maxcontig = nullptr; gs_read_result* out = nullptr; u32* ovList = nullptr; u32* ovCount = nullptr;
     CU(dmalloc(&counters, (size_t)7 * V)); CU(dmalloc(&maxcontig, (size_t)V)); CU(dmalloc(&out, (size_t)n_reads));
-    CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 1));
+    CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 2));
     CU(cudaMemset(counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
     CU(cudaMemset(maxcontig, 0, std::max<size_t>(V, 1) * sizeof(u64)));
-    CU(cudaMemset(ovCount, 0, sizeof(u32)));
+    CU(cudaMemset(ovCount, 0, 2 * sizeof(u32)));
     GsMatchParams P;
     fill_params(s, D, P);
     P.counters = counters; P.maxcontig = maxcontig; P.bitset = nullptr; P.seenTab = nullptr; P.hitCounts = nullptr;
-    P.overflowList = ovList; P.overflowCount = ovCount;
+    P.overflowList = ovList; P.overflowCount = ovCount; P.workCounter = ovCount + 1;
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
     P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
     CU(cudaStreamSynchronize(D.sCompute));

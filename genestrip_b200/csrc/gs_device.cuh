@@ -13,6 +13,9 @@ typedef unsigned int u32;
 #ifndef GS_GROUP
 #define GS_GROUP 4                    // chunks (of 32 positions) whose probe-table loads are in flight together
 #endif
+#ifndef GS_CLAIM
+#define GS_CLAIM 8                    // reads a warp claims per atomic of the work counter
+#endif
 #ifndef GS_MIN_BLOCKS
 #define GS_MIN_BLOCKS 3               // resident CTAs per SM the match kernel is compiled for (register budget)
 #endif

@@ -124,7 +124,24 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
     else { T.vi = P.slowTable + (size_t)gw * 2 * (size_t)V; T.cnt = T.vi + V; T.cap = V; }
     const u32 nItems = MODE == 0 ? P.nReads : *P.overflowCount;
 
-    for (u32 item = gw; item < nItems; item += nw) {
+    // Dynamic distribution: a warp claims GS_CLAIM consecutive reads at a time.  With a static split the SMs that get
+    // more of the saturated memory system finish early and idle (ncu: sm__cycles_active min 58 % of max).
+    u32 claimBase = 0, claimPos = GS_CLAIM;
+    for (;;) {
+        u32 item;
+        if (MODE == 0) {
+            if (claimPos == GS_CLAIM) {
+                if (lane == 0) claimBase = atomicAdd(P.workCounter, (u32)GS_CLAIM);
+                claimBase = __shfl_sync(FULL, claimBase, 0);
+                claimPos = 0;
+            }
+            item = claimBase + claimPos++;
+            if (item >= nItems) { if (claimBase >= nItems) break; claimPos = GS_CLAIM; continue; }
+        } else {
+            item = gw + claimBase * nw;
+            claimBase++;
+            if (item >= nItems) break;
+        }
         const u32 r = MODE == 0 ? item : P.overflowList[item];
         const u64 start = P.offsets[r];
         const u64 end = P.offsets[r + 1];

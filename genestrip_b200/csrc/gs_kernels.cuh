@@ -20,6 +20,7 @@ struct GsMatchParams {
     double maxTaxErr, maxClassErr;
     u32* overflowList;      // reads with more than GS_TABLE_CAP distinct taxa
     u32* overflowCount;
+    u32* workCounter;       // next unclaimed read of the batch (dynamic distribution over the persistent warps)
     u32* errFlag;           // set when a read's offsets are malformed (descending / longer than 2^31)
     u32* slowTable;         // MODE 1: per-warp vote tables in global memory, 2 * nValues u32 each
     // kraken-style runs (want_runs)
