@@ -61,6 +61,7 @@ _SIGS = {
     "gs_db_finalize": (C.c_int, [_P]),
     "gs_db_destroy": (None, [_P]),
     "gs_db_device_bytes": (C.c_uint64, [_P]),
+    "gs_db_n_devices": (C.c_int, [_P]),
     "gs_db_lookup": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
     "gs_match_cfg_default": (None, [C.POINTER(MatchCfg)]),
     "gs_match_open": (_P, [_P, C.POINTER(MatchCfg)]),
@@ -78,6 +79,7 @@ _SIGS = {
     "gs_match_dump_labels": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     "gs_filter_create": (_P, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_uint64]),
     "gs_filter_destroy": (None, [_P]),
+    "gs_filter_n_devices": (C.c_int, [_P]),
     "gs_filter_contains": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "gs_filter_open": (_P, [_P, C.c_int, C.c_int, C.c_double]),
     "gs_filter_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint64)]),

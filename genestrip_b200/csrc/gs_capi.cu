@@ -423,6 +423,7 @@ extern "C" void gs_db_destroy(gs_db* db) {
 }
 
 extern "C" uint64_t gs_db_device_bytes(const gs_db* db) { return db ? db->bytes : 0; }
+extern "C" int gs_db_n_devices(const gs_db* db) { return db ? (int)db->d.size() : 0; }
 
 extern "C" int gs_db_lookup(gs_db* db, const int64_t* kmers, uint64_t n, int use_bloom, int32_t* vidx_out, int64_t* pos_out) {
     if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
@@ -978,6 +979,8 @@ extern "C" void gs_filter_destroy(gs_filter* f) {
     for (DevFilter& d : f->d) { cudaSetDevice(d.dev); cudaFree(d.words); cudaFree(d.factors); }
     delete f;
 }
+
+extern "C" int gs_filter_n_devices(const gs_filter* f) { return f ? (int)f->d.size() : 0; }
 
 extern "C" gs_filter* gs_filter_create(gs_ctx* ctx, int kind, int64_t p0, int64_t p1, const int64_t* factors,
                                        const int64_t* words, uint64_t n_words) {

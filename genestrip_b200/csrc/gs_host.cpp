@@ -1,0 +1,796 @@
+// gs_host.cpp -- see gs_host.hpp.  Host-side mirror of the reference's goal drivers; the per-read work is done by the GPU
+// through the C ABI (gs_match_* / gs_filter_*).  No CPU implementation of the hot path lives here.
+#include "gs_host.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <stdexcept>
+
+namespace gsh {
+
+static void fail(const std::string& what) { throw std::runtime_error(what); }
+static void check(int rc, const char* what) {
+    if (rc != GS_OK) fail(std::string(what) + ": " + gs_last_error());
+}
+
+void DbMeta::resize(int n) {
+    nValues = n;
+    taxid.assign(n, ""); name.assign(n, ""); rank.assign(n, -1); parent.assign(n, -1); position.assign(n, -1); level.assign(n, 0);
+    hasNode.assign(n, 0); dbKmers.assign(n, 0);
+}
+
+// C/tax/Rank.java:39-122 (Rank.toString() == the NCBI rank name)
+static const char* const kRankNames[] = {
+    "cellular root", "acellular root", "superkingdom", "domain", "realm", "kingdom", "phylum", "subphylum", "superclass", "class",
+    "subclass", "superorder", "order", "suborder", "superfamily", "family", "subfamily", "tribe", "genus", "subgenus", "species group",
+    "species", "varietas", "subspecies", "serogroup", "biotype", "strain", "serotype", "genotype", "forma", "forma specialis",
+    "isolate", "clade", "no rank", "subkingdom", "section", "REFINED", "DATA", "FILE", "ID"};
+const char* rankName(int ordinal) {
+    const int n = (int)(sizeof(kRankNames) / sizeof(kRankNames[0]));
+    return (ordinal >= 0 && ordinal < n) ? kRankNames[ordinal] : "";
+}
+
+// java.lang.Double.toString (JDK >= 19 specification: the shortest decimal that rounds to the double; computerized
+// scientific notation outside [1e-3, 1e7)).
+std::string javaDoubleToString(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "Infinity" : "-Infinity";
+    if (v == 0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[48];
+    auto res = std::to_chars(buf, buf + sizeof(buf), std::fabs(v), std::chars_format::scientific);
+    std::string sci(buf, res.ptr);
+    const size_t ePos = sci.find('e');
+    const int exp10 = std::atoi(sci.c_str() + ePos + 1);
+    std::string digits;
+    for (size_t i = 0; i < ePos; i++)
+        if (sci[i] != '.') digits.push_back(sci[i]);
+    std::string out = std::signbit(v) ? "-" : "";
+    if (exp10 >= -3 && exp10 < 7) {
+        if (exp10 >= 0) {
+            const size_t intLen = (size_t)exp10 + 1;
+            for (size_t i = 0; i < intLen; i++) out.push_back(i < digits.size() ? digits[i] : '0');
+            out.push_back('.');
+            if (digits.size() > intLen) out.append(digits, intLen, std::string::npos); else out.push_back('0');
+        } else {
+            out += "0.";
+            out.append((size_t)(-exp10 - 1), '0');
+            out += digits;
+        }
+    } else {
+        out.push_back(digits[0]);
+        out.push_back('.');
+        if (digits.size() > 1) out.append(digits, 1, std::string::npos); else out.push_back('0');
+        out += "E" + std::to_string(exp10);
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// output sinks
+// ---------------------------------------------------------------------------------------------------------
+static bool endsWith(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+bool OutputSink::open() {
+    if (mem || path.empty()) return true;
+    if (endsWith(path, ".gz") || endsWith(path, ".gzip")) { gz = gzopen(path.c_str(), "wb"); return gz != nullptr; }
+    fp = fopen(path.c_str(), "wb");
+    return fp != nullptr;
+}
+void OutputSink::write(const char* p, size_t n) {
+    if (mem) mem->append(p, n);
+    else if (gz) gzwrite((gzFile)gz, p, (unsigned)n);
+    else if (fp) fwrite(p, 1, n, fp);
+}
+void OutputSink::close() {
+    if (gz) { gzclose((gzFile)gz); gz = nullptr; }
+    if (fp) { fclose(fp); fp = nullptr; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BufferedLineReader (B/io/BufferedLineReader.java:114-182): lines end at '\n' only, NUL bytes are dropped.  next()
+// returns the reference's nextLine() count (bytes incl. the '\n', 0 at end of input); callers use count - 1 as the
+// content length exactly like the reference does -- a last line without '\n' therefore loses its final byte.
+// ---------------------------------------------------------------------------------------------------------
+class LineReader {
+   public:
+    explicit LineReader(const Input& in) {
+        if (in.path.empty()) { cur_ = in.data; end_ = in.data + in.len; memory_ = true; }
+        else {
+            gz_ = gzopen(in.path.c_str(), "rb");  // transparently reads plain files too
+            if (!gz_) fail("cannot open " + in.path);
+            gzbuffer(gz_, 1 << 20);
+            buf_.resize(8 << 20);
+            cur_ = end_ = buf_.data();
+        }
+    }
+    ~LineReader() { if (gz_) gzclose(gz_); }
+    // line = content without the '\n'; returns the count as defined above
+    size_t next(const uint8_t*& line, size_t& len) {
+        for (;;) {
+            const uint8_t* nl = (const uint8_t*)memchr(cur_, '\n', (size_t)(end_ - cur_));
+            if (nl) { line = cur_; len = (size_t)(nl - cur_); cur_ = nl + 1; return dropNul(line, len) + 1; }
+            if (memory_ || eof_) {  // last line without '\n'
+                line = cur_; len = (size_t)(end_ - cur_); cur_ = end_;
+                return dropNul(line, len);
+            }
+            refill();
+        }
+    }
+
+   private:
+    size_t dropNul(const uint8_t*& line, size_t& len) {
+        if (len && memchr(line, 0, len)) {
+            scratch_.clear();
+            for (size_t i = 0; i < len; i++) if (line[i]) scratch_.push_back(line[i]);
+            line = scratch_.data(); len = scratch_.size();
+        }
+        return len;
+    }
+    void refill() {
+        const size_t keep = (size_t)(end_ - cur_);
+        if (keep == buf_.size()) buf_.resize(buf_.size() * 2);  // one line longer than the buffer
+        uint8_t* base = buf_.data();
+        if (keep) memmove(base, cur_, keep);
+        const int got = gzread(gz_, base + keep, (unsigned)std::min<size_t>(buf_.size() - keep, 1u << 30));
+        if (got < 0) fail("read error");
+        if (got == 0) eof_ = true;
+        cur_ = base; end_ = base + keep + (size_t)got;
+    }
+    const uint8_t *cur_ = nullptr, *end_ = nullptr;
+    bool memory_ = false, eof_ = false;
+    gzFile gz_ = nullptr;
+    std::vector<uint8_t> buf_, scratch_;
+};
+
+// One parsed read, as AbstractFastqReader hands it to nextEntry.
+struct Record {
+    std::vector<uint8_t> descriptor, read, probs;
+    bool hasProbs = false;   // readProbsSize >= 0 (FASTQ with withProbs)
+    int entry = 0;           // which of the two pooled ReadEntry objects carried it (threads = 0)
+};
+
+// AbstractFastqReader.doReadFastq / doReadFasta (C/fastq/AbstractFastqReader.java:288-438) for threads = 0.
+class FastqReader {
+   public:
+    FastqReader(int k, bool withProbs) : k_(k), withProbs_(withProbs) {}
+    int64_t reads = 0, kMers = 0, readBPs = 0;
+    template <typename F>
+    void readFastq(const Input& in, F&& nextEntry) {
+        reads = kMers = readBPs = 0;
+        LineReader lr(in);
+        if (in.fasta) doReadFasta(lr, nextEntry); else doReadFastq(lr, nextEntry);
+    }
+
+   private:
+    template <typename F>
+    void doReadFastq(LineReader& lr, F&& nextEntry) {
+        Record rec;
+        rec.entry = 0;  // nextFreeReadStruct() always returns pool[0] when threads = 0 (:447-455)
+        const uint8_t* l; size_t n;
+        for (;;) {
+            size_t c = lr.next(l, n);
+            if (c == 0) break;                                   // readDescriptorSize = -1
+            rec.descriptor.assign(l, l + (c - 1));
+            c = lr.next(l, n);
+            if (c == 0) break;                                   // truncated record
+            rec.read.assign(l, l + (c - 1));
+            bool truncated = false;
+            for (;;) {                                           // lines up to the one that starts with '+' (:299-307)
+                c = lr.next(l, n);
+                if (c == 0) { truncated = true; break; }
+                if (n > 0 && l[0] == '+') break;
+                rec.read.insert(rec.read.end(), l, l + (c - 1));
+            }
+            if (truncated) break;
+            const int64_t readSize = (int64_t)rec.read.size();
+            rec.probs.clear();
+            rec.hasProbs = withProbs_;
+            int64_t probsSize;
+            c = lr.next(l, n);                                   // quality: lines until readSize characters (:318-341)
+            probsSize = (int64_t)c - 1;
+            if (withProbs_ && c) rec.probs.assign(l, l + (c - 1));
+            while (probsSize < readSize) {
+                const int64_t old = probsSize;
+                c = lr.next(l, n);
+                probsSize = probsSize + (int64_t)c - 1;
+                if (probsSize == old - 1) break;                 // end of input
+                if (withProbs_) rec.probs.insert(rec.probs.end(), l, l + (c - 1));
+            }
+            if (withProbs_ && probsSize < (int64_t)rec.probs.size()) rec.probs.resize((size_t)std::max<int64_t>(probsSize, 0));
+            emit(rec, nextEntry);
+        }
+    }
+    template <typename F>
+    void doReadFasta(LineReader& lr, F&& nextEntry) {
+        Record rec;
+        int entry = 0;
+        const uint8_t* l; size_t n;
+        size_t c = lr.next(l, n);
+        bool have = c != 0;
+        if (have) rec.descriptor.assign(l, l + (c - 1));
+        while (have) {
+            if (!rec.descriptor.empty()) rec.descriptor[0] = '@';  // :380
+            rec.read.clear();
+            rec.hasProbs = false;
+            rec.entry = entry;
+            have = false;
+            for (;;) {
+                c = lr.next(l, n);
+                if (c == 0) break;                                 // end of input
+                if (n > 0 && l[0] == '>') { have = true; break; }  // next record's descriptor
+                rec.read.insert(rec.read.end(), l, l + (c - 1));
+            }
+            std::vector<uint8_t> nextDesc;
+            if (have) nextDesc.assign(l, l + (c - 1));
+            emit(rec, nextEntry);
+            rec.descriptor.swap(nextDesc);
+            entry ^= 1;                                            // the two pooled entries alternate (:395-437)
+        }
+    }
+    template <typename F>
+    void emit(Record& rec, F&& nextEntry) {
+        const int64_t L = (int64_t)rec.read.size();
+        reads++;
+        if (L >= k_) kMers += L - k_ + 1;                          // :346-349
+        readBPs += L;
+        nextEntry(rec, reads - 1);
+    }
+    int k_;
+    bool withProbs_;
+};
+
+// ReadEntry.write (C/fastq/AbstractFastqReader.java:570-584)
+static void writeRead(OutputSink& out, const uint8_t* desc, size_t descLen, const uint8_t* read, size_t readLen, const uint8_t* probs,
+                      size_t probsLen, bool hasProbs, std::string& scratch) {
+    scratch.clear();
+    scratch.append((const char*)desc, descLen);
+    scratch.push_back('\n');
+    scratch.append((const char*)read, readLen);
+    scratch += "\n+\n";
+    if (hasProbs) scratch.append((const char*)probs, probsLen); else scratch.append(readLen, '~');
+    scratch.push_back('\n');
+    out.write(scratch.data(), scratch.size());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pinned, double-buffered batches
+// ---------------------------------------------------------------------------------------------------------
+struct HostBatch {
+    uint8_t* bases = nullptr; size_t basesCap = 0;       // pinned
+    uint64_t* offsets = nullptr; size_t offsetsCap = 0;  // pinned, [n+1]
+    uint32_t n = 0;
+    uint64_t firstOrdinal = 0, totalKmers = 0;
+    std::string meta;                                    // descriptors (and qualities) back to back
+    std::vector<uint64_t> descOff, probsOff;             // [n+1] / [n+1] offsets into meta
+    std::vector<uint8_t> hasProbs, entry;
+    gs_ticket ticket = 0;
+    ~HostBatch() { gs_free_pinned(bases); gs_free_pinned(offsets); }
+    void ensure(size_t bytes, size_t reads) {
+        if (bytes + 64 > basesCap) {
+            const size_t ncap = std::max(bytes + 64, basesCap * 2);
+            uint8_t* nb = (uint8_t*)gs_alloc_pinned(ncap);
+            if (!nb) fail(std::string("pinned allocation failed: ") + gs_last_error());
+            if (bases) { memcpy(nb, bases, used()); gs_free_pinned(bases); }
+            bases = nb; basesCap = ncap;
+        }
+        if (reads + 1 > offsetsCap) {
+            const size_t ncap = std::max(reads + 1, offsetsCap * 2);
+            uint64_t* no = (uint64_t*)gs_alloc_pinned(ncap * sizeof(uint64_t));
+            if (!no) fail(std::string("pinned allocation failed: ") + gs_last_error());
+            if (offsets) { memcpy(no, offsets, ((size_t)n + 1) * sizeof(uint64_t)); gs_free_pinned(offsets); }
+            else no[0] = 0;
+            offsets = no; offsetsCap = ncap;
+        }
+    }
+    size_t used() const { return offsets ? (size_t)offsets[n] : 0; }
+    void reset(uint64_t ordinal) {
+        n = 0; firstOrdinal = ordinal; totalKmers = 0; meta.clear(); descOff.assign(1, 0); probsOff.assign(1, 0); hasProbs.clear(); entry.clear();
+        if (offsets) offsets[0] = 0;
+    }
+    void add(const Record& r, int k, bool keepProbs) {
+        ensure(used() + r.read.size(), (size_t)n + 1);
+        if (!r.read.empty()) memcpy(bases + offsets[n], r.read.data(), r.read.size());
+        offsets[n + 1] = offsets[n] + r.read.size();
+        meta.append((const char*)r.descriptor.data(), r.descriptor.size());
+        descOff.push_back(meta.size());
+        const bool hp = keepProbs && r.hasProbs;
+        if (hp) meta.append((const char*)r.probs.data(), r.probs.size());
+        probsOff.push_back(meta.size());
+        hasProbs.push_back(hp ? 1 : 0);
+        entry.push_back((uint8_t)r.entry);
+        if ((int64_t)r.read.size() >= k) totalKmers += r.read.size() - k + 1;
+        n++;
+    }
+    const uint8_t* desc(uint32_t i, size_t& len) const {
+        const uint64_t a = i == 0 ? 0 : probsOff[i];
+        len = (size_t)(descOff[i + 1] - a);
+        return (const uint8_t*)meta.data() + a;
+    }
+    const uint8_t* probs(uint32_t i, size_t& len) const {
+        len = (size_t)(probsOff[i + 1] - descOff[i + 1]);
+        return (const uint8_t*)meta.data() + descOff[i + 1];
+    }
+};
+
+int64_t CountsPerTaxid::valueFor(int type) const {
+    switch (type) { case 0: return reads; case 1: return kmers; case 2: return readsBPs; case 3: return reads1KMer; default: return readsKmers; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FastqKMerMatcher
+// ---------------------------------------------------------------------------------------------------------
+struct FastqKMerMatcher::Batch : HostBatch {};
+
+FastqKMerMatcher::FastqKMerMatcher(gs_db* db, const DbMeta& meta, const MatchConfig& cfg) : db_(db), meta_(meta), cfg_(cfg) {}
+FastqKMerMatcher::~FastqKMerMatcher() {}
+
+static void appendInt(std::string& s, long long v) { s += std::to_string(v); }
+
+void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
+                                    std::vector<uint64_t>& bestKey) {
+    const int V = meta_.nValues;
+    std::vector<gs_read_result> res(b.n);
+    std::vector<gs_maxcontig_event> ev((size_t)std::max(V, 1));
+    std::vector<uint64_t> runOff;
+    std::vector<gs_run> runs;
+    uint32_t nEv = 0;
+    if (krakenOut) { runOff.assign((size_t)b.n + 1, 0); runs.resize((size_t)std::max<uint64_t>(b.totalKmers, 1)); }
+    check(gs_match_collect(s, b.ticket, res.data(), ev.data(), (uint32_t)ev.size(), &nEv, krakenOut ? runOff.data() : nullptr,
+                           krakenOut ? runs.data() : nullptr, b.totalKmers), "gs_match_collect");
+    // maxContigDescriptor (FastqKMerMatcher.java:402-409): header[1 .. first ' '), at most initialReadSize-1 bytes, of the
+    // first read (lowest ordinal) that reached the maximum contig length of its taxon
+    for (uint32_t e = 0; e < nEv; e++) {
+        const gs_maxcontig_event& x = ev[e];
+        const uint64_t key = ((uint64_t)x.contig_len << 40) | ((((uint64_t)1 << 40) - 1) - x.read_no);
+        if (key <= bestKey[x.vidx]) continue;
+        bestKey[x.vidx] = key;
+        size_t dl;
+        const uint8_t* d = b.desc((uint32_t)(x.read_no - b.firstOrdinal), dl);
+        std::string& dst = stats[x.vidx].maxContigDescriptor;
+        dst.clear();
+        for (size_t j = 1; j < dl && j < (size_t)cfg_.initialReadSizeBytes && d[j] != ' '; j++) dst.push_back((char)d[j]);
+    }
+    std::string scratch, line;
+    const int k = meta_.k;
+    for (uint32_t i = 0; i < b.n; i++) {
+        const gs_read_result& r = res[i];
+        const uint64_t a = b.offsets[i], e = b.offsets[i + 1];
+        const int64_t L = (int64_t)(e - a);
+        const int64_t max = L - k + 1;
+        size_t dl, pl;
+        const uint8_t* d = b.desc(i, dl);
+        // afterMatch (:304-315)
+        if ((r.flags & GS_READ_FOUND) && filtered) {
+            const uint8_t* p = b.probs(i, pl);
+            writeRead(*filtered, d, dl, b.bases + a, (size_t)L, p, pl, b.hasProbs[i] != 0, scratch);
+        }
+        if (krakenOut) {
+            if (runOff[i + 1] > runOff[i]) entryBufferUsed_[b.entry[i]] = true;  // printKrakenStyleOut allocated the buffer
+            if ((cfg_.writeAll || r.class_vidx >= 0) && entryBufferUsed_[b.entry[i]]) {  // writeMatchDetails (:723-756)
+                line.clear();
+                line += r.class_vidx >= 0 ? "C\t" : "U\t";
+                size_t sp = dl;
+                for (size_t j = 1; j < dl; j++) if (d[j] == ' ') { sp = j; break; }
+                if (sp > 1) line.append((const char*)d + 1, sp - 1);
+                line.push_back('\t');
+                if (r.class_vidx >= 0) line += meta_.taxid[(size_t)r.class_vidx]; else line.push_back('0');
+                line.push_back('\t');
+                appendInt(line, L);
+                line.push_back('\t');
+                for (uint64_t j = runOff[i]; j < runOff[i + 1]; j++) {  // printKrakenStyleOut (:597-611)
+                    if (j > runOff[i]) line.push_back(' ');
+                    if (runs[j].label == GS_RUN_INVALID) line.push_back('A');
+                    else if (runs[j].label == GS_RUN_MISS) line.push_back('0');
+                    else line += meta_.taxid[runs[j].label];
+                    line.push_back(':');
+                    appendInt(line, runs[j].len);
+                }
+                line.push_back('\n');
+                krakenOut->write(line.data(), line.size());
+            }
+        }
+        // classified-read statistics: the four double sums in read order (:511-526)
+        if (r.flags & GS_READ_ACCEPTED) {
+            CountsPerTaxid& st = stats[(size_t)r.class_vidx];
+            const double err = ((double)(int32_t)r.tax_err) / (double)max;
+            const double classErr = ((double)(int32_t)(max - (int64_t)r.read_kmers)) / (double)max;
+            st.errorSum += err;
+            st.errorSquaredSum += err * err;
+            st.classErrorSum += classErr;
+            st.classErrorSquaredSum += classErr * classErr;
+        }
+    }
+}
+
+MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* krakenOut) {
+    const int V = meta_.nValues;
+    gs_match_cfg c;
+    gs_match_cfg_default(&c);
+    c.classify_reads = cfg_.classifyReads; c.count_unique_kmers = cfg_.countUniqueKMers; c.max_kmer_res_counts = cfg_.maxKMerResCounts;
+    c.use_bloom_filter = cfg_.useBloomFilterForMatch; c.max_classification_paths = cfg_.maxClassificationPaths;
+    c.min_kmers_for_class = cfg_.minKMersForClass; c.max_read_tax_error_count = cfg_.maxReadTaxErrorCount;
+    c.max_read_class_error_count = cfg_.maxReadClassErrorCount; c.want_runs = krakenOut ? 1 : 0; c.layout = cfg_.layout;
+    gs_sess* s = gs_match_open(db_, &c);
+    if (!s) fail(std::string("gs_match_open: ") + gs_last_error());
+    struct Closer { gs_sess* s; ~Closer() { gs_match_close(s); } } closer{s};
+    if (filtered && !filtered->open()) fail("cannot open filtered output");
+    if (krakenOut && !krakenOut->open()) fail("cannot open kraken output");
+
+    std::vector<CountsPerTaxid> stats((size_t)V);           // statsIndex (initStats)
+    std::vector<uint64_t> bestKey((size_t)V, 0);
+    const size_t nSlots = (size_t)GS_MAX_INFLIGHT * 8 + 1;  // enough host batches for every device's in-flight slots
+    std::vector<std::unique_ptr<Batch>> pool;
+    std::deque<Batch*> inflight, freeList;
+    size_t maxInflight = 0;
+    {   // in-flight limit = GS_MAX_INFLIGHT per device
+        maxInflight = (size_t)GS_MAX_INFLIGHT * (size_t)std::max(1, gs_db_n_devices(db_));
+        for (size_t i = 0; i < std::min(nSlots, maxInflight + 1); i++) { pool.emplace_back(new Batch()); freeList.push_back(pool.back().get()); }
+    }
+    uint64_t ordinal = 0;
+    int64_t totalReads = 0, totalKMers = 0, totalBPs = 0;
+    Batch* cur = freeList.front(); freeList.pop_front();
+    cur->reset(ordinal);
+    auto collectOldest = [&]() {
+        Batch* b = inflight.front(); inflight.pop_front();
+        processBatch(s, *b, filtered, krakenOut, stats, bestKey);
+        freeList.push_back(b);
+    };
+    auto flush = [&]() {
+        if (cur->n == 0) return;
+        cur->ensure(cur->used(), cur->n);
+        check(gs_match_submit(s, cur->bases, cur->offsets, cur->n, cur->firstOrdinal, &cur->ticket), "gs_match_submit");
+        inflight.push_back(cur);
+        if (inflight.size() >= maxInflight) collectOldest();
+        cur = freeList.front(); freeList.pop_front();
+        cur->reset(ordinal);
+    };
+    const bool keepProbs = filtered != nullptr && cfg_.withProbs;
+    FastqReader reader(meta_.k, cfg_.withProbs);
+    for (const Input& in : fastqs) {   // processFastqStreams (C/fastq/AbstractLoggingFastqStreamer.java:95-131)
+        reader.readFastq(in, [&](const Record& r, int64_t) {
+            if (cur->n >= cfg_.batchReads || (cur->n > 0 && cur->used() + r.read.size() > cfg_.batchBytes)) flush();
+            cur->add(r, meta_.k, keepProbs);
+            ordinal++;
+        });
+        totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+    }
+    flush();
+    while (!inflight.empty()) collectOldest();
+    if (filtered) filtered->close();
+    if (krakenOut) krakenOut->close();
+
+    std::vector<gs_taxon_counts> counts((size_t)std::max(V, 1));
+    std::vector<int16_t> top;
+    const bool withCounts = cfg_.countUniqueKMers && cfg_.maxKMerResCounts > 0;
+    if (withCounts) top.assign((size_t)(V + 1) * (size_t)cfg_.maxKMerResCounts, 0);
+    check(gs_match_finish(s, counts.data(), withCounts ? top.data() : nullptr), "gs_match_finish");
+    launches_ += gs_match_kernel_launches(s);
+
+    // runMatcher tail (:199-234)
+    MatchingResult res;
+    res.k = meta_.k;
+    res.totalReads = totalReads; res.totalKMers = totalKMers; res.totalBPs = totalBPs;
+    for (int v = 0; v < V; v++) {
+        const gs_taxon_counts& g = counts[(size_t)v];
+        if (!g.touched) continue;
+        CountsPerTaxid st = stats[(size_t)v];
+        st.vidx = v; st.level = meta_.level[(size_t)v];
+        st.kmers = g.kmers; st.contigs = (int32_t)g.contigs; st.contigLenSquaredSum = g.contig_len_squared_sum;
+        st.maxContigLen = g.max_contig_len; st.reads1KMer = g.reads_1kmer; st.reads = g.reads; st.readsKmers = g.reads_kmers;
+        st.readsBPs = g.reads_bps;
+        st.uniqueKmers = cfg_.countUniqueKMers ? g.unique_kmers : -1;
+        if (withCounts) {  // countMap.get(taxid): only taxa with at least one hit position have a row
+            if (g.unique_kmers > 0) {
+                st.hasMaxKMerCounts = true;
+                st.maxKMerCounts.assign(top.begin() + (size_t)v * cfg_.maxKMerResCounts, top.begin() + (size_t)(v + 1) * cfg_.maxKMerResCounts);
+            }
+        }
+        res.taxid2Stats[v] = st;
+    }
+    CountsPerTaxid& g = res.globalStats;  // new CountsPerTaxid(0, null, totalReads, totalKMers, totalBPs, totalMaxCounts)
+    g.level = 0; g.vidx = -1; g.reads = totalReads; g.kmers = totalKMers; g.readsBPs = totalBPs;
+    if (withCounts) {
+        res.withMaxKMerCounts = true;
+        g.hasMaxKMerCounts = true;
+        g.maxKMerCounts.assign(top.begin() + (size_t)V * cfg_.maxKMerResCounts, top.end());
+    }
+    return res;
+}
+
+// MatchingResult.completeResults (C/match/MatchingResult.java:84-118)
+void MatchingResult::completeResults(const DbMeta& meta) {
+    std::vector<int> keys;
+    for (auto& kv : taxid2Stats) keys.push_back(kv.first);
+    for (int v : keys) {  // add missing ancestors
+        if (!meta.hasNode[(size_t)v]) continue;
+        for (int p = meta.parent[(size_t)v]; p >= 0; p = meta.parent[(size_t)p]) {
+            if (!taxid2Stats.count(p)) { CountsPerTaxid c; c.vidx = p; c.level = meta.level[(size_t)p]; taxid2Stats[p] = c; }
+        }
+    }
+    // sortTaxidsViaTree: the null key (TOTAL) first, then by tree position; tax ids without node lexicographically before nodes
+    std::vector<CountsPerTaxid*> order;
+    order.push_back(&globalStats);
+    std::vector<CountsPerTaxid*> withNode, withoutNode;
+    for (auto& kv : taxid2Stats) (meta.hasNode[(size_t)kv.first] ? withNode : withoutNode).push_back(&kv.second);
+    std::sort(withoutNode.begin(), withoutNode.end(), [&](CountsPerTaxid* a, CountsPerTaxid* b) { return meta.taxid[(size_t)a->vidx] < meta.taxid[(size_t)b->vidx]; });
+    std::sort(withNode.begin(), withNode.end(), [&](CountsPerTaxid* a, CountsPerTaxid* b) { return meta.position[(size_t)a->vidx] < meta.position[(size_t)b->vidx]; });
+    order.insert(order.end(), withoutNode.begin(), withoutNode.end());
+    order.insert(order.end(), withNode.begin(), withNode.end());
+    int pos = 0;
+    for (CountsPerTaxid* st : order) {
+        st->pos = pos++;
+        st->dbKMers = st->vidx < 0 ? meta.totalKmers : meta.dbKmers[(size_t)st->vidx];
+        st->hasNode = st->vidx >= 0 && meta.hasNode[(size_t)st->vidx];
+        if (!st->hasNode) continue;
+        for (int t = 0; t < 5; t++) {  // new AccValues(value, dbKMers)
+            const int64_t v = st->valueFor(t);
+            st->acc[t] = v;
+            st->accNorm[t] = st->dbKMers > 0 ? ((double)v) / (double)st->dbKMers : 0;
+        }
+        st->accErrorSum = st->errorSum; st->accErrorSquaredSum = st->errorSquaredSum;
+        st->accClassErrorSum = st->classErrorSum; st->accClassErrorSquaredSum = st->classErrorSquaredSum;
+        for (int p = meta.parent[(size_t)st->vidx]; p >= 0; p = meta.parent[(size_t)p]) {  // accumulateFrom
+            auto it = taxid2Stats.find(p);
+            if (it == taxid2Stats.end()) continue;
+            CountsPerTaxid& up = it->second;
+            for (int t = 0; t < 5; t++) { up.acc[t] += st->acc[t]; up.accNorm[t] += st->accNorm[t]; }
+            up.accErrorSum += st->accErrorSum; up.accErrorSquaredSum += st->accErrorSquaredSum;
+            up.accClassErrorSum += st->accClassErrorSum; up.accClassErrorSquaredSum += st->accClassErrorSquaredSum;
+        }
+    }
+    rows.assign(order.begin(), order.end());
+}
+
+// ResultReporter.printMatchResult (C/match/ResultReporter.java:190-279); columns in @MDCDescription.pos order
+std::string MatchingResult::printMatchResult(const DbMeta& meta) const {
+    static const char* const valueTypes[5] = {"reads", "kmers", "reads bps", "read >=1 kmer", "reads kmers"};
+    std::string o;
+    auto col = [&](const std::string& s) { o += s; o.push_back(';'); };
+    for (const char* h : {"pos", "level", "name", "rank", "taxid", "reads", "kmers from reads", "kmers", "unique kmers", "contigs",
+                          "average contig length", "max contig length", "reads >=1 kmer", "reads bps", "avg. read length", "db coverage",
+                          "exp. unique kmers", "unique kmers / exp.", "db kmers", "parent taxid", "mean error", "kmer error std. dev.",
+                          "mean class error", "class error std. dev.", "contig len std. dev."}) col(h);
+    for (const char* t : valueTypes) col(std::string("norm. ") + t);
+    for (const char* t : valueTypes) { col(std::string("acc. ") + t); col(std::string("acc. norm. ") + t); }
+    for (const char* h : {"max contig desc.", "acc. mean error", "acc. error std. dev.", "acc. mean class error", "acc. class error std. dev."}) col(h);
+    if (withMaxKMerCounts) col("max kmer counts");
+    o.push_back('\n');
+    for (const CountsPerTaxid* cp : rows) {
+        const CountsPerTaxid& c = *cp;
+        const bool notTotal = c.pos != 0;
+        auto num = [&](double v, bool allowed) { if (!std::isnan(v) && !std::isinf(v) && allowed) o += javaDoubleToString(v); o.push_back(';'); };
+        const double kmers = (double)c.kmers, reads = (double)c.reads, dbk = (double)c.dbKMers;
+        col(std::to_string(c.pos));
+        col(std::to_string(c.level));
+        col(c.hasNode ? meta.name[(size_t)c.vidx] : std::string("TOTAL"));  // completeValues: no node -> "TOTAL"
+        col(c.hasNode ? std::string(rankName(meta.rank[(size_t)c.vidx])) : std::string());
+        col(c.vidx < 0 ? std::string() : meta.taxid[(size_t)c.vidx]);
+        col(std::to_string(c.reads));
+        col(std::to_string(c.readsKmers));
+        col(std::to_string(c.kmers));
+        col(std::to_string(c.uniqueKmers));
+        col(std::to_string(c.contigs));
+        num(kmers / c.contigs, notTotal);
+        col(std::to_string(c.maxContigLen));
+        col(std::to_string(c.reads1KMer));
+        col(std::to_string(c.readsBPs));
+        num(((double)c.readsBPs) / reads, true);                                      // pos 13: printed on the TOTAL row too
+        num(((double)c.uniqueKmers) / dbk, notTotal);
+        const double expected = (1 - std::pow(1 - 1.0 / dbk, (double)c.kmers)) * dbk;
+        num(expected, notTotal);
+        num((double)c.uniqueKmers / expected, notTotal);
+        col(std::to_string(c.dbKMers));
+        col(c.hasNode ? (meta.parent[(size_t)c.vidx] >= 0 ? meta.taxid[(size_t)meta.parent[(size_t)c.vidx]] : std::string()) : std::string());
+        num(c.errorSum / reads, notTotal);
+        num(std::sqrt((c.errorSquaredSum - c.errorSum * c.errorSum / reads) / (double)(c.reads - 1)), notTotal);
+        num(c.classErrorSum / reads, notTotal);
+        num(std::sqrt((c.classErrorSquaredSum - c.classErrorSum * c.classErrorSum / reads) / (double)(c.reads - 1)), notTotal);
+        num(std::sqrt(((double)c.contigLenSquaredSum - (kmers * kmers) / c.contigs) / (c.contigs - 1)), notTotal);
+        for (int t = 0; t < 5; t++) num(((double)c.valueFor(t)) / dbk, notTotal);
+        for (int t = 0; t < 5; t++) {
+            if (c.hasNode) o += std::to_string(c.acc[t]);
+            o.push_back(';');
+            if (c.hasNode) o += javaDoubleToString(c.accNorm[t]);
+            o.push_back(';');
+        }
+        col(c.maxContigDescriptor);
+        const double accReads = c.hasNode ? (double)c.acc[0] : 0.0;
+        const int64_t accReadsL = c.hasNode ? c.acc[0] : 0;
+        num(c.accErrorSum / accReads, notTotal);
+        num(std::sqrt((c.accErrorSquaredSum - (c.accErrorSum * c.accErrorSum) / accReads) / (double)(accReadsL - 1)), notTotal);
+        num(c.accClassErrorSum / accReads, notTotal);
+        num(std::sqrt((c.accClassErrorSquaredSum - (c.accClassErrorSum * c.accClassErrorSum) / accReads) / (double)(accReadsL - 1)), notTotal);
+        if (withMaxKMerCounts) {
+            if (c.hasMaxKMerCounts)
+                for (size_t i = 0; i < c.maxKMerCounts.size(); i++) { if (i) o.push_back(';'); o += std::to_string(c.maxKMerCounts[i]); }
+            o.push_back(';');
+        }
+        o.push_back('\n');
+    }
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FastqBloomFilter
+// ---------------------------------------------------------------------------------------------------------
+FastqBloomFilter::FastqBloomFilter(gs_filter* f, int k, int minPosCount, double positiveRatio, bool withProbs, uint32_t batchReads)
+    : f_(f), k_(k), minPosCount_(minPosCount), positiveRatio_(positiveRatio), withProbs_(withProbs), batchReads_(batchReads) {}
+
+void FastqBloomFilter::runFilter(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* rest) {
+    gs_fsess* s = gs_filter_open(f_, k_, minPosCount_, positiveRatio_);
+    if (!s) fail(std::string("gs_filter_open: ") + gs_last_error());
+    struct Closer { gs_fsess* s; ~Closer() { gs_filter_close(s); } } closer{s};
+    if (filtered && !filtered->open()) fail("cannot open filtered output");
+    if (rest && !rest->open()) fail("cannot open rest output");
+    const size_t maxInflight = (size_t)GS_MAX_INFLIGHT * (size_t)std::max(1, gs_filter_n_devices(f_));
+    std::vector<std::unique_ptr<HostBatch>> pool;
+    std::deque<HostBatch*> inflight, freeList;
+    for (size_t i = 0; i < maxInflight + 1; i++) { pool.emplace_back(new HostBatch()); freeList.push_back(pool.back().get()); }
+    HostBatch* cur = freeList.front(); freeList.pop_front();
+    cur->reset(0);
+    std::string scratch;
+    std::vector<uint8_t> acc;
+    auto collectOldest = [&]() {
+        HostBatch* b = inflight.front(); inflight.pop_front();
+        acc.resize(b->n);
+        check(gs_filter_collect(s, b->ticket, acc.data()), "gs_filter_collect");
+        for (uint32_t i = 0; i < b->n; i++) {   // nextEntry (:92-105): rewriteInput to `indexed` or `notIndexed`
+            accept.push_back(acc[i]);
+            acceptedReads += acc[i];
+            OutputSink* out = acc[i] ? filtered : rest;
+            if (!out) continue;
+            size_t dl, pl;
+            const uint8_t* d = b->desc(i, dl);
+            const uint8_t* p = b->probs(i, pl);
+            writeRead(*out, d, dl, b->bases + b->offsets[i], (size_t)(b->offsets[i + 1] - b->offsets[i]), p, pl, b->hasProbs[i] != 0, scratch);
+        }
+        freeList.push_back(b);
+    };
+    auto flush = [&]() {
+        if (cur->n == 0) return;
+        check(gs_filter_submit(s, cur->bases, cur->offsets, cur->n, &cur->ticket), "gs_filter_submit");
+        inflight.push_back(cur);
+        if (inflight.size() >= maxInflight) collectOldest();
+        cur = freeList.front(); freeList.pop_front();
+        cur->reset(0);
+    };
+    FastqReader reader(k_, withProbs_);
+    for (const Input& in : fastqs) {
+        reader.readFastq(in, [&](const Record& r, int64_t) {
+            if (cur->n >= batchReads_) flush();
+            cur->add(r, k_, withProbs_);
+        });
+        totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+    }
+    flush();
+    while (!inflight.empty()) collectOldest();
+    if (filtered) filtered->close();
+    if (rest) rest->close();
+}
+
+}  // namespace gsh
+
+// ---------------------------------------------------------------------------------------------------------
+// C entry points of the host layer (what a JNI shim or a test harness calls when it wants the whole goal, not batches)
+// ---------------------------------------------------------------------------------------------------------
+using namespace gsh;
+
+struct gsh_result {
+    std::string csv, filtered, kraken, rest, error;
+    int64_t totals[3] = {0, 0, 0};
+    std::vector<uint8_t> accept;
+    std::vector<double> dsums;  // [4][V]: errorSum, errorSquaredSum, classErrorSum, classErrorSquaredSum
+    uint64_t launches = 0;
+};
+
+extern "C" {
+
+DbMeta* gsh_meta_new(int k, int n_values, int64_t total_kmers) {
+    DbMeta* m = new DbMeta();
+    m->k = k; m->totalKmers = total_kmers; m->resize(n_values);
+    return m;
+}
+void gsh_meta_free(DbMeta* m) { delete m; }
+void gsh_meta_set_node(DbMeta* m, int vidx, const char* taxid, const char* name, int rank, int parent, int position, int level, int has_node,
+                       int64_t db_kmers) {
+    m->taxid[(size_t)vidx] = taxid ? taxid : ""; m->name[(size_t)vidx] = name ? name : ""; m->rank[(size_t)vidx] = rank;
+    m->parent[(size_t)vidx] = parent; m->position[(size_t)vidx] = position; m->level[(size_t)vidx] = level; m->hasNode[(size_t)vidx] = has_node;
+    m->dbKmers[(size_t)vidx] = db_kmers;
+}
+
+typedef struct gsh_match_cfg {
+    int classify_reads, count_unique_kmers, use_bloom_filter, max_kmer_res_counts, max_classification_paths, min_kmers_for_class;
+    double max_read_tax_error_count, max_read_class_error_count;
+    int write_all, with_probs, initial_read_size_bytes, layout, write_filtered, write_kraken;
+    uint32_t batch_reads;
+    uint32_t reserved;
+} gsh_match_cfg;
+
+static std::vector<Input> toInputs(const uint8_t* const* data, const size_t* lens, const char* const* paths, const int* is_fasta, int n) {
+    std::vector<Input> in((size_t)n);
+    for (int i = 0; i < n; i++) {
+        if (paths && paths[i] && paths[i][0]) in[(size_t)i].path = paths[i];
+        else { in[(size_t)i].data = data[i]; in[(size_t)i].len = lens[i]; }
+        in[(size_t)i].fasta = is_fasta && is_fasta[i];
+    }
+    return in;
+}
+
+// The `match` goal for one key: MatchResultGoal.doMakeThis + MatchGoal.makeFile (C/goals/MatchResultGoal.java:91-164,
+// C/goals/MatchGoal.java:84-92).  Inputs are in-memory buffers or file paths; outputs are returned as strings (or written
+// to filtered_path / kraken_path when given).
+gsh_result* gsh_match_goal(gs_db* db, const DbMeta* meta, const gsh_match_cfg* c, const uint8_t* const* data, const size_t* lens,
+                           const char* const* paths, const int* is_fasta, int n_inputs, const char* filtered_path, const char* kraken_path) {
+    gsh_result* r = new gsh_result();
+    try {
+        MatchConfig cfg;
+        cfg.classifyReads = c->classify_reads; cfg.countUniqueKMers = c->count_unique_kmers; cfg.useBloomFilterForMatch = c->use_bloom_filter;
+        cfg.maxKMerResCounts = c->max_kmer_res_counts; cfg.maxClassificationPaths = c->max_classification_paths;
+        cfg.minKMersForClass = c->min_kmers_for_class; cfg.maxReadTaxErrorCount = c->max_read_tax_error_count;
+        cfg.maxReadClassErrorCount = c->max_read_class_error_count; cfg.writeAll = c->write_all; cfg.withProbs = c->with_probs;
+        cfg.initialReadSizeBytes = c->initial_read_size_bytes; cfg.layout = c->layout;
+        if (c->batch_reads) cfg.batchReads = c->batch_reads;
+        FastqKMerMatcher matcher(db, *meta, cfg);
+        OutputSink filtered, kraken;
+        if (filtered_path && filtered_path[0]) filtered.path = filtered_path; else filtered.mem = &r->filtered;
+        if (kraken_path && kraken_path[0]) kraken.path = kraken_path; else kraken.mem = &r->kraken;
+        MatchingResult res = matcher.runMatcher(toInputs(data, lens, paths, is_fasta, n_inputs), c->write_filtered ? &filtered : nullptr,
+                                                c->write_kraken ? &kraken : nullptr);
+        res.completeResults(*meta);
+        r->csv = res.printMatchResult(*meta);
+        r->totals[0] = res.totalReads; r->totals[1] = res.totalKMers; r->totals[2] = res.totalBPs;
+        r->launches = matcher.kernelLaunches();
+        const int V = meta->nValues;
+        r->dsums.assign((size_t)4 * V, 0.0);
+        for (auto& kv : res.taxid2Stats) {
+            r->dsums[(size_t)0 * V + kv.first] = kv.second.errorSum; r->dsums[(size_t)1 * V + kv.first] = kv.second.errorSquaredSum;
+            r->dsums[(size_t)2 * V + kv.first] = kv.second.classErrorSum; r->dsums[(size_t)3 * V + kv.first] = kv.second.classErrorSquaredSum;
+        }
+    } catch (const std::exception& e) { r->error = e.what(); }
+    return r;
+}
+
+// The `filter` goal: FilterGoal.makeFile (C/goals/FilterGoal.java:80-108)
+gsh_result* gsh_filter_goal(gs_filter* f, int k, int min_pos_count, double pos_ratio, int with_probs, uint32_t batch_reads,
+                            const uint8_t* const* data, const size_t* lens, const char* const* paths, const int* is_fasta, int n_inputs,
+                            const char* filtered_path, const char* rest_path, int want_rest) {
+    gsh_result* r = new gsh_result();
+    try {
+        FastqBloomFilter flt(f, k, min_pos_count, pos_ratio, with_probs != 0, batch_reads ? batch_reads : (1u << 20));
+        OutputSink filtered, rest;
+        if (filtered_path && filtered_path[0]) filtered.path = filtered_path; else filtered.mem = &r->filtered;
+        if (rest_path && rest_path[0]) rest.path = rest_path; else rest.mem = &r->rest;
+        flt.runFilter(toInputs(data, lens, paths, is_fasta, n_inputs), &filtered, want_rest ? &rest : nullptr);
+        r->totals[0] = flt.totalReads; r->totals[1] = flt.totalKMers; r->totals[2] = flt.totalBPs;
+        r->accept.swap(flt.accept);
+    } catch (const std::exception& e) { r->error = e.what(); }
+    return r;
+}
+
+void gsh_result_free(gsh_result* r) { delete r; }
+const char* gsh_result_error(const gsh_result* r) { return r->error.c_str(); }
+const char* gsh_result_text(const gsh_result* r, int which, size_t* len) {
+    const std::string& s = which == 0 ? r->csv : which == 1 ? r->filtered : which == 2 ? r->kraken : r->rest;
+    *len = s.size();
+    return s.data();
+}
+void gsh_result_totals(const gsh_result* r, int64_t* out) { out[0] = r->totals[0]; out[1] = r->totals[1]; out[2] = r->totals[2]; }
+const uint8_t* gsh_result_accept(const gsh_result* r, size_t* n) { *n = r->accept.size(); return r->accept.data(); }
+const double* gsh_result_dsums(const gsh_result* r, size_t* n) { *n = r->dsums.size(); return r->dsums.data(); }
+uint64_t gsh_result_launches(const gsh_result* r) { return r->launches; }
+int gsh_java_double_to_string(double v, char* buf, int cap) {
+    const std::string s = javaDoubleToString(v);
+    if ((int)s.size() + 1 > cap) return -1;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+}  // extern "C"

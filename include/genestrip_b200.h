@@ -81,6 +81,7 @@ int gs_db_build_bloom_blocked(gs_db*, int64_t* words_out, uint64_t n_words_out);
 int gs_db_finalize(gs_db*); /* builds the bucket index, replicates to every device of the context */
 void gs_db_destroy(gs_db*);
 uint64_t gs_db_device_bytes(const gs_db*);
+int gs_db_n_devices(const gs_db*);
 /* Lookup probe for tests (KMerStore.getLong, C/store/KMerStore.java:157): vidx_out[i] = value index or -1
  * (miss / value without node), pos_out[i] = storage position or -1.  use_bloom follows useBloomFilterForMatch. */
 int gs_db_lookup(gs_db*, const int64_t* kmers, uint64_t n, int use_bloom, int32_t* vidx_out, int64_t* pos_out);
@@ -197,6 +198,7 @@ int gs_match_dump_labels(gs_sess*, const uint8_t* d_bases, const uint64_t* d_off
 gs_filter* gs_filter_create(gs_ctx*, int kind, int64_t p0, int64_t p1, const int64_t* factors,
                             const int64_t* words, uint64_t n_words);
 void gs_filter_destroy(gs_filter*);
+int gs_filter_n_devices(const gs_filter*);
 /* KMerProbFilter.containsLong (C/bloom/KMerProbFilter.java:66) for tests. */
 int gs_filter_contains(gs_filter*, const int64_t* kmers, uint64_t n, uint8_t* out);
 gs_fsess* gs_filter_open(gs_filter*, int k, int min_pos_count, double pos_ratio);

@@ -1,0 +1,177 @@
+"""GPU parity of the whole goals through the C++ host layer: `match` CSV / filtered FASTQ / kraken-style output and the
+`filter` goal's FASTQ outputs must equal the oracle's (reference at threads=0) byte for byte."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from genestrip_b200 import synth
+
+import util
+from test_oracle_golden import dengue1_project
+
+pytestmark = pytest.mark.gpu
+
+K = 31
+
+
+@pytest.fixture(scope="module")
+def host(native):
+    from genestrip_b200 import host as h
+    return h
+
+
+@pytest.fixture(scope="module")
+def project(oracle, native, gpu_ctx, host):
+    nodes, names, genomes = util.small_project(genome_len=50000, seed=21)
+    leaves = [t for t, _ in genomes]
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, K, nodes, names, genomes, requested=leaves[:3], index_fpp=1e-6)
+    meta = util.host_meta(host, odb)
+    yield odb, gdb, meta, genomes
+    meta.free()
+    gdb.close()
+    odb.free()
+
+
+def _reads(genomes, n, seed, **kw):
+    bases, offsets, src = synth.sample_reads([g for _, g in genomes], n, 150, seed=seed, n_rate=0.002, **kw)
+    return bases, offsets, src
+
+
+def _assert_csv_equal(a, b):
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    assert len(la) == len(lb)
+    for x, y in zip(la, lb):
+        assert x == y
+
+
+CASES = [
+    dict(),
+    dict(count_unique_kmers=0),
+    dict(classify_reads=0),
+    dict(max_read_tax_error_count=0.3, max_read_class_error_count=0.4),
+    dict(min_kmers_for_class=4, max_classification_paths=3),
+    dict(max_kmer_res_counts=5),
+    dict(layout=1),
+]
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=[",".join("%s=%s" % kv for kv in c.items()) or "default" for c in CASES])
+def test_match_goal_csv_filtered_kraken(project, oracle, host, cfg):
+    odb, gdb, meta, genomes = project
+    b1, o1, s1 = _reads(genomes, 3000, 1)
+    b2, o2, s2 = _reads(genomes, 1500, 2, len_jitter=60)
+    files = [synth.fastq_bytes(b1, o1, s1), synth.fastq_bytes(b2, o2, s2, prefix="q")]
+    ocfg = util.oracle_cfg(oracle, K, want_runs=1, **cfg)
+    orun = odb.match_files(ocfg, files)
+    res = host.match_goal(gdb, meta, files, write_filtered=True, write_kraken=True, batch_reads=700, **cfg)
+    assert res.launches > 0
+    assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+    assert res.filtered == orun.filtered
+    assert res.kraken == orun.kraken
+    # the four double sums, accumulated on the host in read order, are bit-identical
+    for i in range(4):
+        np.testing.assert_array_equal(res.dsums[i], orun.dstats[i])
+    _assert_csv_equal(res.csv, orun.csv)
+
+
+def test_match_goal_fasta_gzip_paths_and_probs(project, oracle, host, tmp_path):
+    odb, gdb, meta, genomes = project
+    b, o, s = _reads(genomes, 800, 3)
+    rng = np.random.default_rng(4)
+    qual = bytes(rng.integers(33, 74, size=int(o[-1])).astype(np.uint8))
+    bb = b.tobytes()
+    fq = b"".join(b"@r%d %d\n%s\n+\n%s\n" % (i, s[i], bb[int(o[i]):int(o[i + 1])], qual[int(o[i]):int(o[i + 1])]) for i in range(len(o) - 1))
+    # multi-line FASTA with blank lines, lower-case stretches and no trailing newline (loses its last base, like the reference)
+    fa = b"".join(b">f%d some text\n%s\n\n%s\n" % (i, bb[int(o[i]):int(o[i]) + 70], bb[int(o[i]) + 70:int(o[i + 1])]) for i in range(200)) + b">last\nACGTACGTTTGACA"
+    files = [fq, fa]
+    ocfg = oracle.match_cfg(k=K, write_kraken=True, write_filtered=True, with_probs=True)
+    orun = odb.match_files(ocfg, files, is_fasta=[False, True])
+    res = host.match_goal(gdb, meta, files, is_fasta=[False, True], write_filtered=True, write_kraken=True, with_probs=1, batch_reads=333)
+    assert res.filtered == orun.filtered and res.kraken == orun.kraken
+    _assert_csv_equal(res.csv, orun.csv)
+    # the same through gzip-compressed files and file outputs
+    p1, p2 = str(tmp_path / "a.fastq.gz"), str(tmp_path / "b.fasta")
+    with gzip.open(p1, "wb") as f:
+        f.write(fq)
+    open(p2, "wb").write(fa)
+    fo, ko = str(tmp_path / "filtered.fastq.gz"), str(tmp_path / "kraken.out")
+    res2 = host.match_goal(gdb, meta, [p1, p2], is_fasta=[False, True], write_filtered=True, write_kraken=True, with_probs=1,
+                           filtered_path=fo, kraken_path=ko)
+    assert gzip.open(fo, "rb").read() == orun.filtered
+    assert open(ko, "rb").read() == orun.kraken
+    _assert_csv_equal(res2.csv, orun.csv)
+
+
+def test_match_goal_parser_quirks(project, oracle, host):
+    """CRLF input (the '\\r' stays the last base), multi-line FASTQ, NUL bytes, reads shorter than k, missing final newline."""
+    odb, gdb, meta, genomes = project
+    g = genomes[1][1]
+    recs = [b"@a 1\r\n" + g[100:250] + b"\r\n+\r\n" + b"I" * 150 + b"\r\n",
+            b"@b\n" + g[300:360] + b"\n" + g[360:420] + b"\n" + g[420:470] + b"\n+b\n" + b"J" * 100 + b"\n" + b"J" * 70 + b"\n",
+            b"@c x y\n" + g[500:520] + b"\n+\n" + b"I" * 20 + b"\n",
+            b"@d\0\0 z\n" + g[600:700] + b"\0" + g[700:760] + b"\n+\n" + b"I" * 160 + b"\n",
+            b"@e\n" + g[800:950] + b"\n+\n" + b"I" * 150]
+    fq = b"".join(recs)
+    for with_probs in (False, True):
+        ocfg = oracle.match_cfg(k=K, write_kraken=True, write_filtered=True, with_probs=with_probs)
+        orun = odb.match_files(ocfg, [fq])
+        res = host.match_goal(gdb, meta, [fq], write_filtered=True, write_kraken=True, with_probs=int(with_probs), batch_reads=2)
+        assert orun.total_reads == 5
+        assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+        assert res.filtered == orun.filtered
+        assert res.kraken == orun.kraken
+        _assert_csv_equal(res.csv, orun.csv)
+
+
+def test_dengue1_golden_through_cuda(oracle, native, gpu_ctx, host):
+    """The reference's own end-to-end golden vector R/projects/dengue1/test.out (T/goals/refseq/DBGoalTest.java:127-142),
+    reproduced by the CUDA path + C++ host layer byte for byte."""
+    nodes, names, fasta, fastq, golden = dengue1_project()
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, K, nodes, names, [("11053", fasta), ("9606", fasta)], requested=["11053"], fill=[True, False])
+    meta = util.host_meta(host, odb)
+    try:
+        res = host.match_goal(gdb, meta, [fastq], write_kraken=True)
+        assert res.kraken == golden
+    finally:
+        meta.free(); gdb.close(); odb.free()
+
+
+@pytest.mark.parametrize("kind", ["xor", "murmur", "blocked"])
+def test_filter_goal(project, oracle, native, gpu_ctx, host, kind):
+    """`filter`: FastqBloomFilter with the index filter over the k-mers of the requested taxa (C/goals/refseq/BloomIndexGoal.java:66-111)."""
+    odb, gdb, meta, genomes = project
+    if kind == "xor":
+        flt_o = odb.index_filter()
+    else:
+        keys, vals = odb.export()
+        flt_o = oracle.Bloom(kind=2 if kind == "murmur" else 0, fpp=1e-5)
+        sel = keys[::3]
+        flt_o.ensure(len(sel))
+        flt_o.put(sel)
+    okind, p0, p1, factors, words = flt_o.params()
+    assert okind == {"blocked": 0, "xor": 1, "murmur": 2}[kind]
+    gflt = native.Filter(gpu_ctx, okind, p0, p1, factors, words)
+    try:
+        # containsLong parity on stored, random and extreme keys
+        keys, _ = odb.export()
+        rng = np.random.default_rng(8)
+        q = np.concatenate([keys[:4000], rng.integers(0, 1 << 62, size=4000, dtype=np.int64),
+                            np.array([0, (1 << 62) - 1, -1, -(1 << 63)], dtype=np.int64)])
+        if kind == "xor":  # hash == Long.MIN_VALUE (T/bloom/XORKMerBloomFilterTest.java:50-58)
+            q = np.concatenate([q, np.array([int(factors[0]) ^ -(1 << 63)], dtype=np.int64)])
+        np.testing.assert_array_equal(gflt.contains(q), flt_o.contains(q))
+        b, o, s = _reads(genomes, 3000, 5, frac_db=0.3)
+        fq = synth.fastq_bytes(b, o, s)
+        extra = b"@short\nACGT\n+\nIIII\n@n\n" + b"N" * 150 + b"\n+\n" + b"I" * 150 + b"\n"
+        for (mpc, ratio) in ((1, 0.2), (0, 0.2), (0, 0.0), (3, 0.5), (200, 0.1)):
+            orun = oracle.filter_files(flt_o, K, [fq + extra], min_pos_count=mpc, pos_ratio=ratio)
+            res = host.filter_goal(gflt, K, [fq + extra], min_pos_count=mpc, pos_ratio=ratio, batch_reads=900)
+            np.testing.assert_array_equal(res.accept, orun.accept)
+            assert res.filtered == orun.filtered and res.rest == orun.rest
+            assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+    finally:
+        gflt.close()
+        if kind != "xor":
+            flt_o.free()

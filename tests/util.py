@@ -110,3 +110,9 @@ def kraken_from_runs(taxids, run_off, runs, i):
 
 def small_project(genome_len=20000, seed=7):
     return synth.tiny_project(genome_len=genome_len, seed=seed, shared_frac=0.02)
+
+
+def host_meta(host, odb):
+    """DbMeta of the C++ host layer from the oracle database's metadata (names, ranks, tree, db k-mer counts)."""
+    parent, depth, position, has_node = odb.tree()
+    return host.DbMeta(odb.k, odb.n_kmers, odb.taxids(), odb.node_names(), odb.node_ranks(), parent, position, depth, has_node, odb.db_kmers())
