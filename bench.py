@@ -193,7 +193,7 @@ def as_tensor(torch, ptr, nbytes, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GS_BENCH_WORKLOAD", "viral"), choices=sorted(WORKLOADS))
@@ -316,28 +316,20 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        dist.all_reduce(t_c, op=dist.ReduceOp.SUM)
-        dist.all_reduce(t_m, op=dist.ReduceOp.MAX)   # packed (len << 40 | ~ordinal) keys are < 2^63: signed max == unsigned max
-        # unique bitset: all-to-all of 1/world slices, local OR, per-taxon popcount of the own slice, sum of the counts
-        per = (b_words + world - 1) // world
-        padded = torch.zeros(per * world, dtype=torch.int64, device=dev)
-        padded[:b_words] = t_b
-        recv = torch.empty_like(padded)
-        dist.all_to_all_single(recv, padded)
-        mine = recv.view(world, per)[0].clone()
-        for r in range(1, world):
-            mine |= recv.view(world, per)[r]
-        uniq = torch.zeros(V, dtype=torch.int64, device=dev)
-        lo_w = rank * per
-        hi_w = min(b_words, lo_w + per)
-        # popcount kernel indexes words absolutely: place the merged slice at its position of a scratch bitset
-        t_b.zero_()
-        if hi_w > lo_w:
-            t_b[lo_w:hi_w] = mine[: hi_w - lo_w]
-        torch.cuda.synchronize()
-        sess.unique_popcount(b_ptr, lo_w, hi_w, uniq.data_ptr())
-        sess.sync()
-        dist.all_reduce(uniq, op=dist.ReduceOp.SUM)
+        from genestrip_b200.dist import merge_match_state
+
+        def popcount_slice(merged, lo_w, hi_w):
+            # the popcount kernel addresses bitset words absolutely: put the OR-merged slice back at its place
+            uniq = torch.zeros(V, dtype=torch.int64, device=dev)
+            t_b.zero_()
+            if hi_w > lo_w:
+                t_b[lo_w:hi_w] = merged
+            torch.cuda.synchronize()
+            sess.unique_popcount(b_ptr, lo_w, hi_w, uniq.data_ptr())
+            sess.sync()
+            return uniq
+
+        uniq = merge_match_state(dist, t_c, t_m, t_b, V, popcount_slice)
         e1.record()
         torch.cuda.synchronize()
         red_ms = e0.elapsed_time(e1)
