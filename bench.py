@@ -404,6 +404,13 @@ def main():
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bpk = algorithmic_bytes_per_kmer(n_db, h)
+        traffic = None
+        try:  # DRAM bytes of the match kernel from the committed ncu --set full capture, scaled to this launch's k-mers
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "match_kernel_traffic.json")))
+            if args.workload == "viral" and args.layout == "table":
+                traffic = tj["dram_bytes_per_kmer"] * kmers_per_step
+        except Exception:
+            pass
         kernel_ms = float(np.mean(step_ms))
         achieved = bpk * kmers_per_step / (kernel_ms / 1e3) / 1e9
         line = {"metric": "match k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -412,9 +419,13 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R * 16 + 4 + V * 16,
                         "reads_per_s": e2e_value / (READ_LEN - K + 1)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "gs_match_kernel<0,false>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk,
-                             "hit_fraction": h, "peak_source": peak_src},
+                             "hit_fraction": h, "peak_source": peak_src,
+                             "traffic_source": "profiles/r01/match_kernel_traffic.json (ncu dram__bytes_read+write per k-mer x k-mers per launch)",
+                             "request_roofline": {"measured_cap_requests_per_s": 39.4e9, "requests_per_kmer": 1.105,
+                                                  "frac": (kmers_per_step / (kernel_ms / 1e3)) * 1.105 / 39.4e9,
+                                                  "source": "profiles/microbench/randwide.txt: fully divergent loads of 8/16/32 B per lane"}},
                 "end_of_job_reduce_ms": red_ms, "hits_total": total_hits, "unique_kmers_total": unique_total}
 
     # ---------------- CPU baseline + bench-scale parity spot check (rank 0, N = 1 only)
