@@ -25,13 +25,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K = 31
-READ_LEN = 150
 WORKLOADS = {
-    # name: (levels, fanout, db k-mers, reads per step, fraction of reads from the DB, substitution rate)
-    "viral": dict(levels=4, fanout=10, n_kmers=100_000_000, reads_per_step=4_000_000, frac_db=0.5, sub_rate=0.01,
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "viral": dict(kind="match", levels=4, fanout=10, n_kmers=100_000_000, read_len=150, reads_per_step=4_000_000, frac_db=0.5, sub_rate=0.01,
                   desc="viral-scale synthetic db (~10k leaf taxa, 1e8 31-mers), match on 150 bp Illumina-like reads (BASELINE.json configs[1])"),
-    "tiny": dict(levels=2, fanout=3, n_kmers=2_000_000, reads_per_step=200_000, frac_db=0.7, sub_rate=0.01,
+    "tiny": dict(kind="match", levels=2, fanout=3, n_kmers=2_000_000, read_len=150, reads_per_step=200_000, frac_db=0.7, sub_rate=0.01,
                  desc="tiny synthetic db (9 leaf taxa, 2e6 31-mers), smoke-size"),
+    # configs[2]: bacterial scale (database replicated per GPU), unique k-mer counting on
+    "bacterial": dict(kind="match", levels=4, fanout=15, n_kmers=2_000_000_000, read_len=150, reads_per_step=4_000_000, frac_db=0.1, sub_rate=0.01,
+                      simple_db=True, desc="bacterial-scale synthetic db (50 625 leaf taxa, 2e9 31-mers), match with unique k-mer counting on 150 bp reads (BASELINE.json configs[2])"),
+    # configs[4]: long reads, high hit rate (substitutions only; indels are not generated)
+    "longread": dict(kind="match", levels=4, fanout=10, n_kmers=100_000_000, read_len=10_000, reads_per_step=60_000, frac_db=0.9, sub_rate=0.01,
+                     desc="long-read workload: 10 kb ONT-like reads, 90 % from the viral-scale db, 1 % substitutions (BASELINE.json configs[4])"),
+    # configs[3]: the filter goal, XOR Bloom index (fpp 1e-8, 27 hashes) over the k-mers of the leaf taxa, ~1 % of the reads hit
+    "filter": dict(kind="filter", levels=4, fanout=10, n_kmers=100_000_000, read_len=150, reads_per_step=4_000_000, frac_db=0.01, sub_rate=0.01,
+                   desc="filter goal: XOR Bloom index (fpp 1e-8) of the viral-scale db, 150 bp reads with ~1 % hit rate (BASELINE.json configs[3])"),
 }
 
 
@@ -54,19 +62,36 @@ def make_database(torch, dev, wl, seed):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     codes = torch.randint(0, 4, (n_leaves, glen), generator=g, device=dev, dtype=torch.int8)  # C0 G1 A2 T3
-    nsh = max(K, glen // 100)
-    sib = (torch.arange(n_leaves, device=dev) + 1) % wl["fanout"] + (torch.arange(n_leaves, device=dev) // wl["fanout"]) * wl["fanout"]
-    codes[:, glen // 2: glen // 2 + nsh] = codes[sib, glen // 3: glen // 3 + nsh]
+    if not wl.get("simple_db"):
+        nsh = max(K, glen // 100)
+        sib = (torch.arange(n_leaves, device=dev) + 1) % wl["fanout"] + (torch.arange(n_leaves, device=dev) // wl["fanout"]) * wl["fanout"]
+        codes[:, glen // 2: glen // 2 + nsh] = codes[sib, glen // 3: glen // 3 + nsh]
     # canonical k-mers of every window (CGAT.java:145-265 semantics: fwd big-endian 2-bit, rc = reversed complement, max)
     nwin = glen - K + 1
-    fwd = torch.zeros((n_leaves, nwin), dtype=torch.int64, device=dev)
-    rc = torch.zeros((n_leaves, nwin), dtype=torch.int64, device=dev)
-    for i in range(K):
-        c = codes[:, i:i + nwin].to(torch.int64)
-        fwd = (fwd << 2) | c
-        rc = rc | ((c ^ 1) << (2 * i))
-    canon = torch.maximum(fwd, rc).reshape(-1)
-    del fwd, rc
+    canon = torch.empty((n_leaves, nwin), dtype=torch.int64, device=dev)
+    rows = max(1, (1 << 28) // nwin)                                    # <= 2 GiB temporaries per chunk
+    for r0 in range(0, n_leaves, rows):
+        cc = codes[r0:r0 + rows]
+        fwd = torch.zeros((cc.shape[0], nwin), dtype=torch.int64, device=dev)
+        rc = torch.zeros((cc.shape[0], nwin), dtype=torch.int64, device=dev)
+        for i in range(K):
+            c = cc[:, i:i + nwin].to(torch.int64)
+            fwd = (fwd << 2) | c
+            rc = rc | ((c ^ 1) << (2 * i))
+        canon[r0:r0 + rows] = torch.maximum(fwd, rc)
+        del fwd, rc
+    canon = canon.reshape(-1)
+    if wl.get("simple_db"):
+        # bacterial scale: purely random genomes (duplicates are a handful), first holder wins; kept memory-lean
+        keys, order = torch.sort(canon)
+        del canon
+        leaf32 = (order // nwin).to(torch.int32)
+        del order
+        keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+        keep[1:] = keys[1:] != keys[:-1]
+        keys = keys[keep]
+        vals_raw = (leaf32[keep].to(torch.int32) + (level_start[-1] - 32768)).to(torch.int16)
+        return keys, vals_raw, parent, codes
     leaf = (torch.arange(n_leaves, device=dev, dtype=torch.int64).repeat_interleave(nwin))
     keys, order = torch.sort(canon)
     leaf = leaf[order]
@@ -88,7 +113,8 @@ def make_database(torch, dev, wl, seed):
 
 
 def make_reads(torch, dev, wl, codes, n_reads, seed):
-    """n_reads x READ_LEN ASCII bases on the device (+64 bytes of slack), offsets uint64[n+1]."""
+    """n_reads x read_len ASCII bases on the device (+64 bytes of slack), offsets uint64[n+1]."""
+    READ_LEN = wl["read_len"]
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     n_leaves, glen = codes.shape
@@ -155,7 +181,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(set(norm.get(r, r) for r in rs)), "samples": len(self.samples)}
 
 
-def algorithmic_bytes_per_kmer(n_db, h, use_bloom=True, count_unique=True, f=0.01):
+def algorithmic_bytes_per_kmer(n_db, h, READ_LEN, use_bloom=True, count_unique=True, f=0.01):
     """SURVEY.md §8(d) / DESIGN.md "Roofline": ASCII base stream + two Bloom words + binary-search keys and the short value
     for the k-mers that reach the search + the unique-bitset RMW for hits."""
     s = h + (1.0 - h) * (f if use_bloom else 1.0)
@@ -190,6 +216,143 @@ def as_tensor(torch, ptr, nbytes, dev):
     return torch.as_tensor(r, device=dev)
 
 
+def java_random_longs(seed, n):
+    """java.util.Random(seed).nextLong() sequence (hashFactors of AbstractKMerBloomFilter, C/bloom/AbstractKMerBloomFilter.java:104-110)."""
+    mask = (1 << 48) - 1
+    st = (seed ^ 0x5DEECE66D) & mask
+    out = []
+    for _ in range(n):
+        parts = []
+        for _ in range(2):
+            st = (st * 0x5DEECE66D + 0xB) & mask
+            v = st >> 16
+            parts.append(v - (1 << 32) if v >= (1 << 31) else v)
+        x = ((parts[0] << 32) + parts[1]) & ((1 << 64) - 1)
+        out.append(x - (1 << 64) if x >= (1 << 63) else x)
+    return out
+
+
+def build_xor_index(torch, dev, keys, fpp):
+    """The `filter` goal's index as BloomIndexGoal builds it (XORKMerBloomFilter, fpp 1e-8): bits, hashes, factors, words.
+    torch is plumbing here (the index is built offline by the reference's db goals, outside the timed path)."""
+    n = keys.numel()
+    bits = max(1, int(-n * math.log(fpp) / (math.log(2.0) ** 2)))
+    hashes = max(1, int(math.floor(bits / n * math.log(2.0) + 0.5)))
+    factors = java_random_longs(42, hashes)
+    n_words = (bits + 63) // 64
+    flags = torch.zeros(n_words * 64, dtype=torch.bool, device=dev)
+    for f in factors:
+        idx = torch.fmod(keys ^ f, bits).abs()       # Math.abs((factor ^ key) % bits), Java's truncating remainder
+        flags[idx] = True
+    words = torch.empty(n_words, dtype=torch.int64, device=dev)
+    weights = (torch.ones(64, dtype=torch.int64, device=dev) << torch.arange(64, device=dev))
+    step = 1 << 24
+    for w0 in range(0, n_words, step):
+        blk = flags[w0 * 64:(w0 + step) * 64].view(-1, 64).to(torch.int64)
+        words[w0:w0 + blk.shape[0]] = (blk * weights).sum(dim=1)
+    return bits, hashes, np.array(factors, dtype=np.int64), words
+
+
+def run_filter_workload(torch, dev, args, wl, config, capi, ctx, keys, vals_raw, parent, batches, b0_h, off_h, emit, rank, world, dist):
+    """BASELINE.json configs[3]: FastqBloomFilter.isAcceptRead over the XOR index; same JSON contract, metric = filter k-mers/s."""
+    READ_LEN, R = wl["read_len"], wl["reads_per_step"]
+    leaf0 = len(parent) - wl["fanout"] ** wl["levels"]
+    leaf_keys = keys[(vals_raw.to(torch.int64) + 32768) >= leaf0]   # index = k-mers of the requested (leaf) taxa
+    bits, hashes, factors, words = build_xor_index(torch, dev, leaf_keys, 1e-8)
+    flt = capi.Filter(ctx, capi.GS_BLOOM_XOR, bits, hashes, factors, words.cpu().numpy())
+    del words, keys, vals_raw
+    log("rank %d: XOR index: %d keys, %d bits, %d hashes" % (rank, leaf_keys.numel(), bits, hashes))
+    sess = capi.FilterSession(flt, K, 1, 0.2)
+    stream = torch.cuda.ExternalStream(sess.stream, device=dev)
+    d_acc = torch.zeros(R, dtype=torch.uint8, device=dev)
+    n_batches = len(batches)
+
+    def step(i):
+        b, o = batches[i % n_batches]
+        sess.run_device(b.data_ptr(), o.data_ptr(), R, d_acc.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sess.sync()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record(stream)
+    sess.sync()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.result()
+    accepted = int(d_acc.sum().item())
+    # end to end
+    nb = R * READ_LEN
+    pinned = [capi.PinnedBuffer(nb + 64) for _ in range(n_batches)]
+    pin_off = capi.PinnedBuffer((R + 1) * 8)
+    for b in range(n_batches):
+        pinned[b].array[:nb] = batches[b][0][:nb].cpu().numpy()
+    offs = pin_off.view(np.uint64, R + 1)
+    offs[:] = off_h
+
+    def e2e_run(n_steps, first):
+        pend = []
+        for i in range(n_steps):
+            pend.append(sess.submit(pinned[(first + i) % n_batches].array, offs))
+            if len(pend) == capi.GS_MAX_INFLIGHT:
+                sess.collect(pend.pop(0))
+        while pend:
+            sess.collect(pend.pop(0))
+
+    e2e_run(args.warmup, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps, args.warmup)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    kmers_per_step = R * (READ_LEN - K + 1)
+    value = world * args.steps * kmers_per_step / (float(tt[0]) / 1e3)
+    e2e_value = world * args.steps * kmers_per_step / (float(tt[1]) / 1e3)
+    if rank == 0:
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            peak = 6650.0
+        hfrac = accepted / float(R)
+        probes = (1 - hfrac * 0.73) * 2 + hfrac * 0.73 * hashes   # SURVEY.md §8(d): E[probes] ~ (1-h)*2 + h*27
+        bpk = READ_LEN / (READ_LEN - K + 1) + 8.0 * probes
+        kernel_ms = float(tt[0]) / args.steps
+        achieved = bpk * kmers_per_step / (kernel_ms / 1e3) / 1e9
+        emit({"metric": "filter k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+              "reads_per_s": value / (READ_LEN - K + 1), "config": config, "clocks": clocks,
+              "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R},
+              "gpu_launches": args.steps,
+              "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                           "kernel": "gs_filter_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk},
+              "accepted_read_fraction": hfrac, "index": {"kind": "xor", "bits": bits, "hashes": hashes}})
+    sess.close()
+    flt.close()
+    for p in pinned:
+        p.free()
+    pin_off.free()
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
     # is sent to stderr for the duration of the run
@@ -216,6 +379,9 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.reads_per_step:
         wl["reads_per_step"] = args.reads_per_step
+    READ_LEN = wl["read_len"]
+    if args.workload == "bacterial":
+        args.no_cpu_baseline = True   # a 2e9-key oracle database does not fit the bounded CPU leg; parity at this size: test_gpu_scale
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -258,8 +424,9 @@ def main():
               "l2_policy": "inputs larger than L2: %.0f MB of bases per step, %.0f MB database, alternating batches" % (R * READ_LEN / 1e6, n_db * 10 / 1e6),
               "parallelism": "reads sharded over %d GPU(s), database replicated" % world}
 
-    keys_h = keys.cpu().numpy()
-    vals_h = vals_raw.cpu().numpy()
+    need_host_db = args.impl == "reference" or (rank == 0 and world == 1 and not args.no_cpu_baseline and wl["kind"] == "match")
+    keys_h = keys.cpu().numpy() if need_host_db else None
+    vals_h = vals_raw.cpu().numpy() if need_host_db else None
     b0_h = batches[0][0][: R * READ_LEN].cpu().numpy()
     off_h = batches[0][1].cpu().numpy().astype(np.uint64)
 
@@ -281,8 +448,12 @@ def main():
     # ---------------- native arm
     from genestrip_b200 import capi
     ctx = capi.Context([local])
-    db = capi.Database(ctx, K, keys_h, vals_h, V, parent_by_vidx=parent, build_bloom=True)
+    if wl["kind"] == "filter":
+        return run_filter_workload(torch, dev, args, wl, config, capi, ctx, keys, vals_raw, parent, batches, b0_h, off_h, emit, rank, world, dist)
+    torch.cuda.synchronize()
+    db = capi.Database.from_pointers(ctx, K, keys.data_ptr(), vals_raw.data_ptr(), n_db, V, parent, build_bloom=True)
     del keys, vals_raw
+    torch.cuda.empty_cache()
     log("rank %d: database on device: %.2f GB" % (rank, db.device_bytes / 1e9))
     cfg = capi.default_match_cfg(layout=capi.GS_LAYOUT_CLASSIC if args.layout == "classic" else capi.GS_LAYOUT_TABLE)
     config["layout"] = args.layout
@@ -403,7 +574,7 @@ def main():
             peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        bpk = algorithmic_bytes_per_kmer(n_db, h)
+        bpk = algorithmic_bytes_per_kmer(n_db, h, READ_LEN)
         traffic = None
         try:  # DRAM bytes of the match kernel from the committed ncu --set full capture, scaled to this launch's k-mers
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "match_kernel_traffic.json")))
@@ -431,6 +602,8 @@ def main():
     # ---------------- CPU baseline + bench-scale parity spot check (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import gs_oracle
+        if READ_LEN > 1000:
+            args.cpu_seconds = min(args.cpu_seconds, 8.0)
         n, kmers, per, times = cpu_reference(gs_oracle, keys_h, vals_h, V, parent, b0_h, off_h, threads, args.cpu_seconds)
         sess2.close()
         sess3 = capi.MatchSession(db, cfg)

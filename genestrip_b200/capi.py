@@ -218,6 +218,29 @@ class Database:
             self.h = None
             raise
 
+    @classmethod
+    def from_pointers(cls, ctx, k, keys_ptr, vals_ptr, n_kmers, n_values, parent_by_vidx, build_bloom=True):
+        """Database whose sorted keys / raw values already sit in (device or host) memory at the given addresses."""
+        L = lib()
+        self = cls.__new__(cls)
+        self.ctx, self.k, self.n_values, self.n_kmers, self.bloom_words = ctx, k, int(n_values), int(n_kmers), None
+        self.h = L.gs_db_create(ctx.h, k, self.n_kmers, self.n_values)
+        if not self.h:
+            raise GenestripError(-1, L.gs_last_error().decode())
+        try:
+            _check(L.gs_db_put_keys(self.h, 0, keys_ptr, self.n_kmers))
+            _check(L.gs_db_put_values(self.h, 0, vals_ptr, self.n_kmers))
+            p = _arr(parent_by_vidx, np.int32)
+            _check(L.gs_db_set_tree(self.h, _ptr(p), None, self.n_values))
+            if build_bloom:
+                _check(L.gs_db_build_bloom_blocked(self.h, None, 0))
+            _check(L.gs_db_finalize(self.h))
+        except Exception:
+            L.gs_db_destroy(self.h)
+            self.h = None
+            raise
+        return self
+
     @property
     def device_bytes(self):
         return lib().gs_db_device_bytes(self.h)

@@ -192,7 +192,7 @@ extern "C" int gs_db_put_keys(gs_db* db, uint64_t offset, const int64_t* keys, u
     if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
     if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "key segment [%llu,%llu) exceeds n_kmers=%llu", (unsigned long long)offset, (unsigned long long)(offset + n), (unsigned long long)db->n);
     CU(cudaSetDevice(db->d[0].dev));
-    CU(cudaMemcpy(db->d[0].keys + offset, keys, n * sizeof(u64), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->d[0].keys + offset, keys, n * sizeof(u64), cudaMemcpyDefault));  // host or device source
     return GS_OK;
 }
 
@@ -200,7 +200,7 @@ extern "C" int gs_db_put_values(gs_db* db, uint64_t offset, const int16_t* vidx_
     if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
     if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "value segment exceeds n_kmers");
     CU(cudaSetDevice(db->d[0].dev));
-    CU(cudaMemcpy(db->rawVals + offset, vidx_raw, n * sizeof(int16_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->rawVals + offset, vidx_raw, n * sizeof(int16_t), cudaMemcpyDefault));
     return GS_OK;
 }
 

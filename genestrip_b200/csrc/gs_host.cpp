@@ -775,6 +775,28 @@ gsh_result* gsh_filter_goal(gs_filter* f, int k, int min_pos_count, double pos_r
     return r;
 }
 
+// Parser only (no GPU): every record of the inputs rewritten by ReadEntry.write, plus the reader's totals.  Lets the
+// CPU test-suite check the host-side FASTQ/FASTA parsing against the oracle without a device.
+gsh_result* gsh_parse_only(int k, int with_probs, const uint8_t* const* data, const size_t* lens, const char* const* paths,
+                           const int* is_fasta, int n_inputs) {
+    gsh_result* r = new gsh_result();
+    try {
+        OutputSink out;
+        out.mem = &r->rest;
+        std::string scratch;
+        FastqReader reader(k, with_probs != 0);
+        for (const Input& in : toInputs(data, lens, paths, is_fasta, n_inputs)) {
+            reader.readFastq(in, [&](const Record& rec, int64_t) {
+                writeRead(out, rec.descriptor.data(), rec.descriptor.size(), rec.read.data(), rec.read.size(), rec.probs.data(),
+                          rec.probs.size(), with_probs != 0 && rec.hasProbs, scratch);
+                r->accept.push_back((uint8_t)rec.entry);
+            });
+            r->totals[0] += reader.reads; r->totals[1] += reader.kMers; r->totals[2] += reader.readBPs;
+        }
+    } catch (const std::exception& e) { r->error = e.what(); }
+    return r;
+}
+
 void gsh_result_free(gsh_result* r) { delete r; }
 const char* gsh_result_error(const gsh_result* r) { return r->error.c_str(); }
 const char* gsh_result_text(const gsh_result* r, int which, size_t* len) {

@@ -33,6 +33,8 @@ def _lib():
         L.gsh_match_goal.argtypes = [_P, _P, C.POINTER(HostMatchCfg), _P, _P, _P, _P, C.c_int, C.c_char_p, C.c_char_p]
         L.gsh_filter_goal.restype = _P
         L.gsh_filter_goal.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint32, _P, _P, _P, _P, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.gsh_parse_only.restype = _P
+        L.gsh_parse_only.argtypes = [C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]
         L.gsh_result_free.argtypes = [_P]
         L.gsh_result_error.restype = C.c_char_p
         L.gsh_result_error.argtypes = [_P]
@@ -134,6 +136,12 @@ def filter_goal(flt, k, files, is_fasta=None, min_pos_count=1, pos_ratio=0.2, wi
     h = _lib().gsh_filter_goal(flt.h, k, min_pos_count, pos_ratio, int(with_probs), batch_reads, data, lens, paths, fa, n,
                                filtered_path.encode() if filtered_path else None, rest_path.encode() if rest_path else None, int(want_rest))
     return GoalResult(h)
+
+
+def parse_only(k, files, is_fasta=None, with_probs=False):
+    """Host parser alone (no GPU): .rest = every record rewritten by ReadEntry.write, totals, .accept = pooled entry index."""
+    keep, data, lens, paths, fa, n = _inputs(files, is_fasta)
+    return GoalResult(_lib().gsh_parse_only(k, int(with_probs), data, lens, paths, fa, n))
 
 
 def java_double_to_string(v):

@@ -56,7 +56,8 @@ void gs_free_pinned(void*);
  * Replaces: Database.load + convertKMerStore (C/store/Database.java:136-143, 265-314) as the data source,
  * KMerSortedArray's arrays (C/store/KMerSortedArray.java:63-66) as the layout that is uploaded.
  * keys: sorted ascending, distinct, < 2^62, storage position == array index (KMerSortedArray.getLong :298-349).
- * vidx_raw: the Java short as stored (value index + Short.MIN_VALUE).  Segments may be streamed in any order. */
+ * vidx_raw: the Java short as stored (value index + Short.MIN_VALUE).  Segments may be streamed in any order; the
+ * source pointers may be host or device memory (cudaMemcpyDefault). */
 gs_db* gs_db_create(gs_ctx*, int k, uint64_t n_kmers, int n_values);
 int gs_db_put_keys(gs_db*, uint64_t offset, const int64_t* keys, uint64_t n);
 int gs_db_put_values(gs_db*, uint64_t offset, const int16_t* vidx_raw, uint64_t n);

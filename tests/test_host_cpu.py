@@ -1,4 +1,4 @@
-"""CPU-side checks of the C++ host layer that need no GPU: Java Double.toString formatting."""
+"""CPU-side checks of the C++ host layer that need no GPU: FASTQ/FASTA parsing against the oracle, Double.toString."""
 import math
 
 
@@ -16,3 +16,51 @@ def test_java_double_to_string_matches_oracle_and_known_values(native, oracle):
         assert host.java_double_to_string(v) == oracle.java_double_to_string(v)
         assert float(host.java_double_to_string(v).replace("E", "e")) == v
     assert host.java_double_to_string(math.nan) == "NaN" and host.java_double_to_string(math.inf) == "Infinity"
+
+
+def _oracle_rewrite(oracle, k, files, is_fasta, with_probs):
+    flt = oracle.Bloom(kind=0)   # empty filter: nothing is accepted, every record goes to `rest`
+    flt.ensure(10)
+    run = oracle.filter_files(flt, k, files, with_probs=with_probs, is_fasta=is_fasta, initial_read_size=256)  # the smallest legal initialReadSizeBytes (C/GSConfigKey.java:348)
+    flt.free()
+    return run
+
+
+def test_parser_matches_oracle_on_fixtures_and_quirks(native, oracle, tmp_path):
+    import gzip
+    import os
+    import numpy as np
+    from genestrip_b200 import host, synth
+    here = os.path.dirname(os.path.abspath(__file__))
+    simple = open(os.path.join(here, "golden", "SimpleTest.fastq"), "rb").read()
+    dengue_fa = open(os.path.join(here, "golden", "dengue1.fasta"), "rb").read()
+    rng = np.random.default_rng(0)
+    g = synth.random_genome(rng, 5000).tobytes()
+    crlf = b"@a 1\r\n" + g[:150] + b"\r\n+\r\n" + b"I" * 150 + b"\r\n@b\r\n" + g[200:260] + b"\r\n+\r\n" + b"J" * 60 + b"\r\n"
+    multi = b"@m desc\n" + g[300:360] + b"\n" + g[360:400] + b"\n\n" + g[400:410] + b"\n+m desc\n" + b"K" * 50 + b"\n" + b"K" * 60 + b"\n"
+    nul = b"@n\0x\n" + g[500:540] + b"\0\0" + g[540:600] + b"\n+\n" + b"I" * 100 + b"\n"
+    no_final_newline = b"@e\n" + g[700:850] + b"\n+\n" + b"I" * 150
+    plus_in_quality = b"@p\n" + g[900:1000] + b"\n+\n" + b"+" + b"I" * 99 + b"\n@q\n" + g[1000:1100] + b"\n+\n" + b"@" * 100 + b"\n"
+    fasta = b">f1 x\n" + g[1200:1270] + b"\n" + g[1270:1300] + b"\n\n>f2\n" + g[1400:1500] + b"\n>f3 empty\n>f4\n" + g[1600:1650]
+    cases = [([simple], [False]), ([crlf], [False]), ([multi, nul], [False, False]), ([no_final_newline], [False]),
+             ([plus_in_quality], [False]), ([fasta], [True]), ([dengue_fa], [True]), ([simple, fasta, crlf], [False, True, False]), ([b""], [False])]
+    for files, fa in cases:
+        for with_probs in (False, True):
+            for k in (2, 31):
+                o = _oracle_rewrite(oracle, k, files, fa, with_probs)
+                h = host.parse_only(k, files, fa, with_probs)
+                assert (h.total_reads, h.total_kmers, h.total_bps) == (o.total_reads, o.total_kmers, o.total_bps)
+                assert h.rest == o.rest
+    # SimpleTest.fastq: the reference test's expectations (T/fastq/FastqReaderTest.java:43-75)
+    h = host.parse_only(2, [simple], [False], True)
+    lines = h.rest.split(b"\n")
+    assert lines[1] == b"GATTTGGGGTTCAAAGCAGTATCGATCAAATAGTAAATCCATTTGTTCAACTCACAGTTT" and lines[5] == b"CGAT" and lines[7] == b"!**>"
+    # files (plain and gzip) give the same records as memory; FASTA entries alternate between the two pooled ReadEntry objects
+    p1, p2 = str(tmp_path / "x.fastq"), str(tmp_path / "x.fastq.gz")
+    big = synth.fastq_bytes(*synth.sample_reads([g], 5000, 150, seed=2)[:2])
+    open(p1, "wb").write(big)
+    with gzip.open(p2, "wb") as f:
+        f.write(big)
+    m = host.parse_only(31, [big])
+    assert host.parse_only(31, [p1]).rest == m.rest == host.parse_only(31, [p2]).rest and m.total_reads == 5000
+    assert list(host.parse_only(31, [fasta], [True]).accept) == [0, 1, 0, 1]
