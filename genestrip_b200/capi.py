@@ -11,7 +11,7 @@ import numpy as np
 from .build import LIB_PATH
 
 GS_ABI_VERSION = 1
-GS_MAX_INFLIGHT = 2
+GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
 GS_BLOOM_BLOCKED, GS_BLOOM_XOR, GS_BLOOM_MURMUR = 0, 1, 2

@@ -147,7 +147,7 @@ gs_sess* gs_match_open(gs_db*, const gs_match_cfg*);
  * global ordinal of read 0 (file order; used for the maxContigDescriptor tie-break).  Host buffers must stay
  * valid until the ticket is collected.  Batches are dealt round-robin to the devices of the context; up to
  * GS_MAX_INFLIGHT tickets may be pending per device (collect in submission order). */
-#define GS_MAX_INFLIGHT 2
+#define GS_MAX_INFLIGHT 3
 int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                     uint64_t first_read_no, gs_ticket* ticket);
 /* Wait for a ticket.  out[n_reads]; events[ev_cap] / n_events may be NULL.  If want_runs: run_offsets
