@@ -374,6 +374,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="table", choices=["table", "classic"],
                     help="device index: 128-byte probe table (default) or the reference's Bloom filter + sorted-array search")
+    ap.add_argument("--no-prefilter", action="store_true", help="A/B: probe the table for every k-mer (no minimizer prefilter)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     wl = dict(WORKLOADS[args.workload])
@@ -456,14 +457,16 @@ def main():
     torch.cuda.empty_cache()
     log("rank %d: database on device: %.2f GB" % (rank, db.device_bytes / 1e9))
     cfg = capi.default_match_cfg(layout=capi.GS_LAYOUT_CLASSIC if args.layout == "classic" else capi.GS_LAYOUT_TABLE)
+    cfg.prefilter = 0 if args.no_prefilter else 1
     config["layout"] = args.layout
+    config["minimizer_prefilter"] = bool(cfg.prefilter) and args.layout == "table"
     sess = capi.MatchSession(db, cfg)
     stream = torch.cuda.ExternalStream(sess.stream, device=dev)
     d_out = torch.zeros(R * 16, dtype=torch.uint8, device=dev)
 
     def device_step(i):
         bases, offsets = batches[i % n_batches]
-        sess.run_device(bases.data_ptr(), offsets.data_ptr(), R, i * R, d_out.data_ptr())
+        sess.run_device(bases.data_ptr(), offsets.data_ptr(), R, R * READ_LEN, i * R, d_out.data_ptr())
 
     def barrier():
         torch.cuda.synchronize()

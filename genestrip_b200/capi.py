@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 1
+GS_ABI_VERSION = 2
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -29,7 +29,7 @@ class MatchCfg(C.Structure):
     _fields_ = [("classify_reads", C.c_int), ("count_unique_kmers", C.c_int), ("max_kmer_res_counts", C.c_int),
                 ("use_bloom_filter", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
                 ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
-                ("want_runs", C.c_int), ("layout", C.c_int)]
+                ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int)]
 
 
 READ_RESULT_DTYPE = np.dtype([("class_vidx", "<i4"), ("read_kmers", "<u4"), ("tax_err", "<u4"), ("flags", "<u4")])
@@ -70,7 +70,7 @@ _SIGS = {
     "gs_match_collect_view": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(C.c_uint32)]),
     "gs_match_finish": (C.c_int, [_P, _P, _P]),
     "gs_match_close": (None, [_P]),
-    "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _P]),
+    "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "gs_match_sync": (C.c_int, [_P]),
     "gs_match_device_state": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gs_match_unique_popcount": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
@@ -325,8 +325,8 @@ class MatchSession:
         return counts[:V], top
 
     # ---- device-resident variants (bench kernel-only number, NCCL reduction of raw state)
-    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, first_read_no, d_out_ptr):
-        _check(lib().gs_match_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, int(first_read_no), d_out_ptr))
+    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, first_read_no, d_out_ptr):
+        _check(lib().gs_match_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, int(n_bases), int(first_read_no), d_out_ptr))
 
     def sync(self):
         _check(lib().gs_match_sync(self.h))

@@ -142,6 +142,7 @@ struct DevDb {
     u32* bstart = nullptr;
     u64* bloom = nullptr;
     u64* tab = nullptr;
+    u64* mzFilter = nullptr;
     int *parent = nullptr, *depth = nullptr, *pre = nullptr, *last = nullptr;
     GsDbView view;
 };
@@ -165,6 +166,7 @@ struct gs_db {
     u64 nBuckets = 0;
     // probe table
     int tbits = 0, rbits = 0;
+    int mzBits = 0;  // log2 of the minimizer prefilter's size in bits; 0 = none
     bool seenLeased = false;  // the table's in-line seen bits belong to at most one unique-counting session at a time
     // radix source staging
     std::vector<std::pair<u64, int16_t>> radixItems;
@@ -369,6 +371,16 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaDeviceSynchronize());
         CU(cudaFree(counts));
     }
+    // minimizer prefilter: ~0.22 distinct minimizers per stored k-mer (window of 9), one bit each, fill <= ~12 %
+    if (db->k >= GS_MZ_MIN_K && db->n > 0) {
+        int fb = 16;
+        while (fb < 32 && (double)(1ULL << fb) < 1.8 * (double)db->n) fb++;
+        db->mzBits = fb;
+        CU(dmalloc(&d0.mzFilter, (size_t)(1ULL << (fb - 6))));
+        CU(cudaMemset(d0.mzFilter, 0, (size_t)(1ULL << (fb - 3))));
+        gs_launch_mz_build(d0.keys, db->n, db->k, d0.mzFilter, (u32)((1ULL << fb) - 1), 0);
+        CU(cudaGetLastError());
+    }
     // tree
     CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));
     CU(cudaMemcpy(d0.parent, db->hParent.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
@@ -391,6 +403,10 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaMemcpyPeer(di.depth, di.dev, d0.depth, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.pre, di.dev, d0.pre, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.last, di.dev, d0.last, d0.dev, (size_t)V * sizeof(int)));
+        if (db->mzBits) {
+            CU(dmalloc(&di.mzFilter, (size_t)(1ULL << (db->mzBits - 6))));
+            CU(cudaMemcpyPeer(di.mzFilter, di.dev, d0.mzFilter, d0.dev, (size_t)(1ULL << (db->mzBits - 3))));
+        }
         if (db->hasBloom) {
             CU(dmalloc(&di.bloom, db->bloomWords));
             CU(cudaMemcpyPeer(di.bloom, di.dev, d0.bloom, d0.dev, db->bloomWords * sizeof(u64)));
@@ -403,9 +419,10 @@ extern "C" int gs_db_finalize(gs_db* db) {
         v.k = db->k; v.bloom = d.bloom; v.bloomBuckets = db->bloomBuckets; v.bloomMagic = magic_for(db->bloomBuckets);
         v.bloomSeed = db->bloomSeed; v.hasBloom = db->hasBloom ? 1 : 0;
         v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits;
+        v.mzFilter = d.mzFilter; v.mzMask = db->mzBits ? (u32)((1ULL << db->mzBits) - 1) : 0u;
         v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
     }
-    db->bytes = (32ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16;
+    db->bytes = (32ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16 + (db->mzBits ? (1ULL << (db->mzBits - 3)) : 0);
     CU(cudaSetDevice(d0.dev));
     db->finalized = true;
     return GS_OK;
@@ -415,7 +432,7 @@ extern "C" void gs_db_destroy(gs_db* db) {
     if (!db) return;
     for (DevDb& d : db->d) {
         cudaSetDevice(d.dev);
-        cudaFree(d.keys); cudaFree(d.vals); cudaFree(d.bstart); cudaFree(d.bloom); cudaFree(d.tab);
+        cudaFree(d.keys); cudaFree(d.vals); cudaFree(d.bstart); cudaFree(d.bloom); cudaFree(d.tab); cudaFree(d.mzFilter);
         cudaFree(d.parent); cudaFree(d.depth); cudaFree(d.pre); cudaFree(d.last);
     }
     if (db->rawVals) { cudaSetDevice(db->d[0].dev); cudaFree(db->rawVals); }
@@ -474,7 +491,11 @@ struct DevSess {
     u32* overflowList = nullptr; size_t ovCap = 0;
     u32* overflowCount = nullptr;
     u32* slowTable = nullptr;
-    int fastBlocks = 0, slowBlocks = 0;
+    int fastBlocks = 0, slowBlocks = 0, labelBlocks = 0;
+    // label kernel -> reduce kernel hand-over (one set per device: the kernels of successive batches run in stream order)
+    u32* labels = nullptr; size_t labelsCap = 0;
+    u32* validBits = nullptr; size_t validCap = 0;
+    u32* startBits = nullptr; size_t startCap = 0;
     MatchSlot slots[GS_MAX_INFLIGHT];
 };
 
@@ -502,6 +523,8 @@ extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
     c->max_read_tax_error_count = -1;   // :328
     c->max_read_class_error_count = -1; // :337
     c->want_runs = 0;
+    c->layout = GS_LAYOUT_TABLE;
+    c->prefilter = 1;
 }
 
 static int sess_alloc_dev(gs_sess* s, DevSess& D) {
@@ -530,9 +553,10 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
             CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
         }
     }
-    CU(dmalloc(&D.overflowCount, 2));  // [0] overflow list length, [1] work counter
+    CU(dmalloc(&D.overflowCount, 4));  // [0] overflow list length, [1] read claim counter, [2] segment claim counter
     const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
     D.fastBlocks = D.sms * occ0;
+    D.labelBlocks = D.sms * std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
     D.slowBlocks = std::max(1, D.sms / 4);
     CU(dmalloc(&D.slowTable, (size_t)D.slowBlocks * GS_WARPS_PER_BLOCK * 2 * std::max(V, 1)));
     for (MatchSlot& sl : D.slots) {
@@ -566,6 +590,7 @@ extern "C" void gs_match_close(gs_sess* s) {
         }
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
+        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits);
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
         if (D.sCompute) cudaStreamDestroy(D.sCompute);
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
@@ -601,6 +626,7 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
 static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     memset(&P, 0, sizeof(P));
     P.db = s->db->d[D.devIndex].view;
+    if (!s->cfg.prefilter) P.db.mzFilter = nullptr;
     P.counters = D.counters; P.maxcontig = D.maxcontig; P.hitCounts = D.hitCounts;
     if (s->inlineSeen) { P.bitset = nullptr; P.seenTab = (u32*)s->db->d[D.devIndex].tab; }
     else { P.bitset = D.bitset; P.seenTab = nullptr; }
@@ -614,23 +640,50 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.workCounter = D.overflowCount + 1; P.slowTable = D.slowTable;
 }
 
-// kernels of one batch on the compute stream: fast path, slow path over the overflow list, max-contig events
-static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv) {
+// flat geometry of a batch whose bases cover byte offsets [off0, off0 + nBytes) of P.bases; grows the hand-over buffers
+static int prepare_flat(DevSess& D, GsMatchParams& P, u64 off0, u64 nBytes) {
+    P.off0 = off0;
+    P.lead = (u32)((uintptr_t)(P.bases + off0) & 15);
+    P.flatLen = (u64)P.lead + nBytes;
+    const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+    const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
+    if (P.flatLen + 32 > D.labelsCap || words > D.validCap || words > D.startCap) {
+        CU(cudaStreamSynchronize(D.sCompute));
+        CU(dgrow(&D.labels, &D.labelsCap, (size_t)P.flatLen + 32));
+        CU(dgrow(&D.validBits, &D.validCap, words));
+        CU(dgrow(&D.startBits, &D.startCap, words));
+    }
+    P.labels = D.labels; P.validBits = D.validBits; P.startBits = D.startBits; P.segCounter = D.overflowCount + 2;
+    return GS_OK;
+}
+
+// kernels of one batch on the compute stream: read-start bitmap, label kernel, reduce kernel (fast path, then the slow path
+// over the overflow list), max-contig events
+static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv, u64 off0, u64 nBytes) {
     if (P.nReads > D.ovCap || !D.overflowList) {
         CU(cudaStreamSynchronize(D.sCompute));
         CU(dgrow(&D.overflowList, &D.ovCap, (size_t)P.nReads));
     }
     P.overflowList = D.overflowList;
-    CU(cudaMemsetAsync(D.overflowCount, 0, 2 * sizeof(u32), D.sCompute));
+    int rc = prepare_flat(D, P, off0, nBytes);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(D.overflowCount, 0, 4 * sizeof(u32), D.sCompute));
     if (dNEv) CU(cudaMemsetAsync(dNEv, 0, 2 * sizeof(u32), D.sCompute));
     P.errFlag = dNEv ? dNEv + 1 : nullptr;
     if (P.nReads == 0) return GS_OK;
+    const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+    CU(cudaMemsetAsync(D.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
+    gs_launch_mark_starts(P, D.sCompute);
+    CU(cudaGetLastError());
+    const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)D.labelBlocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
+    gs_launch_label(P, false, labelBlocks, D.sCompute);
+    CU(cudaGetLastError());
     const int fastBlocks = (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
-    gs_launch_match(P, 0, false, fastBlocks, D.sCompute);
+    gs_launch_reduce(P, 0, false, fastBlocks, D.sCompute);
     CU(cudaGetLastError());
-    gs_launch_match(P, 1, false, D.slowBlocks, D.sCompute);
+    gs_launch_reduce(P, 1, false, D.slowBlocks, D.sCompute);
     CU(cudaGetLastError());
-    s->launches += 2;
+    s->launches += 4;
     if (dEv) {
         gs_launch_maxcontig_events(D.maxcontig, s->db->V, P.firstReadNo, P.nReads, dEv, dNEv, D.sCompute);
         CU(cudaGetLastError());
@@ -693,7 +746,7 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     // offsets are relative to bases + offsets[0] on the device: the kernel subtracts nothing, so rebase here
     // (the device copy of the base stream starts at host offset base0)
     P.bases = sl.dBases - base0;
-    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv);
+    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, base0, nBytes);
     if (rc) return rc;
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
     // results: device -> pinned host on the copy-out stream
@@ -768,7 +821,7 @@ extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs
 }
 
 extern "C" int gs_match_run_device(gs_sess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
-                                   uint64_t first_read_no, gs_read_result* d_out) {
+                                   uint64_t n_bases, uint64_t first_read_no, gs_read_result* d_out) {
     if (!s || s->finished) return gs_fail(GS_ERR_STATE, "session missing or finished");
     if (((uintptr_t)d_bases & 15) != 0) return gs_fail(GS_ERR_ARG, "d_bases must be 16-byte aligned");
     DevSess& D = s->devs[0];
@@ -776,7 +829,7 @@ extern "C" int gs_match_run_device(gs_sess* s, const uint8_t* d_bases, const uin
     GsMatchParams P;
     fill_params(s, D, P);
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = d_out;
-    return launch_batch(s, D, P, nullptr, nullptr);
+    return launch_batch(s, D, P, nullptr, nullptr, 0, n_bases);
 }
 
 extern "C" int gs_match_sync(gs_sess* s) {
@@ -840,10 +893,10 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     const int V = s->db->V;
     long long* counters = nullptr; u64* maxcontig = nullptr; gs_read_result* out = nullptr; u32* ovList = nullptr; u32* ovCount = nullptr;
     CU(dmalloc(&counters, (size_t)7 * V)); CU(dmalloc(&maxcontig, (size_t)V)); CU(dmalloc(&out, (size_t)n_reads));
-    CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 2));
+    CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 4));
     CU(cudaMemset(counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
     CU(cudaMemset(maxcontig, 0, std::max<size_t>(V, 1) * sizeof(u64)));
-    CU(cudaMemset(ovCount, 0, 2 * sizeof(u32)));
+    CU(cudaMemset(ovCount, 0, 4 * sizeof(u32)));
     GsMatchParams P;
     fill_params(s, D, P);
     P.counters = counters; P.maxcontig = maxcontig; P.bitset = nullptr; P.seenTab = nullptr; P.hitCounts = nullptr;
@@ -851,10 +904,26 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
     P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
     CU(cudaStreamSynchronize(D.sCompute));
-    if (n_reads) gs_launch_match(P, 0, true, D.fastBlocks, D.sCompute);
+    long long* flatPos = nullptr;
+    if (n_reads) {
+        u64 ends[2] = {0, 0};
+        CU(cudaMemcpy(&ends[0], d_offsets, sizeof(u64), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&ends[1], d_offsets + n_reads, sizeof(u64), cudaMemcpyDeviceToHost));
+        if (ends[1] < ends[0]) return gs_fail(GS_ERR_ARG, "offsets not ascending");
+        int rc = prepare_flat(D, P, ends[0], ends[1] - ends[0]);
+        if (rc) return rc;
+        P.segCounter = ovCount + 2;
+        const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+        CU(dmalloc(&flatPos, (size_t)P.flatLen + 32));
+        P.flatPos = flatPos;
+        CU(cudaMemsetAsync(D.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
+        gs_launch_mark_starts(P, D.sCompute);
+        gs_launch_label(P, true, D.labelBlocks, D.sCompute);
+        gs_launch_reduce(P, 0, true, D.fastBlocks, D.sCompute);
+    }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(D.sCompute));
-    CU(cudaFree(counters)); CU(cudaFree(maxcontig)); CU(cudaFree(out)); CU(cudaFree(ovList)); CU(cudaFree(ovCount));
+    CU(cudaFree(counters)); CU(cudaFree(maxcontig)); CU(cudaFree(out)); CU(cudaFree(ovList)); CU(cudaFree(ovCount)); CU(cudaFree(flatPos));
     return GS_OK;
 }
 

@@ -24,6 +24,14 @@ typedef unsigned int u32;
 #define GS_LAYOUT_CLASSIC 1           // the reference's structures: blocked Bloom filter + (bucketed) binary search
 #define GS_VAL_NONODE 0xFFFFu         // stored value whose tax id has no tree node -> null (C/store/Database.java:136-143)
 
+// label kernel: a warp labels a segment of GS_SEG_POS consecutive positions of the batch's flat base array
+#define GS_SEG_CHUNKS 31
+#define GS_SEG_POS (GS_SEG_CHUNKS * 32)    // 992 positions ...
+#define GS_SEG_BASES 1024                  // ... need 992 + k - 1 <= 1023 bases: 64 aligned 16-byte groups
+#define GS_SEG_WORDS 34                    // 32 words of codes / validity / read starts + zero padding for the funnel shifts
+#ifndef GS_LABEL_MIN_BLOCKS
+#define GS_LABEL_MIN_BLOCKS 4
+#endif
 #define GS_WARPS_PER_BLOCK 8
 #define GS_TILE_POS 1024                   // k-mer positions per tile
 #define GS_TILE_BASES (GS_TILE_POS + 32)   // bases staged per tile (positions + k-1 <= +30, padded to 16)
@@ -52,6 +60,10 @@ struct GsDbView {
     // answers hit/miss and yields the value and the position's seen bit (see "probe table" below)
     const u64* tab;
     int tbits, rbits;       // bucket = mix62(key) >> rbits, remainder = low rbits bits, rbits = 62 - tbits
+    // minimizer prefilter (see "minimizer prefilter" below): bit (h & mzMask) of mzFilter is set for the hash h of the
+    // minimizer of every stored k-mer; NULL = no prefilter (k too small)
+    const u64* mzFilter;
+    u32 mzMask;
     const int* parent;      // by value index, -1 root / none
     const int* depth;
     const int* pre;         // DFS interval labels: a is ancestor-or-self of b  <=>  pre[a] <= pre[b] <= last[a]
@@ -84,10 +96,14 @@ __device__ __forceinline__ void gs_conv4(u32 w, u32& code8, u32& valid4) {
 
 // forward k-mer of the window starting at tile-relative position p from the packed big-endian 2-bit stream
 __device__ __forceinline__ u64 gs_extract(const u64* cw, int p, int k) {
-    int w = p >> 5, o = (p & 31) * 2;
-    u64 hi = cw[w], lo = cw[w + 1];
-    u64 x = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-    return x >> (64 - 2 * k);
+    // 32-bit view of the big-endian stream: stream word q sits at c32[q ^ 1] (u64 word w = (c32[2w+1] << 32) | c32[2w]).
+    // Two funnel shifts give the 64 bits that start at base p (branch-free: a shift of 0 needs no special case).
+    const u32* c32 = (const u32*)cw;
+    const int q = p >> 4;
+    const u32 sh = (u32)(p & 15) * 2;
+    const u32 w0 = c32[q ^ 1], w1 = c32[(q + 1) ^ 1], w2 = c32[(q + 2) ^ 1];
+    const u32 x1 = __funnelshift_l(w1, w0, sh), x0 = __funnelshift_l(w2, w1, sh);
+    return (((u64)x1 << 32) | x0) >> (64 - 2 * k);
 }
 
 // reverse complement in 2-bit space: complement = code ^ 1 (C<->G, A<->T; CGAT.java:71-74), order reversed
@@ -222,6 +238,68 @@ __device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64&
     const u64 h = gs_mix62(key);
     bool seen;
     return gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
+}
+
+// ---- minimizer prefilter -------------------------------------------------------------------------------------
+// Measured (profiles/microbench/randsize.*): the request cap only counts DISTINCT sectors that miss the L2 -- lanes that
+// share a sector are served together, and a footprint <= 64 MiB is served by the L2 at ~270 G requests/s.  A k-mer that is
+// not in the store can therefore be answered without touching the probe table if a small, shared structure proves it absent:
+// the minimizer of a k-mer = the smallest hash among its GS_MZ_W = 9 windows of m = k - 8 bases (hash of the CANONICAL m-mer,
+// so both strands of a k-mer give the same value; any deterministic function of the canonical k-mer keeps the lookup exact).
+// Neighbouring k-mers of a read share their minimizer (~5 in a row), so a warp's 32 lanes touch ~7 filter words instead of 32
+// table sectors, and the set of minimizers of the store is ~5x smaller than the store.  One bit per minimizer hash; no false
+// negatives by construction (built from the stored keys with gs_mz_of_key, same hash as the read path).
+#define GS_MZ_S 8                  // windows per k-mer minus one (power of two: van Herk blocks = 8-lane shuffle segments)
+#define GS_MZ_W (GS_MZ_S + 1)
+#define GS_MZ_MIN_K 24             // m = k - 8 >= 16: below that the minimizer space is too small to filter anything
+
+// hash of the canonical form of an m-mer given both strands (x = forward value, r = reverse complement, 2m bits each).
+// In the label kernel both come for free: x = top 2m bits of the forward k-mer, r = low 2m bits of its reverse complement.
+__device__ __forceinline__ u32 gs_mmer_hash2(u64 x, u64 r) {
+    const u64 y = (x > r ? x : r) * 0x9E3779B97F4A7C15ULL;
+    u32 h = (u32)(y >> 32);
+    h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+    return h;
+}
+__device__ __forceinline__ u32 gs_mmer_hash(u64 x, int m) {
+    u64 c = x ^ 0x5555555555555555ULL;
+    u64 r = __brevll(c);
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    return gs_mmer_hash2(x, r >> (64 - 2 * m));
+}
+
+// minimizer hash of a stored (canonical) k-mer: min over its GS_MZ_W windows (database build, gs_db_lookup self check)
+__device__ __forceinline__ u32 gs_mz_of_key(u64 key, int k) {
+    const int m = k - GS_MZ_S;
+    const u64 mmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1);
+    u32 best = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j <= GS_MZ_S; j++) best = min(best, gs_mmer_hash((key >> (2 * (GS_MZ_S - j))) & mmask, m));
+    return best;
+}
+
+__device__ __forceinline__ bool gs_mz_test(const u64* __restrict__ filter, u32 mask, u32 h) {
+    const u32 idx = h & mask;
+    return (__ldg(filter + (idx >> 6)) >> (idx & 63)) & 1ULL;
+}
+
+// Sliding minimum over GS_MZ_W consecutive positions held one per lane: cur = hashes of 32 positions, nxt = hashes of the
+// following 32 (only lanes < GS_MZ_S matter).  van Herk: prefix/suffix minima inside 8-lane blocks, then
+// min(suffix[i], prefix[i + 8]).  preNxt = block prefix minima of nxt (computed by the caller for the next chunk anyway).
+__device__ __forceinline__ u32 gs_seg_prefix_min(u32 v, int lane) {
+#pragma unroll
+    for (int d = 1; d < GS_MZ_S; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) >= d) v = min(v, t); }
+    return v;
+}
+__device__ __forceinline__ u32 gs_seg_suffix_min(u32 v, int lane) {
+#pragma unroll
+    for (int d = 1; d < GS_MZ_S; d <<= 1) { const u32 t = __shfl_down_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) + d < GS_MZ_S) v = min(v, t); }
+    return v;
+}
+__device__ __forceinline__ u32 gs_window_min(u32 sufCur, u32 preCur, u32 preNxt, int lane) {
+    // position lane + 8 lives in lane + 8 of the current chunk or in lane - 24 of the next one: one rotate of the merged register
+    const u32 merged = lane < GS_MZ_S ? preNxt : preCur;
+    return min(sufCur, __shfl_sync(0xFFFFFFFFu, merged, (lane + GS_MZ_S) & 31));
 }
 
 // value stored at a "storage position" of the unique-k-mer bitset: sorted-array index (classic) or table slot id

@@ -21,8 +21,6 @@
 
 #define FULL 0xFFFFFFFFu
 
-__device__ __forceinline__ bool gs_is_cgat(uint8_t c) { return c == 'C' || c == 'G' || c == 'A' || c == 'T'; }
-
 // ---------------------------------------------------------------------------------------------------------
 // match
 // ---------------------------------------------------------------------------------------------------------
@@ -97,14 +95,131 @@ __device__ __forceinline__ void gs_hit_count_inc(uint16_t* hitCounts, u64 pos) {
     } while (old != assumed);
 }
 
-// MODE 0: fast path (table in shared memory).  MODE 1: slow path for reads that overflowed the fast table
-// (table in global scratch sized nValues; contig statistics and unique bits were already applied by the fast
-// path, only reads1KMer beyond the first GS_TABLE_CAP taxa and the classification are done here).
-// DUMP: additionally write the per-position labels / positions (parity tests).
+// ---- K0: read-start bitmap over the flat base array (bit f = a read starts at flat position f)
+__global__ void gs_mark_starts_kernel(const u64* __restrict__ offsets, u32 nReads, u64 off0, u32 lead, u64 flatLen, u32* startBits) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < nReads; r += stride) {
+        const u64 f = offsets[r] - off0 + lead;
+        if (offsets[r] >= off0 && f < flatLen) atomicOr(startBits + (f >> 5), 1u << (f & 31));
+    }
+}
+
+// ---- K1: label kernel.  The batch's bases are one flat array (reads back to back); position f gets the label of the k-mer
+// that starts there: value index, MISS, INVALID (window holds a non-CGAT byte) or END (window crosses a read boundary or the
+// end of the batch: never read by the reduce kernel, and no side effects).  A warp claims segments of GS_SEG_POS positions:
+// 64 aligned 128-bit loads stage 1024 bases as a packed 2-bit stream + validity bits; then chunk by chunk every lane takes
+// one position: forward / reverse-complement k-mer in registers, minimizer prefilter (L2-resident bit filter, shared by
+// neighbouring lanes), one 256-bit probe-table load for the k-mers that pass, seen bit / hit counter for the hits.
+// The k-mer and m-mer hash of chunk c+1 are computed while chunk c is finished (the sliding minimum needs them anyway).
+template <int LAYOUT, bool DUMP>
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {
+    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
+    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
+    __shared__ u32 s_start[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GsDbView& db = P.db;
+    const int k = db.k;
+    const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    const u32 k1mask = (1u << (k - 1)) - 1u;   // read starts inside (f, f + k - 1] = the window crosses a read boundary
+    const bool useBloom = P.useBloom && db.hasBloom;
+    const bool mz = LAYOUT == GS_LAYOUT_TABLE && db.mzFilter != nullptr;
+    const int m = k - GS_MZ_S;
+    const u64 mmask = (1ULL << (2 * (m > 0 ? m : 1))) - 1;
+    u64* cw = s_code[warp];
+    u32* vw = s_valid[warp];
+    u32* sw = s_start[warp];
+    const uint8_t* fb = P.bases + P.off0 - P.lead;  // 16-byte aligned start of the flat array
+    const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+    for (;;) {
+        u32 seg = 0;
+        if (lane == 0) seg = atomicAdd(P.segCounter, 1u);
+        seg = __shfl_sync(FULL, seg, 0);
+        if (seg >= nSeg) break;
+        const u64 f0 = (u64)seg * GS_SEG_POS;
+        const int nb = (int)min((u64)GS_SEG_BASES, P.flatLen - f0);
+        __syncwarp();
+        // ---- stage: ASCII -> packed 2-bit codes + validity bits (C/util/CGAT.java:60-69)
+        const uint4* ap = (const uint4*)(fb + f0);
+#pragma unroll
+        for (int j = lane; j < GS_SEG_BASES / 16; j += 32) {
+            u32 code = 0, valid = 0;
+            const int rem = nb - j * 16;
+            if (rem > 0) {
+                const uint4 A = __ldg(ap + j);
+                u32 c0, c1, c2, c3, v0, v1, v2, v3;
+                gs_conv4(A.x, c0, v0); gs_conv4(A.y, c1, v1); gs_conv4(A.z, c2, v2); gs_conv4(A.w, c3, v3);
+                code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+                valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+                if (rem < 16) valid &= (1u << rem) - 1u;
+                if (seg == 0) {  // alignment bytes in front of the first read are not bases
+                    const int lo = (int)P.lead - j * 16;
+                    if (lo > 0) valid &= lo >= 16 ? 0u : ~((1u << lo) - 1u);
+                }
+            }
+            ((u32*)cw)[j ^ 1] = code;
+            ((uint16_t*)vw)[j] = (uint16_t)valid;
+        }
+        sw[lane] = __ldg(P.startBits + (u64)seg * GS_SEG_CHUNKS + lane);
+        if (lane < 2) { cw[32 + lane] = 0; vw[32 + lane] = 0; sw[32 + lane] = lane == 0 ? __ldg(P.startBits + (u64)seg * GS_SEG_CHUNKS + 32) : 0u; }
+        __syncwarp();
+        if (lane < GS_SEG_CHUNKS) P.validBits[(u64)seg * GS_SEG_CHUNKS + lane] = vw[lane];  // for the reduce kernel's INVALID count
+
+        // ---- chunks
+        u64 fwdN = gs_extract(cw, lane, k), rcN = gs_revcomp(fwdN, k);
+        u32 hN = 0, preN = 0;
+        if (mz) { hN = gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask); preN = gs_seg_prefix_min(hN, lane); }
+#pragma unroll 1
+        for (int c = 0; c < GS_SEG_CHUNKS; c++) {
+            const int prel = c * 32 + lane;
+            const u64 f = f0 + (u64)prel;
+            const u64 fwd = fwdN, rc = rcN;
+            const u32 hC = hN, preC = preN;
+            fwdN = gs_extract(cw, prel + 32, k);
+            rcN = gs_revcomp(fwdN, k);
+            const u32 vbits = __funnelshift_r(vw[c], vw[c + 1], lane);
+            const u32 sbits = __funnelshift_rc(sw[c], sw[c + 1], lane + 1);
+            u32 lab = (sbits & k1mask) ? GS_LABEL_END : ((vbits & kmask) != kmask ? GS_LABEL_INVALID : GS_LABEL_PENDING);
+            if (mz) {
+                hN = gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask);
+                preN = gs_seg_prefix_min(hN, lane);
+                const u32 mzv = gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane) & db.mzMask;
+                if (lab == GS_LABEL_PENDING && !((__ldg(db.mzFilter + (mzv >> 6)) >> (mzv & 63)) & 1ULL)) lab = GS_LABEL_MISS;
+            }
+            if (lab == GS_LABEL_PENDING) {
+                const u64 key = fwd > rc ? fwd : rc;  // standardKMer (CGAT.java:145-147)
+                u64 pos = 0;
+                bool seen = false;
+                if (LAYOUT == GS_LAYOUT_TABLE) {
+                    const u64 h = gs_mix62(key);
+                    lab = gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
+                } else {
+                    lab = gs_lookup(db, key, useBloom, pos);
+                }
+                if (lab < GS_LABEL_INVALID) {
+                    // unique k-mer bit / hit counter (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143)
+                    if (P.seenTab) { if (!seen) atomicOr(P.seenTab + pos * 2, (u32)GS_TAB_SEEN); }  // seen bit came with the bucket
+                    else if (P.bitset) {
+                        const u64 bit = 1ULL << (pos & 63);
+                        if (!(*(volatile u64*)(P.bitset + (pos >> 6)) & bit)) atomicOr(P.bitset + (pos >> 6), bit);
+                    }
+                    if (P.hitCounts) gs_hit_count_inc(P.hitCounts, pos);
+                    if (DUMP) P.flatPos[f] = (long long)pos;
+                }
+            }
+            __syncwarp();  // reconverge here, not at the compiler's leisure: the shuffles of the next chunk need the full warp
+            if (f < P.flatLen) P.labels[f] = lab;
+        }
+    }
+}
+
+// ---- K2: reduce kernel, one warp per read: the reference's sequential contig logic (C/match/FastqKMerMatcher.java:327-535)
+// over the read's labels, 32 positions per step.
+// MODE 0: fast path (vote table in shared memory).  MODE 1: slow path for reads that overflowed the fast table
+// (table in global scratch sized nValues; contig statistics were already applied by the fast path, only reads1KMer
+// beyond the first GS_TABLE_CAP taxa and the classification are done here).
+// DUMP: additionally write the per-position labels / positions in k-mer order (parity tests).
 template <int MODE, bool DUMP>
-__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_match_kernel(const GsMatchParams P) {
-    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_CODE_WORDS];
-    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_VALID_WORDS];
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_reduce_kernel(const GsMatchParams P) {
     __shared__ u32 s_tabVi[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
     __shared__ u32 s_tabCnt[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
     __shared__ u32 s_cand[GS_WARPS_PER_BLOCK][GS_MAX_PATHS];
@@ -113,19 +228,14 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
     const u32 gw = blockIdx.x * GS_WARPS_PER_BLOCK + warp, nw = gridDim.x * GS_WARPS_PER_BLOCK;
     const GsDbView& db = P.db;
     const int k = db.k;
-    const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
     const int V = db.nValues;
-    const bool useBloom = P.useBloom && db.hasBloom;
-    u64* cw = s_code[warp];
-    u32* vw = s_valid[warp];
     u32* cand = s_cand[warp];
     WarpTable T;
     if (MODE == 0) { T.vi = s_tabVi[warp]; T.cnt = s_tabCnt[warp]; T.cap = GS_TABLE_CAP; }
     else { T.vi = P.slowTable + (size_t)gw * 2 * (size_t)V; T.cnt = T.vi + V; T.cap = V; }
     const u32 nItems = MODE == 0 ? P.nReads : *P.overflowCount;
 
-    // Dynamic distribution: a warp claims GS_CLAIM consecutive reads at a time.  With a static split the SMs that get
-    // more of the saturated memory system finish early and idle (ncu: sm__cycles_active min 58 % of max).
+    // Dynamic distribution: a warp claims GS_CLAIM consecutive reads at a time.
     u32 claimBase = 0, claimPos = GS_CLAIM;
     for (;;) {
         u32 item;
@@ -146,7 +256,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
         const u64 start = P.offsets[r];
         const u64 end = P.offsets[r + 1];
         int L = (int)(end - start);
-        if (end < start || end - start > 0x7FFFFFF0ULL) {  // malformed offsets: reported by gs_match_collect
+        if (end < start || end - start > 0x7FFFFFF0ULL || start < P.off0 || end - P.off0 + P.lead > P.flatLen) {  // malformed offsets: reported by gs_match_collect
             if (lane == 0 && P.errFlag) atomicOr(P.errFlag, 1u);
             L = 0;
         }
@@ -158,135 +268,63 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
             if (lane == 0 && MODE == 0) P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
             continue;
         }
-        const uint8_t* rb = P.bases + start;
-        int nTab = 0, misses = 0, badLow = 0, badTail = 0, carryLen = 0;
-        bool overflow = false;
+        const u64 fs = start - P.off0 + P.lead;  // flat position of the read's first base
+        const u32* lp = P.labels + fs;
+        int nTab = 0, misses = 0, carryLen = 0;
+        bool overflow = false, sawInvalid = false;
         u32 carryLabel = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
         u64 runCursor = 0;               // want_runs: next free slot of this read's run list
 
-        for (int t0 = 0; t0 <= max; t0 += GS_TILE_POS) {
-            const int nb = min(L - t0, GS_TILE_BASES);
-            const bool lastTile = t0 + GS_TILE_POS > max;
-            __syncwarp();
-            gs_stage_tile(rb + t0, nb, lane, (u32*)cw, (uint16_t*)vw, max - t0, lastTile ? GS_TILE_BASES : GS_TILE_POS, badLow, badTail);
-            __syncwarp();
-            const int lim = max - t0;  // tile-relative index of the terminator position
-            const int nchunks = (min(lim, GS_TILE_POS - 1) >> 5) + 1;
 #pragma unroll 1
-            for (int c0 = 0; c0 < nchunks; c0 += GS_GROUP) {
-              // ---- phase A/B: labels of GS_GROUP chunks; with the probe table all header loads of the group are
-              // issued before the first one is consumed (memory-level parallelism: GS_GROUP line touches in flight per lane)
-              u32 labs[GS_GROUP];
-              u64 poss[GS_GROUP];
-              bool seens[GS_GROUP];
-              if (P.layout == GS_LAYOUT_TABLE) {
-                  u64 hs[GS_GROUP];
-                  GsBucket hds[GS_GROUP];
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++) {
-                      const int prel = (c0 + g) * 32 + lane;
-                      labs[g] = GS_LABEL_END; poss[g] = 0; seens[g] = true; hs[g] = 0; hds[g] = GsBucket{{0, 0, 0, 0}};
-                      if (c0 + g < nchunks && prel < lim) {
-                          const u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
-                          if ((vbits & kmask) != kmask) labs[g] = GS_LABEL_INVALID;
-                          else {
-                              hs[g] = gs_mix62(gs_canonical(gs_extract(cw, prel, k), k));
-                              hds[g] = gs_load_bucket(db.tab, hs[g] >> db.rbits);
-                              labs[g] = GS_LABEL_PENDING;
-                          }
-                      }
-                  }
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++)
-                      if (labs[g] == GS_LABEL_PENDING) labs[g] = gs_table_resolve(db, hs[g], hds[g], poss[g], seens[g]);
-              } else {
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++) {
-                      const int prel = (c0 + g) * 32 + lane;
-                      labs[g] = GS_LABEL_END; poss[g] = 0;
-                      if (c0 + g < nchunks && prel < lim) {
-                          const u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
-                          if ((vbits & kmask) != kmask) labs[g] = GS_LABEL_INVALID;
-                          else labs[g] = gs_lookup(db, gs_canonical(gs_extract(cw, prel, k), k), useBloom, poss[g]);
-                      }
-                  }
-              }
-              // ---- phase C: unique k-mer bits (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143):
-              // all test loads of the group first, then the atomics of the bits that were still clear
-              if (MODE == 0 && P.seenTab) {  // seen bits live in the probe-table line that was just fetched: no extra load
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++) {
-                      if (labs[g] >= GS_LABEL_INVALID) continue;
-                      if (!seens[g]) atomicOr(P.seenTab + poss[g] * 2, (u32)GS_TAB_SEEN);  // low word of the slot's entry
-                      if (P.hitCounts) gs_hit_count_inc(P.hitCounts, poss[g]);
-                  }
-              } else if (MODE == 0 && P.bitset) {
-                  u64 seen[GS_GROUP];
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++)
-                      seen[g] = labs[g] < GS_LABEL_INVALID ? *(volatile u64*)(P.bitset + (poss[g] >> 6)) : ~0ULL;
-#pragma unroll
-                  for (int g = 0; g < GS_GROUP; g++) {
-                      if (labs[g] >= GS_LABEL_INVALID) continue;
-                      const u64 bit = 1ULL << (poss[g] & 63);
-                      if (!(seen[g] & bit)) atomicOr(P.bitset + (poss[g] >> 6), bit);
-                      if (P.hitCounts) gs_hit_count_inc(P.hitCounts, poss[g]);
-                  }
-              }
-              // ---- phase D: the reference's sequential contig logic, chunk by chunk
-#pragma unroll
-              for (int g = 0; g < GS_GROUP; g++) {
-                if (c0 + g >= nchunks) break;
-                const u32 lab = labs[g];
-                if (DUMP) {
-                    const int prel = (c0 + g) * 32 + lane;
-                    if (prel < lim) {
-                        u64 o = P.kmerOffsets[r] + (u64)(t0 + prel);
-                        P.dumpLabels[o] = lab == GS_LABEL_INVALID ? -2 : (lab == GS_LABEL_MISS ? -1 : (int)lab);
-                        P.dumpPos[o] = lab < GS_LABEL_INVALID ? (long long)poss[g] : -1LL;
-                    }
-                }
-                if (P.classify) misses += __popc(__ballot_sync(FULL, lab == GS_LABEL_MISS));
-                // ---- contigs = maximal runs of equal labels (FastqKMerMatcher.java:370, 390-421)
-                u32 prev = __shfl_up_sync(FULL, lab, 1);
-                if (lane == 0) prev = carryLabel;
-                const bool isStart = lab != prev;
-                const u32 S = __ballot_sync(FULL, isStart);
-                const u32 below = S & ((1u << lane) - 1u);
-                int runLen;  // length of the run that ends right before this lane (meaningful if isStart)
-                if (lane == 0) runLen = carryLen;
-                else if (below) runLen = lane - (31 - __clz(below));
-                else runLen = carryLen + lane;
-                const bool flushTax = isStart && prev < GS_LABEL_INVALID && runLen > 0;
-                if (MODE == 0 && flushTax) {  // :396-410 (contig boundary) and :458-471 (final contig)
-                    atomicAdd((u64*)(P.counters + 0 * (size_t)V + prev), (u64)runLen);
-                    atomicAdd((u64*)(P.counters + 1 * (size_t)V + prev), 1ULL);
-                    atomicAdd((u64*)(P.counters + 2 * (size_t)V + prev), (u64)runLen * (u64)runLen);
-                    atomicMax(P.maxcontig + prev, ((u64)runLen << GS_MAXCONTIG_SHIFT) | (GS_ORDINAL_MASK - (ordinal & GS_ORDINAL_MASK)));
-                }
-                if (MODE == 0 && P.runs) {  // printKrakenStyleOut (:597-611): every finished run incl. '0' and 'A'
-                    const bool flushAny = isStart && runLen > 0;
-                    const u32 FA = __ballot_sync(FULL, flushAny);
-                    if (flushAny) {
-                        u64 slot = P.runOffsets[r] + runCursor + (u64)__popc(FA & ((1u << lane) - 1u));
-                        if (slot < P.runsCap) P.runs[slot] = gs_run{prev, (u32)runLen};
-                    }
-                    runCursor += (u64)__popc(FA);
-                }
-                u32 F = __ballot_sync(FULL, flushTax);
-                while (F) {
-                    const int src = __ffs(F) - 1;
-                    F &= F - 1;
-                    const u32 v = __shfl_sync(FULL, prev, src);
-                    const u32 n = (u32)__shfl_sync(FULL, runLen, src);
-                    if (!overflow) {
-                        if (!gs_table_add(T, nTab, v, n, lane, P.counters + 3 * (size_t)V, MODE == 0 ? 0 : GS_TABLE_CAP)) overflow = true;
-                    }
-                }
-                if (S) carryLen = 32 - (31 - __clz(S)); else carryLen += 32;
-                carryLabel = __shfl_sync(FULL, lab, 31);
-              }
+        for (int c0 = 0; c0 <= max; c0 += 32) {  // position `max` is the terminator that flushes the last run
+            const int p = c0 + lane;
+            const u32 lab = p < max ? __ldcs(lp + p) : GS_LABEL_END;
+            if (DUMP && p < max) {
+                const u64 o = P.kmerOffsets[r] + (u64)p;
+                P.dumpLabels[o] = lab == GS_LABEL_INVALID ? -2 : (lab == GS_LABEL_MISS ? -1 : (int)lab);
+                P.dumpPos[o] = lab < GS_LABEL_INVALID ? P.flatPos[fs + p] : -1LL;
             }
+            if (P.classify) misses += __popc(__ballot_sync(FULL, lab == GS_LABEL_MISS));
+            // ---- contigs = maximal runs of equal labels (FastqKMerMatcher.java:370, 390-421)
+            u32 prev = __shfl_up_sync(FULL, lab, 1);
+            if (lane == 0) prev = carryLabel;
+            const bool isStart = lab != prev;
+            const u32 S = __ballot_sync(FULL, isStart);
+            if (S == 0) { carryLen += 32; continue; }  // the current run covers the whole chunk
+            sawInvalid |= __any_sync(FULL, lab == GS_LABEL_INVALID);
+            const u32 below = S & ((1u << lane) - 1u);
+            int runLen;  // length of the run that ends right before this lane (meaningful if isStart)
+            if (lane == 0) runLen = carryLen;
+            else if (below) runLen = lane - (31 - __clz(below));
+            else runLen = carryLen + lane;
+            const bool flushTax = isStart && prev < GS_LABEL_INVALID && runLen > 0;
+            if (MODE == 0 && flushTax) {  // :396-410 (contig boundary) and :458-471 (final contig)
+                atomicAdd((u64*)(P.counters + 0 * (size_t)V + prev), (u64)runLen);
+                atomicAdd((u64*)(P.counters + 1 * (size_t)V + prev), 1ULL);
+                atomicAdd((u64*)(P.counters + 2 * (size_t)V + prev), (u64)runLen * (u64)runLen);
+                atomicMax(P.maxcontig + prev, ((u64)runLen << GS_MAXCONTIG_SHIFT) | (GS_ORDINAL_MASK - (ordinal & GS_ORDINAL_MASK)));
+            }
+            if (MODE == 0 && P.runs) {  // printKrakenStyleOut (:597-611): every finished run incl. '0' and 'A'
+                const bool flushAny = isStart && runLen > 0;
+                const u32 FA = __ballot_sync(FULL, flushAny);
+                if (flushAny) {
+                    u64 slot = P.runOffsets[r] + runCursor + (u64)__popc(FA & ((1u << lane) - 1u));
+                    if (slot < P.runsCap) P.runs[slot] = gs_run{prev, (u32)runLen};
+                }
+                runCursor += (u64)__popc(FA);
+            }
+            u32 F = __ballot_sync(FULL, flushTax);
+            while (F) {
+                const int src = __ffs(F) - 1;
+                F &= F - 1;
+                const u32 v = __shfl_sync(FULL, prev, src);
+                const u32 n = (u32)__shfl_sync(FULL, runLen, src);
+                if (!overflow) {
+                    if (!gs_table_add(T, nTab, v, n, lane, P.counters + 3 * (size_t)V, MODE == 0 ? 0 : GS_TABLE_CAP)) overflow = true;
+                }
+            }
+            if (S) carryLen = 32 - (31 - __clz(S)); else carryLen += 32;
+            carryLabel = __shfl_sync(FULL, lab, 31);
         }
         if (MODE == 0 && P.runs && lane == 0) P.runCounts[r] = (u32)runCursor;
 
@@ -296,15 +334,41 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
             if (lane == 0) { u32 slot = atomicAdd(P.overflowCount, 1u); P.overflowList[slot] = r; }
         }
         if (P.classify) {
-            // INVALID iterations (:346-363, 372-373): see file header
+            // INVALID iterations (:346-363, 372-373), see file header: one per bad base b <= max-1, plus one if there is a
+            // bad base in [max, L-1] and base max-1 is fine.  Validity bits of the batch come from the label kernel.
+            int badLow = 0, badTail = 0;
+            const u64 bLow = fs + (u64)max, bEnd = fs + (u64)L;  // [fs, bLow) and [bLow, bEnd)
+            // (a bad base makes at least one window INVALID, so reads without an INVALID label skip this)
+            for (u64 w = (fs >> 5) + lane; sawInvalid && w * 32 < bEnd; w += 32) {
+                const u32 inval = ~P.validBits[w];
+                const u64 w0 = w * 32;
+                // bits of this word inside [a, b): a_rel = clamp(a - w0), b_rel = clamp(b - w0)
+                const int a0 = fs > w0 ? (int)(fs - w0) : 0;
+                const int lo1 = bLow > w0 ? (int)min((u64)32, bLow - w0) : 0;
+                const int e1 = (int)min((u64)32, bEnd - w0);
+                const u32 mLow = lo1 > a0 ? (u32)((((1ULL << lo1) - 1) >> a0) << a0) : 0u;
+                const int t0 = lo1 > a0 ? lo1 : a0;
+                const u32 mTail = e1 > t0 ? (u32)((((1ULL << e1) - 1) >> t0) << t0) : 0u;
+                badLow += __popc(inval & mLow);
+                badTail |= (inval & mTail) != 0;
+            }
             const int bl = __reduce_add_sync(FULL, badLow);
             const bool bt = __any_sync(FULL, badTail);
-            const int inv = bl + ((bt && gs_is_cgat(rb[max - 1])) ? 1 : 0);
+            const u64 fLast = fs + (u64)max - 1;
+            const bool lastOk = !sawInvalid || ((P.validBits[fLast >> 5] >> (fLast & 31)) & 1u);
+            const int inv = bl + ((bt && lastOk) ? 1 : 0);
             const int E = inv + misses;
             const double mte = P.maxTaxErr;
             const bool closed = mte >= 0 && ((mte >= 1 && (double)E > mte) || ((double)E > mte * (double)max));  // :374-379
             taxErr = closed ? 0xFFFFFFFFu : (u32)E;
             if (found && !closed && !overflow) {
+                int best = 0, ties = 0, node;
+                if (nTab == 1 && P.threshold <= 1) {
+                    // one taxon in the read: it is the only candidate, its score is its vote count
+                    node = (int)T.vi[0]; best = (int)T.cnt[0];
+                    if (lane == 0) cand[0] = (u32)node;
+                    __syncwarp();
+                } else {
                 // ---- mergeReadTaxidPath over the distinct taxa in first-occurrence order (:568-586)
                 int used = 0;
                 for (int j = 0; j < nTab; j++) {
@@ -329,7 +393,6 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
                     __syncwarp();
                 }
                 // ---- score candidates, keep maxima and ties in order (:474-487)
-                int best = 0, ties = 0;
                 for (int i = 0; i < used; i++) {
                     const int cnode = (int)cand[i];
                     const int sum = gs_sum_counts(db, T, nTab, cnode, lane);
@@ -353,8 +416,9 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
                     }
                 }
                 // ---- LCA of the ties (:493-497)
-                int node = (int)cand[0];
+                node = (int)cand[0];
                 for (int i = 1; i <= ties; i++) node = gs_lca(db, node, (int)cand[i]);
+                }
                 classV = node;
                 if (node < 0) {
                     found = false;  // `return false` (:498-500)
@@ -384,13 +448,26 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_mat
     }
 }
 
-void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
+void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st) {
+    if (P.nReads) gs_mark_starts_kernel<<<148 * 4, 256, 0, st>>>(P.offsets, P.nReads, P.off0, P.lead, P.flatLen, P.startBits);
+}
+void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t st) {
+    const int threads = GS_WARPS_PER_BLOCK * 32;
+    if (P.layout == GS_LAYOUT_TABLE) {
+        if (dump) gs_label_kernel<GS_LAYOUT_TABLE, true><<<blocks, threads, 0, st>>>(P);
+        else gs_label_kernel<GS_LAYOUT_TABLE, false><<<blocks, threads, 0, st>>>(P);
+    } else {
+        if (dump) gs_label_kernel<GS_LAYOUT_CLASSIC, true><<<blocks, threads, 0, st>>>(P);
+        else gs_label_kernel<GS_LAYOUT_CLASSIC, false><<<blocks, threads, 0, st>>>(P);
+    }
+}
+void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
     const int threads = GS_WARPS_PER_BLOCK * 32;
     if (mode == 0) {
-        if (dump) gs_match_kernel<0, true><<<blocks, threads, 0, st>>>(P);
-        else gs_match_kernel<0, false><<<blocks, threads, 0, st>>>(P);
+        if (dump) gs_reduce_kernel<0, true><<<blocks, threads, 0, st>>>(P);
+        else gs_reduce_kernel<0, false><<<blocks, threads, 0, st>>>(P);
     } else {
-        gs_match_kernel<1, false><<<blocks, threads, 0, st>>>(P);
+        gs_reduce_kernel<1, false><<<blocks, threads, 0, st>>>(P);
     }
 }
 
@@ -499,6 +576,16 @@ __global__ void gs_table_extract_seen_kernel(const u64* __restrict__ tab, u64 nS
         if (lane == 0) out[w] = ((u64)hi << 32) | lo;
     }
 }
+// minimizer prefilter of the store: one bit per minimizer hash of every stored key (gs_device.cuh "minimizer prefilter")
+__global__ void gs_mz_build_kernel(const u64* __restrict__ keys, u64 n, int k, u64* filter, u32 mask) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 idx = gs_mz_of_key(keys[i], k) & mask;
+        const u64 bit = 1ULL << (idx & 63);
+        if (!(filter[idx >> 6] & bit)) atomicOr(filter + (idx >> 6), bit);
+    }
+}
+void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, cudaStream_t st) { gs_mz_build_kernel<<<148 * 8, 256, 0, st>>>(keys, n, k, filter, mask); }
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st) { gs_table_clear_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots); }
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st) { gs_table_extract_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots, out); }
 void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
@@ -581,6 +668,8 @@ __global__ void gs_lookup_kernel(GsDbView db, const u64* __restrict__ kmers, u64
         // the probe table must agree with the reference structures on every query
         u64 p2 = 0;
         if (db.tab && gs_lookup_table(db, kmers[i], p2) != lab) lab = 0x7FFFFFFFu;
+        // ... and the minimizer prefilter must pass every stored key
+        if (db.mzFilter && lab != GS_LABEL_MISS && !gs_mz_test(db.mzFilter, db.mzMask, gs_mz_of_key(kmers[i], db.k))) lab = 0x7FFFFFFEu;
         vidx[i] = lab == GS_LABEL_MISS ? -1 : (int)lab;
         pos[i] = lab == GS_LABEL_MISS ? -1LL : (long long)p;
     }
@@ -663,8 +752,10 @@ void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st) {
 
 int gs_match_kernel_occupancy(int mode) {
     int nb = 0;
-    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_match_kernel<0, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_match_kernel<1, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<0, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
     return nb;
 }

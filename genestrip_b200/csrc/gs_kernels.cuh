@@ -23,6 +23,14 @@ struct GsMatchParams {
     u32* workCounter;       // next unclaimed read of the batch (dynamic distribution over the persistent warps)
     u32* errFlag;           // set when a read's offsets are malformed (descending / longer than 2^31)
     u32* slowTable;         // MODE 1: per-warp vote tables in global memory, 2 * nValues u32 each
+    // flat geometry of the batch (label kernel): flat position f = byte offset - off0 + lead, lead = alignment bytes in front
+    u64 off0, flatLen;
+    u32 lead;
+    u32* labels;            // [flatLen] label of the k-mer starting at each flat position
+    u32* validBits;         // [segments * 31 (+pad)] bit f = base f is one of CGAT
+    u32* startBits;         // same size: bit f = a read starts at f
+    u32* segCounter;        // next unclaimed segment of the label kernel
+    long long* flatPos;     // label dump only: storage position per flat position
     // kraken-style runs (want_runs)
     gs_run* runs; const u64* runOffsets; u64 runsCap; u32* runCounts;
     // label dump (parity tests)
@@ -48,13 +56,16 @@ struct GsFilterParams {
     u32* errFlag;
 };
 
-void gs_launch_match(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
+void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st);
+void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t st);
+void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
 void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st);
 void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st);
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st);
 void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
+void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, cudaStream_t st);
 void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
 void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 1
+#define GS_ABI_VERSION 2
 
 typedef enum gs_status {
     GS_OK = 0,
@@ -101,6 +101,8 @@ typedef struct gs_match_cfg {
     double max_read_class_error_count; /* maxReadClassErrorCount                                 */
     int want_runs;                     /* writeKrakenStyleOut: return per-read contig runs       */
     int layout;                        /* device index: GS_LAYOUT_TABLE (default) or GS_LAYOUT_CLASSIC; same results  */
+    int prefilter;                     /* 1 (default): skip the probe table for k-mers whose minimizer is in no stored k-mer
+                                          (L2-resident bit filter built by gs_db_finalize; same results, k >= 24 only)   */
 } gs_match_cfg;
 #define GS_LAYOUT_TABLE 0   /* 128-byte probe table built from the store's arrays: one DRAM line touch per k-mer      */
 #define GS_LAYOUT_CLASSIC 1 /* the reference's own structures: blocked Bloom filter + binary search of the sorted array */
@@ -166,10 +168,11 @@ int gs_match_finish(gs_sess*, gs_taxon_counts* counts, int16_t* top_counts);
 void gs_match_close(gs_sess*);
 
 /* Device-resident variants (inputs already in HBM; used by bench.py's kernel-only number and by a host that
- * decodes on the GPU).  d_bases must be 16-byte aligned and readable 32 bytes past the last base.  Runs on the
- * session's device 0, asynchronously on the session's stream; gs_match_sync waits. */
+ * decodes on the GPU).  d_bases must be 16-byte aligned and readable 32 bytes past the last base; d_offsets[0] == 0 and
+ * d_offsets[n_reads] == n_bases (checked on the device).  Runs on the session's device 0, asynchronously on the session's
+ * stream; gs_match_sync waits. */
 int gs_match_run_device(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
-                        uint64_t first_read_no, gs_read_result* d_out);
+                        uint64_t n_bases, uint64_t first_read_no, gs_read_result* d_out);
 int gs_match_sync(gs_sess*);
 /* Raw device state for cross-process reduction over NCCL (one process per GPU, DESIGN.md "Multi-GPU"):
  * counters = int64[7][n_values] (kmers, contigs, sqsum, reads1, reads, readsKmers, readsBPs),
