@@ -496,6 +496,7 @@ struct DevSess {
     u32* labels = nullptr; size_t labelsCap = 0;
     u32* validBits = nullptr; size_t validCap = 0;
     u32* startBits = nullptr; size_t startCap = 0;
+    u32* redoList = nullptr; size_t redoCap = 0;
     MatchSlot slots[GS_MAX_INFLIGHT];
 };
 
@@ -553,7 +554,7 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
             CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
         }
     }
-    CU(dmalloc(&D.overflowCount, 4));  // [0] overflow list length, [1] read claim counter, [2] segment claim counter
+    CU(dmalloc(&D.overflowCount, 8));  // [0] overflow list length, [1] read claim counter, [2] segment claim counter, [3] redo list length, [4] read-group claim counter
     const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
     D.fastBlocks = D.sms * occ0;
     D.labelBlocks = D.sms * std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
@@ -590,7 +591,7 @@ extern "C" void gs_match_close(gs_sess* s) {
         }
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
-        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits);
+        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList);
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
         if (D.sCompute) cudaStreamDestroy(D.sCompute);
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
@@ -667,7 +668,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     P.overflowList = D.overflowList;
     int rc = prepare_flat(D, P, off0, nBytes);
     if (rc) return rc;
-    CU(cudaMemsetAsync(D.overflowCount, 0, 4 * sizeof(u32), D.sCompute));
+    CU(cudaMemsetAsync(D.overflowCount, 0, 8 * sizeof(u32), D.sCompute));
     if (dNEv) CU(cudaMemsetAsync(dNEv, 0, 2 * sizeof(u32), D.sCompute));
     P.errFlag = dNEv ? dNEv + 1 : nullptr;
     if (P.nReads == 0) return GS_OK;
@@ -678,7 +679,19 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)D.labelBlocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
     gs_launch_label(P, false, labelBlocks, D.sCompute);
     CU(cudaGetLastError());
-    const int fastBlocks = (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
+    // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
+    const bool threadPath = !s->cfg.want_runs && nBytes / P.nReads <= 512;
+    if (threadPath) {
+        if (P.nReads > D.redoCap) {
+            CU(cudaStreamSynchronize(D.sCompute));
+            CU(dgrow(&D.redoList, &D.redoCap, (size_t)P.nReads));
+        }
+        P.redoList = D.redoList; P.redoCount = D.overflowCount + 3; P.groupCounter = D.overflowCount + 4;
+        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 4, ((u64)P.nReads + 127) / 128), D.sCompute);
+        CU(cudaGetLastError());
+        s->launches += 1;
+    }
+    const int fastBlocks = threadPath ? D.slowBlocks : (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
     gs_launch_reduce(P, 0, false, fastBlocks, D.sCompute);
     CU(cudaGetLastError());
     gs_launch_reduce(P, 1, false, D.slowBlocks, D.sCompute);

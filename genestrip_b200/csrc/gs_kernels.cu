@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
     WarpTable T;
     if (MODE == 0) { T.vi = s_tabVi[warp]; T.cnt = s_tabCnt[warp]; T.cap = GS_TABLE_CAP; }
     else { T.vi = P.slowTable + (size_t)gw * 2 * (size_t)V; T.cnt = T.vi + V; T.cap = V; }
-    const u32 nItems = MODE == 0 ? P.nReads : *P.overflowCount;
+    const u32 nItems = MODE == 0 ? (P.redoList ? *P.redoCount : P.nReads) : *P.overflowCount;
 
     // Dynamic distribution: a warp claims GS_CLAIM consecutive reads at a time.
     u32 claimBase = 0, claimPos = GS_CLAIM;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
             claimBase++;
             if (item >= nItems) break;
         }
-        const u32 r = MODE == 0 ? item : P.overflowList[item];
+        const u32 r = MODE == 0 ? (P.redoList ? P.redoList[item] : item) : P.overflowList[item];
         const u64 start = P.offsets[r];
         const u64 end = P.offsets[r + 1];
         int L = (int)(end - start);
@@ -446,6 +446,238 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
             P.out[r] = gs_read_result{-1, 0u, taxErr, flags | GS_READ_FOUND};
         }
     }
+}
+
+// ---- K2T: reduce kernel for short reads, one THREAD per read.  A 150-base read has 120 labels: a warp per read spends
+// most of its instructions on per-read set-up and warp-wide bookkeeping, a thread per read just walks its labels.  A warp
+// takes 32 consecutive reads; their labels are staged 32 positions at a time through a [32][33] shared-memory tile (row i =
+// read i: coalesced 128-byte global loads, conflict-free transposed reads), so global traffic is one pass over the labels.
+// The contig statistics are accumulated per (read, taxon) in a small per-thread table and applied once at the end of the read
+// (sums and maxima: same result as the reference's per-contig updates, FastqKMerMatcher.java:396-410), so a read that turns
+// out to need more than GS_T_CAP table entries has had no side effects yet and is handed to the warp-per-read kernel.
+#define GS_T_CAP 8
+#define GS_T_THREADS 128
+#define GS_T_MAX_LEN 2047  // cnt (11 bits) | contigs (10 bits) | maxlen (11 bits) share one word
+__global__ void __launch_bounds__(GS_T_THREADS) gs_reduce_thread_kernel(const GsMatchParams P) {
+    __shared__ u32 s_vi[GS_T_CAP][GS_T_THREADS];
+    __shared__ u32 s_pk[GS_T_CAP][GS_T_THREADS];   // cnt << 21 | contigs << 11 | maxlen
+    __shared__ u32 s_sq[GS_T_CAP][GS_T_THREADS];
+    __shared__ u32 s_tile[GS_T_THREADS / 32][2 * 32 * 33];
+    __shared__ u64 s_fs[GS_T_THREADS / 32][32];
+    __shared__ int s_max[GS_T_THREADS / 32][32];
+    const GsDbView& db = P.db;
+    const int k = db.k, V = db.nValues, t = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32* tile = s_tile[warp];
+    int* cand = (int*)tile;  // classification scratch: the tile is idle once the labels are walked
+    const u32 nGroups = (P.nReads + 31) / 32;
+    for (;;) {
+        u32 g = 0;
+        if (lane == 0) g = atomicAdd(P.groupCounter, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= nGroups) break;
+        const u32 r = g * 32 + lane;
+        const bool have = r < P.nReads;
+        u64 start = 0, end = 0;
+        if (have) { start = P.offsets[r]; end = P.offsets[r + 1]; }
+        int L = (int)(end - start);
+        if (have && (end < start || end - start > 0x7FFFFFF0ULL || start < P.off0 || end - P.off0 + P.lead > P.flatLen)) {
+            if (P.errFlag) atomicOr(P.errFlag, 1u);
+            L = 0;
+        }
+        const int max = L - k + 1;
+        int classV = -1;
+        u32 readKmers = 0, flags = 0, taxErr = P.classify ? 0u : 0xFFFFFFFFu;
+        const u64 fs = start - P.off0 + P.lead;
+        bool walk = have && max > 0;
+        if (have && max <= 0) P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
+        if (walk && L > GS_T_MAX_LEN) { P.redoList[atomicAdd(P.redoCount, 1u)] = r; walk = false; }
+        __syncwarp();
+        s_fs[warp][lane] = fs;
+        s_max[warp][lane] = walk ? max : 0;
+        const int wmax = __reduce_max_sync(FULL, walk ? max + 1 : 0);  // + the terminator position that flushes the last run
+        __syncwarp();
+        int nTab = 0, misses = 0, len = 0;
+        bool overflow = false, sawInvalid = false;
+        u32 prev = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
+        // ---- stage positions [b, b + 32) of the warp's 32 reads with 4-byte cp.async (global -> shared without registers),
+        // double-buffered: the copies of round b + 32 are in flight while round b is walked
+        auto stage = [&](int b, u32* dst) {
+            const int p = b + lane;
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+                if (p < s_max[warp][i]) {
+                    const u32 sa = (u32)__cvta_generic_to_shared(dst + i * 33 + lane);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(P.labels + s_fs[warp][i] + p) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (wmax > 0) stage(0, tile);
+        for (int b = 0; b < wmax; b += 32) {
+            u32* cur = tile + ((b >> 5) & 1) * (32 * 33);
+            if (b + 32 < wmax) {
+                stage(b + 32, tile + (((b >> 5) & 1) ^ 1) * (32 * 33));
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+            if (walk) {
+                const int n = min(32, max + 1 - b);  // position `max` is the terminator that flushes the last run
+                for (int i = 0; i < n; i++) {
+                    const u32 lab = b + i == max ? GS_LABEL_END : cur[lane * 33 + i];
+                    if (lab == prev) { len++; continue; }
+                    if (prev < GS_LABEL_INVALID && len > 0) {  // a contig of taxon `prev` ends (:396-410, 458-471)
+                        int j = 0;
+                        while (j < nTab && s_vi[j][t] != prev) j++;
+                        if (j < nTab) {
+                            const u32 pk = s_pk[j][t];
+                            const u32 ml = pk & 0x7FFu;
+                            s_pk[j][t] = (((pk >> 21) + (u32)len) << 21) | ((((pk >> 11) & 0x3FFu) + 1u) << 11) | ((u32)len > ml ? (u32)len : ml);
+                            s_sq[j][t] += (u32)len * (u32)len;
+                        } else if (nTab < GS_T_CAP) {
+                            s_vi[nTab][t] = prev;
+                            s_pk[nTab][t] = ((u32)len << 21) | (1u << 11) | (u32)len;
+                            s_sq[nTab][t] = (u32)len * (u32)len;
+                            nTab++;
+                        } else {
+                            overflow = true;
+                            break;
+                        }
+                    } else if (prev == GS_LABEL_MISS) {
+                        misses += len;
+                    } else if (prev == GS_LABEL_INVALID) {
+                        sawInvalid = true;
+                    }
+                    prev = lab;
+                    len = 1;
+                }
+                if (overflow) { P.redoList[atomicAdd(P.redoCount, 1u)] = r; walk = false; }
+                else if (b + 32 > max) walk = false;  // terminator consumed: the read is complete
+            }
+            __syncwarp();
+        }
+        if (!have || max <= 0 || overflow || L > GS_T_MAX_LEN) continue;
+        // ---- apply the read's contig statistics
+        const u64 ordinal = P.firstReadNo + r;
+        for (int j = 0; j < nTab; j++) {
+            const u32 v = s_vi[j][t], pk = s_pk[j][t];
+            atomicAdd((u64*)(P.counters + 0 * (size_t)V + v), (u64)(pk >> 21));
+            atomicAdd((u64*)(P.counters + 1 * (size_t)V + v), (u64)((pk >> 11) & 0x3FFu));
+            atomicAdd((u64*)(P.counters + 2 * (size_t)V + v), (u64)s_sq[j][t]);
+            atomicAdd((u64*)(P.counters + 3 * (size_t)V + v), 1ULL);  // reads1KMer (:434-439)
+            atomicMax(P.maxcontig + v, ((u64)(pk & 0x7FFu) << GS_MAXCONTIG_SHIFT) | (GS_ORDINAL_MASK - (ordinal & GS_ORDINAL_MASK)));
+            s_pk[j][t] = pk >> 21;  // from here on: the taxon's votes
+        }
+        bool found = nTab > 0;
+        if (P.classify) {
+            int inv = 0;
+            if (sawInvalid) {  // INVALID iterations (:346-363, 372-373), see the warp kernel
+                int badLow = 0;
+                bool badTail = false;
+                const u64 bLow = fs + (u64)max, bEnd = fs + (u64)L;
+                for (u64 w = fs >> 5; w * 32 < bEnd; w++) {
+                    const u32 inval = ~P.validBits[w];
+                    const u64 w0 = w * 32;
+                    const int a0 = fs > w0 ? (int)(fs - w0) : 0;
+                    const int lo1 = bLow > w0 ? (int)min((u64)32, bLow - w0) : 0;
+                    const int e1 = (int)min((u64)32, bEnd - w0);
+                    const u32 mLow = lo1 > a0 ? (u32)((((1ULL << lo1) - 1) >> a0) << a0) : 0u;
+                    const int t0 = lo1 > a0 ? lo1 : a0;
+                    const u32 mTail = e1 > t0 ? (u32)((((1ULL << e1) - 1) >> t0) << t0) : 0u;
+                    badLow += __popc(inval & mLow);
+                    badTail |= (inval & mTail) != 0;
+                }
+                const u64 fLast = fs + (u64)max - 1;
+                inv = badLow + ((badTail && ((P.validBits[fLast >> 5] >> (fLast & 31)) & 1u)) ? 1 : 0);
+            }
+            const int E = inv + misses;
+            const double mte = P.maxTaxErr;
+            const bool closed = mte >= 0 && ((mte >= 1 && (double)E > mte) || ((double)E > mte * (double)max));  // :374-379
+            taxErr = closed ? 0xFFFFFFFFu : (u32)E;
+            if (found && !closed) {
+                int best = 0, ties = 0, node;
+                if (nTab == 1 && P.threshold <= 1) {
+                    node = (int)s_vi[0][t]; best = (int)s_pk[0][t];
+                    cand[(0) * 32 + lane] = node;
+                } else {
+                    // ---- mergeReadTaxidPath over the distinct taxa in first-occurrence order (:568-586)
+                    int used = 0;
+                    for (int j = 0; j < nTab; j++) {
+                        const int n = (int)s_vi[j][t];
+                        const int pn = __ldg(db.pre + n), ln = __ldg(db.last + n);
+                        int hit = -1;
+                        bool repl = false;
+                        for (int i = 0; i < used; i++) {
+                            const int cnode = cand[(i) * 32 + lane];
+                            const int pc = __ldg(db.pre + cnode), lc = __ldg(db.last + cnode);
+                            const bool r1 = pc <= pn && pn <= lc, r2 = pn <= pc && pc <= ln;
+                            if (r1 || r2) { hit = i; repl = r1; break; }
+                        }
+                        if (hit >= 0) { if (repl) cand[(hit) * 32 + lane] = n; }
+                        else if (used < P.maxPaths) { cand[(used) * 32 + lane] = n; used++; }
+                    }
+                    // ---- score candidates, keep maxima and ties in order (:474-487); sumCounts via the DFS intervals
+                    for (int i = 0; i < used; i++) {
+                        const int cnode = cand[(i) * 32 + lane];
+                        const int pc = __ldg(db.pre + cnode);
+                        int sum = 0;
+                        for (int j = 0; j < nTab; j++) {
+                            const int e = (int)s_vi[j][t];
+                            if (__ldg(db.pre + e) <= pc && pc <= __ldg(db.last + e)) sum += (int)s_pk[j][t];
+                        }
+                        if (sum > best) { best = sum; cand[(0) * 32 + lane] = cnode; ties = 0; }
+                        else if (sum == best) { ties++; cand[(ties) * 32 + lane] = cnode; }
+                    }
+                    // ---- lowestNodeWhereSumAboveThreshold (:488-492, C/tax/SmallTaxTree.java:208-221)
+                    if (P.threshold > 1) {
+                        for (int i = 0; i <= ties; i++) {
+                            int nd = cand[(i) * 32 + lane], res = 0, outn = -1;
+                            while (nd >= 0) {
+                                int cnt = 0;
+                                for (int j = 0; j < nTab; j++) if ((int)s_vi[j][t] == nd) cnt = (int)s_pk[j][t];
+                                if (cnt > 0) { res += cnt; if (res >= P.threshold) { outn = nd; break; } }
+                                nd = __ldg(db.parent + nd);
+                            }
+                            cand[(i) * 32 + lane] = outn;
+                        }
+                    }
+                    // ---- LCA of the ties (:493-497)
+                    node = cand[(0) * 32 + lane];
+                    for (int i = 1; i <= ties; i++) node = gs_lca(db, node, cand[(i) * 32 + lane]);
+                }
+                classV = node;
+                if (node < 0) {
+                    found = false;  // `return false` (:498-500)
+                } else {
+                    int rk = best;
+                    if (ties > 0 || P.threshold > 1) {  // :506-507
+                        const int c0 = cand[(0) * 32 + lane];
+                        const int pc = __ldg(db.pre + c0);
+                        rk = 0;
+                        for (int j = 0; j < nTab; j++) {
+                            const int e = (int)s_vi[j][t];
+                            if (__ldg(db.pre + e) <= pc && pc <= __ldg(db.last + e)) rk += (int)s_pk[j][t];
+                        }
+                    }
+                    readKmers = (u32)rk;
+                    const int classErrC = max - rk;
+                    const double mce = P.maxClassErr;
+                    if (mce < 0 || (mce >= 1 && (double)classErrC <= mce) || ((double)classErrC <= mce * (double)max)) {  // :509-510
+                        flags |= GS_READ_ACCEPTED;
+                        atomicAdd((u64*)(P.counters + 4 * (size_t)V + node), 1ULL);
+                        atomicAdd((u64*)(P.counters + 5 * (size_t)V + node), (u64)rk);
+                        atomicAdd((u64*)(P.counters + 6 * (size_t)V + node), (u64)L);
+                    }
+                }
+            }
+        }
+        if (found) flags |= GS_READ_FOUND;
+        P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
+    }
+}
+void gs_launch_reduce_thread(const GsMatchParams& P, int blocks, cudaStream_t st) {
+    gs_reduce_thread_kernel<<<blocks, GS_T_THREADS, 0, st>>>(P);
 }
 
 void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st) {

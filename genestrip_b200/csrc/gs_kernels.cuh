@@ -30,6 +30,9 @@ struct GsMatchParams {
     u32* validBits;         // [segments * 31 (+pad)] bit f = base f is one of CGAT
     u32* startBits;         // same size: bit f = a read starts at f
     u32* segCounter;        // next unclaimed segment of the label kernel
+    u32* redoList;          // reads the thread-per-read reduce kernel hands to the warp-per-read kernel (NULL: warp kernel takes all reads)
+    u32* redoCount;
+    u32* groupCounter;      // next unclaimed group of 32 reads of the thread-per-read kernel
     long long* flatPos;     // label dump only: storage position per flat position
     // kraken-style runs (want_runs)
     gs_run* runs; const u64* runOffsets; u64 runsCap; u32* runCounts;
@@ -59,6 +62,7 @@ struct GsFilterParams {
 void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st);
 void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t st);
 void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
+void gs_launch_reduce_thread(const GsMatchParams& P, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
 void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st);
 void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
