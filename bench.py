@@ -477,6 +477,7 @@ def main():
     for i in range(args.warmup):
         device_step(i)
     sess.sync()
+    sess.set_timing(True)   # CUDA events on the compute stream around the label kernel and the reduce kernels of every step
     launches0 = sess.kernel_launches
     sampler = ClockSampler(local)
     sampler.start()
@@ -493,6 +494,8 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     clocks = sampler.result()
     launches = sess.kernel_launches - launches0
+    label_ms, reduce_ms, _nb = sess.kernel_times()
+    sess.set_timing(False)
 
     # ---------------- end of job: merge the per-rank state (only exchange step of the path)
     red_ms = 0.0
@@ -578,28 +581,35 @@ def main():
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bpk = algorithmic_bytes_per_kmer(n_db, h, READ_LEN)
-        traffic = None
-        try:  # DRAM bytes of the match kernel from the committed ncu --set full capture, scaled to this launch's k-mers
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "match_kernel_traffic.json")))
-            if args.workload == "viral" and args.layout == "table":
+        traffic, tj = None, None
+        try:  # DRAM bytes of the label kernel from the committed ncu --set full capture, scaled to this launch's k-mers
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "label_kernel_traffic.json")))
+            if args.workload == "viral" and args.layout == "table" and bool(cfg.prefilter) == bool(tj.get("minimizer_prefilter", True)):
                 traffic = tj["dram_bytes_per_kmer"] * kmers_per_step
         except Exception:
-            pass
-        kernel_ms = float(np.mean(step_ms))
+            tj = None
+        step_ms = float(np.mean(step_ms))
+        # the dominant kernel: gs_label_kernel does everything B_kmer counts (bases, filter words, store search, unique bits);
+        # the reduce kernels only re-read its 4-byte labels and write the 16-byte per-read records
+        kernel_ms = label_ms if label_ms > 0 else step_ms
         achieved = bpk * kmers_per_step / (kernel_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "gs_label_kernel<%s>" % args.layout, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
+                "reduce_kernels_ms": reduce_ms, "step_ms": step_ms, "step_frac": bpk * kmers_per_step / (step_ms / 1e3) / 1e9 / peak,
+                "timing": "CUDA events on the session's compute stream around the kernel, every timed step (gs_match_kernel_times)",
+                "algorithmic_bytes_per_kmer": bpk, "hit_fraction": h, "peak_source": peak_src,
+                "traffic_source": "profiles/r01/label_kernel_traffic.json (ncu --set full: dram__bytes_read+write per k-mer x k-mers per launch)" if traffic else None}
+        if traffic and tj and "dram_lines_per_kmer" in tj:
+            lps = kmers_per_step / (kernel_ms / 1e3) * tj["dram_lines_per_kmer"]
+            roof["request_roofline"] = {"measured_cap_lines_per_s": 39.4e9, "dram_lines_per_kmer": tj["dram_lines_per_kmer"], "lines_per_s": lps, "frac": lps / 39.4e9,
+                                        "source": "profiles/microbench/randgroup.txt: divergent loads are capped at ~39.4 G distinct 128-byte lines/s"}
         line = {"metric": "match k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
                 "data": "synthetic", "reads_per_s": value / (READ_LEN - K + 1), "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R * 16 + 4 + V * 16,
                         "reads_per_s": e2e_value / (READ_LEN - K + 1)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "gs_match_kernel<0,false>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk,
-                             "hit_fraction": h, "peak_source": peak_src,
-                             "traffic_source": "profiles/r01/match_kernel_traffic.json (ncu dram__bytes_read+write per k-mer x k-mers per launch)",
-                             "request_roofline": {"measured_cap_requests_per_s": 39.4e9, "requests_per_kmer": 1.105,
-                                                  "frac": (kmers_per_step / (kernel_ms / 1e3)) * 1.105 / 39.4e9,
-                                                  "source": "profiles/microbench/randwide.txt: fully divergent loads of 8/16/32 B per lane"}},
+                "roofline": roof,
                 "end_of_job_reduce_ms": red_ms, "hits_total": total_hits, "unique_kmers_total": unique_total}
 
     # ---------------- CPU baseline + bench-scale parity spot check (rank 0, N = 1 only)

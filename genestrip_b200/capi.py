@@ -76,6 +76,8 @@ _SIGS = {
     "gs_match_unique_popcount": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "gs_match_stream": (_P, [_P]),
     "gs_match_kernel_launches": (C.c_uint64, [_P]),
+    "gs_match_set_timing": (C.c_int, [_P, C.c_int]),
+    "gs_match_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gs_match_dump_labels": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, _P]),
     "gs_filter_create": (_P, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_uint64]),
     "gs_filter_destroy": (None, [_P]),
@@ -350,6 +352,15 @@ class MatchSession:
     @property
     def kernel_launches(self):
         return lib().gs_match_kernel_launches(self.h)
+
+    def set_timing(self, on=True):
+        _check(lib().gs_match_set_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """(label_ms, reduce_ms, n_batches): average CUDA-event durations per batch since set_timing(True)."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        _check(lib().gs_match_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def close(self):
         if self.h:

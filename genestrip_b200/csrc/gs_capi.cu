@@ -355,6 +355,16 @@ extern "C" int gs_db_finalize(gs_db* db) {
     CU(dmalloc(&d0.bstart, db->nBuckets + 1));
     gs_launch_bucket_index(d0.keys, db->n, db->bshift, db->nBuckets, d0.bstart, 0);
     CU(cudaGetLastError());
+    // minimizer prefilter: ~0.22 distinct minimizers per stored k-mer (window of 9), one bit each, fill <= ~12 %
+    if (db->k >= GS_MZ_MIN_K && db->n > 0) {
+        int fb = 16;
+        while (fb < 32 && (double)(1ULL << fb) < 1.8 * (double)db->n) fb++;
+        db->mzBits = fb;
+        CU(dmalloc(&d0.mzFilter, (size_t)(1ULL << (fb - 6))));
+        CU(cudaMemset(d0.mzFilter, 0, (size_t)(1ULL << (fb - 3))));
+        gs_launch_mz_build(d0.keys, db->n, db->k, d0.mzFilter, (u32)((1ULL << fb) - 1), 0);
+        CU(cudaGetLastError());
+    }
     // probe table: 1..2 keys per 4-slot bucket
     {
         int tb = GS_TAB_MIN_BITS;
@@ -370,16 +380,6 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
         CU(cudaFree(counts));
-    }
-    // minimizer prefilter: ~0.22 distinct minimizers per stored k-mer (window of 9), one bit each, fill <= ~12 %
-    if (db->k >= GS_MZ_MIN_K && db->n > 0) {
-        int fb = 16;
-        while (fb < 32 && (double)(1ULL << fb) < 1.8 * (double)db->n) fb++;
-        db->mzBits = fb;
-        CU(dmalloc(&d0.mzFilter, (size_t)(1ULL << (fb - 6))));
-        CU(cudaMemset(d0.mzFilter, 0, (size_t)(1ULL << (fb - 3))));
-        gs_launch_mz_build(d0.keys, db->n, db->k, d0.mzFilter, (u32)((1ULL << fb) - 1), 0);
-        CU(cudaGetLastError());
     }
     // tree
     CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));
@@ -497,6 +497,7 @@ struct DevSess {
     u32* validBits = nullptr; size_t validCap = 0;
     u32* startBits = nullptr; size_t startCap = 0;
     u32* redoList = nullptr; size_t redoCap = 0;
+    std::vector<cudaEvent_t> timingEv;  // gs_match_set_timing: 3 events per batch (before label, after label, after reduce)
     MatchSlot slots[GS_MAX_INFLIGHT];
 };
 
@@ -507,6 +508,7 @@ struct gs_sess {
     u64 nextTicket = 1;
     u64 launches = 0;
     bool finished = false;
+    bool timing = false;
     int layout = GS_LAYOUT_TABLE;
     bool inlineSeen = false;  // unique k-mer bits are kept in the probe-table lines (leased from the database)
     u64 nPos = 0;  // "storage positions" addressed by the unique-k-mer bitset: table slot ids or sorted-array indices
@@ -592,6 +594,8 @@ extern "C" void gs_match_close(gs_sess* s) {
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
         cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList);
+        for (cudaEvent_t e : D.timingEv) cudaEventDestroy(e);
+        D.timingEv.clear();
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
         if (D.sCompute) cudaStreamDestroy(D.sCompute);
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
@@ -677,8 +681,14 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     gs_launch_mark_starts(P, D.sCompute);
     CU(cudaGetLastError());
     const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)D.labelBlocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+    if (s->timing) {
+        for (int i = 0; i < 3; i++) { CU(cudaEventCreate(&tev[i])); D.timingEv.push_back(tev[i]); }
+        CU(cudaEventRecord(tev[0], D.sCompute));
+    }
     gs_launch_label(P, false, labelBlocks, D.sCompute);
     CU(cudaGetLastError());
+    if (s->timing) CU(cudaEventRecord(tev[1], D.sCompute));
     // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
     const bool threadPath = !s->cfg.want_runs && nBytes / P.nReads <= 512;
     if (threadPath) {
@@ -696,6 +706,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     CU(cudaGetLastError());
     gs_launch_reduce(P, 1, false, D.slowBlocks, D.sCompute);
     CU(cudaGetLastError());
+    if (s->timing) CU(cudaEventRecord(tev[2], D.sCompute));
     s->launches += 4;
     if (dEv) {
         gs_launch_maxcontig_events(D.maxcontig, s->db->V, P.firstReadNo, P.nReads, dEv, dNEv, D.sCompute);
@@ -896,6 +907,35 @@ extern "C" int gs_match_unique_popcount(gs_sess* s, const uint64_t* d_bitset, ui
 
 extern "C" void* gs_match_stream(gs_sess* s) { return s ? (void*)s->devs[0].sCompute : nullptr; }
 extern "C" uint64_t gs_match_kernel_launches(const gs_sess* s) { return s ? s->launches : 0; }
+
+static void timing_clear(DevSess& D) {
+    for (cudaEvent_t e : D.timingEv) cudaEventDestroy(e);
+    D.timingEv.clear();
+}
+extern "C" int gs_match_set_timing(gs_sess* s, int on) {
+    if (!s) return gs_fail(GS_ERR_ARG, "null session");
+    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); CU(cudaStreamSynchronize(D.sCompute)); timing_clear(D); }
+    s->timing = on != 0;
+    return GS_OK;
+}
+extern "C" int gs_match_kernel_times(gs_sess* s, double* label_ms, double* reduce_ms, uint64_t* n_batches) {
+    if (!s) return gs_fail(GS_ERR_ARG, "null session");
+    double lab = 0, red = 0; u64 n = 0;
+    for (DevSess& D : s->devs) {
+        CU(cudaSetDevice(D.dev));
+        CU(cudaStreamSynchronize(D.sCompute));
+        for (size_t i = 0; i + 2 < D.timingEv.size(); i += 3) {
+            float a = 0, b = 0;
+            CU(cudaEventElapsedTime(&a, D.timingEv[i], D.timingEv[i + 1]));
+            CU(cudaEventElapsedTime(&b, D.timingEv[i + 1], D.timingEv[i + 2]));
+            lab += a; red += b; n++;
+        }
+    }
+    if (label_ms) *label_ms = n ? lab / (double)n : 0.0;
+    if (reduce_ms) *reduce_ms = n ? red / (double)n : 0.0;
+    if (n_batches) *n_batches = n;
+    return GS_OK;
+}
 
 extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                                     const uint64_t* d_kmer_offsets, int32_t* d_labels, int64_t* d_pos) {

@@ -186,6 +186,11 @@ int gs_match_unique_popcount(gs_sess*, const uint64_t* d_bitset, uint64_t word_b
 /* CUDA stream (cudaStream_t) the device-resident calls are issued on; kernels launched since open. */
 void* gs_match_stream(gs_sess*);
 uint64_t gs_match_kernel_launches(const gs_sess*);
+/* Measurement: with timing on, every batch records CUDA events on the compute stream around the label kernel (encode ->
+ * prefilter -> store lookup -> unique bits) and around the reduce kernels (per-taxon counting, classification);
+ * gs_match_kernel_times waits for the stream and returns the average duration per batch since timing was switched on. */
+int gs_match_set_timing(gs_sess*, int on);
+int gs_match_kernel_times(gs_sess*, double* label_ms, double* reduce_ms, uint64_t* n_batches);
 /* Debug/parity: per-position labels of a device-resident batch: labels[i] = value index, -1 miss, -2 invalid;
  * pos[i] = storage position or -1; kmer_offsets[n_reads+1] = prefix sums of max(0, L-k+1). All device pointers. */
 int gs_match_dump_labels(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,

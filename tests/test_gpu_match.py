@@ -380,3 +380,30 @@ def test_two_sessions_share_one_database(project, reads, oracle, native):
     util.assert_match_parity(native, orun, rb, cb)
     res, _, counts, _, _, _ = util.gpu_match(native, gdb, bases, off)   # new lease: bits were cleared
     util.assert_match_parity(native, orun, res, counts)
+
+
+@pytest.mark.parametrize("k", [31, 24, 21], ids=["k31", "k24-smallest-with-minimizer-prefilter", "k21-no-prefilter"])
+def test_match_parity_other_k(oracle, native, gpu_ctx, k):
+    """Lookups, per-taxon counts, unique k-mers and hit counters for other k-mer sizes: the minimizer prefilter needs
+    k >= 24 (GS_MZ_MIN_K), below that every k-mer probes the table (KMerSortedArray.getLong :298-349,
+    KMerUniqueCounterBits :117-199)."""
+    nodes, names, genomes = util.small_project(genome_len=12000, seed=23)
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, k, nodes, names, genomes)
+    try:
+        keys, _ = odb.export()
+        rng = np.random.default_rng(3)
+        q = np.concatenate([keys, rng.integers(0, 1 << (2 * k), size=4000, dtype=np.int64)])
+        v, p = gdb.lookup(q, use_bloom=False)
+        exp = [odb.get(int(x)) for x in q[::7]]
+        np.testing.assert_array_equal(v[::7], np.array([e[0] for e in exp], dtype=np.int32))
+        assert (p[:len(keys)] == np.arange(len(keys))).all()
+        bases, offsets, src = synth.sample_reads([g for _, g in genomes], 3000, 150, seed=77, frac_db=0.8, sub_rate=0.01, n_rate=0.002)
+        fq = synth.fastq_bytes(bases, offsets, src)
+        for cfg in (dict(), dict(max_kmer_res_counts=4), dict(prefilter=0)):
+            ocfg = {kk: vv for kk, vv in cfg.items() if kk != "prefilter"}
+            orun = odb.match_files(util.oracle_cfg(oracle, k, **ocfg), [fq])
+            res, ev, counts, top, _, _ = util.gpu_match(native, gdb, bases, offsets, batch=1100, **cfg)
+            util.assert_match_parity(native, orun, res, counts, top)
+    finally:
+        gdb.close()
+        odb.free()
