@@ -32,6 +32,12 @@ class MatchCfg(C.Structure):
                 ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int)]
 
 
+class FastqInfo(C.Structure):
+    """gs_fastq_info"""
+    _fields_ = [("n_reads", C.c_uint32), ("status", C.c_uint32), ("total_kmers", C.c_uint64), ("total_bps", C.c_uint64)]
+
+
+FASTQ_REC_DTYPE = np.dtype([("hdr_start", "<u4"), ("seq_start", "<u4"), ("seq_len", "<u4"), ("qual_start", "<u4")])
 READ_RESULT_DTYPE = np.dtype([("class_vidx", "<i4"), ("read_kmers", "<u4"), ("tax_err", "<u4"), ("flags", "<u4")])
 RUN_DTYPE = np.dtype([("label", "<u4"), ("len", "<u4")])
 EVENT_DTYPE = np.dtype([("vidx", "<u4"), ("contig_len", "<u4"), ("read_no", "<u8")])
@@ -68,6 +74,8 @@ _SIGS = {
     "gs_match_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
     "gs_match_collect": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, _P, C.c_uint64]),
     "gs_match_collect_view": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(C.c_uint32)]),
+    "gs_match_submit_fastq": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(FastqInfo), C.POINTER(C.c_uint64)]),
+    "gs_match_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     "gs_match_finish": (C.c_int, [_P, _P, _P]),
     "gs_match_close": (None, [_P]),
     "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
@@ -316,6 +324,28 @@ class MatchSession:
         res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value * 16,)).view(READ_RESULT_DTYPE) if n.value else np.zeros(0, READ_RESULT_DTYPE)
         evs = np.ctypeslib.as_array(C.cast(ev, C.POINTER(C.c_uint8)), shape=(nev.value * 16,)).view(EVENT_DTYPE) if nev.value else np.zeros(0, EVENT_DTYPE)
         return res, evs
+
+    def submit_fastq(self, text, first_read_no=0, n_bytes=None):
+        """Raw FASTQ text (whole records, '\\n'-terminated).  Returns (ticket, FastqInfo); ticket == 0 means the chunk is not
+        strict 4-line FASTQ (info.status holds the GS_FASTQ_* bits) and must be parsed on the CPU."""
+        text = _arr(text, np.uint8)
+        n = len(text) if n_bytes is None else int(n_bytes)
+        info = FastqInfo()
+        t = C.c_uint64(0)
+        _check(lib().gs_match_submit_fastq(self.h, _ptr(text), n, int(first_read_no), C.byref(info), C.byref(t)))
+        if t.value:
+            self._keep[t.value] = (text, None, info.n_reads)
+        return t.value, info
+
+    def collect_fastq(self, ticket):
+        """(results, events, event header offsets, records[n + 1]) as numpy views of the session's pinned staging."""
+        self._keep.pop(ticket)
+        out, ev, eh, rc = _P(), _P(), _P(), _P()
+        n, nev = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().gs_match_collect_fastq(self.h, ticket, C.byref(out), C.byref(n), C.byref(ev), C.byref(eh), C.byref(nev), C.byref(rc)))
+        view = lambda p, cnt, size, dt: (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(cnt * size,)).view(dt) if cnt else np.zeros(0, dt))
+        return (view(out, n.value, 16, READ_RESULT_DTYPE), view(ev, nev.value, 16, EVENT_DTYPE), view(eh, nev.value, 4, np.dtype("<u4")),
+                view(rc, n.value + 1, 16, FASTQ_REC_DTYPE))
 
     def finish(self):
         V = self.db.n_values

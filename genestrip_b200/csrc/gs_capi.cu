@@ -477,6 +477,18 @@ struct MatchSlot {
     gs_run* dRuns = nullptr; size_t runsCap = 0;
     u32* dRunCounts = nullptr; size_t runCountsCap = 0;
     u32* hRunCounts = nullptr; size_t hRunCountsCap = 0;
+    // raw FASTQ text batches (gs_match_submit_fastq)
+    uint8_t* dText = nullptr; size_t textCap = 0;
+    u32* dLineEnd = nullptr; size_t lineCap = 0;
+    u32* dBlockCounts = nullptr; size_t blockCountsCap = 0;
+    u32* dTextMeta = nullptr;              // [0] lines, [1] records, [2] status bits, [3] pad, then u64 totals[2] (k-mers, bases)
+    u32* hTextMeta = nullptr;              // pinned copy
+    gs_fastq_rec* dRecs = nullptr; size_t recsCap = 0;
+    gs_fastq_rec* hRecs = nullptr; size_t hRecsCap = 0;
+    u32* dLens = nullptr; size_t lensCap = 0;
+    u64* dTileSums = nullptr; size_t tileSumsCap = 0;
+    u32* dEvHdr = nullptr; u32* hEvHdr = nullptr;
+    bool isText = false;
     cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
 };
 
@@ -587,6 +599,11 @@ extern "C" void gs_match_close(gs_sess* s) {
             if (sl.hNEv) cudaFreeHost(sl.hNEv);
             if (sl.hKmerOff) cudaFreeHost(sl.hKmerOff);
             if (sl.hRunCounts) cudaFreeHost(sl.hRunCounts);
+            cudaFree(sl.dText); cudaFree(sl.dLineEnd); cudaFree(sl.dBlockCounts); cudaFree(sl.dTextMeta); cudaFree(sl.dRecs);
+            cudaFree(sl.dLens); cudaFree(sl.dTileSums); cudaFree(sl.dEvHdr);
+            if (sl.hTextMeta) cudaFreeHost(sl.hTextMeta);
+            if (sl.hRecs) cudaFreeHost(sl.hRecs);
+            if (sl.hEvHdr) cudaFreeHost(sl.hEvHdr);
             if (sl.evH2D) cudaEventDestroy(sl.evH2D);
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
@@ -780,7 +797,87 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     CU(cudaMemcpyAsync(sl.hEv, sl.dEv, std::max<size_t>(s->db->V, 1) * sizeof(gs_maxcontig_event), cudaMemcpyDeviceToHost, D.sCopyOut));
     if (s->cfg.want_runs && n_reads) CU(cudaMemcpyAsync(sl.hRunCounts, sl.dRunCounts, (size_t)n_reads * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaEventRecord(sl.evDone, D.sCopyOut));
-    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.firstReadNo = first_read_no; sl.totalKmers = totalKmers;
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.firstReadNo = first_read_no; sl.totalKmers = totalKmers; sl.isText = false;
+    s->nextTicket++;
+    *ticket = t;
+    return GS_OK;
+}
+
+// Raw FASTQ text: the chunk goes to the device as it is; the record splitter (gs_text.cu) runs on the copy-in stream right
+// behind the copy, so it overlaps the match kernels of the previous batch; the host waits only for the splitter's verdict
+// (number of reads, strict-format flags), then the bases are compacted and the usual kernels follow on the compute stream.
+extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n_bytes, uint64_t first_read_no, gs_fastq_info* info,
+                                     gs_ticket* ticket) {
+    if (!s || s->finished) return gs_fail(GS_ERR_STATE, "session missing or finished");
+    if (!ticket || !info || (!text && n_bytes)) return gs_fail(GS_ERR_ARG, "null argument");
+    if (s->cfg.want_runs) return gs_fail(GS_ERR_ARG, "want_runs needs host-parsed batches (gs_match_submit)");
+    if (n_bytes >= 0xFFFFFF00ULL) return gs_fail(GS_ERR_LIMIT, "text chunk of %llu bytes (limit 2^32 - 256)", (unsigned long long)n_bytes);
+    memset(info, 0, sizeof(*info));
+    *ticket = 0;
+    const gs_ticket t = s->nextTicket;
+    const size_t nDev = s->devs.size();
+    DevSess& D = s->devs[(t - 1) % nDev];
+    MatchSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
+    const int V = s->db->V;
+    CU(cudaSetDevice(D.dev));
+    const size_t lineCap = (size_t)(n_bytes / 16 + 64);
+    const size_t nBlocks = (size_t)((n_bytes + GS_TEXT_SEG - 1) / GS_TEXT_SEG);
+    CU(dgrow(&sl.dText, &sl.textCap, (size_t)n_bytes + 64));
+    CU(dgrow(&sl.dLineEnd, &sl.lineCap, lineCap));
+    CU(dgrow(&sl.dBlockCounts, &sl.blockCountsCap, nBlocks + 1));
+    CU(dgrow(&sl.dRecs, &sl.recsCap, lineCap / 4 + 2));
+    CU(dgrow(&sl.dLens, &sl.lensCap, lineCap / 4 + 2));
+    if (!sl.dTextMeta) { CU(dmalloc(&sl.dTextMeta, 8)); CU(cudaMallocHost((void**)&sl.hTextMeta, 8 * sizeof(u32))); }
+    if (!sl.dEvHdr) { CU(dmalloc(&sl.dEvHdr, (size_t)std::max(V, 1))); CU(cudaMallocHost((void**)&sl.hEvHdr, (size_t)std::max(V, 1) * sizeof(u32))); }
+    CU(cudaMemsetAsync(sl.dTextMeta, 0, 8 * sizeof(u32), D.sCopyIn));
+    if (n_bytes) CU(cudaMemcpyAsync(sl.dText, text, n_bytes, cudaMemcpyHostToDevice, D.sCopyIn));
+    CU(cudaMemsetAsync(sl.dText + n_bytes, 0, 64, D.sCopyIn));
+    gs_launch_text_split(sl.dText, n_bytes, sl.dBlockCounts, sl.dLineEnd, (u32)std::min<size_t>(lineCap, 0xFFFFFFFFu), sl.dTextMeta, sl.dRecs, sl.dLens,
+                         s->db->k, (unsigned long long*)(sl.dTextMeta + 4), D.sCopyIn);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sl.hTextMeta, sl.dTextMeta, 8 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyIn));
+    CU(cudaStreamSynchronize(D.sCopyIn));
+    s->launches += n_bytes ? 4 : 0;
+    info->status = sl.hTextMeta[2];
+    if (info->status) return GS_OK;   // not strict 4-line FASTQ: the caller parses this chunk on the CPU (nothing is pending)
+    const u32 n_reads = sl.hTextMeta[1];
+    info->n_reads = n_reads;
+    memcpy(&info->total_kmers, sl.hTextMeta + 4, sizeof(u64));
+    memcpy(&info->total_bps, sl.hTextMeta + 6, sizeof(u64));
+    if (first_read_no + n_reads > GS_ORDINAL_MASK) return gs_fail(GS_ERR_LIMIT, "read ordinal exceeds 2^40");
+    const u64 nBytes = info->total_bps;
+    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
+    CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
+    CU(dgrow(&sl.dOut, &sl.outCap, (size_t)n_reads));
+    CU(hgrow(&sl.hOut, &sl.hOutCap, (size_t)n_reads));
+    CU(hgrow(&sl.hRecs, &sl.hRecsCap, (size_t)n_reads + 1));
+    CU(dgrow(&sl.dTileSums, &sl.tileSumsCap, (size_t)n_reads / 1024 + 2));
+    if (n_reads == 0) CU(cudaMemsetAsync(sl.dOffsets, 0, sizeof(u64), D.sCopyIn));
+    gs_launch_text_compact(sl.dText, sl.dRecs, sl.dLens, n_reads, sl.dTileSums, sl.dOffsets, sl.dBases, D.sCopyIn);
+    CU(cudaGetLastError());
+    s->launches += n_reads ? 4 : 0;
+    GsMatchParams P;
+    fill_params(s, D, P);
+    CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
+    CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
+    // the record table goes back while the match kernels run
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evH2D, 0));
+    CU(cudaMemcpyAsync(sl.hRecs, sl.dRecs, ((size_t)n_reads + 1) * sizeof(gs_fastq_rec), cudaMemcpyDeviceToHost, D.sCopyOut));
+    P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
+    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, 0, nBytes);
+    if (rc) return rc;
+    gs_launch_text_event_headers(sl.dEv, sl.dNEv, (u32)std::max(V, 1), sl.dRecs, first_read_no, n_reads, sl.dEvHdr, D.sCompute);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    CU(cudaEventRecord(sl.evCompute, D.sCompute));
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
+    if (n_reads) CU(cudaMemcpyAsync(sl.hOut, sl.dOut, (size_t)n_reads * sizeof(gs_read_result), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, 2 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hEv, sl.dEv, std::max<size_t>(V, 1) * sizeof(gs_maxcontig_event), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hEvHdr, sl.dEvHdr, std::max<size_t>(V, 1) * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaEventRecord(sl.evDone, D.sCopyOut));
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.firstReadNo = first_read_no; sl.totalKmers = info->total_kmers; sl.isText = true;
     s->nextTicket++;
     *ticket = t;
     return GS_OK;
@@ -810,6 +907,21 @@ extern "C" int gs_match_collect_view(gs_sess* s, gs_ticket t, const gs_read_resu
     if (n_reads) *n_reads = sl->nReads;
     if (events) *events = sl->hEv;
     if (n_events) *n_events = sl->hNEv[0];
+    return GS_OK;
+}
+
+extern "C" int gs_match_collect_fastq(gs_sess* s, gs_ticket t, const gs_read_result** out, uint32_t* n_reads, const gs_maxcontig_event** events,
+                                      const uint32_t** event_hdr_start, uint32_t* n_events, const gs_fastq_rec** recs) {
+    DevSess* D; MatchSlot* sl;
+    int rc = wait_ticket(s, t, &D, &sl);
+    if (rc) return rc;
+    if (!sl->isText) return gs_fail(GS_ERR_STATE, "ticket %llu was not submitted as FASTQ text", (unsigned long long)t);
+    if (out) *out = sl->hOut;
+    if (n_reads) *n_reads = sl->nReads;
+    if (events) *events = sl->hEv;
+    if (event_hdr_start) *event_hdr_start = sl->hEvHdr;
+    if (n_events) *n_events = sl->hNEv[0];
+    if (recs) *recs = sl->hRecs;
     return GS_OK;
 }
 
@@ -1163,6 +1275,18 @@ struct FilterSlot {
     uint8_t* dAccept = nullptr; size_t accCap = 0;
     uint8_t* hAccept = nullptr; size_t hAccCap = 0;
     u32* dErr = nullptr; u32* hErr = nullptr;
+    // raw FASTQ text batches (gs_match_submit_fastq)
+    uint8_t* dText = nullptr; size_t textCap = 0;
+    u32* dLineEnd = nullptr; size_t lineCap = 0;
+    u32* dBlockCounts = nullptr; size_t blockCountsCap = 0;
+    u32* dTextMeta = nullptr;              // [0] lines, [1] records, [2] status bits, [3] pad, then u64 totals[2] (k-mers, bases)
+    u32* hTextMeta = nullptr;              // pinned copy
+    gs_fastq_rec* dRecs = nullptr; size_t recsCap = 0;
+    gs_fastq_rec* hRecs = nullptr; size_t hRecsCap = 0;
+    u32* dLens = nullptr; size_t lensCap = 0;
+    u64* dTileSums = nullptr; size_t tileSumsCap = 0;
+    u32* dEvHdr = nullptr; u32* hEvHdr = nullptr;
+    bool isText = false;
     cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
 };
 struct DevFsess {

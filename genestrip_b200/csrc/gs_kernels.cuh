@@ -80,3 +80,10 @@ void gs_launch_lookup(const GsDbView& db, const u64* kmers, u64 n, int useBloom,
 void gs_launch_filter_contains(const GsFilterView& f, const u64* kmers, u64 n, uint8_t* out, cudaStream_t st);
 void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st);
 int gs_match_kernel_occupancy(int mode);
+
+// gs_text.cu: FASTQ record splitting and base compaction on the device
+#define GS_TEXT_SEG 16384          // bytes per block segment
+void gs_launch_text_split(const uint8_t* text, u64 n, u32* blockCounts, u32* lineEnd, u32 lineCap, u32* meta, gs_fastq_rec* recs, u32* lens,
+                          int k, unsigned long long* totals, cudaStream_t st);
+void gs_launch_text_compact(const uint8_t* text, const gs_fastq_rec* recs, const u32* lens, u32 n, u64* tileSums, u64* offsets, uint8_t* bases, cudaStream_t st);
+void gs_launch_text_event_headers(const gs_maxcontig_event* ev, const u32* nEv, u32 evCap, const gs_fastq_rec* recs, u64 firstReadNo, u32 n, u32* hdr, cudaStream_t st);

@@ -152,6 +152,37 @@ gs_sess* gs_match_open(gs_db*, const gs_match_cfg*);
 #define GS_MAX_INFLIGHT 3
 int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                     uint64_t first_read_no, gs_ticket* ticket);
+/* ---- raw FASTQ text (the parallel feeder: record splitting on the GPU instead of AbstractFastqReader's single producer
+ * thread, C/fastq/AbstractFastqReader.java:288-368 + B/io/BufferedLineReader.java:114-182).
+ * text = n_bytes of FASTQ that consist of WHOLE records (the host cuts its input at a record boundary) and end with '\n'.
+ * The device finds the line ends, takes lines 4i .. 4i+3 as record i and checks that the chunk is strict 4-line FASTQ
+ * under the reference parser's rules (no NUL byte, third line starts with '+', quality at least as long as the sequence,
+ * line count a multiple of 4).  If it is not, info->status holds GS_FASTQ_* bits, *ticket is 0, nothing is pending, and the
+ * caller parses this chunk with the sequential parser (gs_match_submit) -- results never depend on the fast path.
+ * Otherwise the batch runs exactly like gs_match_submit of the same reads.  n_bytes < 2^32 - 256; not with want_runs. */
+typedef struct gs_fastq_info {
+    uint32_t n_reads;
+    uint32_t status;       /* 0 = strict 4-line FASTQ, batch submitted */
+    uint64_t total_kmers;  /* sum of max(0, L - k + 1): AbstractFastqReader.kMers (:346-349) */
+    uint64_t total_bps;    /* sum of L: AbstractFastqReader.readBPs */
+} gs_fastq_info;
+#define GS_FASTQ_NUL 1u      /* a NUL byte (the reference drops them, BufferedLineReader.java:166-169) */
+#define GS_FASTQ_LINES 2u    /* number of lines not a multiple of 4 */
+#define GS_FASTQ_CAP 4u      /* lines shorter than 16 bytes on average */
+#define GS_FASTQ_RECORD 8u   /* multi-line sequence / '+' line missing / quality shorter than the sequence */
+#define GS_FASTQ_TAIL 16u    /* last line without '\n' */
+/* Where record i sits in the text chunk: the header line starts at hdr_start (incl. '@'), the sequence at seq_start with
+ * seq_len bytes, the quality line at qual_start and ends right before recs[i + 1].hdr_start - 1 (its '\n'). */
+typedef struct gs_fastq_rec {
+    uint32_t hdr_start, seq_start, seq_len, qual_start;
+} gs_fastq_rec;
+int gs_match_submit_fastq(gs_sess*, const uint8_t* text, uint64_t n_bytes, uint64_t first_read_no, gs_fastq_info* info,
+                          gs_ticket* ticket);
+/* Zero-copy views (valid like gs_match_collect_view's): out[n_reads], recs[n_reads + 1] (the last entry marks the end of
+ * the text), events[n_events] with event_hdr_start[e] = header offset of the read that caused event e. */
+int gs_match_collect_fastq(gs_sess*, gs_ticket, const gs_read_result** out, uint32_t* n_reads,
+                           const gs_maxcontig_event** events, const uint32_t** event_hdr_start, uint32_t* n_events,
+                           const gs_fastq_rec** recs);
 /* Wait for a ticket.  out[n_reads]; events[ev_cap] / n_events may be NULL.  If want_runs: run_offsets
  * [n_reads+1] and runs[runs_cap] receive the contig runs (GS_ERR_LIMIT if runs_cap is too small). */
 int gs_match_collect(gs_sess*, gs_ticket, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,
