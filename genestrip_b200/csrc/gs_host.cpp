@@ -111,7 +111,15 @@ class LineReader {
             cur_ = end_ = buf_.data();
         }
     }
-    ~LineReader() { if (gz_) gzclose(gz_); }
+    // continue an open stream whose first bytes were already consumed into memory (GPU feeder falling back to this parser)
+    LineReader(gzFile gz, const uint8_t* prefix, size_t prefixLen) {
+        gz_ = gz; ownGz_ = false;
+        buf_.resize(std::max<size_t>(8 << 20, prefixLen * 2));
+        if (prefixLen) memcpy(buf_.data(), prefix, prefixLen);
+        cur_ = buf_.data(); end_ = cur_ + prefixLen;
+        if (!gz_) { memory_ = true; }
+    }
+    ~LineReader() { if (gz_ && ownGz_) gzclose(gz_); }
     // line = content without the '\n'; returns the count as defined above
     size_t next(const uint8_t*& line, size_t& len) {
         for (;;) {
@@ -145,7 +153,7 @@ class LineReader {
         cur_ = base; end_ = base + keep + (size_t)got;
     }
     const uint8_t *cur_ = nullptr, *end_ = nullptr;
-    bool memory_ = false, eof_ = false;
+    bool memory_ = false, eof_ = false, ownGz_ = true;
     gzFile gz_ = nullptr;
     std::vector<uint8_t> buf_, scratch_;
 };
@@ -167,6 +175,11 @@ class FastqReader {
         reads = kMers = readBPs = 0;
         LineReader lr(in);
         if (in.fasta) doReadFasta(lr, nextEntry); else doReadFastq(lr, nextEntry);
+    }
+    template <typename F>
+    void readFastqFrom(LineReader& lr, F&& nextEntry) {
+        reads = kMers = readBPs = 0;
+        doReadFastq(lr, nextEntry);
     }
 
    private:
@@ -272,7 +285,17 @@ struct HostBatch {
     std::vector<uint64_t> descOff, probsOff;             // [n+1] / [n+1] offsets into meta
     std::vector<uint8_t> hasProbs, entry;
     gs_ticket ticket = 0;
-    ~HostBatch() { gs_free_pinned(bases); gs_free_pinned(offsets); }
+    // raw FASTQ text batches (gs_match_submit_fastq)
+    bool isText = false;
+    uint8_t* text = nullptr; size_t textCap = 0, textLen = 0;  // pinned
+    void ensureText(size_t bytes) {
+        if (bytes <= textCap) return;
+        uint8_t* nt = (uint8_t*)gs_alloc_pinned(bytes);
+        if (!nt) fail(std::string("pinned allocation failed: ") + gs_last_error());
+        if (text) { memcpy(nt, text, textLen); gs_free_pinned(text); }
+        text = nt; textCap = bytes;
+    }
+    ~HostBatch() { gs_free_pinned(bases); gs_free_pinned(offsets); gs_free_pinned(text); }
     void ensure(size_t bytes, size_t reads) {
         if (bytes + 64 > basesCap) {
             const size_t ncap = std::max(bytes + 64, basesCap * 2);
@@ -292,7 +315,7 @@ struct HostBatch {
     }
     size_t used() const { return offsets ? (size_t)offsets[n] : 0; }
     void reset(uint64_t ordinal) {
-        n = 0; firstOrdinal = ordinal; totalKmers = 0; meta.clear(); descOff.assign(1, 0); probsOff.assign(1, 0); hasProbs.clear(); entry.clear();
+        n = 0; firstOrdinal = ordinal; totalKmers = 0; isText = false; textLen = 0; meta.clear(); descOff.assign(1, 0); probsOff.assign(1, 0); hasProbs.clear(); entry.clear();
         if (offsets) offsets[0] = 0;
     }
     void add(const Record& r, int k, bool keepProbs) {
@@ -410,6 +433,66 @@ void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, 
     }
 }
 
+// A batch that went to the device as raw FASTQ text: descriptors, bases and qualities are read from the (pinned) text through
+// the record table the device returns; same bookkeeping as processBatch.
+void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filtered, std::vector<CountsPerTaxid>& stats, std::vector<uint64_t>& bestKey) {
+    const gs_read_result* res = nullptr; const gs_maxcontig_event* ev = nullptr; const uint32_t* evHdr = nullptr; const gs_fastq_rec* recs = nullptr;
+    uint32_t n = 0, nEv = 0;
+    check(gs_match_collect_fastq(s, b.ticket, &res, &n, &ev, &evHdr, &nEv, &recs), "gs_match_collect_fastq");
+    for (uint32_t e = 0; e < nEv; e++) {  // maxContigDescriptor (FastqKMerMatcher.java:402-409)
+        const gs_maxcontig_event& x = ev[e];
+        const uint64_t key = ((uint64_t)x.contig_len << 40) | ((((uint64_t)1 << 40) - 1) - x.read_no);
+        if (key <= bestKey[x.vidx]) continue;
+        bestKey[x.vidx] = key;
+        const gs_fastq_rec& rc = recs[(size_t)(x.read_no - b.firstOrdinal)];
+        const uint8_t* d = b.text + rc.hdr_start;
+        const size_t dl = (size_t)(rc.seq_start - 1 - rc.hdr_start);
+        std::string& dst = stats[x.vidx].maxContigDescriptor;
+        dst.clear();
+        for (size_t j = 1; j < dl && j < (size_t)cfg_.initialReadSizeBytes && d[j] != ' '; j++) dst.push_back((char)d[j]);
+    }
+    std::string scratch;
+    const int k = meta_.k;
+    for (uint32_t i = 0; i < n; i++) {
+        const gs_read_result& r = res[i];
+        const gs_fastq_rec& rc = recs[i];
+        const int64_t L = (int64_t)rc.seq_len;
+        const int64_t max = L - k + 1;
+        if ((r.flags & GS_READ_FOUND) && filtered)  // afterMatch (:304-315)
+            writeRead(*filtered, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), b.text + rc.seq_start, (size_t)L,
+                      b.text + rc.qual_start, (size_t)(recs[i + 1].hdr_start - 1 - rc.qual_start), cfg_.withProbs, scratch);
+        if (r.flags & GS_READ_ACCEPTED) {  // the four double sums in read order (:511-526)
+            CountsPerTaxid& st = stats[(size_t)r.class_vidx];
+            const double err = ((double)(int32_t)r.tax_err) / (double)max;
+            const double classErr = ((double)(int32_t)(max - (int64_t)r.read_kmers)) / (double)max;
+            st.errorSum += err;
+            st.errorSquaredSum += err * err;
+            st.classErrorSum += classErr;
+            st.classErrorSquaredSum += classErr * classErr;
+        }
+    }
+}
+
+// Last byte offset in text[0, len) at which a record starts such that everything before it consists of whole records: a
+// line that starts with '@' whose second-next line starts with '+' (a quality line may start with '@', but then the line
+// two further down is a sequence).  Looks at the last few dozen lines only; 0 = none found.
+static size_t lastRecordStart(const uint8_t* text, size_t len) {
+    size_t starts[64];
+    int ns = 0;
+    size_t p = len;
+    while (ns < 64 && p > 0) {  // line starts from the back: position after each '\n'
+        const void* q = memrchr(text, '\n', p - 1);
+        const size_t st = q ? (size_t)((const uint8_t*)q - text) + 1 : 0;
+        starts[ns++] = st;
+        if (!q) break;
+        p = st;
+    }
+    // starts[0] = start of the last (possibly incomplete) line, starts[i] ascending towards the front
+    for (int i = 2; i < ns; i++)
+        if (text[starts[i]] == '@' && starts[i - 2] < len && text[starts[i - 2]] == '+') return starts[i];
+    return 0;
+}
+
 MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* krakenOut) {
     const int V = meta_.nValues;
     gs_match_cfg c;
@@ -440,7 +523,8 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
     cur->reset(ordinal);
     auto collectOldest = [&]() {
         Batch* b = inflight.front(); inflight.pop_front();
-        processBatch(s, *b, filtered, krakenOut, stats, bestKey);
+        if (b->isText) processTextBatch(s, *b, filtered, stats, bestKey);
+        else processBatch(s, *b, filtered, krakenOut, stats, bestKey);
         freeList.push_back(b);
     };
     auto flush = [&]() {
@@ -454,13 +538,95 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
     };
     const bool keepProbs = filtered != nullptr && cfg_.withProbs;
     FastqReader reader(meta_.k, cfg_.withProbs);
+    auto onRecord = [&](const Record& r, int64_t) {
+        if (cur->n >= cfg_.batchReads || (cur->n > 0 && cur->used() + r.read.size() > cfg_.batchBytes)) flush();
+        cur->add(r, meta_.k, keepProbs);
+        ordinal++;
+    };
     for (const Input& in : fastqs) {   // processFastqStreams (C/fastq/AbstractLoggingFastqStreamer.java:95-131)
-        reader.readFastq(in, [&](const Record& r, int64_t) {
-            if (cur->n >= cfg_.batchReads || (cur->n > 0 && cur->used() + r.read.size() > cfg_.batchBytes)) flush();
-            cur->add(r, meta_.k, keepProbs);
-            ordinal++;
-        });
-        totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+        if (!cfg_.gpuParse || in.fasta || krakenOut) {
+            reader.readFastq(in, onRecord);
+            totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+            continue;
+        }
+        // ---- GPU feeder: text chunks cut at record boundaries; `cur` is the batch being filled
+        flush();  // host-parsed reads of an earlier input keep their place in the order
+        gzFile gz = nullptr;
+        if (!in.path.empty()) {
+            gz = gzopen(in.path.c_str(), "rb");
+            if (!gz) fail("cannot open " + in.path);
+            gzbuffer(gz, 1 << 20);
+        }
+        struct GzCloser { gzFile g; ~GzCloser() { if (g) gzclose(g); } } gzCloser{gz};
+        const size_t chunk = std::max<size_t>(cfg_.textChunkBytes, 1 << 12);
+        size_t memPos = 0;
+        bool eof = false, refused = false;
+        std::vector<uint8_t> carry;
+        while (!eof || !carry.empty()) {
+            cur->isText = true;
+            size_t len = carry.size(), target = std::max(chunk, carry.size() + 1);
+            cur->textLen = 0;
+            cur->ensureText(target + 64);
+            if (len) memcpy(cur->text, carry.data(), len);
+            carry.clear();
+            size_t cut = 0;
+            for (;;) {
+                while (!eof && len < target) {   // fill the pinned chunk straight from the stream / the caller's memory
+                    if (gz) {
+                        const int got = gzread(gz, cur->text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
+                        if (got < 0) fail("read error");
+                        if (got == 0) eof = true;
+                        len += (size_t)got;
+                    } else {
+                        const size_t take = std::min(target - len, in.len - memPos);
+                        if (take) memcpy(cur->text + len, in.data + memPos, take);
+                        memPos += take; len += take;
+                        if (memPos == in.len) eof = true;
+                    }
+                }
+                cut = eof ? len : lastRecordStart(cur->text, len);
+                if (eof || cut > 0) break;
+                if (target >= ((size_t)1 << 31)) { refused = true; break; }  // no record boundary in 2 GiB: not 4-line FASTQ
+                target *= 2;                                                   // records longer than the chunk: widen it
+                cur->textLen = len;
+                cur->ensureText(target + 64);
+            }
+            gs_fastq_info info;
+            memset(&info, 0, sizeof(info));
+            gs_ticket t = 0;
+            if (!refused && cut > 0) {
+                check(gs_match_submit_fastq(s, cur->text, cut, ordinal, &info, &t), "gs_match_submit_fastq");
+                textChunks++;
+                if (t == 0 && info.status) refused = true;
+            }
+            if (refused) {
+                // sequential parser over the bytes not yet consumed: this chunk, then the rest of the stream
+                textChunksRefused++;
+                std::vector<uint8_t> pending(cur->text, cur->text + len);
+                cur->reset(ordinal);
+                LineReader lr(gz, pending.data(), pending.size());
+                if (!gz) {  // in-memory input: the rest follows in memory
+                    pending.insert(pending.end(), in.data + memPos, in.data + in.len);
+                    LineReader lrm(nullptr, pending.data(), pending.size());
+                    reader.readFastqFrom(lrm, onRecord);
+                } else {
+                    reader.readFastqFrom(lr, onRecord);
+                }
+                totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+                eof = true;
+                break;
+            }
+            if (cut < len) carry.assign(cur->text + cut, cur->text + len);
+            if (t) {
+                cur->ticket = t; cur->textLen = cut; cur->n = info.n_reads; cur->firstOrdinal = ordinal;
+                ordinal += info.n_reads;
+                totalReads += info.n_reads; totalKMers += (int64_t)info.total_kmers; totalBPs += (int64_t)info.total_bps;
+                inflight.push_back(cur);
+                if (inflight.size() >= maxInflight) collectOldest();
+                cur = freeList.front(); freeList.pop_front();
+            }
+            cur->reset(ordinal);
+        }
     }
     flush();
     while (!inflight.empty()) collectOldest();
@@ -689,6 +855,7 @@ struct gsh_result {
     std::vector<uint8_t> accept;
     std::vector<double> dsums;  // [4][V]: errorSum, errorSquaredSum, classErrorSum, classErrorSquaredSum
     uint64_t launches = 0;
+    uint64_t feeder[2] = {0, 0};  // text chunks split on the GPU / chunks handed back to the sequential parser
 };
 
 extern "C" {
@@ -711,7 +878,7 @@ typedef struct gsh_match_cfg {
     double max_read_tax_error_count, max_read_class_error_count;
     int write_all, with_probs, initial_read_size_bytes, layout, write_filtered, write_kraken;
     uint32_t batch_reads;
-    uint32_t reserved;
+    uint32_t text_chunk_bytes;  // GPU FASTQ feeder: 0 = default chunk size, 0xFFFFFFFF = parse on the host only
 } gsh_match_cfg;
 
 static std::vector<Input> toInputs(const uint8_t* const* data, const size_t* lens, const char* const* paths, const int* is_fasta, int n) {
@@ -738,6 +905,8 @@ gsh_result* gsh_match_goal(gs_db* db, const DbMeta* meta, const gsh_match_cfg* c
         cfg.maxReadClassErrorCount = c->max_read_class_error_count; cfg.writeAll = c->write_all; cfg.withProbs = c->with_probs;
         cfg.initialReadSizeBytes = c->initial_read_size_bytes; cfg.layout = c->layout;
         if (c->batch_reads) cfg.batchReads = c->batch_reads;
+        if (c->text_chunk_bytes == 0xFFFFFFFFu) cfg.gpuParse = false;
+        else if (c->text_chunk_bytes) cfg.textChunkBytes = c->text_chunk_bytes;
         FastqKMerMatcher matcher(db, *meta, cfg);
         OutputSink filtered, kraken;
         if (filtered_path && filtered_path[0]) filtered.path = filtered_path; else filtered.mem = &r->filtered;
@@ -748,6 +917,7 @@ gsh_result* gsh_match_goal(gs_db* db, const DbMeta* meta, const gsh_match_cfg* c
         r->csv = res.printMatchResult(*meta);
         r->totals[0] = res.totalReads; r->totals[1] = res.totalKMers; r->totals[2] = res.totalBPs;
         r->launches = matcher.kernelLaunches();
+        r->feeder[0] = matcher.textChunks; r->feeder[1] = matcher.textChunksRefused;
         const int V = meta->nValues;
         r->dsums.assign((size_t)4 * V, 0.0);
         for (auto& kv : res.taxid2Stats) {
@@ -808,6 +978,7 @@ void gsh_result_totals(const gsh_result* r, int64_t* out) { out[0] = r->totals[0
 const uint8_t* gsh_result_accept(const gsh_result* r, size_t* n) { *n = r->accept.size(); return r->accept.data(); }
 const double* gsh_result_dsums(const gsh_result* r, size_t* n) { *n = r->dsums.size(); return r->dsums.data(); }
 uint64_t gsh_result_launches(const gsh_result* r) { return r->launches; }
+void gsh_result_feeder(const gsh_result* r, uint64_t* out) { out[0] = r->feeder[0]; out[1] = r->feeder[1]; }
 int gsh_java_double_to_string(double v, char* buf, int cap) {
     const std::string s = javaDoubleToString(v);
     if ((int)s.size() + 1 > cap) return -1;

@@ -18,7 +18,7 @@ class HostMatchCfg(C.Structure):
                 ("max_kmer_res_counts", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
                 ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
                 ("write_all", C.c_int), ("with_probs", C.c_int), ("initial_read_size_bytes", C.c_int), ("layout", C.c_int),
-                ("write_filtered", C.c_int), ("write_kraken", C.c_int), ("batch_reads", C.c_uint32), ("reserved", C.c_uint32)]
+                ("write_filtered", C.c_int), ("write_kraken", C.c_int), ("batch_reads", C.c_uint32), ("text_chunk_bytes", C.c_uint32)]
 
 
 def _lib():
@@ -47,6 +47,7 @@ def _lib():
         L.gsh_result_dsums.argtypes = [_P, C.POINTER(C.c_size_t)]
         L.gsh_result_launches.restype = C.c_uint64
         L.gsh_result_launches.argtypes = [_P]
+        L.gsh_result_feeder.argtypes = [_P, _P]
         L.gsh_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]
         _ready = True
     return L
@@ -93,6 +94,9 @@ class GoalResult:
             p = L.gsh_result_dsums(h, C.byref(n))
             self.dsums = np.frombuffer(C.string_at(p, n.value * 8), dtype=np.float64).copy().reshape(4, -1) if n.value else None
             self.launches = L.gsh_result_launches(h)
+            fd = np.zeros(2, dtype=np.uint64)
+            L.gsh_result_feeder(h, fd.ctypes.data_as(_P))
+            self.text_chunks, self.text_chunks_refused = int(fd[0]), int(fd[1])
         finally:
             L.gsh_result_free(h)
 
@@ -117,13 +121,16 @@ def _inputs(files, is_fasta):
 
 
 def match_goal(db, meta, files, is_fasta=None, write_filtered=False, write_kraken=False, filtered_path=None, kraken_path=None,
-               batch_reads=0, **cfg):
-    """`match` for one key over files (bytes or paths).  cfg: gs_match_cfg style keywords + write_all / with_probs / initial_read_size_bytes."""
+               batch_reads=0, gpu_parse=True, text_chunk_bytes=0, **cfg):
+    """`match` for one key over files (bytes or paths).  cfg: gs_match_cfg style keywords + write_all / with_probs / initial_read_size_bytes.
+    gpu_parse: FASTQ inputs go to the GPU as raw text chunks of text_chunk_bytes (the device splits the records); chunks that
+    are not strict 4-line FASTQ fall back to the sequential host parser."""
     c = HostMatchCfg(cfg.get("classify_reads", 1), cfg.get("count_unique_kmers", 1), cfg.get("use_bloom_filter", 1),
                      cfg.get("max_kmer_res_counts", 0), cfg.get("max_classification_paths", 10), cfg.get("min_kmers_for_class", 1),
                      cfg.get("max_read_tax_error_count", -1.0), cfg.get("max_read_class_error_count", -1.0),
                      int(cfg.get("write_all", 1)), int(cfg.get("with_probs", 0)), cfg.get("initial_read_size_bytes", 4096),
-                     cfg.get("layout", 0), int(write_filtered), int(write_kraken), batch_reads, 0)
+                     cfg.get("layout", 0), int(write_filtered), int(write_kraken), batch_reads,
+                     (int(text_chunk_bytes) if gpu_parse else 0xFFFFFFFF))
     keep, data, lens, paths, fa, n = _inputs(files, is_fasta)
     h = _lib().gsh_match_goal(db.h, meta.h, C.byref(c), data, lens, paths, fa, n,
                               filtered_path.encode() if filtered_path else None, kraken_path.encode() if kraken_path else None)

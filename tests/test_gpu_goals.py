@@ -175,3 +175,59 @@ def test_filter_goal(project, oracle, native, gpu_ctx, host, kind):
         gflt.close()
         if kind != "xor":
             flt_o.free()
+
+
+@pytest.mark.parametrize("with_probs", [False, True], ids=["noprobs", "probs"])
+def test_match_goal_gpu_fastq_feeder(project, oracle, host, tmp_path, with_probs):
+    """`match` with the GPU FASTQ feeder (text chunks split on the device) == the oracle (sequential parser + matchRead):
+    CSV, filtered FASTQ, totals and the four double sums; many small chunks, two inputs, one of them gzip on disk."""
+    odb, gdb, meta, genomes = project
+    b1, o1, s1 = _reads(genomes, 4000, 11)
+    b2, o2, s2 = _reads(genomes, 1500, 12, len_jitter=60)
+    rng = np.random.default_rng(6)
+    qual = bytes(rng.integers(33, 74, size=int(o1[-1])).astype(np.uint8))
+    bb = b1.tobytes()
+    f1 = b"".join(b"@r%d %d\n%s\n+\n%s\n" % (i, s1[i], bb[int(o1[i]):int(o1[i + 1])], qual[int(o1[i]):int(o1[i + 1])]) for i in range(len(o1) - 1))
+    f2 = synth.fastq_bytes(b2, o2, s2, prefix="q", qual=b"@")   # quality lines that start with '@' (record-boundary ambiguity)
+    p2 = str(tmp_path / "b.fastq.gz")
+    with gzip.open(p2, "wb") as f:
+        f.write(f2)
+    ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=with_probs)
+    orun = odb.match_files(ocfg, [f1, f2])
+    for chunk in (30000, 1 << 20):
+        res = host.match_goal(gdb, meta, [f1, p2], write_filtered=True, with_probs=int(with_probs), text_chunk_bytes=chunk)
+        assert res.text_chunks_refused == 0 and res.text_chunks >= (40 if chunk == 30000 else 2)
+        assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+        assert res.filtered == orun.filtered
+        for i in range(4):
+            np.testing.assert_array_equal(res.dsums[i], orun.dstats[i])
+        _assert_csv_equal(res.csv, orun.csv)
+    # host-only parsing gives the same bytes
+    res0 = host.match_goal(gdb, meta, [f1, p2], write_filtered=True, with_probs=int(with_probs), gpu_parse=False)
+    assert res0.text_chunks == 0 and res0.filtered == orun.filtered
+    _assert_csv_equal(res0.csv, orun.csv)
+
+
+def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host):
+    """Inputs that are not strict 4-line FASTQ: the device refuses the chunk and the sequential parser takes over from
+    exactly there -- a strict prefix stays on the GPU, the results are those of the reference parser throughout."""
+    odb, gdb, meta, genomes = project
+    g = genomes[1][1]
+    b1, o1, s1 = _reads(genomes, 1200, 13)
+    strict = synth.fastq_bytes(b1, o1, s1)
+    odd = [b"@a 1\r\n" + g[100:250] + b"\r\n+\r\n" + b"I" * 150 + b"\r\n",
+           b"@b\n" + g[300:360] + b"\n" + g[360:420] + b"\n" + g[420:470] + b"\n+b\n" + b"J" * 100 + b"\n" + b"J" * 70 + b"\n",
+           b"@c x y\n" + g[500:520] + b"\n+\n" + b"I" * 20 + b"\n",
+           b"@d\0\0 z\n" + g[600:700] + b"\0" + g[700:760] + b"\n+\n" + b"I" * 160 + b"\n"]
+    tail = b"@e\n" + g[800:950] + b"\n+\n" + b"I" * 150   # no final newline: the reference drops the last quality byte
+    for name, fq, min_gpu in (("odd records in the middle", strict + b"".join(odd) + strict + tail, 3),
+                              ("only the tail", strict + tail, 3),
+                              ("multi-line from the start", odd[1] + strict, 0)):
+        ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=True)
+        orun = odb.match_files(ocfg, [fq])
+        res = host.match_goal(gdb, meta, [fq], write_filtered=True, with_probs=1, text_chunk_bytes=50000, batch_reads=500)
+        assert res.text_chunks_refused == 1, name
+        assert res.text_chunks - res.text_chunks_refused >= min_gpu, name
+        assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps), name
+        assert res.filtered == orun.filtered, name
+        _assert_csv_equal(res.csv, orun.csv)
