@@ -375,6 +375,7 @@ def main():
     ap.add_argument("--layout", default="table", choices=["table", "classic"],
                     help="device index: 128-byte probe table (default) or the reference's Bloom filter + sorted-array search")
     ap.add_argument("--no-prefilter", action="store_true", help="A/B: probe the table for every k-mer (no minimizer prefilter)")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the raw-FASTQ end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     wl = dict(WORKLOADS[args.workload])
@@ -394,6 +395,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # run on the cores next to this rank's GPU so that the pinned batches are allocated on its NUMA node (restored for the CPU leg)
+    affinity0 = os.sched_getaffinity(0)
+    if args.impl == "native":
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            cpus = {i for i in range(os.cpu_count()) if (words[i // 64] >> (i % 64)) & 1} & affinity0
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception as e:  # no NVML / no topology information: keep the default placement
+            log("rank %d: cpu affinity not set (%s)" % (rank, e))
     dist = None
     if world > 1 and args.impl == "native":
         import torch.distributed as dist
@@ -563,11 +577,57 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # ---------------- end-to-end from raw FASTQ text (GPU feeder: the device splits the records; no host parsing at all)
+    fq_s, fq_bytes = 0.0, 0
+    if READ_LEN <= 1000 and not args.no_fastq:
+        HDR = 11  # "@r%09d\n"
+        rec_len = HDR + READ_LEN + 3 + READ_LEN + 1
+        fq_bytes = R * rec_len
+        pinned_fq = []
+        for b in range(n_batches):
+            t = torch.empty((R, rec_len), dtype=torch.uint8, device=dev)
+            t[:, 0] = ord("@"); t[:, 1] = ord("r")
+            idx = torch.arange(R, device=dev)
+            for d in range(9):
+                t[:, 2 + d] = (idx // (10 ** (8 - d)) % 10 + 48).to(torch.uint8)
+            t[:, HDR - 1] = 10
+            t[:, HDR:HDR + READ_LEN] = batches[b][0][:nb].view(R, READ_LEN)
+            t[:, HDR + READ_LEN] = 10; t[:, HDR + READ_LEN + 1] = ord("+"); t[:, HDR + READ_LEN + 2] = 10
+            t[:, HDR + READ_LEN + 3:HDR + 2 * READ_LEN + 3] = ord("I")
+            t[:, rec_len - 1] = 10
+            pb = capi.PinnedBuffer(fq_bytes + 64)
+            pb.array[:fq_bytes] = t.view(-1).cpu().numpy()
+            pinned_fq.append(pb)
+            del t
+        torch.cuda.empty_cache()
+        fq_reads = [0]
+
+        def fq_run(n_steps, first):
+            pend = []
+            for i in range(n_steps):
+                tk, info = sess2.submit_fastq(pinned_fq[(first + i) % n_batches].array, (first + i) * R, n_bytes=fq_bytes)
+                assert tk and info.n_reads == R, "FASTQ feeder refused the synthetic chunk (status %d)" % info.status
+                pend.append(tk)
+                if len(pend) == capi.GS_MAX_INFLIGHT:
+                    fq_reads[0] += len(sess2.collect_fastq(pend.pop(0))[0])
+            while pend:
+                fq_reads[0] += len(sess2.collect_fastq(pend.pop(0))[0])
+
+        fq_run(args.warmup, 0)
+        barrier()
+        t0 = time.perf_counter()
+        fq_run(args.steps, args.warmup)
+        torch.cuda.synchronize()
+        fq_s = time.perf_counter() - t0
+        barrier()
+        for pb in pinned_fq:
+            pb.free()
+
     # max over ranks of the timed region
-    tt = torch.tensor([total_ms + red_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms + red_ms, e2e_s * 1e3, fq_s * 1e3], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    total_ms_max, e2e_ms_max, fq_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
     steps_done = args.warmup + args.steps
     h = total_hits / float(steps_done * kmers_per_step * world) if dist else total_hits / float(steps_done * kmers_per_step)
     value = world * args.steps * kmers_per_step / (total_ms_max / 1e3)
@@ -610,11 +670,17 @@ def main():
                         "reads_per_s": e2e_value / (READ_LEN - K + 1)},
                 "gpu_launches": int(launches),
                 "roofline": roof,
+                "e2e_fastq": ({"value": world * args.steps * kmers_per_step / (fq_ms_max / 1e3), "unit": "k-mers/s",
+                               "reads_per_s": world * args.steps * R / (fq_ms_max / 1e3), "h2d_bytes_per_step": fq_bytes,
+                               "d2h_bytes_per_step": R * 32 + 16 + V * 20,
+                               "what": "gs_match_submit_fastq / gs_match_collect_fastq: raw 4-line FASTQ text in pinned host memory, records split on the GPU"}
+                              if fq_ms_max > 0 else None),
                 "end_of_job_reduce_ms": red_ms, "hits_total": total_hits, "unique_kmers_total": unique_total}
 
     # ---------------- CPU baseline + bench-scale parity spot check (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import gs_oracle
+        os.sched_setaffinity(0, affinity0)
         if READ_LEN > 1000:
             args.cpu_seconds = min(args.cpu_seconds, 8.0)
         n, kmers, per, times = cpu_reference(gs_oracle, keys_h, vals_h, V, parent, b0_h, off_h, threads, args.cpu_seconds)
