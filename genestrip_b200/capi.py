@@ -65,6 +65,8 @@ _SIGS = {
     "gs_db_set_bloom_blocked": (C.c_int, [_P, C.c_int64, C.c_uint64, _P, C.c_uint64]),
     "gs_db_build_bloom_blocked": (C.c_int, [_P, _P, C.c_uint64]),
     "gs_db_finalize": (C.c_int, [_P]),
+    "gs_db_update": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "gs_db_get_values": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "gs_db_destroy": (None, [_P]),
     "gs_db_device_bytes": (C.c_uint64, [_P]),
     "gs_db_n_devices": (C.c_int, [_P]),
@@ -254,6 +256,21 @@ class Database:
     @property
     def device_bytes(self):
         return lib().gs_db_device_bytes(self.h)
+
+    def update(self, seq, region_offsets, region_vidx, upper_case=True):
+        """DBGoal update phase: value = LCA(value, region node) for every stored k-mer of the regions; returns #changes."""
+        seq = _arr(seq, np.uint8)
+        off = _arr(region_offsets, np.uint64)
+        vid = _arr(region_vidx, np.int32)
+        ch = C.c_uint64(0)
+        _check(lib().gs_db_update(self.h, _ptr(seq), len(seq), _ptr(off), _ptr(vid), len(vid), int(upper_case), C.byref(ch)))
+        return ch.value
+
+    def values(self, offset=0, n=None):
+        n = self.n_kmers - offset if n is None else n
+        out = np.empty(n, dtype=np.int16)
+        _check(lib().gs_db_get_values(self.h, offset, _ptr(out), n))
+        return out
 
     def lookup(self, kmers, use_bloom=True):
         kmers = _arr(kmers, np.int64)

@@ -428,6 +428,101 @@ extern "C" int gs_db_finalize(gs_db* db) {
     return GS_OK;
 }
 
+// ---- database update phase --------------------------------------------------------------------------------
+extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, const uint64_t* region_offsets, const int32_t* region_vidx,
+                            uint32_t n_regions, int upper_case, uint64_t* n_changed) {
+    if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
+    if (db->seenLeased) return gs_fail(GS_ERR_STATE, "a match session holds the probe table's seen bits: close it before updating");
+    if (n_changed) *n_changed = 0;
+    if (n_regions == 0 || n_bytes == 0) return GS_OK;
+    if (!seq || !region_offsets || !region_vidx) return gs_fail(GS_ERR_ARG, "null argument");
+    if (region_offsets[0] != 0 || region_offsets[n_regions] != n_bytes) return gs_fail(GS_ERR_ARG, "region offsets must span [0, n_bytes]");
+    for (u32 i = 0; i < n_regions; i++) {
+        if (region_offsets[i + 1] < region_offsets[i]) return gs_fail(GS_ERR_ARG, "region offsets not ascending at region %u", i);
+        if (region_offsets[i + 1] - region_offsets[i] > 0x7FFFFFF0ULL) return gs_fail(GS_ERR_LIMIT, "region %u longer than 2^31 bases", i);
+    }
+    DevDb& d0 = db->d[0];
+    CU(cudaSetDevice(d0.dev));
+    const u64 kGroup = 64ULL << 20;  // bases per pass (labels + positions take 12 bytes per base)
+    unsigned long long* dChanged = nullptr;
+    u32* dCtr = nullptr;
+    CU(dmalloc(&dChanged, 1)); CU(cudaMemset(dChanged, 0, sizeof(unsigned long long)));
+    CU(dmalloc(&dCtr, 8));
+    uint8_t* dSeq = nullptr; u64* dOff = nullptr; int* dNode = nullptr; u32* dLab = nullptr; long long* dPos = nullptr; u32* dValid = nullptr; u32* dStart = nullptr;
+    size_t seqCap = 0, offCap = 0, nodeCap = 0, labCap = 0, posCap = 0, validCap = 0, startCap = 0;
+    int rc = GS_OK;
+    std::vector<u64> rel;
+    for (u32 r0 = 0; r0 < n_regions && rc == GS_OK;) {
+        u32 r1 = r0 + 1;
+        while (r1 < n_regions && region_offsets[r1 + 1] - region_offsets[r0] <= kGroup) r1++;
+        const u64 b0 = region_offsets[r0], nb = region_offsets[r1] - b0;
+        const u32 nr = r1 - r0;
+        rel.resize((size_t)nr + 1);
+        for (u32 i = 0; i <= nr; i++) rel[i] = region_offsets[r0 + i] - b0;
+        const u64 nSeg = (nb + GS_SEG_POS - 1) / GS_SEG_POS;
+        const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
+        CU(dgrow(&dSeq, &seqCap, (size_t)nb + 64)); CU(dgrow(&dOff, &offCap, (size_t)nr + 1)); CU(dgrow(&dNode, &nodeCap, (size_t)nr));
+        CU(dgrow(&dLab, &labCap, (size_t)nb + 32)); CU(dgrow(&dPos, &posCap, (size_t)nb + 32));
+        CU(dgrow(&dValid, &validCap, words)); CU(dgrow(&dStart, &startCap, words));
+        if (nb) CU(cudaMemcpy(dSeq, seq + b0, nb, cudaMemcpyHostToDevice));
+        CU(cudaMemset(dSeq + nb, 0, 64));
+        CU(cudaMemcpy(dOff, rel.data(), ((size_t)nr + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dNode, region_vidx + r0, (size_t)nr * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemset(dCtr, 0, 8 * sizeof(u32)));
+        CU(cudaMemset(dStart, 0, words * sizeof(u32)));
+        if (upper_case) gs_launch_cgat_upper(dSeq, nb, 0);
+        GsMatchParams P;
+        memset(&P, 0, sizeof(P));
+        P.db = d0.view;
+        P.bases = dSeq; P.offsets = dOff; P.nReads = nr; P.layout = GS_LAYOUT_CLASSIC; P.useBloom = db->hasBloom ? 1 : 0;
+        P.off0 = 0; P.lead = 0; P.flatLen = nb; P.labels = dLab; P.validBits = dValid; P.startBits = dStart; P.segCounter = dCtr + 2;
+        P.flatPos = dPos;
+        gs_launch_mark_starts(P, 0);
+        gs_launch_label(P, true, (int)std::max<u64>(1, std::min<u64>((u64)db->ctx->sms[0] * 4, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK)), 0);
+        gs_launch_db_update(d0.view, dLab, dPos, nb, dOff, dNode, nr, d0.vals, dChanged, 0);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        r0 = r1;
+    }
+    unsigned long long changed = 0;
+    CU(cudaMemcpy(&changed, dChanged, sizeof(changed), cudaMemcpyDeviceToHost));
+    if (n_changed) *n_changed = changed;
+    cudaFree(dSeq); cudaFree(dOff); cudaFree(dNode); cudaFree(dLab); cudaFree(dPos); cudaFree(dValid); cudaFree(dStart); cudaFree(dChanged); cudaFree(dCtr);
+    if (changed) {  // the probe table carries the values in its entries: rebuild it, then refresh the replicas
+        const u64 nB = 1ULL << db->tbits;
+        u32* counts = nullptr;
+        CU(dmalloc(&counts, nB));
+        CU(cudaMemset(d0.tab, 0, nB * 32));
+        CU(cudaMemset(counts, 0, nB * sizeof(u32)));
+        gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, db->tbits, db->rbits, 0);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(counts));
+        for (size_t i = 1; i < db->d.size(); i++) {
+            DevDb& di = db->d[i];
+            CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
+            CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (32ULL << db->tbits)));
+        }
+        CU(cudaDeviceSynchronize());
+    }
+    return rc;
+}
+
+extern "C" int gs_db_get_values(gs_db* db, uint64_t offset, int16_t* vidx_raw, uint64_t n) {
+    if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
+    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "range beyond the %llu stored k-mers", (unsigned long long)db->n);
+    if (n == 0) return GS_OK;
+    if (!vidx_raw) return gs_fail(GS_ERR_ARG, "null argument");
+    CU(cudaSetDevice(db->d[0].dev));
+    int16_t* dRaw = nullptr;
+    CU(dmalloc(&dRaw, (size_t)n));
+    gs_launch_values_to_raw(db->d[0].vals + offset, n, dRaw, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(vidx_raw, dRaw, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    CU(cudaFree(dRaw));
+    return GS_OK;
+}
+
 extern "C" void gs_db_destroy(gs_db* db) {
     if (!db) return;
     for (DevDb& d : db->d) {

@@ -991,3 +991,58 @@ int gs_match_kernel_occupancy(int mode) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
     return nb;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// database update phase (C/goals/refseq/DBGoal.java:234-311): value = LCA(value, node of the region) for every stored
+// k-mer of a genome region.  The label kernel (classic layout, dump mode) has left the storage position of every hit in
+// flatPos; LCA only moves values towards the root, so a compare-and-swap loop on the 16-bit value makes the result
+// independent of the order in which regions and positions are applied (C/goals/refseq/FastaReaderGoal.java:104-108).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gs_db_update_kernel(const GsDbView db, const u32* __restrict__ labels, const long long* __restrict__ flatPos, u64 flatLen,
+                                    const u64* __restrict__ offsets, const int* __restrict__ regionNode, u32 nRegions, uint16_t* vals,
+                                    unsigned long long* nChanged) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x; f < flatLen; f += stride) {
+        if (labels[f] >= GS_LABEL_INVALID) continue;
+        u32 lo = 0, hi = nRegions;  // region r with offsets[r] <= f < offsets[r + 1]
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= f) lo = mid; else hi = mid; }
+        const int node = __ldg(regionNode + lo);
+        if (node < 0 || node >= db.nValues) continue;
+        const u64 pos = (u64)flatPos[f];
+        u32* wp = (u32*)vals + (pos >> 1);
+        const int sh = (int)(pos & 1) * 16;
+        u32 old = *(volatile u32*)wp;
+        for (;;) {
+            const u32 cur = (old >> sh) & 0xFFFFu;
+            if (cur == GS_VAL_NONODE) break;                       // getNodeByTaxId(oldValue) == null: unchanged
+            const int lca = gs_lca(db, (int)cur, node);
+            if (lca < 0 || (u32)lca == cur) break;                 // lcaNode == null keeps the old value (:252)
+            const u32 nv = (old & ~(0xFFFFu << sh)) | ((u32)lca << sh);
+            const u32 seen = atomicCAS(wp, old, nv);
+            if (seen == old) { atomicAdd(nChanged, 1ULL); break; }
+            old = seen;
+        }
+    }
+}
+void gs_launch_db_update(const GsDbView& db, const u32* labels, const long long* flatPos, u64 flatLen, const u64* offsets, const int* regionNode,
+                         u32 nRegions, uint16_t* vals, unsigned long long* nChanged, cudaStream_t st) {
+    gs_db_update_kernel<<<148 * 8, 256, 0, st>>>(db, labels, flatPos, flatLen, offsets, regionNode, nRegions, vals, nChanged);
+}
+// cgatToUpperCase (C/util/CGAT.java:91-99) over a byte buffer, 16 bytes per thread step
+__global__ void gs_cgat_upper_kernel(uint8_t* buf, u64 n) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += stride) {
+        u32 w = ((u32*)buf)[i];
+        const u32 m = __vcmpeq4(w, 0x61616161u) | __vcmpeq4(w, 0x63636363u) | __vcmpeq4(w, 0x67676767u) | __vcmpeq4(w, 0x74747474u);
+        ((u32*)buf)[i] = w ^ (m & 0x20202020u);
+    }
+}
+void gs_launch_cgat_upper(uint8_t* buf, u64 n, cudaStream_t st) { gs_cgat_upper_kernel<<<148 * 8, 256, 0, st>>>(buf, n); }
+__global__ void gs_values_to_raw_kernel(const uint16_t* __restrict__ vals, u64 n, int16_t* raw) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 v = vals[i];
+        raw[i] = v == GS_VAL_NONODE ? (int16_t)-1 : (int16_t)((int)v - 32768);  // value index + Short.MIN_VALUE (KMerSortedArray.java:348)
+    }
+}
+void gs_launch_values_to_raw(const uint16_t* vals, u64 n, int16_t* raw, cudaStream_t st) { gs_values_to_raw_kernel<<<148 * 8, 256, 0, st>>>(vals, n, raw); }

@@ -87,3 +87,9 @@ void gs_launch_text_split(const uint8_t* text, u64 n, u32* blockCounts, u32* lin
                           int k, unsigned long long* totals, cudaStream_t st);
 void gs_launch_text_compact(const uint8_t* text, const gs_fastq_rec* recs, const u32* lens, u32 n, u64* tileSums, u64* offsets, uint8_t* bases, cudaStream_t st);
 void gs_launch_text_event_headers(const gs_maxcontig_event* ev, const u32* nEv, u32 evCap, const gs_fastq_rec* recs, u64 firstReadNo, u32 n, u32* hdr, cudaStream_t st);
+
+// database update phase
+void gs_launch_db_update(const GsDbView& db, const u32* labels, const long long* flatPos, u64 flatLen, const u64* offsets, const int* regionNode,
+                         u32 nRegions, uint16_t* vals, unsigned long long* nChanged, cudaStream_t st);
+void gs_launch_cgat_upper(uint8_t* buf, u64 n, cudaStream_t st);
+void gs_launch_values_to_raw(const uint16_t* vals, u64 n, int16_t* raw, cudaStream_t st);

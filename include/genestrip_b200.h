@@ -80,6 +80,19 @@ int gs_db_set_bloom_blocked(gs_db*, int64_t seed, uint64_t buckets, const int64_
  * buckets+17 words for comparison with a host-built filter. */
 int gs_db_build_bloom_blocked(gs_db*, int64_t* words_out, uint64_t n_words_out);
 int gs_db_finalize(gs_db*); /* builds the bucket index, replicates to every device of the context */
+/* The update phase of the `db` goal (C/goals/refseq/DBGoal.java:234-311, C/store/KMerSortedArray.java update): for every
+ * stored k-mer that occurs in a genome region, value = LCA(value, node of the region) (unchanged when there is no common
+ * ancestor or the value has no tree node).  seq = the regions' sequence bytes back to back WITHOUT line terminators (the
+ * FASTA reader strips them, C/refseq/AbstractStoreFastaReader.java:88-120), region r = [region_offsets[r],
+ * region_offsets[r + 1]) with node value index region_vidx[r] (< 0: region skipped); the k-mer window restarts at every region
+ * and at every byte that is not one of CGAT (after cgatToUpperCase when upper_case != 0, C/util/CGAT.java:91-99).
+ * stepSize = 1 and no dust filter (the defaults).  Needs a finalized database with its tree and no open unique-counting
+ * session; the order of calls and regions does not matter (LCA is associative and commutative).  n_changed (may be NULL)
+ * counts value changes.  gs_db_get_values reads the Java shorts back in storage order (value index + Short.MIN_VALUE; -1 for
+ * values without a tree node). */
+int gs_db_update(gs_db*, const uint8_t* seq, uint64_t n_bytes, const uint64_t* region_offsets, const int32_t* region_vidx,
+                 uint32_t n_regions, int upper_case, uint64_t* n_changed);
+int gs_db_get_values(gs_db*, uint64_t offset, int16_t* vidx_raw, uint64_t n);
 void gs_db_destroy(gs_db*);
 uint64_t gs_db_device_bytes(const gs_db*);
 int gs_db_n_devices(const gs_db*);

@@ -245,7 +245,7 @@ class OracleDb:
 
     @classmethod
     def build(cls, k, nodes_dmp, names_dmp, genomes, requested=(), use_radix=False, radix_bits=17, opt_fpp=0.01,
-              index_fpp=0.0, index_xor=True, fill=None):
+              index_fpp=0.0, index_xor=True, fill=None, skip_update=False):
         """genomes: list of (taxid str, bytes sequence).  fill[i]=False -> genome only takes part in the LCA update."""
         L = lib()
         nodes_dmp = nodes_dmp if isinstance(nodes_dmp, bytes) else nodes_dmp.encode()
@@ -258,6 +258,9 @@ class OracleDb:
             b = np.frombuffer(seq, dtype=np.uint8)
             if L.gso_db_add_genome(h, str(taxid).encode(), _ptr(b), len(b), 1 if (fill is None or fill[i]) else 0) != 0:
                 raise ValueError("unknown genome taxid %s" % taxid)
+        if skip_update:  # database as the fill phase leaves it (the GPU update phase is then checked against a full build)
+            L.gso_db_set_skip_update.argtypes = [_P, C.c_int]
+            L.gso_db_set_skip_update(h, 1)
         if L.gso_db_finalize(h, index_fpp, int(index_xor)) != 0:
             raise RuntimeError(L.gso_db_error(h).decode())
         return cls(h)

@@ -23,6 +23,7 @@ struct gso_db {
     Database db;
     std::unique_ptr<KMerProbFilter> index;  // `filter` goal index (BloomIndexGoal)
     std::string error;
+    bool skipUpdate = false;  // tests of the GPU update phase: stop after the fill phase (FillDBGoal) so that the update can be replayed
 };
 
 struct gso_run {
@@ -125,6 +126,7 @@ gso_db* gso_db_new(int k, const char* nodes, size_t nodesLen, const char* names,
     return d;
 }
 void gso_db_free(gso_db* d) { delete d; }
+void gso_db_set_skip_update(gso_db* d, int skip) { d->skipUpdate = skip != 0; }
 const char* gso_db_error(gso_db* d) { return d->error.c_str(); }
 int gso_db_request(gso_db* d, const char* taxid) {  // taxids.txt entry: requested node; required up to the root
     TaxNode* n = d->full.getNodeByTaxId(taxid);
@@ -194,6 +196,7 @@ int gso_db_finalize(gso_db* d, double indexFpp, int indexXor) {
         // ---- update: value = LCA(value, genomeNode) for every genome (DBGoal.java:234-253, 300-311)
         KMerStoreBase* st = d->db.store.get();
         for (const Genome& g : d->genomes) {
+            if (d->skipUpdate) break;
             TaxNode* node = d->full.getNodeByTaxId(g.taxid);
             scanGenome(k, g.seq, [&](jlong km) {
                 jlong pos;
