@@ -96,6 +96,8 @@ _SIGS = {
     "gs_filter_open": (_P, [_P, C.c_int, C.c_int, C.c_double]),
     "gs_filter_submit": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gs_filter_collect": (C.c_int, [_P, C.c_uint64, _P]),
+    "gs_filter_submit_fastq": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(FastqInfo), C.POINTER(C.c_uint64)]),
+    "gs_filter_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     "gs_filter_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
     "gs_filter_sync": (C.c_int, [_P]),
     "gs_filter_stream": (_P, [_P]),
@@ -458,6 +460,26 @@ class FilterSession:
         out = np.empty(n, dtype=np.uint8)
         _check(lib().gs_filter_collect(self.h, ticket, _ptr(out)))
         return out
+
+    def submit_fastq(self, text, n_bytes=None):
+        """Raw FASTQ text; returns (ticket, FastqInfo), ticket == 0 if the chunk is not strict 4-line FASTQ."""
+        text = _arr(text, np.uint8)
+        n = len(text) if n_bytes is None else int(n_bytes)
+        info = FastqInfo()
+        t = C.c_uint64(0)
+        _check(lib().gs_filter_submit_fastq(self.h, _ptr(text), n, C.byref(info), C.byref(t)))
+        if t.value:
+            self._keep[t.value] = (text, None, info.n_reads)
+        return t.value, info
+
+    def collect_fastq(self, ticket):
+        self._keep.pop(ticket)
+        acc, rc = _P(), _P()
+        n = C.c_uint32(0)
+        _check(lib().gs_filter_collect_fastq(self.h, ticket, C.byref(acc), C.byref(n), C.byref(rc)))
+        a = np.ctypeslib.as_array(C.cast(acc, C.POINTER(C.c_uint8)), shape=(n.value,)) if n.value else np.zeros(0, np.uint8)
+        r = np.ctypeslib.as_array(C.cast(rc, C.POINTER(C.c_uint8)), shape=((n.value + 1) * 16,)).view(FASTQ_REC_DTYPE)
+        return a, r
 
     def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr):
         _check(lib().gs_filter_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr))

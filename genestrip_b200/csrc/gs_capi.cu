@@ -554,6 +554,7 @@ extern "C" int gs_db_lookup(gs_db* db, const int64_t* kmers, uint64_t n, int use
 // ---------------------------------------------------------------------------------------------------------
 // match sessions
 // ---------------------------------------------------------------------------------------------------------
+template <typename Slot> static void text_stage_free(Slot& sl);
 struct MatchSlot {
     bool pending = false;
     gs_ticket ticket = 0;
@@ -694,11 +695,7 @@ extern "C" void gs_match_close(gs_sess* s) {
             if (sl.hNEv) cudaFreeHost(sl.hNEv);
             if (sl.hKmerOff) cudaFreeHost(sl.hKmerOff);
             if (sl.hRunCounts) cudaFreeHost(sl.hRunCounts);
-            cudaFree(sl.dText); cudaFree(sl.dLineEnd); cudaFree(sl.dBlockCounts); cudaFree(sl.dTextMeta); cudaFree(sl.dRecs);
-            cudaFree(sl.dLens); cudaFree(sl.dTileSums); cudaFree(sl.dEvHdr);
-            if (sl.hTextMeta) cudaFreeHost(sl.hTextMeta);
-            if (sl.hRecs) cudaFreeHost(sl.hRecs);
-            if (sl.hEvHdr) cudaFreeHost(sl.hEvHdr);
+            text_stage_free(sl);
             if (sl.evH2D) cudaEventDestroy(sl.evH2D);
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
@@ -898,6 +895,53 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     return GS_OK;
 }
 
+// Shared by the match and filter sessions: text chunk -> device, record splitter, verdict to the host (the only wait), then
+// read offsets + compacted bases on the same stream.  On return info->status != 0 means "not strict 4-line FASTQ" (nothing
+// else was done); otherwise sl.dBases / sl.dOffsets / sl.dRecs describe info->n_reads reads.
+template <typename Slot>
+static int text_stage(Slot& sl, cudaStream_t st, const uint8_t* text, u64 n_bytes, int k, gs_fastq_info* info, u64* launches) {
+    const size_t lineCap = (size_t)(n_bytes / 16 + 64);
+    const size_t nBlocks = (size_t)((n_bytes + GS_TEXT_SEG - 1) / GS_TEXT_SEG);
+    CU(dgrow(&sl.dText, &sl.textCap, (size_t)n_bytes + 64));
+    CU(dgrow(&sl.dLineEnd, &sl.lineCap, lineCap));
+    CU(dgrow(&sl.dBlockCounts, &sl.blockCountsCap, nBlocks + 1));
+    CU(dgrow(&sl.dRecs, &sl.recsCap, lineCap / 4 + 2));
+    CU(dgrow(&sl.dLens, &sl.lensCap, lineCap / 4 + 2));
+    if (!sl.dTextMeta) { CU(dmalloc(&sl.dTextMeta, 8)); CU(cudaMallocHost((void**)&sl.hTextMeta, 8 * sizeof(u32))); }
+    CU(cudaMemsetAsync(sl.dTextMeta, 0, 8 * sizeof(u32), st));
+    if (n_bytes) CU(cudaMemcpyAsync(sl.dText, text, n_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(sl.dText + n_bytes, 0, 64, st));
+    gs_launch_text_split(sl.dText, n_bytes, sl.dBlockCounts, sl.dLineEnd, (u32)std::min<size_t>(lineCap, 0xFFFFFFFFu), sl.dTextMeta, sl.dRecs, sl.dLens,
+                         k, (unsigned long long*)(sl.dTextMeta + 4), st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sl.hTextMeta, sl.dTextMeta, 8 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *launches += n_bytes ? 4 : 0;
+    info->status = sl.hTextMeta[2];
+    if (info->status) return GS_OK;
+    const u32 n_reads = sl.hTextMeta[1];
+    info->n_reads = n_reads;
+    memcpy(&info->total_kmers, sl.hTextMeta + 4, sizeof(u64));
+    memcpy(&info->total_bps, sl.hTextMeta + 6, sizeof(u64));
+    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)info->total_bps + 64));
+    CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
+    CU(hgrow(&sl.hRecs, &sl.hRecsCap, (size_t)n_reads + 1));
+    CU(dgrow(&sl.dTileSums, &sl.tileSumsCap, (size_t)n_reads / 1024 + 2));
+    if (n_reads == 0) CU(cudaMemsetAsync(sl.dOffsets, 0, sizeof(u64), st));
+    gs_launch_text_compact(sl.dText, sl.dRecs, sl.dLens, n_reads, sl.dTileSums, sl.dOffsets, sl.dBases, st);
+    CU(cudaGetLastError());
+    *launches += n_reads ? 4 : 0;
+    return GS_OK;
+}
+template <typename Slot>
+static void text_stage_free(Slot& sl) {
+    cudaFree(sl.dText); cudaFree(sl.dLineEnd); cudaFree(sl.dBlockCounts); cudaFree(sl.dTextMeta); cudaFree(sl.dRecs);
+    cudaFree(sl.dLens); cudaFree(sl.dTileSums); cudaFree(sl.dEvHdr);
+    if (sl.hTextMeta) cudaFreeHost(sl.hTextMeta);
+    if (sl.hRecs) cudaFreeHost(sl.hRecs);
+    if (sl.hEvHdr) cudaFreeHost(sl.hEvHdr);
+}
+
 // Raw FASTQ text: the chunk goes to the device as it is; the record splitter (gs_text.cu) runs on the copy-in stream right
 // behind the copy, so it overlaps the match kernels of the previous batch; the host waits only for the splitter's verdict
 // (number of reads, strict-format flags), then the bases are compacted and the usual kernels follow on the compute stream.
@@ -916,42 +960,15 @@ extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n
     if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
     const int V = s->db->V;
     CU(cudaSetDevice(D.dev));
-    const size_t lineCap = (size_t)(n_bytes / 16 + 64);
-    const size_t nBlocks = (size_t)((n_bytes + GS_TEXT_SEG - 1) / GS_TEXT_SEG);
-    CU(dgrow(&sl.dText, &sl.textCap, (size_t)n_bytes + 64));
-    CU(dgrow(&sl.dLineEnd, &sl.lineCap, lineCap));
-    CU(dgrow(&sl.dBlockCounts, &sl.blockCountsCap, nBlocks + 1));
-    CU(dgrow(&sl.dRecs, &sl.recsCap, lineCap / 4 + 2));
-    CU(dgrow(&sl.dLens, &sl.lensCap, lineCap / 4 + 2));
-    if (!sl.dTextMeta) { CU(dmalloc(&sl.dTextMeta, 8)); CU(cudaMallocHost((void**)&sl.hTextMeta, 8 * sizeof(u32))); }
     if (!sl.dEvHdr) { CU(dmalloc(&sl.dEvHdr, (size_t)std::max(V, 1))); CU(cudaMallocHost((void**)&sl.hEvHdr, (size_t)std::max(V, 1) * sizeof(u32))); }
-    CU(cudaMemsetAsync(sl.dTextMeta, 0, 8 * sizeof(u32), D.sCopyIn));
-    if (n_bytes) CU(cudaMemcpyAsync(sl.dText, text, n_bytes, cudaMemcpyHostToDevice, D.sCopyIn));
-    CU(cudaMemsetAsync(sl.dText + n_bytes, 0, 64, D.sCopyIn));
-    gs_launch_text_split(sl.dText, n_bytes, sl.dBlockCounts, sl.dLineEnd, (u32)std::min<size_t>(lineCap, 0xFFFFFFFFu), sl.dTextMeta, sl.dRecs, sl.dLens,
-                         s->db->k, (unsigned long long*)(sl.dTextMeta + 4), D.sCopyIn);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(sl.hTextMeta, sl.dTextMeta, 8 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyIn));
-    CU(cudaStreamSynchronize(D.sCopyIn));
-    s->launches += n_bytes ? 4 : 0;
-    info->status = sl.hTextMeta[2];
+    int rcs = text_stage(sl, D.sCopyIn, text, n_bytes, s->db->k, info, &s->launches);
+    if (rcs) return rcs;
     if (info->status) return GS_OK;   // not strict 4-line FASTQ: the caller parses this chunk on the CPU (nothing is pending)
-    const u32 n_reads = sl.hTextMeta[1];
-    info->n_reads = n_reads;
-    memcpy(&info->total_kmers, sl.hTextMeta + 4, sizeof(u64));
-    memcpy(&info->total_bps, sl.hTextMeta + 6, sizeof(u64));
+    const u32 n_reads = info->n_reads;
     if (first_read_no + n_reads > GS_ORDINAL_MASK) return gs_fail(GS_ERR_LIMIT, "read ordinal exceeds 2^40");
     const u64 nBytes = info->total_bps;
-    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
-    CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
     CU(dgrow(&sl.dOut, &sl.outCap, (size_t)n_reads));
     CU(hgrow(&sl.hOut, &sl.hOutCap, (size_t)n_reads));
-    CU(hgrow(&sl.hRecs, &sl.hRecsCap, (size_t)n_reads + 1));
-    CU(dgrow(&sl.dTileSums, &sl.tileSumsCap, (size_t)n_reads / 1024 + 2));
-    if (n_reads == 0) CU(cudaMemsetAsync(sl.dOffsets, 0, sizeof(u64), D.sCopyIn));
-    gs_launch_text_compact(sl.dText, sl.dRecs, sl.dLens, n_reads, sl.dTileSums, sl.dOffsets, sl.dBases, D.sCopyIn);
-    CU(cudaGetLastError());
-    s->launches += n_reads ? 4 : 0;
     GsMatchParams P;
     fill_params(s, D, P);
     CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
@@ -1404,6 +1421,7 @@ extern "C" void gs_filter_close(gs_fsess* s) {
         cudaDeviceSynchronize();
         for (FilterSlot& sl : D.slots) {
             cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dAccept); cudaFree(sl.dErr);
+            text_stage_free(sl);
             if (sl.hAccept) cudaFreeHost(sl.hAccept);
             if (sl.hErr) cudaFreeHost(sl.hErr);
             if (sl.evH2D) cudaEventDestroy(sl.evH2D);
@@ -1481,9 +1499,69 @@ extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_
     if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaMemcpyAsync(sl.hErr, sl.dErr, sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaEventRecord(sl.evDone, D.sCopyOut));
-    sl.pending = true; sl.ticket = t; sl.nReads = n_reads;
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.isText = false;
     s->nextTicket++;
     *ticket = t;
+    return GS_OK;
+}
+
+extern "C" int gs_filter_submit_fastq(gs_fsess* s, const uint8_t* text, uint64_t n_bytes, gs_fastq_info* info, gs_ticket* ticket) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (!ticket || !info || (!text && n_bytes)) return gs_fail(GS_ERR_ARG, "null argument");
+    if (n_bytes >= 0xFFFFFF00ULL) return gs_fail(GS_ERR_LIMIT, "text chunk of %llu bytes (limit 2^32 - 256)", (unsigned long long)n_bytes);
+    memset(info, 0, sizeof(*info));
+    *ticket = 0;
+    const gs_ticket t = s->nextTicket;
+    const size_t nDev = s->devs.size();
+    DevFsess& D = s->devs[(t - 1) % nDev];
+    FilterSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (sl.pending) return gs_fail(GS_ERR_STATE, "more than %d batches in flight on a device: collect ticket %llu first", GS_MAX_INFLIGHT, (unsigned long long)sl.ticket);
+    CU(cudaSetDevice(D.dev));
+    u64 launches = 0;
+    int rcs = text_stage(sl, D.sCopyIn, text, n_bytes, s->k, info, &launches);
+    if (rcs) return rcs;
+    if (info->status) return GS_OK;
+    const u32 n_reads = info->n_reads;
+    CU(dgrow(&sl.dAccept, &sl.accCap, (size_t)n_reads));
+    CU(hgrow(&sl.hAccept, &sl.hAccCap, (size_t)n_reads));
+    CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
+    CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evH2D, 0));
+    CU(cudaMemcpyAsync(sl.hRecs, sl.dRecs, ((size_t)n_reads + 1) * sizeof(gs_fastq_rec), cudaMemcpyDeviceToHost, D.sCopyOut));
+    GsFilterParams P;
+    fill_fparams(s, D, P);
+    P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept; P.errFlag = sl.dErr;
+    CU(cudaMemsetAsync(sl.dErr, 0, sizeof(u32), D.sCompute));
+    if (n_reads) {
+        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
+        gs_launch_filter(P, blocks, D.sCompute);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(sl.evCompute, D.sCompute));
+    CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
+    if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaMemcpyAsync(sl.hErr, sl.dErr, sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    CU(cudaEventRecord(sl.evDone, D.sCopyOut));
+    sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.isText = true;
+    s->nextTicket++;
+    *ticket = t;
+    return GS_OK;
+}
+
+extern "C" int gs_filter_collect_fastq(gs_fsess* s, gs_ticket t, const uint8_t** accept, uint32_t* n_reads, const gs_fastq_rec** recs) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    if (t == 0 || t >= s->nextTicket) return gs_fail(GS_ERR_STATE, "unknown ticket %llu", (unsigned long long)t);
+    const size_t nDev = s->devs.size();
+    DevFsess& D = s->devs[(t - 1) % nDev];
+    FilterSlot& sl = D.slots[((t - 1) / nDev) % GS_MAX_INFLIGHT];
+    if (!sl.pending || sl.ticket != t || !sl.isText) return gs_fail(GS_ERR_STATE, "ticket %llu is not a pending FASTQ text batch", (unsigned long long)t);
+    CU(cudaSetDevice(D.dev));
+    CU(cudaEventSynchronize(sl.evDone));
+    sl.pending = false;
+    if (sl.hErr[0]) return gs_fail(GS_ERR_ARG, "batch of ticket %llu holds malformed read offsets", (unsigned long long)t);
+    if (accept) *accept = sl.hAccept;
+    if (n_reads) *n_reads = sl.nReads;
+    if (recs) *recs = sl.hRecs;
     return GS_OK;
 }
 

@@ -347,6 +347,92 @@ int64_t CountsPerTaxid::valueFor(int type) const {
     switch (type) { case 0: return reads; case 1: return kmers; case 2: return readsBPs; case 3: return reads1KMer; default: return readsKmers; }
 }
 
+// Last byte offset in text[0, len) at which a record starts such that everything before it consists of whole records: a
+// line that starts with '@' whose second-next line starts with '+' (a quality line may start with '@', but then the line
+// two further down is a sequence).  Looks at the last few dozen lines only; 0 = none found.
+static size_t lastRecordStart(const uint8_t* text, size_t len) {
+    size_t starts[64];
+    int ns = 0;
+    size_t p = len;
+    while (ns < 64 && p > 0) {  // line starts from the back: position after each '\n'
+        const void* q = memrchr(text, '\n', p - 1);
+        const size_t st = q ? (size_t)((const uint8_t*)q - text) + 1 : 0;
+        starts[ns++] = st;
+        if (!q) break;
+        p = st;
+    }
+    // starts[0] = start of the last (possibly incomplete) line, starts[i] ascending towards the front
+    for (int i = 2; i < ns; i++)
+        if (text[starts[i]] == '@' && starts[i - 2] < len && text[starts[i - 2]] == '+') return starts[i];
+    return 0;
+}
+
+
+// The GPU feeder's host side, shared by the match and filter drivers: stream one FASTQ input as pinned text chunks that end
+// at a record boundary.  cur() = the batch to fill; submit(batch, cut) hands text[0, cut) to the device and returns true if the
+// device took it (the driver then parks the batch and cur() yields a fresh one), false if it refused (not strict 4-line
+// FASTQ); from the first refusal on, the rest of the input -- the refused chunk included -- goes through the sequential
+// parser (`sequential(LineReader&)`), so the results never depend on this fast path.
+template <typename CurFn, typename SubmitFn, typename SeqFn>
+static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, SubmitFn&& submit, SeqFn&& sequential) {
+    gzFile gz = nullptr;
+    if (!in.path.empty()) {
+        gz = gzopen(in.path.c_str(), "rb");
+        if (!gz) fail("cannot open " + in.path);
+        gzbuffer(gz, 1 << 20);
+    }
+    struct GzCloser { gzFile g; ~GzCloser() { if (g) gzclose(g); } } gzCloser{gz};
+    const size_t chunk = std::max<size_t>(chunkBytes, 1 << 12);
+    size_t memPos = 0;
+    bool eof = false;
+    std::vector<uint8_t> carry;
+    while (!eof || !carry.empty()) {
+        HostBatch* b = cur();
+        b->isText = true;
+        size_t len = carry.size(), target = std::max(chunk, carry.size() + 1);
+        b->textLen = 0;
+        b->ensureText(target + 64);
+        if (len) memcpy(b->text, carry.data(), len);
+        carry.clear();
+        size_t cut = 0;
+        bool refused = false;
+        for (;;) {
+            while (!eof && len < target) {   // fill the pinned chunk straight from the stream / the caller's memory
+                if (gz) {
+                    const int got = gzread(gz, b->text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
+                    if (got < 0) fail("read error");
+                    if (got == 0) eof = true;
+                    len += (size_t)got;
+                } else {
+                    const size_t take = std::min(target - len, in.len - memPos);
+                    if (take) memcpy(b->text + len, in.data + memPos, take);
+                    memPos += take; len += take;
+                    if (memPos == in.len) eof = true;
+                }
+            }
+            cut = eof ? len : lastRecordStart(b->text, len);
+            if (eof || cut > 0) break;
+            if (target >= ((size_t)1 << 31)) { refused = true; break; }  // no record boundary in 2 GiB: not 4-line FASTQ
+            target *= 2;                                                   // records longer than the chunk: widen it
+            b->textLen = len;
+            b->ensureText(target + 64);
+        }
+        if (!refused && cut > 0) {
+            b->textLen = cut;
+            std::vector<uint8_t> tail(b->text + cut, b->text + len);   // the submit may recycle the batch
+            if (submit(b, cut)) { carry.swap(tail); continue; }
+            refused = true;
+        }
+        if (refused) {
+            std::vector<uint8_t> pending(b->text, b->text + len);
+            if (!gz) pending.insert(pending.end(), in.data + memPos, in.data + in.len);   // in-memory input: the rest follows in memory
+            LineReader lr(gz, pending.data(), pending.size());
+            sequential(lr);
+            return;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FastqKMerMatcher
 // ---------------------------------------------------------------------------------------------------------
@@ -473,26 +559,6 @@ void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filter
     }
 }
 
-// Last byte offset in text[0, len) at which a record starts such that everything before it consists of whole records: a
-// line that starts with '@' whose second-next line starts with '+' (a quality line may start with '@', but then the line
-// two further down is a sequence).  Looks at the last few dozen lines only; 0 = none found.
-static size_t lastRecordStart(const uint8_t* text, size_t len) {
-    size_t starts[64];
-    int ns = 0;
-    size_t p = len;
-    while (ns < 64 && p > 0) {  // line starts from the back: position after each '\n'
-        const void* q = memrchr(text, '\n', p - 1);
-        const size_t st = q ? (size_t)((const uint8_t*)q - text) + 1 : 0;
-        starts[ns++] = st;
-        if (!q) break;
-        p = st;
-    }
-    // starts[0] = start of the last (possibly incomplete) line, starts[i] ascending towards the front
-    for (int i = 2; i < ns; i++)
-        if (text[starts[i]] == '@' && starts[i - 2] < len && text[starts[i - 2]] == '+') return starts[i];
-    return 0;
-}
-
 MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* krakenOut) {
     const int V = meta_.nValues;
     gs_match_cfg c;
@@ -551,82 +617,30 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
         }
         // ---- GPU feeder: text chunks cut at record boundaries; `cur` is the batch being filled
         flush();  // host-parsed reads of an earlier input keep their place in the order
-        gzFile gz = nullptr;
-        if (!in.path.empty()) {
-            gz = gzopen(in.path.c_str(), "rb");
-            if (!gz) fail("cannot open " + in.path);
-            gzbuffer(gz, 1 << 20);
-        }
-        struct GzCloser { gzFile g; ~GzCloser() { if (g) gzclose(g); } } gzCloser{gz};
-        const size_t chunk = std::max<size_t>(cfg_.textChunkBytes, 1 << 12);
-        size_t memPos = 0;
-        bool eof = false, refused = false;
-        std::vector<uint8_t> carry;
-        while (!eof || !carry.empty()) {
-            cur->isText = true;
-            size_t len = carry.size(), target = std::max(chunk, carry.size() + 1);
-            cur->textLen = 0;
-            cur->ensureText(target + 64);
-            if (len) memcpy(cur->text, carry.data(), len);
-            carry.clear();
-            size_t cut = 0;
-            for (;;) {
-                while (!eof && len < target) {   // fill the pinned chunk straight from the stream / the caller's memory
-                    if (gz) {
-                        const int got = gzread(gz, cur->text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
-                        if (got < 0) fail("read error");
-                        if (got == 0) eof = true;
-                        len += (size_t)got;
-                    } else {
-                        const size_t take = std::min(target - len, in.len - memPos);
-                        if (take) memcpy(cur->text + len, in.data + memPos, take);
-                        memPos += take; len += take;
-                        if (memPos == in.len) eof = true;
-                    }
-                }
-                cut = eof ? len : lastRecordStart(cur->text, len);
-                if (eof || cut > 0) break;
-                if (target >= ((size_t)1 << 31)) { refused = true; break; }  // no record boundary in 2 GiB: not 4-line FASTQ
-                target *= 2;                                                   // records longer than the chunk: widen it
-                cur->textLen = len;
-                cur->ensureText(target + 64);
-            }
-            gs_fastq_info info;
-            memset(&info, 0, sizeof(info));
-            gs_ticket t = 0;
-            if (!refused && cut > 0) {
-                check(gs_match_submit_fastq(s, cur->text, cut, ordinal, &info, &t), "gs_match_submit_fastq");
+        feedFastqText(in, cfg_.textChunkBytes,
+            [&]() -> HostBatch* { return cur; },
+            [&](HostBatch* b, size_t cut) -> bool {
+                gs_fastq_info info;
+                gs_ticket t = 0;
+                check(gs_match_submit_fastq(s, b->text, cut, ordinal, &info, &t), "gs_match_submit_fastq");
                 textChunks++;
-                if (t == 0 && info.status) refused = true;
-            }
-            if (refused) {
-                // sequential parser over the bytes not yet consumed: this chunk, then the rest of the stream
-                textChunksRefused++;
-                std::vector<uint8_t> pending(cur->text, cur->text + len);
-                cur->reset(ordinal);
-                LineReader lr(gz, pending.data(), pending.size());
-                if (!gz) {  // in-memory input: the rest follows in memory
-                    pending.insert(pending.end(), in.data + memPos, in.data + in.len);
-                    LineReader lrm(nullptr, pending.data(), pending.size());
-                    reader.readFastqFrom(lrm, onRecord);
-                } else {
-                    reader.readFastqFrom(lr, onRecord);
-                }
-                totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
-                eof = true;
-                break;
-            }
-            if (cut < len) carry.assign(cur->text + cut, cur->text + len);
-            if (t) {
-                cur->ticket = t; cur->textLen = cut; cur->n = info.n_reads; cur->firstOrdinal = ordinal;
+                if (info.status) return false;
+                b->ticket = t; b->n = info.n_reads; b->firstOrdinal = ordinal;
                 ordinal += info.n_reads;
                 totalReads += info.n_reads; totalKMers += (int64_t)info.total_kmers; totalBPs += (int64_t)info.total_bps;
                 inflight.push_back(cur);
                 if (inflight.size() >= maxInflight) collectOldest();
                 cur = freeList.front(); freeList.pop_front();
-            }
-            cur->reset(ordinal);
-        }
+                cur->reset(ordinal);
+                return true;
+            },
+            [&](LineReader& lr) {
+                textChunksRefused++;
+                cur->reset(ordinal);
+                reader.readFastqFrom(lr, onRecord);
+                totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+            });
+        if (cur->isText) cur->reset(ordinal);   // a chunk buffer that was filled but never submitted (empty input)
     }
     flush();
     while (!inflight.empty()) collectOldest();
@@ -806,6 +820,21 @@ void FastqBloomFilter::runFilter(const std::vector<Input>& fastqs, OutputSink* f
     std::vector<uint8_t> acc;
     auto collectOldest = [&]() {
         HostBatch* b = inflight.front(); inflight.pop_front();
+        if (b->isText) {   // records are read from the pinned text through the device's record table
+            const uint8_t* a = nullptr; const gs_fastq_rec* recs = nullptr; uint32_t n = 0;
+            check(gs_filter_collect_fastq(s, b->ticket, &a, &n, &recs), "gs_filter_collect_fastq");
+            for (uint32_t i = 0; i < n; i++) {
+                accept.push_back(a[i]);
+                acceptedReads += a[i];
+                OutputSink* out = a[i] ? filtered : rest;
+                if (!out) continue;
+                const gs_fastq_rec& rc = recs[i];
+                writeRead(*out, b->text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), b->text + rc.seq_start, (size_t)rc.seq_len,
+                          b->text + rc.qual_start, (size_t)(recs[i + 1].hdr_start - 1 - rc.qual_start), withProbs_, scratch);
+            }
+            freeList.push_back(b);
+            return;
+        }
         acc.resize(b->n);
         check(gs_filter_collect(s, b->ticket, acc.data()), "gs_filter_collect");
         for (uint32_t i = 0; i < b->n; i++) {   // nextEntry (:92-105): rewriteInput to `indexed` or `notIndexed`
@@ -829,12 +858,40 @@ void FastqBloomFilter::runFilter(const std::vector<Input>& fastqs, OutputSink* f
         cur->reset(0);
     };
     FastqReader reader(k_, withProbs_);
+    auto onRecord = [&](const Record& r, int64_t) {
+        if (cur->n >= batchReads_) flush();
+        cur->add(r, k_, withProbs_);
+    };
     for (const Input& in : fastqs) {
-        reader.readFastq(in, [&](const Record& r, int64_t) {
-            if (cur->n >= batchReads_) flush();
-            cur->add(r, k_, withProbs_);
-        });
-        totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+        if (!gpuParse || in.fasta) {
+            reader.readFastq(in, onRecord);
+            totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+            continue;
+        }
+        flush();
+        feedFastqText(in, textChunkBytes,
+            [&]() -> HostBatch* { return cur; },
+            [&](HostBatch* b, size_t cut) -> bool {
+                gs_fastq_info info;
+                gs_ticket t = 0;
+                check(gs_filter_submit_fastq(s, b->text, cut, &info, &t), "gs_filter_submit_fastq");
+                textChunks++;
+                if (info.status) return false;
+                b->ticket = t; b->n = info.n_reads;
+                totalReads += info.n_reads; totalKMers += (int64_t)info.total_kmers; totalBPs += (int64_t)info.total_bps;
+                inflight.push_back(cur);
+                if (inflight.size() >= maxInflight) collectOldest();
+                cur = freeList.front(); freeList.pop_front();
+                cur->reset(0);
+                return true;
+            },
+            [&](LineReader& lr) {
+                textChunksRefused++;
+                cur->reset(0);
+                reader.readFastqFrom(lr, onRecord);
+                totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
+            });
+        if (cur->isText) cur->reset(0);
     }
     flush();
     while (!inflight.empty()) collectOldest();
@@ -931,15 +988,18 @@ gsh_result* gsh_match_goal(gs_db* db, const DbMeta* meta, const gsh_match_cfg* c
 // The `filter` goal: FilterGoal.makeFile (C/goals/FilterGoal.java:80-108)
 gsh_result* gsh_filter_goal(gs_filter* f, int k, int min_pos_count, double pos_ratio, int with_probs, uint32_t batch_reads,
                             const uint8_t* const* data, const size_t* lens, const char* const* paths, const int* is_fasta, int n_inputs,
-                            const char* filtered_path, const char* rest_path, int want_rest) {
+                            const char* filtered_path, const char* rest_path, int want_rest, uint32_t text_chunk_bytes) {
     gsh_result* r = new gsh_result();
     try {
         FastqBloomFilter flt(f, k, min_pos_count, pos_ratio, with_probs != 0, batch_reads ? batch_reads : (1u << 20));
+        if (text_chunk_bytes == 0xFFFFFFFFu) flt.gpuParse = false;
+        else if (text_chunk_bytes) flt.textChunkBytes = text_chunk_bytes;
         OutputSink filtered, rest;
         if (filtered_path && filtered_path[0]) filtered.path = filtered_path; else filtered.mem = &r->filtered;
         if (rest_path && rest_path[0]) rest.path = rest_path; else rest.mem = &r->rest;
         flt.runFilter(toInputs(data, lens, paths, is_fasta, n_inputs), &filtered, want_rest ? &rest : nullptr);
         r->totals[0] = flt.totalReads; r->totals[1] = flt.totalKMers; r->totals[2] = flt.totalBPs;
+        r->feeder[0] = flt.textChunks; r->feeder[1] = flt.textChunksRefused;
         r->accept.swap(flt.accept);
     } catch (const std::exception& e) { r->error = e.what(); }
     return r;

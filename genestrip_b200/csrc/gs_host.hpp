@@ -134,6 +134,9 @@ class FastqBloomFilter {
     void runFilter(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* rest);
     int64_t totalReads = 0, totalKMers = 0, totalBPs = 0, acceptedReads = 0;
     std::vector<uint8_t> accept;  // per read, input order (kept for the parity tests)
+    bool gpuParse = true;         // FASTQ inputs as raw text chunks, records split on the GPU (see MatchConfig::gpuParse)
+    size_t textChunkBytes = (size_t)256 << 20;
+    uint64_t textChunks = 0, textChunksRefused = 0;
 
    private:
     gs_filter* f_;

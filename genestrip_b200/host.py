@@ -32,7 +32,7 @@ def _lib():
         L.gsh_match_goal.restype = _P
         L.gsh_match_goal.argtypes = [_P, _P, C.POINTER(HostMatchCfg), _P, _P, _P, _P, C.c_int, C.c_char_p, C.c_char_p]
         L.gsh_filter_goal.restype = _P
-        L.gsh_filter_goal.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint32, _P, _P, _P, _P, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.gsh_filter_goal.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint32, _P, _P, _P, _P, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32]
         L.gsh_parse_only.restype = _P
         L.gsh_parse_only.argtypes = [C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]
         L.gsh_result_free.argtypes = [_P]
@@ -138,10 +138,11 @@ def match_goal(db, meta, files, is_fasta=None, write_filtered=False, write_krake
 
 
 def filter_goal(flt, k, files, is_fasta=None, min_pos_count=1, pos_ratio=0.2, with_probs=False, batch_reads=0, filtered_path=None,
-                rest_path=None, want_rest=True):
+                rest_path=None, want_rest=True, gpu_parse=True, text_chunk_bytes=0):
     keep, data, lens, paths, fa, n = _inputs(files, is_fasta)
     h = _lib().gsh_filter_goal(flt.h, k, min_pos_count, pos_ratio, int(with_probs), batch_reads, data, lens, paths, fa, n,
-                               filtered_path.encode() if filtered_path else None, rest_path.encode() if rest_path else None, int(want_rest))
+                               filtered_path.encode() if filtered_path else None, rest_path.encode() if rest_path else None, int(want_rest),
+                               (int(text_chunk_bytes) if gpu_parse else 0xFFFFFFFF))
     return GoalResult(h)
 
 

@@ -258,6 +258,10 @@ gs_fsess* gs_filter_open(gs_filter*, int k, int min_pos_count, double pos_ratio)
 int gs_filter_submit(gs_fsess*, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, gs_ticket*);
 /* accept[n_reads]: 1 = isAcceptRead (C/bloom/FastqBloomFilter.java:120-161). */
 int gs_filter_collect(gs_fsess*, gs_ticket, uint8_t* accept);
+/* Raw FASTQ text (see gs_match_submit_fastq): accept[n_reads] and recs[n_reads + 1] are views of the session's pinned
+ * staging, valid until GS_MAX_INFLIGHT further batches were submitted to the same device. */
+int gs_filter_submit_fastq(gs_fsess*, const uint8_t* text, uint64_t n_bytes, gs_fastq_info* info, gs_ticket* ticket);
+int gs_filter_collect_fastq(gs_fsess*, gs_ticket, const uint8_t** accept, uint32_t* n_reads, const gs_fastq_rec** recs);
 int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                          uint8_t* d_accept);
 int gs_filter_sync(gs_fsess*);

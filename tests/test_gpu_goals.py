@@ -231,3 +231,29 @@ def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host):
         assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps), name
         assert res.filtered == orun.filtered, name
         _assert_csv_equal(res.csv, orun.csv)
+
+
+def test_filter_goal_gpu_fastq_feeder(project, oracle, native, gpu_ctx, host):
+    """`filter` with the GPU FASTQ feeder: accepted / rejected FASTQ byte-identical with the oracle (ReadEntry.write,
+    C/fastq/AbstractFastqReader.java:570-584), with and without qualities, incl. the fall-back on a non-strict tail."""
+    odb, gdb, meta, genomes = project
+    flt_o = odb.index_filter()
+    okind, p0, p1, factors, words = flt_o.params()
+    gflt = native.Filter(gpu_ctx, okind, p0, p1, factors, words)
+    try:
+        b, o, s = _reads(genomes, 4000, 15, frac_db=0.3)
+        rng = np.random.default_rng(9)
+        qual = bytes(rng.integers(33, 74, size=int(o[-1])).astype(np.uint8))
+        bb = b.tobytes()
+        fq = b"".join(b"@r%d %d\n%s\n+r%d\n%s\n" % (i, s[i], bb[int(o[i]):int(o[i + 1])], i, qual[int(o[i]):int(o[i + 1])]) for i in range(len(o) - 1))
+        tail = b"@last\n" + genomes[0][1][100:250] + b"\n+\n" + b"I" * 150   # no trailing newline
+        for text, refused in ((fq, 0), (fq + tail, 1)):
+            for with_probs in (False, True):
+                orun = oracle.filter_files(flt_o, K, [text], min_pos_count=1, pos_ratio=0.2, with_probs=with_probs)
+                res = host.filter_goal(gflt, K, [text], with_probs=with_probs, text_chunk_bytes=60000, batch_reads=900)
+                assert res.text_chunks >= 10 and res.text_chunks_refused == refused
+                np.testing.assert_array_equal(res.accept, orun.accept)
+                assert res.filtered == orun.filtered and res.rest == orun.rest
+                assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+    finally:
+        gflt.close()
