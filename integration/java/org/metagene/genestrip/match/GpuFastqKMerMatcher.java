@@ -36,6 +36,14 @@ final class GsNative {
     static native ByteBuffer[] matchCollect(long sess, long ticket);
     static native void matchFinish(long sess, ByteBuffer counts, ByteBuffer topCounts);
     static native void matchClose(long sess);
+    // raw FASTQ text chunks (records split on the GPU); {ticket, nReads, status, totalKmers, totalBps}
+    static native long[] matchSubmitFastq(long sess, ByteBuffer text, long nBytes, long firstReadNo);
+    static native ByteBuffer[] matchCollectFastq(long sess, long ticket);   // results, events, event header offsets, record table
+    static native long[] filterSubmitFastq(long fsess, ByteBuffer text, long nBytes);
+    static native ByteBuffer[] filterCollectFastq(long fsess, long ticket);
+    // db goal, update phase (DBGoal.MyFastaReader): value = LCA(value, region node) for the stored k-mers of the regions
+    static native long dbUpdate(long db, ByteBuffer seq, long nBytes, long[] regionOffsets, int[] regionValueIndex, boolean upperCase);
+    static native void dbGetValues(long db, long offset, short[] vals, int n);
 }
 
 /**

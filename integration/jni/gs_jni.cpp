@@ -132,6 +132,62 @@ JNIEXPORT jlong JNICALL J(filterSubmit)(JNIEnv* env, jclass, jlong s, jobject ba
 JNIEXPORT void JNICALL J(filterCollect)(JNIEnv* env, jclass, jlong s, jlong ticket, jobject accept) {
     CHECK(gs_filter_collect((gs_fsess*)s, (gs_ticket)ticket, (uint8_t*)env->GetDirectBufferAddress(accept)));
 }
+// ---- raw FASTQ text (GPU feeder): text = direct buffer over pinned memory holding whole records.
+// Returns {ticket, nReads, status, totalKmers, totalBps}; ticket == 0 && status != 0: parse this chunk with the Java reader.
+JNIEXPORT jlongArray JNICALL J(matchSubmitFastq)(JNIEnv* env, jclass, jlong s, jobject text, jlong nBytes, jlong firstReadNo) {
+    gs_fastq_info info; gs_ticket t = 0;
+    if (gs_match_submit_fastq((gs_sess*)s, (const uint8_t*)env->GetDirectBufferAddress(text), (uint64_t)nBytes, (uint64_t)firstReadNo, &info, &t) != GS_OK) { throwLast(env); return nullptr; }
+    const jlong v[5] = {(jlong)t, (jlong)info.n_reads, (jlong)info.status, (jlong)info.total_kmers, (jlong)info.total_bps};
+    jlongArray arr = env->NewLongArray(5);
+    env->SetLongArrayRegion(arr, 0, 5, v);
+    return arr;
+}
+// [0] results, [1] max-contig events, [2] header offset per event (u32), [3] record table (nReads + 1) x gs_fastq_rec
+JNIEXPORT jobjectArray JNICALL J(matchCollectFastq)(JNIEnv* env, jclass, jlong s, jlong ticket) {
+    const gs_read_result* out; const gs_maxcontig_event* ev; const uint32_t* eh; const gs_fastq_rec* recs; uint32_t n = 0, nev = 0;
+    if (gs_match_collect_fastq((gs_sess*)s, (gs_ticket)ticket, &out, &n, &ev, &eh, &nev, &recs) != GS_OK) { throwLast(env); return nullptr; }
+    jobjectArray arr = env->NewObjectArray(4, env->FindClass("java/nio/ByteBuffer"), nullptr);
+    env->SetObjectArrayElement(arr, 0, env->NewDirectByteBuffer((void*)out, (jlong)n * (jlong)sizeof(gs_read_result)));
+    env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer((void*)ev, (jlong)nev * (jlong)sizeof(gs_maxcontig_event)));
+    env->SetObjectArrayElement(arr, 2, env->NewDirectByteBuffer((void*)eh, (jlong)nev * 4));
+    env->SetObjectArrayElement(arr, 3, env->NewDirectByteBuffer((void*)recs, ((jlong)n + 1) * (jlong)sizeof(gs_fastq_rec)));
+    return arr;
+}
+JNIEXPORT jlongArray JNICALL J(filterSubmitFastq)(JNIEnv* env, jclass, jlong s, jobject text, jlong nBytes) {
+    gs_fastq_info info; gs_ticket t = 0;
+    if (gs_filter_submit_fastq((gs_fsess*)s, (const uint8_t*)env->GetDirectBufferAddress(text), (uint64_t)nBytes, &info, &t) != GS_OK) { throwLast(env); return nullptr; }
+    const jlong v[5] = {(jlong)t, (jlong)info.n_reads, (jlong)info.status, (jlong)info.total_kmers, (jlong)info.total_bps};
+    jlongArray arr = env->NewLongArray(5);
+    env->SetLongArrayRegion(arr, 0, 5, v);
+    return arr;
+}
+JNIEXPORT jobjectArray JNICALL J(filterCollectFastq)(JNIEnv* env, jclass, jlong s, jlong ticket) {
+    const uint8_t* acc; const gs_fastq_rec* recs; uint32_t n = 0;
+    if (gs_filter_collect_fastq((gs_fsess*)s, (gs_ticket)ticket, &acc, &n, &recs) != GS_OK) { throwLast(env); return nullptr; }
+    jobjectArray arr = env->NewObjectArray(2, env->FindClass("java/nio/ByteBuffer"), nullptr);
+    env->SetObjectArrayElement(arr, 0, env->NewDirectByteBuffer((void*)acc, (jlong)n));
+    env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer((void*)recs, ((jlong)n + 1) * (jlong)sizeof(gs_fastq_rec)));
+    return arr;
+}
+// ---- db goal, update phase (DBGoal.MyFastaReader.handleStore): the regions of one FASTA batch, line ends stripped
+JNIEXPORT jlong JNICALL J(dbUpdate)(JNIEnv* env, jclass, jlong db, jobject seq, jlong nBytes, jlongArray regionOffsets, jintArray regionValueIndex, jboolean upperCase) {
+    const jsize nr = env->GetArrayLength(regionValueIndex);
+    jlong* off = env->GetLongArrayElements(regionOffsets, nullptr);
+    jint* vid = env->GetIntArrayElements(regionValueIndex, nullptr);
+    uint64_t changed = 0;
+    const int rc = gs_db_update((gs_db*)db, (const uint8_t*)env->GetDirectBufferAddress(seq), (uint64_t)nBytes, (const uint64_t*)off, (const int32_t*)vid,
+                                (uint32_t)nr, upperCase ? 1 : 0, &changed);
+    env->ReleaseLongArrayElements(regionOffsets, off, JNI_ABORT);
+    env->ReleaseIntArrayElements(regionValueIndex, vid, JNI_ABORT);
+    if (rc != GS_OK) throwLast(env);
+    return (jlong)changed;
+}
+JNIEXPORT void JNICALL J(dbGetValues)(JNIEnv* env, jclass, jlong db, jlong offset, jshortArray vals, jint n) {
+    void* p = env->GetPrimitiveArrayCritical(vals, nullptr);
+    const int rc = gs_db_get_values((gs_db*)db, (uint64_t)offset, (int16_t*)p, (uint64_t)n);
+    env->ReleasePrimitiveArrayCritical(vals, p, 0);
+    if (rc != GS_OK) throwLast(env);
+}
 JNIEXPORT void JNICALL J(filterClose)(JNIEnv*, jclass, jlong s) { gs_filter_close((gs_fsess*)s); }
 JNIEXPORT void JNICALL J(filterDestroy)(JNIEnv*, jclass, jlong f) { gs_filter_destroy((gs_filter*)f); }
 
