@@ -1027,6 +1027,9 @@ gsh_result* gsh_parse_only(int k, int with_probs, const uint8_t* const* data, co
     return r;
 }
 
+// The feeder's record-boundary search alone (no GPU): offset of the last record start in text[0, len), 0 = none in sight.
+size_t gsh_last_record_start(const uint8_t* text, size_t len) { return lastRecordStart(text, len); }
+
 void gsh_result_free(gsh_result* r) { delete r; }
 const char* gsh_result_error(const gsh_result* r) { return r->error.c_str(); }
 const char* gsh_result_text(const gsh_result* r, int which, size_t* len) {

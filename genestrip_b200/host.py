@@ -48,6 +48,8 @@ def _lib():
         L.gsh_result_launches.restype = C.c_uint64
         L.gsh_result_launches.argtypes = [_P]
         L.gsh_result_feeder.argtypes = [_P, _P]
+        L.gsh_last_record_start.restype = C.c_size_t
+        L.gsh_last_record_start.argtypes = [_P, C.c_size_t]
         L.gsh_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]
         _ready = True
     return L
@@ -150,6 +152,12 @@ def parse_only(k, files, is_fasta=None, with_probs=False):
     """Host parser alone (no GPU): .rest = every record rewritten by ReadEntry.write, totals, .accept = pooled entry index."""
     keep, data, lens, paths, fa, n = _inputs(files, is_fasta)
     return GoalResult(_lib().gsh_parse_only(k, int(with_probs), data, lens, paths, fa, n))
+
+
+def last_record_start(text):
+    """Where the GPU feeder would cut a text chunk: offset of the last record start (0 = no boundary found)."""
+    b = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, dtype=np.uint8)
+    return int(_lib().gsh_last_record_start(b.ctypes.data, len(text)))
 
 
 def java_double_to_string(v):

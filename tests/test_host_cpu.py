@@ -64,3 +64,36 @@ def test_parser_matches_oracle_on_fixtures_and_quirks(native, oracle, tmp_path):
     m = host.parse_only(31, [big])
     assert host.parse_only(31, [p1]).rest == m.rest == host.parse_only(31, [p2]).rest and m.total_reads == 5000
     assert list(host.parse_only(31, [fasta], [True]).accept) == [0, 1, 0, 1]
+
+
+def test_feeder_record_boundary_search(native):
+    """Where the GPU FASTQ feeder cuts a text chunk (feedFastqText / lastRecordStart in gs_host.cpp): at a line that starts
+    with '@' whose second-next line starts with '+', searched from the end; a quality line that starts with '@' is never
+    taken for a header, and everything before the cut consists of whole records."""
+    import numpy as np
+    from genestrip_b200 import host, synth
+    rng = np.random.default_rng(3)
+    g = synth.random_genome(rng, 4000).tobytes()
+    recs = []
+    for i in range(40):
+        L = int(rng.integers(1, 120))
+        q = bytes(rng.integers(33, 74, size=L).astype(np.uint8))
+        if i % 3 == 0:
+            q = b"@" + q[1:]          # quality starting with '@'
+        if i % 5 == 0:
+            q = b"+" + q[1:]          # ... or with '+'
+        recs.append(b"@r%d d\n%s\n+%s\n%s\n" % (i, g[i * 50:i * 50 + L], b"r%d" % i if i % 2 else b"", q))
+    text = b"".join(recs)
+    starts = np.cumsum([0] + [len(r) for r in recs])
+    for cut_at in list(range(len(recs[0]) + len(recs[1]) + len(recs[2]) + 1, len(text), 37)) + [len(text)]:
+        c = host.last_record_start(text[:cut_at])
+        assert c in starts, "cut %d of %d is not a record start" % (c, cut_at)
+        assert c <= cut_at
+        # the search finds one of the last records (never further back than the 64 lines it looks at)
+        assert cut_at - c <= 64 * 125
+    # a complete record must follow the cut's header within the chunk: header + sequence + '+' line seen
+    c = host.last_record_start(recs[0] + recs[1][:len(recs[1]) // 4])
+    assert c in (0, len(recs[0])) or c == 0
+    assert host.last_record_start(b"") == 0
+    assert host.last_record_start(b"no newline at all") == 0
+    assert host.last_record_start(b"ACGT\nACGT\nACGT\nACGT\n" * 30) == 0     # no '@' header anywhere
