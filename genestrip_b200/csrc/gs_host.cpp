@@ -11,6 +11,10 @@
 #include <cstring>
 #include <deque>
 #include <stdexcept>
+#include <thread>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 namespace gsh {
 
@@ -376,12 +380,51 @@ static size_t lastRecordStart(const uint8_t* text, size_t len) {
 template <typename CurFn, typename SubmitFn, typename SeqFn>
 static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, SubmitFn&& submit, SeqFn&& sequential) {
     gzFile gz = nullptr;
+    int fd = -1;        // uncompressed files are read with parallel pread() straight into the pinned chunk
+    size_t filePos = 0;
     if (!in.path.empty()) {
-        gz = gzopen(in.path.c_str(), "rb");
-        if (!gz) fail("cannot open " + in.path);
-        gzbuffer(gz, 1 << 20);
+        fd = open(in.path.c_str(), O_RDONLY);
+        if (fd < 0) fail("cannot open " + in.path);
+        unsigned char magic[2] = {0, 0};
+        const ssize_t m = pread(fd, magic, 2, 0);
+        if (m == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {   // gzip: zlib inflates on this thread
+            close(fd); fd = -1;
+            gz = gzopen(in.path.c_str(), "rb");
+            if (!gz) fail("cannot open " + in.path);
+            gzbuffer(gz, 1 << 20);
+        }
     }
-    struct GzCloser { gzFile g; ~GzCloser() { if (g) gzclose(g); } } gzCloser{gz};
+    struct Closer { gzFile& g; int& f; ~Closer() { if (g) gzclose(g); if (f >= 0) close(f); } } closer{gz, fd};
+    auto readPlain = [&](uint8_t* dst, size_t want) -> size_t {
+        const size_t slice = (size_t)4 << 20;
+        static const size_t maxThreads = [] { const char* e = getenv("GS_FEEDER_THREADS"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 8); }();
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>({maxThreads, (size_t)std::max(1u, std::thread::hardware_concurrency()), (want + slice - 1) / slice}));
+        std::vector<size_t> got(nt, 0);
+        std::vector<int> err(nt, 0);
+        auto work = [&](unsigned t) {
+            const size_t a = want * t / nt, b = want * (t + 1) / nt;
+            size_t done = 0;
+            while (a + done < b) {
+                const ssize_t r = pread(fd, dst + a + done, b - a - done, (off_t)(filePos + a + done));
+                if (r < 0) { err[t] = 1; break; }
+                if (r == 0) break;
+                done += (size_t)r;
+            }
+            got[t] = done;
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        size_t total = 0;
+        for (unsigned t = 0; t < nt; t++) {
+            if (err[t]) fail("read error");
+            total += got[t];
+            if (got[t] < want * (t + 1) / nt - want * t / nt) break;   // end of file inside this slice
+        }
+        filePos += total;
+        return total;
+    };
     const size_t chunk = std::max<size_t>(chunkBytes, 1 << 12);
     size_t memPos = 0;
     bool eof = false;
@@ -403,6 +446,11 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, Submi
                     if (got < 0) fail("read error");
                     if (got == 0) eof = true;
                     len += (size_t)got;
+                } else if (fd >= 0) {
+                    const size_t want = target - len;
+                    const size_t got = readPlain(b->text + len, want);
+                    if (got < want) eof = true;
+                    len += got;
                 } else {
                     const size_t take = std::min(target - len, in.len - memPos);
                     if (take) memcpy(b->text + len, in.data + memPos, take);
@@ -425,7 +473,14 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, Submi
         }
         if (refused) {
             std::vector<uint8_t> pending(b->text, b->text + len);
-            if (!gz) pending.insert(pending.end(), in.data + memPos, in.data + in.len);   // in-memory input: the rest follows in memory
+            if (fd >= 0) {   // plain file: hand the rest of it to zlib's transparent reader, positioned behind what was consumed
+                gz = gzopen(in.path.c_str(), "rb");
+                if (!gz) fail("cannot open " + in.path);
+                gzbuffer(gz, 1 << 20);
+                if (gzseek(gz, (z_off_t)filePos, SEEK_SET) < 0) fail("seek error");
+            } else if (!gz) {
+                pending.insert(pending.end(), in.data + memPos, in.data + in.len);   // in-memory input: the rest follows in memory
+            }
             LineReader lr(gz, pending.data(), pending.size());
             sequential(lr);
             return;

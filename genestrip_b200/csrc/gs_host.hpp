@@ -54,7 +54,7 @@ struct MatchConfig {  // the config keys the path reads (C/GSConfigKey.java:302-
     // FASTQ inputs (not FASTA, no kraken-style output): raw text chunks go to the GPU, which splits the records
     // (gs_match_submit_fastq); the first chunk the device refuses switches the rest of that input to the sequential parser
     bool gpuParse = true;
-    size_t textChunkBytes = (size_t)256 << 20;
+    size_t textChunkBytes = (size_t)64 << 20;
 };
 
 struct CountsPerTaxid {
@@ -135,7 +135,7 @@ class FastqBloomFilter {
     int64_t totalReads = 0, totalKMers = 0, totalBPs = 0, acceptedReads = 0;
     std::vector<uint8_t> accept;  // per read, input order (kept for the parity tests)
     bool gpuParse = true;         // FASTQ inputs as raw text chunks, records split on the GPU (see MatchConfig::gpuParse)
-    size_t textChunkBytes = (size_t)256 << 20;
+    size_t textChunkBytes = (size_t)64 << 20;
     uint64_t textChunks = 0, textChunksRefused = 0;
 
    private:

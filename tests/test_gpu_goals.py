@@ -194,8 +194,10 @@ def test_match_goal_gpu_fastq_feeder(project, oracle, host, tmp_path, with_probs
         f.write(f2)
     ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=with_probs)
     orun = odb.match_files(ocfg, [f1, f2])
+    p1 = str(tmp_path / "a.fastq")   # plain file: parallel pread() straight into the pinned chunks
+    open(p1, "wb").write(f1)
     for chunk in (30000, 1 << 20):
-        res = host.match_goal(gdb, meta, [f1, p2], write_filtered=True, with_probs=int(with_probs), text_chunk_bytes=chunk)
+        res = host.match_goal(gdb, meta, [f1 if chunk == 30000 else p1, p2], write_filtered=True, with_probs=int(with_probs), text_chunk_bytes=chunk)
         assert res.text_chunks_refused == 0 and res.text_chunks >= (40 if chunk == 30000 else 2)
         assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
         assert res.filtered == orun.filtered
@@ -208,7 +210,7 @@ def test_match_goal_gpu_fastq_feeder(project, oracle, host, tmp_path, with_probs
     _assert_csv_equal(res0.csv, orun.csv)
 
 
-def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host):
+def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host, tmp_path):
     """Inputs that are not strict 4-line FASTQ: the device refuses the chunk and the sequential parser takes over from
     exactly there -- a strict prefix stays on the GPU, the results are those of the reference parser throughout."""
     odb, gdb, meta, genomes = project
@@ -225,7 +227,13 @@ def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host):
                               ("multi-line from the start", odd[1] + strict, 0)):
         ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=True)
         orun = odb.match_files(ocfg, [fq])
-        res = host.match_goal(gdb, meta, [fq], write_filtered=True, with_probs=1, text_chunk_bytes=50000, batch_reads=500)
+        path = str(tmp_path / "in.fastq")
+        open(path, "wb").write(fq)
+        for src in (fq, path):   # memory, and a plain file (the sequential parser re-opens it behind the consumed bytes)
+            res = host.match_goal(gdb, meta, [src], write_filtered=True, with_probs=1, text_chunk_bytes=50000, batch_reads=500)
+            assert res.text_chunks_refused == 1, name
+            assert res.filtered == orun.filtered, name
+            _assert_csv_equal(res.csv, orun.csv)
         assert res.text_chunks_refused == 1, name
         assert res.text_chunks - res.text_chunks_refused >= min_gpu, name
         assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps), name
