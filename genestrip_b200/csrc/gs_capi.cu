@@ -167,6 +167,7 @@ struct gs_db {
     // probe table
     int tbits = 0, rbits = 0;
     int mzBits = 0;  // log2 of the minimizer prefilter's size in bits; 0 = none
+    bool mzWide = false;  // minimizers ordered by a 64-bit hash (stores whose filter would use most of the 32-bit hash space)
     bool seenLeased = false;  // the table's in-line seen bits belong to at most one unique-counting session at a time
     // radix source staging
     std::vector<std::pair<u64, int16_t>> radixItems;
@@ -360,9 +361,11 @@ extern "C" int gs_db_finalize(gs_db* db) {
         int fb = 16;
         while (fb < 32 && (double)(1ULL << fb) < 1.8 * (double)db->n) fb++;
         db->mzBits = fb;
+        db->mzWide = fb > 30;
+        if (const char* e = getenv("GS_DEBUG_MZ_WIDE")) db->mzWide = atoi(e) != 0;   // tests: force the 64-bit minimizer order on small stores
         CU(dmalloc(&d0.mzFilter, (size_t)(1ULL << (fb - 6))));
         CU(cudaMemset(d0.mzFilter, 0, (size_t)(1ULL << (fb - 3))));
-        gs_launch_mz_build(d0.keys, db->n, db->k, d0.mzFilter, (u32)((1ULL << fb) - 1), 0);
+        gs_launch_mz_build(d0.keys, db->n, db->k, d0.mzFilter, (u32)((1ULL << fb) - 1), db->mzWide ? 1 : 0, 0);
         CU(cudaGetLastError());
     }
     // probe table: 1..2 keys per 4-slot bucket
@@ -419,7 +422,7 @@ extern "C" int gs_db_finalize(gs_db* db) {
         v.k = db->k; v.bloom = d.bloom; v.bloomBuckets = db->bloomBuckets; v.bloomMagic = magic_for(db->bloomBuckets);
         v.bloomSeed = db->bloomSeed; v.hasBloom = db->hasBloom ? 1 : 0;
         v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits;
-        v.mzFilter = d.mzFilter; v.mzMask = db->mzBits ? (u32)((1ULL << db->mzBits) - 1) : 0u;
+        v.mzFilter = d.mzFilter; v.mzMask = db->mzBits ? (u32)((1ULL << db->mzBits) - 1) : 0u; v.mzWide = db->mzWide ? 1 : 0;
         v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
     }
     db->bytes = (32ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16 + (db->mzBits ? (1ULL << (db->mzBits - 3)) : 0);

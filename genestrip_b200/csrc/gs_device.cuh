@@ -60,10 +60,11 @@ struct GsDbView {
     // answers hit/miss and yields the value and the position's seen bit (see "probe table" below)
     const u64* tab;
     int tbits, rbits;       // bucket = mix62(key) >> rbits, remainder = low rbits bits, rbits = 62 - tbits
-    // minimizer prefilter (see "minimizer prefilter" below): bit (h & mzMask) of mzFilter is set for the hash h of the
+    // minimizer prefilter (see "minimizer prefilter" below): bit gs_mz_index(h, mzMask) of mzFilter is set for the hash h of the
     // minimizer of every stored k-mer; NULL = no prefilter (k too small)
     const u64* mzFilter;
     u32 mzMask;
+    int mzWide;             // 1: minimizers are ordered by the 64-bit hash and the filter bit comes from its lower half (large stores)
     const int* parent;      // by value index, -1 root / none
     const int* depth;
     const int* pre;         // DFS interval labels: a is ancestor-or-self of b  <=>  pre[a] <= pre[b] <= last[a]
@@ -268,6 +269,34 @@ __device__ __forceinline__ u32 gs_mmer_hash(u64 x, int m) {
     return gs_mmer_hash2(x, r >> (64 - 2 * m));
 }
 
+// Wide variant for stores with more than ~6e8 k-mers: the 32-bit hash space is too small there -- a minimizer hash is a
+// minimum of nine, so the store's and the reads' minimizers crowd into the lowest ninth of it and unrelated m-mers collide on
+// the hash VALUE itself (measured on the 2e9-k-mer database: 40 % of the absent k-mers passed the prefilter instead of 9 %).
+// The order is then taken on 64 bits (the 32-bit hash on top, an independent 32-bit hash below) and the filter bit comes from
+// the lower half, which is uniform.
+__device__ __forceinline__ u64 gs_mmer_hash2w(u64 x, u64 r) {
+    const u64 c = x > r ? x : r;
+    const u64 y = c * 0x9E3779B97F4A7C15ULL;
+    u32 h = (u32)(y >> 32);
+    h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+    const u32 l = (u32)((c * 0xD6E8FEB86659FD93ULL) >> 32);
+    return ((u64)h << 32) | l;
+}
+__device__ __forceinline__ u64 gs_mmer_hashw(u64 x, int m) {
+    u64 c = x ^ 0x5555555555555555ULL;
+    u64 r = __brevll(c);
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    return gs_mmer_hash2w(x, r >> (64 - 2 * m));
+}
+__device__ __forceinline__ u64 gs_mz_of_key_w(u64 key, int k) {
+    const int m = k - GS_MZ_S;
+    const u64 mmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1);
+    u64 best = ~0ULL;
+#pragma unroll
+    for (int j = 0; j <= GS_MZ_S; j++) best = min(best, gs_mmer_hashw((key >> (2 * (GS_MZ_S - j))) & mmask, m));
+    return best;
+}
+
 // minimizer hash of a stored (canonical) k-mer: min over its GS_MZ_W windows (database build, gs_db_lookup self check)
 __device__ __forceinline__ u32 gs_mz_of_key(u64 key, int k) {
     const int m = k - GS_MZ_S;
@@ -278,28 +307,36 @@ __device__ __forceinline__ u32 gs_mz_of_key(u64 key, int k) {
     return best;
 }
 
+// Bit index of a minimizer hash.  A minimizer hash is the MINIMUM of nine hashes, i.e. its distribution is concentrated near
+// zero (density 9(1-x)^8): used as it is, a filter with close to 2^32 bits would be ~9x fuller where both the store's and the
+// reads' minimizers fall (measured on the 2e9-k-mer database: 40 % of the absent k-mers passed instead of 9 %).  The odd
+// multiplication is a bijection on 32 bits that spreads the small values over the whole range.
+__device__ __forceinline__ u32 gs_mz_index(u32 h, u32 mask) { return (h * 0x9E3779B1u) & mask; }
 __device__ __forceinline__ bool gs_mz_test(const u64* __restrict__ filter, u32 mask, u32 h) {
-    const u32 idx = h & mask;
+    const u32 idx = gs_mz_index(h, mask);
     return (__ldg(filter + (idx >> 6)) >> (idx & 63)) & 1ULL;
 }
 
 // Sliding minimum over GS_MZ_W consecutive positions held one per lane: cur = hashes of 32 positions, nxt = hashes of the
 // following 32 (only lanes < GS_MZ_S matter).  van Herk: prefix/suffix minima inside 8-lane blocks, then
 // min(suffix[i], prefix[i + 8]).  preNxt = block prefix minima of nxt (computed by the caller for the next chunk anyway).
-__device__ __forceinline__ u32 gs_seg_prefix_min(u32 v, int lane) {
+template <typename T>
+__device__ __forceinline__ T gs_seg_prefix_min(T v, int lane) {
 #pragma unroll
-    for (int d = 1; d < GS_MZ_S; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) >= d) v = min(v, t); }
+    for (int d = 1; d < GS_MZ_S; d <<= 1) { const T t = __shfl_up_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) >= d) v = min(v, t); }
     return v;
 }
-__device__ __forceinline__ u32 gs_seg_suffix_min(u32 v, int lane) {
+template <typename T>
+__device__ __forceinline__ T gs_seg_suffix_min(T v, int lane) {
 #pragma unroll
-    for (int d = 1; d < GS_MZ_S; d <<= 1) { const u32 t = __shfl_down_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) + d < GS_MZ_S) v = min(v, t); }
+    for (int d = 1; d < GS_MZ_S; d <<= 1) { const T t = __shfl_down_sync(0xFFFFFFFFu, v, d, GS_MZ_S); if ((lane & (GS_MZ_S - 1)) + d < GS_MZ_S) v = min(v, t); }
     return v;
 }
-__device__ __forceinline__ u32 gs_window_min(u32 sufCur, u32 preCur, u32 preNxt, int lane) {
+template <typename T>
+__device__ __forceinline__ T gs_window_min(T sufCur, T preCur, T preNxt, int lane) {
     // position lane + 8 lives in lane + 8 of the current chunk or in lane - 24 of the next one: one rotate of the merged register
-    const u32 merged = lane < GS_MZ_S ? preNxt : preCur;
-    return min(sufCur, __shfl_sync(0xFFFFFFFFu, merged, (lane + GS_MZ_S) & 31));
+    const T merged = lane < GS_MZ_S ? preNxt : preCur;
+    return min(sufCur, (T)__shfl_sync(0xFFFFFFFFu, merged, (lane + GS_MZ_S) & 31));
 }
 
 // value stored at a "storage position" of the unique-k-mer bitset: sorted-array index (classic) or table slot id

@@ -19,6 +19,8 @@
 //  * mergeReadTaxidPath (:568-586) is idempotent per node, so only first occurrences of distinct taxa matter.
 #include "gs_kernels.cuh"
 
+#include <type_traits>
+
 #define FULL 0xFFFFFFFFu
 
 // ---------------------------------------------------------------------------------------------------------
@@ -111,8 +113,9 @@ __global__ void gs_mark_starts_kernel(const u64* __restrict__ offsets, u32 nRead
 // one position: forward / reverse-complement k-mer in registers, minimizer prefilter (L2-resident bit filter, shared by
 // neighbouring lanes), one 256-bit probe-table load for the k-mers that pass, seen bit / hit counter for the hits.
 // The k-mer and m-mer hash of chunk c+1 are computed while chunk c is finished (the sliding minimum needs them anyway).
-template <int LAYOUT, bool DUMP>
-__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {
+template <int LAYOUT, bool DUMP, bool WIDE>
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? 6 : GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {  // WIDE: 40 registers keep six CTAs per SM
+    typedef typename std::conditional<WIDE, u64, u32>::type MzT;  // the minimizer order: 32-bit hash, or 64 bits for large stores
     __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
     __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
     __shared__ u32 s_start[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
@@ -166,23 +169,23 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_LABEL_MIN_BLOCKS) 
 
         // ---- chunks
         u64 fwdN = gs_extract(cw, lane, k), rcN = gs_revcomp(fwdN, k);
-        u32 hN = 0, preN = 0;
-        if (mz) { hN = gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask); preN = gs_seg_prefix_min(hN, lane); }
+        MzT hN = 0, preN = 0;
+        if (mz) { hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcN & mmask) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask); preN = gs_seg_prefix_min(hN, lane); }
 #pragma unroll 1
         for (int c = 0; c < GS_SEG_CHUNKS; c++) {
             const int prel = c * 32 + lane;
             const u64 f = f0 + (u64)prel;
             const u64 fwd = fwdN, rc = rcN;
-            const u32 hC = hN, preC = preN;
+            const MzT hC = hN, preC = preN;
             fwdN = gs_extract(cw, prel + 32, k);
             rcN = gs_revcomp(fwdN, k);
             const u32 vbits = __funnelshift_r(vw[c], vw[c + 1], lane);
             const u32 sbits = __funnelshift_rc(sw[c], sw[c + 1], lane + 1);
             u32 lab = (sbits & k1mask) ? GS_LABEL_END : ((vbits & kmask) != kmask ? GS_LABEL_INVALID : GS_LABEL_PENDING);
             if (mz) {
-                hN = gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask);
+                hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcN & mmask) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask);
                 preN = gs_seg_prefix_min(hN, lane);
-                const u32 mzv = gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane) & db.mzMask;
+                const u32 mzv = gs_mz_index((u32)gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane), db.mzMask);
                 if (lab == GS_LABEL_PENDING && !((__ldg(db.mzFilter + (mzv >> 6)) >> (mzv & 63)) & 1ULL)) lab = GS_LABEL_MISS;
             }
             if (lab == GS_LABEL_PENDING) {
@@ -686,11 +689,12 @@ void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st) {
 void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t st) {
     const int threads = GS_WARPS_PER_BLOCK * 32;
     if (P.layout == GS_LAYOUT_TABLE) {
-        if (dump) gs_label_kernel<GS_LAYOUT_TABLE, true><<<blocks, threads, 0, st>>>(P);
-        else gs_label_kernel<GS_LAYOUT_TABLE, false><<<blocks, threads, 0, st>>>(P);
+        const bool wide = P.db.mzFilter != nullptr && P.db.mzWide;
+        if (dump) { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, true, true><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, true, false><<<blocks, threads, 0, st>>>(P); }
+        else { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, false, true><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, false, false><<<blocks, threads, 0, st>>>(P); }
     } else {
-        if (dump) gs_label_kernel<GS_LAYOUT_CLASSIC, true><<<blocks, threads, 0, st>>>(P);
-        else gs_label_kernel<GS_LAYOUT_CLASSIC, false><<<blocks, threads, 0, st>>>(P);
+        if (dump) gs_label_kernel<GS_LAYOUT_CLASSIC, true, false><<<blocks, threads, 0, st>>>(P);
+        else gs_label_kernel<GS_LAYOUT_CLASSIC, false, false><<<blocks, threads, 0, st>>>(P);
     }
 }
 void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
@@ -809,15 +813,15 @@ __global__ void gs_table_extract_seen_kernel(const u64* __restrict__ tab, u64 nS
     }
 }
 // minimizer prefilter of the store: one bit per minimizer hash of every stored key (gs_device.cuh "minimizer prefilter")
-__global__ void gs_mz_build_kernel(const u64* __restrict__ keys, u64 n, int k, u64* filter, u32 mask) {
+__global__ void gs_mz_build_kernel(const u64* __restrict__ keys, u64 n, int k, u64* filter, u32 mask, int wide) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u32 idx = gs_mz_of_key(keys[i], k) & mask;
+        const u32 idx = gs_mz_index(wide ? (u32)gs_mz_of_key_w(keys[i], k) : gs_mz_of_key(keys[i], k), mask);
         const u64 bit = 1ULL << (idx & 63);
         if (!(filter[idx >> 6] & bit)) atomicOr(filter + (idx >> 6), bit);
     }
 }
-void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, cudaStream_t st) { gs_mz_build_kernel<<<148 * 8, 256, 0, st>>>(keys, n, k, filter, mask); }
+void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, int wide, cudaStream_t st) { gs_mz_build_kernel<<<148 * 8, 256, 0, st>>>(keys, n, k, filter, mask, wide); }
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st) { gs_table_clear_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots); }
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st) { gs_table_extract_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots, out); }
 void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
@@ -901,7 +905,7 @@ __global__ void gs_lookup_kernel(GsDbView db, const u64* __restrict__ kmers, u64
         u64 p2 = 0;
         if (db.tab && gs_lookup_table(db, kmers[i], p2) != lab) lab = 0x7FFFFFFFu;
         // ... and the minimizer prefilter must pass every stored key
-        if (db.mzFilter && lab != GS_LABEL_MISS && !gs_mz_test(db.mzFilter, db.mzMask, gs_mz_of_key(kmers[i], db.k))) lab = 0x7FFFFFFEu;
+        if (db.mzFilter && lab != GS_LABEL_MISS && !gs_mz_test(db.mzFilter, db.mzMask, db.mzWide ? (u32)gs_mz_of_key_w(kmers[i], db.k) : gs_mz_of_key(kmers[i], db.k))) lab = 0x7FFFFFFEu;
         vidx[i] = lab == GS_LABEL_MISS ? -1 : (int)lab;
         pos[i] = lab == GS_LABEL_MISS ? -1LL : (long long)p;
     }
@@ -986,8 +990,8 @@ int gs_match_kernel_occupancy(int mode) {
     int nb = 0;
     if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<0, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
     return nb;
 }

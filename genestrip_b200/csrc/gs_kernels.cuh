@@ -69,7 +69,7 @@ void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCoun
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st);
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st);
 void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
-void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, cudaStream_t st);
+void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, int wide, cudaStream_t st);
 void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
 void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);

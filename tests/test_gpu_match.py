@@ -407,3 +407,26 @@ def test_match_parity_other_k(oracle, native, gpu_ctx, k):
     finally:
         gdb.close()
         odb.free()
+
+
+def test_wide_minimizer_order(oracle, native, gpu_ctx, monkeypatch):
+    """Stores beyond ~6e8 k-mers order their minimizers by a 64-bit hash (the 32-bit space is too crowded for a minimum of
+    nine); GS_DEBUG_MZ_WIDE forces that mode on a small store: same labels, counts and unique k-mers."""
+    nodes, names, genomes = util.small_project(genome_len=15000, seed=29)
+    monkeypatch.setenv("GS_DEBUG_MZ_WIDE", "1")
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, K, nodes, names, genomes)
+    monkeypatch.delenv("GS_DEBUG_MZ_WIDE")
+    try:
+        keys, _ = odb.export()
+        v, p = gdb.lookup(keys, use_bloom=False)   # includes the self check: every stored key passes the prefilter
+        assert (v >= -1).all() and (p == np.arange(len(keys))).all() and (v < 0x7FFFFFF0).all()
+        bases, offsets, src = synth.sample_reads([g for _, g in genomes], 4000, 150, seed=78, frac_db=0.6, sub_rate=0.02, n_rate=0.002)
+        fq = synth.fastq_bytes(bases, offsets, src)
+        for cfg in (dict(), dict(prefilter=0), dict(max_kmer_res_counts=3)):
+            ocfg = {kk: vv for kk, vv in cfg.items() if kk != "prefilter"}
+            orun = odb.match_files(util.oracle_cfg(oracle, K, **ocfg), [fq])
+            res, ev, counts, top, _, _ = util.gpu_match(native, gdb, bases, offsets, batch=1500, **cfg)
+            util.assert_match_parity(native, orun, res, counts, top)
+    finally:
+        gdb.close()
+        odb.free()
