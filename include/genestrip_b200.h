@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 2
+#define GS_ABI_VERSION 3
 
 typedef enum gs_status {
     GS_OK = 0,
