@@ -218,20 +218,25 @@ __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBuc
     u64 b = h >> db.rbits;
     const u64 want = ((h & ((1ULL << db.rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;
     const u64 cmpMask = ~((1ULL << GS_TAB_REM_SHIFT) - 1) | GS_TAB_OCC;
-    for (;;) {
+    u32 lab = GS_LABEL_MISS;
+    for (;;) {  // single exit, slot match by selects: no branch per slot, one structured join for the warp
+        int j = -1;
+        u64 e = 0;
 #pragma unroll
-        for (int j = 0; j < GS_TAB_SLOTS; j++) {
-            if ((bk.e[j] & cmpMask) == want) {
-                pos = b * GS_TAB_SLOT_STRIDE + (u64)j;
-                seen = bk.e[j] & GS_TAB_SEEN;
-                const u32 v = (u32)(bk.e[j] >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
-                return v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
-            }
+        for (int jj = GS_TAB_SLOTS - 1; jj >= 0; jj--)
+            if ((bk.e[jj] & cmpMask) == want) { j = jj; e = bk.e[jj]; }
+        if (j >= 0) {
+            pos = b * GS_TAB_SLOT_STRIDE + (u64)j;
+            seen = e & GS_TAB_SEEN;
+            const u32 v = (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
+            lab = v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
+            break;
         }
-        if (!(bk.e[0] & GS_TAB_SPILL)) return GS_LABEL_MISS;  // nothing spilled past this bucket
+        if (!(bk.e[0] & GS_TAB_SPILL)) break;  // nothing spilled past this bucket
         b = (b + 1) & ((1ULL << db.tbits) - 1);
         bk = gs_load_bucket(db.tab, b);
     }
+    return lab;
 }
 
 __device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {
