@@ -67,6 +67,9 @@ _SIGS = {
     "gs_db_finalize": (C.c_int, [_P]),
     "gs_db_update": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "gs_db_get_values": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "gs_db_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "gs_db_save_file": (C.c_int, [_P, C.c_char_p]),
+    "gs_db_load_file": (_P, [_P, C.c_char_p]),
     "gs_db_destroy": (None, [_P]),
     "gs_db_device_bytes": (C.c_uint64, [_P]),
     "gs_db_n_devices": (C.c_int, [_P]),
@@ -258,6 +261,24 @@ class Database:
     @property
     def device_bytes(self):
         return lib().gs_db_device_bytes(self.h)
+
+    def save(self, path):
+        """Flat GSB1 file (keys, Java-short values, tree by value index, blocked Bloom filter)."""
+        _check(lib().gs_db_save_file(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, ctx, path):
+        """Database from a GSB1 file, without the arrays passing through Python."""
+        L = lib()
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.h = L.gs_db_load_file(ctx.h, str(path).encode())
+        if not self.h:
+            raise GenestripError(-1, L.gs_last_error().decode())
+        k, n, v = C.c_int(0), C.c_uint64(0), C.c_int(0)
+        _check(L.gs_db_info(self.h, C.byref(k), C.byref(n), C.byref(v)))
+        self.k, self.n_kmers, self.n_values, self.bloom_words = k.value, int(n.value), v.value, None
+        return self
 
     def update(self, seq, region_offsets, region_vidx, upper_case=True):
         """DBGoal update phase: value = LCA(value, region node) for every stored k-mer of the regions; returns #changes."""

@@ -431,6 +431,122 @@ extern "C" int gs_db_finalize(gs_db* db) {
     return GS_OK;
 }
 
+// ---- flat database file ("GSB1") -----------------------------------------------------------------------------
+// What Database.save puts into a zip of Java-serialized objects (C/store/Database.java:201-260), as flat little-endian
+// arrays a C program (and a 40-line Java exporter, integration/java/.../GsbExporter.java) can stream:
+//   header: char magic[8] = "GSB1", u32 version, u32 k, u64 n_kmers, u32 n_values, u32 flags (bit 0: blocked Bloom filter),
+//           i64 bloom_seed, u64 bloom_buckets, u64 bloom_words                       (56 bytes)
+//   i64 keys[n_kmers]; i16 values[n_kmers] (Java shorts) + pad to 8; i32 parent[n_values]; i32 has_node[n_values] + pad to 8;
+//   i64 bloom[bloom_words]
+struct GsbHeader {
+    char magic[8];
+    uint32_t version, k;
+    uint64_t n_kmers;
+    uint32_t n_values, flags;
+    int64_t bloom_seed;
+    uint64_t bloom_buckets, bloom_words;
+};
+static_assert(sizeof(GsbHeader) == 56, "GSB1 header layout");
+
+extern "C" int gs_db_info(const gs_db* db, int* k, uint64_t* n_kmers, int* n_values) {
+    if (!db) return gs_fail(GS_ERR_ARG, "null database");
+    if (k) *k = db->k;
+    if (n_kmers) *n_kmers = db->n;
+    if (n_values) *n_values = db->V;
+    return GS_OK;
+}
+
+extern "C" int gs_db_save_file(gs_db* db, const char* path) {
+    if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
+    if (!path) return gs_fail(GS_ERR_ARG, "null path");
+    FILE* f = fopen(path, "wb");
+    if (!f) return gs_fail(GS_ERR_ARG, "cannot create %s", path);
+    struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
+    GsbHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "GSB1", 4);
+    h.version = 1; h.k = (uint32_t)db->k; h.n_kmers = db->n; h.n_values = (uint32_t)db->V; h.flags = db->hasBloom ? 1u : 0u;
+    h.bloom_seed = db->bloomSeed; h.bloom_buckets = db->bloomBuckets; h.bloom_words = db->hasBloom ? db->bloomWords : 0;
+    if (fwrite(&h, sizeof(h), 1, f) != 1) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    DevDb& d0 = db->d[0];
+    CU(cudaSetDevice(d0.dev));
+    const u64 seg = 1ULL << 24;
+    std::vector<u64> buf((size_t)std::min<u64>(seg, std::max<u64>(db->n, 1)));
+    for (u64 off = 0; off < db->n; off += seg) {
+        const u64 n = std::min(seg, db->n - off);
+        CU(cudaMemcpy(buf.data(), d0.keys + off, n * sizeof(u64), cudaMemcpyDeviceToHost));
+        if (fwrite(buf.data(), sizeof(u64), n, f) != n) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    }
+    std::vector<int16_t> vb((size_t)std::min<u64>(seg, std::max<u64>(db->n, 1)));
+    for (u64 off = 0; off < db->n; off += seg) {
+        const u64 n = std::min(seg, db->n - off);
+        int rc = gs_db_get_values(db, off, vb.data(), n);
+        if (rc) return rc;
+        if (fwrite(vb.data(), sizeof(int16_t), n, f) != n) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    }
+    const char zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t padV = (size_t)((8 - (db->n * 2) % 8) % 8);
+    if (padV && fwrite(zeros, 1, padV, f) != padV) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    const size_t V = (size_t)db->V;
+    if (V && (fwrite(db->hParent.data(), sizeof(int), V, f) != V || fwrite(db->hHasNode.data(), sizeof(int), V, f) != V))
+        return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    const size_t padT = (size_t)((8 - (V * 8) % 8) % 8);
+    if (padT && fwrite(zeros, 1, padT, f) != padT) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    if (db->hasBloom) {
+        std::vector<u64> bw((size_t)db->bloomWords);
+        CU(cudaMemcpy(bw.data(), d0.bloom, db->bloomWords * sizeof(u64), cudaMemcpyDeviceToHost));
+        if (fwrite(bw.data(), sizeof(u64), bw.size(), f) != bw.size()) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    }
+    if (fflush(f) != 0) return gs_fail(GS_ERR_ARG, "write error on %s", path);
+    return GS_OK;
+}
+
+extern "C" gs_db* gs_db_load_file(gs_ctx* ctx, const char* path) {
+    if (!ctx || !path) { gs_fail(GS_ERR_ARG, "null argument"); return nullptr; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { gs_fail(GS_ERR_ARG, "cannot open %s", path); return nullptr; }
+    struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
+    GsbHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "GSB1\0\0\0\0", 8) != 0 || h.version != 1) { gs_fail(GS_ERR_ARG, "%s is not a GSB1 database file", path); return nullptr; }
+    gs_db* db = gs_db_create(ctx, (int)h.k, h.n_kmers, (int)h.n_values);
+    if (!db) return nullptr;
+    auto bail = [&](const char* what) -> gs_db* { std::string msg = gs_last_error(); gs_db_destroy(db); gs_fail(GS_ERR_ARG, "%s: %s %s", path, what, msg.c_str()); return nullptr; };
+    const u64 seg = 1ULL << 24;
+    {
+        std::vector<int64_t> buf((size_t)std::min<u64>(seg, std::max<u64>(h.n_kmers, 1)));
+        for (u64 off = 0; off < h.n_kmers; off += seg) {
+            const u64 n = std::min(seg, h.n_kmers - off);
+            if (fread(buf.data(), sizeof(int64_t), n, f) != n) return bail("truncated key section");
+            if (gs_db_put_keys(db, off, buf.data(), n) != GS_OK) return bail("keys:");
+        }
+        std::vector<int16_t> vb((size_t)std::min<u64>(seg, std::max<u64>(h.n_kmers, 1)));
+        for (u64 off = 0; off < h.n_kmers; off += seg) {
+            const u64 n = std::min(seg, h.n_kmers - off);
+            if (fread(vb.data(), sizeof(int16_t), n, f) != n) return bail("truncated value section");
+            if (gs_db_put_values(db, off, vb.data(), n) != GS_OK) return bail("values:");
+        }
+        char pad[8];
+        const size_t padV = (size_t)((8 - (h.n_kmers * 2) % 8) % 8);
+        if (padV && fread(pad, 1, padV, f) != padV) return bail("truncated");
+    }
+    {
+        const size_t V = h.n_values;
+        std::vector<int> parent(std::max<size_t>(V, 1)), has(std::max<size_t>(V, 1));
+        if (V && (fread(parent.data(), sizeof(int), V, f) != V || fread(has.data(), sizeof(int), V, f) != V)) return bail("truncated tree section");
+        char pad[8];
+        const size_t padT = (size_t)((8 - (V * 8) % 8) % 8);
+        if (padT && fread(pad, 1, padT, f) != padT) return bail("truncated");
+        if (gs_db_set_tree(db, parent.data(), has.data(), (int)V) != GS_OK) return bail("tree:");
+    }
+    if (h.flags & 1u) {
+        std::vector<int64_t> bw((size_t)h.bloom_words);
+        if (fread(bw.data(), sizeof(int64_t), bw.size(), f) != bw.size()) return bail("truncated Bloom filter section");
+        if (gs_db_set_bloom_blocked(db, h.bloom_seed, h.bloom_buckets, bw.data(), h.bloom_words) != GS_OK) return bail("bloom:");
+    }
+    if (gs_db_finalize(db) != GS_OK) return bail("finalize:");
+    return db;
+}
+
 // ---- database update phase --------------------------------------------------------------------------------
 extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, const uint64_t* region_offsets, const int32_t* region_vidx,
                             uint32_t n_regions, int upper_case, uint64_t* n_changed) {

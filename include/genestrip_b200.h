@@ -93,6 +93,13 @@ int gs_db_finalize(gs_db*); /* builds the bucket index, replicates to every devi
 int gs_db_update(gs_db*, const uint8_t* seq, uint64_t n_bytes, const uint64_t* region_offsets, const int32_t* region_vidx,
                  uint32_t n_regions, int upper_case, uint64_t* n_changed);
 int gs_db_get_values(gs_db*, uint64_t offset, int16_t* vidx_raw, uint64_t n);
+/* Flat little-endian database file "GSB1" (layout in gs_capi.cu): the arrays Database.save serializes with Java object streams
+ * (C/store/Database.java:201-260: k-mers, value indices, tax tree by value index, blocked Bloom filter), written by
+ * gs_db_save_file -- e.g. after gs_db_update -- or by the Java-side exporter (integration/java/.../GsbExporter.java), and
+ * loaded without a JVM by gs_db_load_file (create + put_* + set_tree + set_bloom_blocked + finalize). */
+int gs_db_info(const gs_db*, int* k, uint64_t* n_kmers, int* n_values);
+int gs_db_save_file(gs_db*, const char* path);
+gs_db* gs_db_load_file(gs_ctx*, const char* path);
 void gs_db_destroy(gs_db*);
 uint64_t gs_db_device_bytes(const gs_db*);
 int gs_db_n_devices(const gs_db*);

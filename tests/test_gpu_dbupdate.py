@@ -105,3 +105,52 @@ def test_db_update_argument_checks(oracle, native, gpu_ctx):
     finally:
         gdb.close()
         odb.free()
+
+
+def test_db_file_round_trip(oracle, native, gpu_ctx, tmp_path):
+    """gs_db_save_file / gs_db_load_file (flat GSB1 file instead of Database.save's Java object streams, C/store/Database.java:201-314):
+    an updated database written to disk and loaded again answers and matches exactly like the oracle's full build."""
+    nodes, names, genomes, fill = _project()
+    odb_full = oracle.OracleDb.build(K, nodes, names, genomes, fill=fill)
+    odb_fill = oracle.OracleDb.build(K, nodes, names, genomes, fill=fill, skip_update=True)
+    gdb = util.upload(oracle, native, gpu_ctx, odb_fill)
+    path = str(tmp_path / "db.gsb")
+    try:
+        taxids = odb_fill.taxids()
+        vidx_of = {t: i for i, t in enumerate(taxids)}
+        seq = np.frombuffer(b"".join(g for _, g in genomes), dtype=np.uint8)
+        offsets = np.zeros(len(genomes) + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum([len(g) for _, g in genomes])
+        gdb.update(seq, offsets, np.array([vidx_of[t] for t, _ in genomes], dtype=np.int32))
+        gdb.save(path)
+    finally:
+        gdb.close()
+    g2 = native.Database.load(gpu_ctx, path)
+    try:
+        keys_u, vals_u = odb_full.export()
+        assert (g2.k, g2.n_kmers, g2.n_values) == (K, len(keys_u), odb_full.n_values)
+        np.testing.assert_array_equal(g2.values(), vals_u)
+        rng = np.random.default_rng(2)
+        q = np.concatenate([keys_u[::3], rng.integers(0, 1 << 62, size=3000, dtype=np.int64)])
+        for use_bloom in (True, False):   # the Bloom filter words travelled with the file
+            v, p = g2.lookup(q, use_bloom=use_bloom)
+            exp = [odb_full.get(int(x)) for x in q]
+            np.testing.assert_array_equal(v, np.array([e[0] for e in exp], dtype=np.int32))
+        bases, offs, src = synth.sample_reads([g.upper() for _, g in genomes[:5]], 2000, 150, seed=6, frac_db=0.8, sub_rate=0.01, n_rate=0.002)
+        bases[bases == 0] = ord("N")
+        fq = synth.fastq_bytes(bases, offs, src)
+        for cfg in (dict(), dict(layout=1)):
+            orun = odb_full.match_files(util.oracle_cfg(oracle, K, **cfg), [fq])
+            res, ev, counts, top, _, _ = util.gpu_match(native, g2, bases, offs, batch=800, **cfg)
+            util.assert_match_parity(native, orun, res, counts, top)
+        # a truncated or foreign file is refused
+        open(str(tmp_path / "bad.gsb"), "wb").write(open(path, "rb").read()[:1000])
+        with pytest.raises(native.GenestripError):
+            native.Database.load(gpu_ctx, str(tmp_path / "bad.gsb"))
+        open(str(tmp_path / "bad2.gsb"), "wb").write(b"not a database")
+        with pytest.raises(native.GenestripError):
+            native.Database.load(gpu_ctx, str(tmp_path / "bad2.gsb"))
+    finally:
+        g2.close()
+        odb_fill.free()
+        odb_full.free()
