@@ -265,3 +265,62 @@ def test_filter_goal_gpu_fastq_feeder(project, oracle, native, gpu_ctx, host):
                 assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
     finally:
         gflt.close()
+
+
+def test_fastq_feeder_fuzz_against_reference_parser(project, oracle, host):
+    """Random FASTQ-like inputs -- strict records mixed with CRLF, multi-line sequences and qualities, empty lines, '@' / '+'
+    at the start of quality lines, NUL bytes, truncated tails -- at random chunk sizes: whatever the device accepts or
+    refuses, the goal's outputs are those of the sequential reference parser + matchRead."""
+    odb, gdb, meta, genomes = project
+    rng = np.random.default_rng(2024)
+    g = genomes[2][1]
+    ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=True)
+
+    def record(i):
+        L = int(rng.integers(0, 220))
+        a = int(rng.integers(0, len(g) - 300))
+        seq = bytearray(g[a:a + L])
+        kind = int(rng.integers(0, 20))
+        eol = b"\r\n" if kind == 1 else b"\n"
+        qual = bytes(rng.integers(33, 74, size=L).astype(np.uint8))
+        if L and kind == 2:
+            qual = b"@" + qual[1:]
+        if L and kind == 3:
+            qual = b"+" + qual[1:]
+        hdr = b"@f%d %d" % (i, kind)
+        plus = b"+" + (hdr[1:] if kind == 4 else b"")
+        if kind == 5 and L > 40:      # multi-line sequence and quality
+            return hdr + b"\n" + bytes(seq[:30]) + b"\n" + bytes(seq[30:]) + b"\n+\n" + qual[:50] + b"\n" + qual[50:] + b"\n"
+        if kind == 6 and L > 10:      # NUL bytes in the sequence
+            seq[5] = 0
+        if kind == 7:                 # quality longer than the sequence
+            qual = qual + b"II"
+        if kind == 8 and L > 10:      # lower case / N
+            seq[3] = ord("n"); seq[7] = ord("N")
+        return hdr + eol + bytes(seq) + eol + plus + eol + qual + eol
+
+    n_refused = n_gpu = 0
+    for trial in range(80):
+        n = int(rng.integers(1, 400))
+        strict_only = trial % 2 == 0
+        recs = []
+        for i in range(n):
+            r = record(i)
+            if strict_only and (b"\0" in r or r.count(b"\n") != 4):
+                continue
+            recs.append(r)
+        text = b"".join(recs)
+        if trial % 5 == 1 and text:
+            # truncated tail, but only inside the last quality line: a file that ends inside a header / sequence / '+' line (or
+            # with a stray empty line) makes the reference index read[-1] (AbstractFastqReader.java:295-307) -- outside the contract
+            last_line = len(text) - (text.rfind(b"\n", 0, len(text) - 1) + 1)
+            text = text[:-int(rng.integers(1, last_line + 1))]
+        chunk = int(rng.integers(4096, 60000))
+        orun = odb.match_files(ocfg, [text])
+        res = host.match_goal(gdb, meta, [text], write_filtered=True, with_probs=1, text_chunk_bytes=chunk, batch_reads=97)
+        assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps), trial
+        assert res.filtered == orun.filtered, trial
+        _assert_csv_equal(res.csv, orun.csv)
+        n_refused += res.text_chunks_refused
+        n_gpu += res.text_chunks - res.text_chunks_refused
+    assert n_gpu > 20 and n_refused > 5   # both paths were exercised
