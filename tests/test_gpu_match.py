@@ -430,3 +430,44 @@ def test_wide_minimizer_order(oracle, native, gpu_ctx, monkeypatch):
     finally:
         gdb.close()
         odb.free()
+
+
+def test_thread_kernel_hand_over_paths(oracle, native, gpu_ctx):
+    """Short-read batches go to the thread-per-read reduce kernel; reads it cannot take -- more than 8 distinct taxa, or
+    longer than 2047 bases -- are handed to the warp-per-read kernel, reads with more than 128 taxa on to the slow path.
+    A 160-species project with chimeric reads exercises all three in one batch (FastqKMerMatcher.java:327-535)."""
+    n_sp = 160
+    edges = [(1, 1, "no rank")] + [(10 + g, 1, "genus") for g in range(8)] + [(1000 + s, 10 + s % 8, "species") for s in range(n_sp)]
+    nodes = "".join("%d\t|\t%d\t|\t%s\t|\t\t|\n" % e for e in edges)
+    names = "".join("%d\t|\ttaxon %d\t|\t\t|\tscientific name\t|\n" % (e[0], e[0]) for e in edges)
+    rng = np.random.default_rng(77)
+    genomes = [(str(1000 + s), synth.random_genome(rng, 3000).tobytes()) for s in range(n_sp)]
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, K, nodes, names, genomes)
+    try:
+        reads = []
+        for i in range(1500):                      # plain short reads: the thread kernel keeps them
+            s = int(rng.integers(0, n_sp)); a = int(rng.integers(0, 2800))
+            reads.append(genomes[s][1][a:a + 150])
+        for i in range(60):                        # 9 .. 20 taxa in one read (40 bases = 10 k-mers of each): warp kernel
+            parts = [genomes[int(s)][1][int(a):int(a) + 40] for s, a in zip(rng.choice(n_sp, size=int(rng.integers(9, 21)), replace=False), rng.integers(0, 2900, size=20))]
+            reads.append(b"".join(parts))
+        for i in range(3):                         # more than 128 taxa: slow path (vote table in global memory)
+            parts = [genomes[int(s)][1][int(a):int(a) + 32] for s, a in zip(rng.permutation(n_sp)[:150], rng.integers(0, 2900, size=150))]
+            reads.append(b"".join(parts))
+        for i in range(4):                         # longer than 2047 bases
+            s = int(rng.integers(0, n_sp))
+            reads.append(genomes[s][1][:2900] if i % 2 else genomes[s][1][100:2148])
+        order = rng.permutation(len(reads))
+        reads = [reads[int(i)] for i in order]
+        bases, offsets = _pack(reads)
+        assert len(bases) / len(reads) <= 512      # the batch qualifies for the thread kernel
+        fq = _fastq(reads)
+        for cfg in (dict(), dict(max_classification_paths=3, min_kmers_for_class=2), dict(max_read_tax_error_count=0.4), dict(max_kmer_res_counts=3)):
+            orun = odb.match_files(util.oracle_cfg(oracle, K, **cfg), [fq])
+            res, ev, counts, top, _, _ = util.gpu_match(native, gdb, bases, offsets, batch=len(reads), **cfg)
+            util.assert_match_parity(native, orun, res, counts, top)
+            slow = (res["flags"] & native.GS_READ_SLOWPATH) != 0
+            assert slow.sum() == 3
+    finally:
+        gdb.close()
+        odb.free()
