@@ -471,3 +471,35 @@ def test_thread_kernel_hand_over_paths(oracle, native, gpu_ctx):
     finally:
         gdb.close()
         odb.free()
+
+
+def test_radix_upload_gives_same_database(project, reads, oracle, native, gpu_ctx):
+    """A RadixKMerStore as the source (C/store/RadixKMerStore.java:369-412, 714-730): buckets by the low r bits, entries =
+    (valueIndex << (62 - r)) | (kmer >>> r) sorted by the remaining bits.  gs_db_put_radix_bucket rebuilds the keys and merges
+    them into the sorted layout: same positions, values, and match results as the KMerSortedArray upload
+    (T/match/RadixKMerStoreBenchmarkTest.java:186-229)."""
+    odb, gdb, _ = project
+    bases, offsets, _, fq = reads
+    keys, vals = odb.export()
+    r = 17
+    vi = vals.astype(np.int64) + 32768
+    bucket = keys & ((1 << r) - 1)
+    rem = keys >> r
+    order = np.lexsort((rem, bucket))
+    b_sorted, entries = bucket[order], (vi[order] << (62 - r)) | rem[order]
+    starts = np.flatnonzero(np.concatenate([[True], b_sorted[1:] != b_sorted[:-1]]))
+    ends = np.concatenate([starts[1:], [len(b_sorted)]])
+    buckets = [(int(b_sorted[a]), np.ascontiguousarray(entries[a:e])) for a, e in zip(starts, ends)]
+    parent, depth, position, has_node = odb.tree()
+    _, seed, nb, _, words = odb.store_filter().params()
+    g2 = native.Database(gpu_ctx, K, None, None, odb.n_values, parent_by_vidx=parent, has_node=has_node, bloom=(seed, nb, words), radix=(r, buckets))
+    try:
+        assert g2.n_kmers == len(keys)
+        np.testing.assert_array_equal(g2.values(), vals)
+        v, p = g2.lookup(keys[::11])
+        np.testing.assert_array_equal(p, np.arange(len(keys))[::11])
+        orun = odb.match_files(util.oracle_cfg(oracle, K), [fq])
+        res, ev, counts, top, _, _ = util.gpu_match(native, g2, bases, offsets, batch=3000)
+        util.assert_match_parity(native, orun, res, counts, top)
+    finally:
+        g2.close()
