@@ -787,6 +787,7 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
     const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
     D.fastBlocks = D.sms * occ0;
     D.labelBlocks = D.sms * std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
+    if (const char* e = getenv("GS_DEBUG_LABEL_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0) D.labelBlocks = D.sms * v; }  // tuning experiments
     D.slowBlocks = std::max(1, D.sms / 4);
     CU(dmalloc(&D.slowTable, (size_t)D.slowBlocks * GS_WARPS_PER_BLOCK * 2 * std::max(V, 1)));
     for (MatchSlot& sl : D.slots) {

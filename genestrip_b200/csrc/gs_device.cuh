@@ -29,8 +29,13 @@ typedef unsigned int u32;
 #define GS_SEG_POS (GS_SEG_CHUNKS * 32)    // 992 positions ...
 #define GS_SEG_BASES 1024                  // ... need 992 + k - 1 <= 1023 bases: 64 aligned 16-byte groups
 #define GS_SEG_WORDS 34                    // 32 words of codes / validity / read starts + zero padding for the funnel shifts
+// Resident CTAs per SM the label kernel is compiled for.  Measured (viral workload, 4 M reads): 4 CTAs 8.16 ms, 5 CTAs 7.25 ms,
+// 6 CTAs 6.71 ms, 8 CTAs (32 registers, no spills) 6.51 ms -- the kernel hides DRAM latency with resident warps.
 #ifndef GS_LABEL_MIN_BLOCKS
-#define GS_LABEL_MIN_BLOCKS 4
+#define GS_LABEL_MIN_BLOCKS 8
+#endif
+#ifndef GS_LABEL_MIN_BLOCKS_WIDE
+#define GS_LABEL_MIN_BLOCKS_WIDE 8
 #endif
 #define GS_WARPS_PER_BLOCK 8
 #define GS_TILE_POS 1024                   // k-mer positions per tile

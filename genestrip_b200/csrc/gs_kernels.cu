@@ -114,7 +114,7 @@ __global__ void gs_mark_starts_kernel(const u64* __restrict__ offsets, u32 nRead
 // neighbouring lanes), one 256-bit probe-table load for the k-mers that pass, seen bit / hit counter for the hits.
 // The k-mer and m-mer hash of chunk c+1 are computed while chunk c is finished (the sliding minimum needs them anyway).
 template <int LAYOUT, bool DUMP, bool WIDE>
-__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? 6 : GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {  // WIDE: 40 registers keep six CTAs per SM
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_BLOCKS_WIDE : GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {
     typedef typename std::conditional<WIDE, u64, u32>::type MzT;  // the minimizer order: 32-bit hash, or 64 bits for large stores
     __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
     __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
