@@ -334,13 +334,25 @@ def run_filter_workload(torch, dev, args, wl, config, capi, ctx, keys, vals_raw,
         bpk = READ_LEN / (READ_LEN - K + 1) + 8.0 * probes
         kernel_ms = float(tt[0]) / args.steps
         achieved = bpk * kmers_per_step / (kernel_ms / 1e3) / 1e9
+        traffic, dram, reqroof = None, None, None
+        try:  # ncu capture of the filter kernel: every 8-byte Bloom probe drags a 128-byte line out of DRAM
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "filter_kernel_traffic.json")))
+            traffic = tj["dram_bytes_per_kmer"] * kmers_per_step
+            dram = {"achieved_dram_GBs": traffic / (kernel_ms / 1e3) / 1e9, "frac_of_peak": traffic / (kernel_ms / 1e3) / 1e9 / peak,
+                    "note": "real DRAM bytes per second: the kernel is bound by the lines its probes drag in, not by the 8 algorithmic bytes per probe"}
+            lps = kmers_per_step / (kernel_ms / 1e3) * tj["dram_lines_per_kmer"]
+            reqroof = {"measured_cap_lines_per_s": 39.4e9, "dram_lines_per_kmer": tj["dram_lines_per_kmer"], "lines_per_s": lps, "frac": lps / 39.4e9,
+                       "source": "profiles/microbench/randgroup.txt"}
+        except Exception:
+            pass
         emit({"metric": "filter k-mers/s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
               "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
               "reads_per_s": value / (READ_LEN - K + 1), "config": config, "clocks": clocks,
               "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R},
               "gpu_launches": args.steps,
-              "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                           "kernel": "gs_filter_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk},
+              "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                           "kernel": "gs_filter_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk,
+                           "dram": dram, "request_roofline": reqroof},
               "accepted_read_fraction": hfrac, "index": {"kind": "xor", "bits": bits, "hashes": hashes}})
     sess.close()
     flt.close()
