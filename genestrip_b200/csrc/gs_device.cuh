@@ -244,6 +244,39 @@ __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBuc
     return lab;
 }
 
+// The same split in two for the label kernel: the first bucket is matched without a branch (every lane of the warp runs it,
+// lanes without a pending lookup on bucket 0), the rare continuation into the following buckets is a loop of its own.
+// Returns the slot index of the match in bk (or -1) and the matching entry.
+__device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& bk, u64& e) {
+    const u64 want = ((h & ((1ULL << rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;
+    const u64 cmpMask = ~((1ULL << GS_TAB_REM_SHIFT) - 1) | GS_TAB_OCC;
+    int j = -1;
+    e = 0;
+#pragma unroll
+    for (int jj = GS_TAB_SLOTS - 1; jj >= 0; jj--)
+        if ((bk.e[jj] & cmpMask) == want) { j = jj; e = bk.e[jj]; }
+    return j;
+}
+// (scalars instead of the view: a reference to the kernel parameter block would force a local copy of it)
+static __device__ __noinline__ u32 gs_table_chain(const u64* tab, int tbits, int rbits, u64 h, u64 b, u64* posOut, u32* seenOut) {
+    u32 lab = GS_LABEL_MISS;
+    for (;;) {
+        b = (b + 1) & ((1ULL << tbits) - 1);
+        const GsBucket bk = gs_load_bucket(tab, b);
+        u64 e;
+        const int j = gs_table_match(rbits, h, bk, e);
+        if (j >= 0) {
+            *posOut = b * GS_TAB_SLOT_STRIDE + (u64)j;
+            *seenOut = (u32)(e & GS_TAB_SEEN);
+            const u32 v = (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
+            lab = v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
+            break;
+        }
+        if (!(bk.e[0] & GS_TAB_SPILL)) break;
+    }
+    return lab;
+}
+
 __device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {
     if (key > GS_M62) return GS_LABEL_MISS;
     const u64 h = gs_mix62(key);

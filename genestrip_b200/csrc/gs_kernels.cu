@@ -188,17 +188,45 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                 const u32 mzv = gs_mz_index((u32)gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane), db.mzMask);
                 if (lab == GS_LABEL_PENDING && !((__ldg(db.mzFilter + (mzv >> 6)) >> (mzv & 63)) & 1ULL)) lab = GS_LABEL_MISS;
             }
-            if (lab == GS_LABEL_PENDING) {
+            {
+                // The lookup.  Two shapes of the same probe (template parameter, same results):
+                //  * large stores (WIDE): EVERY lane runs the first-bucket probe -- lanes without a pending k-mer read bucket 0, one
+                //    shared L2-resident sector -- so that the warp does not split into a few lanes that wait for DRAM and many
+                //    that run ahead into the next chunk (measured on the 2e9-k-mer store, 10 % of the reads from the database:
+                //    31 % more warp instructions and 7.70 instead of 6.58 ms with the divergent shape);
+                //  * otherwise only the pending lanes probe (fewer instructions when most chunks are either all pending or all
+                //    rejected by the prefilter: 6.53 instead of 6.69 ms on the viral workload).
+                const bool pend = lab == GS_LABEL_PENDING;
                 const u64 key = fwd > rc ? fwd : rc;  // standardKMer (CGAT.java:145-147)
                 u64 pos = 0;
                 bool seen = false;
-                if (LAYOUT == GS_LAYOUT_TABLE) {
-                    const u64 h = gs_mix62(key);
-                    lab = gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
-                } else {
-                    lab = gs_lookup(db, key, useBloom, pos);
+                if (LAYOUT == GS_LAYOUT_TABLE && WIDE) {
+                    if (__any_sync(FULL, pend)) {
+                        const u64 h = gs_mix62(key);
+                        const u64 b0 = pend ? (h >> db.rbits) : 0ULL;
+                        const GsBucket bk = gs_load_bucket(db.tab, b0);
+                        u64 e;
+                        const int j = gs_table_match(db.rbits, h, bk, e);
+                        const u32 v = (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
+                        const bool more = pend && j < 0 && (bk.e[0] & GS_TAB_SPILL);
+                        if (pend) lab = (j >= 0 && v != GS_VAL_NONODE) ? v : GS_LABEL_MISS;
+                        pos = b0 * GS_TAB_SLOT_STRIDE + (u64)(j >= 0 ? j : 0);
+                        seen = e & GS_TAB_SEEN;
+                        if (more) {  // rare: the key was pushed to a following bucket
+                            u32 sn = 0;
+                            lab = gs_table_chain(db.tab, db.tbits, db.rbits, h, b0, &pos, &sn);
+                            seen = sn != 0;
+                        }
+                    }
+                } else if (pend) {
+                    if (LAYOUT == GS_LAYOUT_TABLE) {
+                        const u64 h = gs_mix62(key);
+                        lab = gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
+                    } else {
+                        lab = gs_lookup(db, key, useBloom, pos);
+                    }
                 }
-                if (lab < GS_LABEL_INVALID) {
+                if (pend && lab < GS_LABEL_INVALID) {
                     // unique k-mer bit / hit counter (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143)
                     if (P.seenTab) { if (!seen) atomicOr(P.seenTab + pos * 2, (u32)GS_TAB_SEEN); }  // seen bit came with the bucket
                     else if (P.bitset) {
