@@ -373,12 +373,13 @@ static size_t lastRecordStart(const uint8_t* text, size_t len) {
 
 
 // The GPU feeder's host side, shared by the match and filter drivers: stream one FASTQ input as pinned text chunks that end
-// at a record boundary.  cur() = the batch to fill; submit(batch, cut) hands text[0, cut) to the device and returns true if the
-// device took it (the driver then parks the batch and cur() yields a fresh one), false if it refused (not strict 4-line
+// at a record boundary.  cur() = the batch to fill, next() = the batch cur() will yield after the next successful submit (the
+// read-ahead target); submit(batch, cut) hands text[0, cut) to the device and returns true if the device took it (the driver
+// then parks the batch and cur() yields the next one), false if it refused (not strict 4-line
 // FASTQ); from the first refusal on, the rest of the input -- the refused chunk included -- goes through the sequential
 // parser (`sequential(LineReader&)`), so the results never depend on this fast path.
-template <typename CurFn, typename SubmitFn, typename SeqFn>
-static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, SubmitFn&& submit, SeqFn&& sequential) {
+template <typename CurFn, typename NextFn, typename SubmitFn, typename SeqFn>
+static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextFn&& next, SubmitFn&& submit, SeqFn&& sequential) {
     gzFile gz = nullptr;
     int fd = -1;        // uncompressed files are read with parallel pread() straight into the pinned chunk
     size_t filePos = 0;
@@ -428,51 +429,79 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, Submi
     const size_t chunk = std::max<size_t>(chunkBytes, 1 << 12);
     size_t memPos = 0;
     bool eof = false;
-    std::vector<uint8_t> carry;
-    while (!eof || !carry.empty()) {
-        HostBatch* b = cur();
-        b->isText = true;
-        size_t len = carry.size(), target = std::max(chunk, carry.size() + 1);
-        b->textLen = 0;
-        b->ensureText(target + 64);
-        if (len) memcpy(b->text, carry.data(), len);
-        carry.clear();
-        size_t cut = 0;
+    // bytes [len, target) of a chunk buffer from the stream / file / caller's memory; sets eof at the end of the input
+    auto fill = [&](uint8_t* text, size_t& len, size_t target) {
+        while (!eof && len < target) {
+            if (gz) {
+                const int got = gzread(gz, text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
+                if (got < 0) fail("read error");
+                if (got == 0) eof = true;
+                len += (size_t)got;
+            } else if (fd >= 0) {
+                const size_t want = target - len;
+                const size_t got = readPlain(text + len, want);
+                if (got < want) eof = true;
+                len += got;
+            } else {
+                const size_t take = std::min(target - len, in.len - memPos);
+                if (take) memcpy(text + len, in.data + memPos, take);
+                memPos += take; len += take;
+                if (memPos == in.len) eof = true;
+            }
+        }
+    };
+    HostBatch* b = cur();
+    b->isText = true;
+    b->textLen = 0;
+    b->ensureText(chunk + 64);
+    size_t len = 0;
+    fill(b->text, len, chunk);
+    for (;;) {
+        // ---- cut at the last record boundary (widen the chunk if a single record is longer than it)
+        size_t cut = 0, target = std::max(chunk, len);
         bool refused = false;
         for (;;) {
-            while (!eof && len < target) {   // fill the pinned chunk straight from the stream / the caller's memory
-                if (gz) {
-                    const int got = gzread(gz, b->text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
-                    if (got < 0) fail("read error");
-                    if (got == 0) eof = true;
-                    len += (size_t)got;
-                } else if (fd >= 0) {
-                    const size_t want = target - len;
-                    const size_t got = readPlain(b->text + len, want);
-                    if (got < want) eof = true;
-                    len += got;
-                } else {
-                    const size_t take = std::min(target - len, in.len - memPos);
-                    if (take) memcpy(b->text + len, in.data + memPos, take);
-                    memPos += take; len += take;
-                    if (memPos == in.len) eof = true;
-                }
-            }
             cut = eof ? len : lastRecordStart(b->text, len);
             if (eof || cut > 0) break;
             if (target >= ((size_t)1 << 31)) { refused = true; break; }  // no record boundary in 2 GiB: not 4-line FASTQ
-            target *= 2;                                                   // records longer than the chunk: widen it
+            target *= 2;
             b->textLen = len;
             b->ensureText(target + 64);
+            fill(b->text, len, target);
         }
-        if (!refused && cut > 0) {
+        if (!refused && cut == 0) return;   // end of the input, nothing left
+        // ---- read ahead: the next chunk (tail of this one first) is read by a helper thread into the batch that cur() will
+        // yield next, while this thread hands the current chunk to the device and collects the oldest batch
+        HostBatch* nb = nullptr;
+        size_t nlen = 0;
+        std::thread reader;
+        std::string readErr;
+        const bool more = !refused && (!eof || cut < len);
+        if (more) {
+            nb = next();
+            nb->isText = true;
+            nb->textLen = 0;
+            nlen = len - cut;
+            nb->ensureText(std::max(chunk, nlen + 1) + 64);
+            if (nlen) memcpy(nb->text, b->text + cut, nlen);
+            if (!eof) {
+                const size_t ntarget = std::max(chunk, nlen + 1);
+                reader = std::thread([&, ntarget] { try { fill(nb->text, nlen, ntarget); } catch (const std::exception& e) { readErr = e.what(); } });
+            }
+        }
+        bool taken = false;
+        std::string submitErr;
+        if (!refused) {
             b->textLen = cut;
-            std::vector<uint8_t> tail(b->text + cut, b->text + len);   // the submit may recycle the batch
-            if (submit(b, cut)) { carry.swap(tail); continue; }
-            refused = true;
+            try { taken = submit(b, cut); } catch (const std::exception& e) { submitErr = e.what(); }
         }
-        if (refused) {
+        if (reader.joinable()) reader.join();
+        if (!submitErr.empty()) fail(submitErr);
+        if (!readErr.empty()) fail(readErr);
+        if (!taken) {
+            // sequential parser over everything not yet consumed: this chunk, what was read ahead, then the rest of the input
             std::vector<uint8_t> pending(b->text, b->text + len);
+            if (nb && nlen > len - cut) pending.insert(pending.end(), nb->text + (len - cut), nb->text + nlen);
             if (fd >= 0) {   // plain file: hand the rest of it to zlib's transparent reader, positioned behind what was consumed
                 gz = gzopen(in.path.c_str(), "rb");
                 if (!gz) fail("cannot open " + in.path);
@@ -485,6 +514,11 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, Submi
             sequential(lr);
             return;
         }
+        if (!more) return;
+        b = cur();          // the batch the read-ahead went into
+        if (b != nb) fail("feeder: batch rotation out of step");
+        b->isText = true;   // (the driver's reset() of the fresh batch cleared the flag; the text is already in place)
+        len = nlen;
     }
 }
 
@@ -674,6 +708,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
         flush();  // host-parsed reads of an earlier input keep their place in the order
         feedFastqText(in, cfg_.textChunkBytes,
             [&]() -> HostBatch* { return cur; },
+            [&]() -> HostBatch* { return freeList.front(); },
             [&](HostBatch* b, size_t cut) -> bool {
                 gs_fastq_info info;
                 gs_ticket t = 0;
@@ -926,6 +961,7 @@ void FastqBloomFilter::runFilter(const std::vector<Input>& fastqs, OutputSink* f
         flush();
         feedFastqText(in, textChunkBytes,
             [&]() -> HostBatch* { return cur; },
+            [&]() -> HostBatch* { return freeList.front(); },
             [&](HostBatch* b, size_t cut) -> bool {
                 gs_fastq_info info;
                 gs_ticket t = 0;
