@@ -80,7 +80,8 @@ _SIGS = {
     "gs_match_collect": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint32, C.POINTER(C.c_uint32), _P, _P, C.c_uint64]),
     "gs_match_collect_view": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(C.c_uint32)]),
     "gs_match_submit_fastq": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(FastqInfo), C.POINTER(C.c_uint64)]),
-    "gs_match_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P)]),
+    "gs_match_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P),
+                                        _P, _P, C.c_uint64]),
     "gs_match_finish": (C.c_int, [_P, _P, _P]),
     "gs_match_close": (None, [_P]),
     "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
@@ -374,18 +375,27 @@ class MatchSession:
         t = C.c_uint64(0)
         _check(lib().gs_match_submit_fastq(self.h, _ptr(text), n, int(first_read_no), C.byref(info), C.byref(t)))
         if t.value:
-            self._keep[t.value] = (text, None, info.n_reads)
+            self._keep[t.value] = (text, int(info.total_kmers), info.n_reads)
         return t.value, info
 
     def collect_fastq(self, ticket):
-        """(results, events, event header offsets, records[n + 1]) as numpy views of the session's pinned staging."""
-        self._keep.pop(ticket)
+        """(results, events, event header offsets, records[n + 1]) as numpy views of the session's pinned staging; with
+        want_runs two more items: run_offsets[n + 1], runs."""
+        _, total_kmers, n_reads = self._keep.pop(ticket)
         out, ev, eh, rc = _P(), _P(), _P(), _P()
         n, nev = C.c_uint32(0), C.c_uint32(0)
-        _check(lib().gs_match_collect_fastq(self.h, ticket, C.byref(out), C.byref(n), C.byref(ev), C.byref(eh), C.byref(nev), C.byref(rc)))
+        run_off = runs = None
+        if self.cfg.want_runs:
+            run_off = np.zeros(n_reads + 1, dtype=np.uint64)
+            runs = np.empty(max(total_kmers, 1), dtype=RUN_DTYPE)
+        _check(lib().gs_match_collect_fastq(self.h, ticket, C.byref(out), C.byref(n), C.byref(ev), C.byref(eh), C.byref(nev), C.byref(rc),
+                                            _ptr(run_off), _ptr(runs), total_kmers if runs is not None else 0))
         view = lambda p, cnt, size, dt: (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(cnt * size,)).view(dt) if cnt else np.zeros(0, dt))
-        return (view(out, n.value, 16, READ_RESULT_DTYPE), view(ev, nev.value, 16, EVENT_DTYPE), view(eh, nev.value, 4, np.dtype("<u4")),
-                view(rc, n.value + 1, 16, FASTQ_REC_DTYPE))
+        res = (view(out, n.value, 16, READ_RESULT_DTYPE), view(ev, nev.value, 16, EVENT_DTYPE), view(eh, nev.value, 4, np.dtype("<u4")),
+               view(rc, n.value + 1, 16, FASTQ_REC_DTYPE))
+        if runs is not None:
+            res = res + (run_off, runs[:int(run_off[n_reads])])
+        return res
 
     def finish(self):
         V = self.db.n_values

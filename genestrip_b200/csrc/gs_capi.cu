@@ -1069,7 +1069,6 @@ extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n
                                      gs_ticket* ticket) {
     if (!s || s->finished) return gs_fail(GS_ERR_STATE, "session missing or finished");
     if (!ticket || !info || (!text && n_bytes)) return gs_fail(GS_ERR_ARG, "null argument");
-    if (s->cfg.want_runs) return gs_fail(GS_ERR_ARG, "want_runs needs host-parsed batches (gs_match_submit)");
     if (n_bytes >= 0xFFFFFF00ULL) return gs_fail(GS_ERR_LIMIT, "text chunk of %llu bytes (limit 2^32 - 256)", (unsigned long long)n_bytes);
     memset(info, 0, sizeof(*info));
     *ticket = 0;
@@ -1091,6 +1090,19 @@ extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n
     CU(hgrow(&sl.hOut, &sl.hOutCap, (size_t)n_reads));
     GsMatchParams P;
     fill_params(s, D, P);
+    if (s->cfg.want_runs) {  // contig runs of read i go to dRuns[kmerOff[i] ...): offsets by a scan of the k-mer counts on the device
+        CU(dgrow(&sl.dKmerOff, &sl.kmerOffCap, (size_t)n_reads + 1));
+        CU(hgrow(&sl.hKmerOff, &sl.hKmerOffCap, (size_t)n_reads + 1));
+        CU(dgrow(&sl.dRuns, &sl.runsCap, (size_t)info->total_kmers));
+        CU(dgrow(&sl.dRunCounts, &sl.runCountsCap, (size_t)n_reads));
+        CU(hgrow(&sl.hRunCounts, &sl.hRunCountsCap, (size_t)n_reads));
+        gs_launch_text_kmer_offsets(sl.dLens, n_reads, s->db->k, sl.dRunCounts, sl.dTileSums, sl.dKmerOff, D.sCopyIn);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(sl.dRunCounts, 0, std::max<size_t>(n_reads, 1) * sizeof(u32), D.sCopyIn));
+        CU(cudaMemcpyAsync(sl.hKmerOff, sl.dKmerOff, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyDeviceToHost, D.sCopyIn));
+        P.runs = sl.dRuns; P.runOffsets = sl.dKmerOff; P.runsCap = info->total_kmers; P.runCounts = sl.dRunCounts;
+        s->launches += n_reads ? 4 : 0;
+    }
     CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
     CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
     // the record table goes back while the match kernels run
@@ -1108,6 +1120,7 @@ extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n
     CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, 2 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaMemcpyAsync(sl.hEv, sl.dEv, std::max<size_t>(V, 1) * sizeof(gs_maxcontig_event), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaMemcpyAsync(sl.hEvHdr, sl.dEvHdr, std::max<size_t>(V, 1) * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
+    if (s->cfg.want_runs && n_reads) CU(cudaMemcpyAsync(sl.hRunCounts, sl.dRunCounts, (size_t)n_reads * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaEventRecord(sl.evDone, D.sCopyOut));
     sl.pending = true; sl.ticket = t; sl.nReads = n_reads; sl.firstReadNo = first_read_no; sl.totalKmers = info->total_kmers; sl.isText = true;
     s->nextTicket++;
@@ -1142,12 +1155,30 @@ extern "C" int gs_match_collect_view(gs_sess* s, gs_ticket t, const gs_read_resu
     return GS_OK;
 }
 
+// contig runs of a collected batch: run_offsets[n + 1] = prefix sums of the per-read run counts, runs = the lists back to back
+static int collect_runs(MatchSlot& sl, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap) {
+    u64 acc = 0;
+    for (u32 i = 0; i < sl.nReads; i++) { run_offsets[i] = acc; acc += sl.hRunCounts[i]; }
+    run_offsets[sl.nReads] = acc;
+    if (runs) {
+        if (acc > runs_cap) return gs_fail(GS_ERR_LIMIT, "%llu contig runs, capacity %llu", (unsigned long long)acc, (unsigned long long)runs_cap);
+        // runs of read i sit at dRuns[kmerOff[i] .. + count): copy the dense prefix region back, then compact
+        std::vector<gs_run> tmp((size_t)sl.totalKmers);
+        if (sl.totalKmers) CU(cudaMemcpy(tmp.data(), sl.dRuns, (size_t)sl.totalKmers * sizeof(gs_run), cudaMemcpyDeviceToHost));
+        for (u32 i = 0; i < sl.nReads; i++)
+            if (sl.hRunCounts[i]) memcpy(runs + run_offsets[i], tmp.data() + sl.hKmerOff[i], (size_t)sl.hRunCounts[i] * sizeof(gs_run));
+    }
+    return GS_OK;
+}
+
 extern "C" int gs_match_collect_fastq(gs_sess* s, gs_ticket t, const gs_read_result** out, uint32_t* n_reads, const gs_maxcontig_event** events,
-                                      const uint32_t** event_hdr_start, uint32_t* n_events, const gs_fastq_rec** recs) {
+                                      const uint32_t** event_hdr_start, uint32_t* n_events, const gs_fastq_rec** recs,
+                                      uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap) {
     DevSess* D; MatchSlot* sl;
     int rc = wait_ticket(s, t, &D, &sl);
     if (rc) return rc;
     if (!sl->isText) return gs_fail(GS_ERR_STATE, "ticket %llu was not submitted as FASTQ text", (unsigned long long)t);
+    if (s->cfg.want_runs && run_offsets) { rc = collect_runs(*sl, run_offsets, runs, runs_cap); if (rc) return rc; }
     if (out) *out = sl->hOut;
     if (n_reads) *n_reads = sl->nReads;
     if (events) *events = sl->hEv;
@@ -1172,19 +1203,7 @@ extern "C" int gs_match_collect(gs_sess* s, gs_ticket t, gs_read_result* out, gs
         }
         *n_events = ne;
     }
-    if (s->cfg.want_runs && run_offsets) {
-        u64 acc = 0;
-        for (u32 i = 0; i < sl.nReads; i++) { run_offsets[i] = acc; acc += sl.hRunCounts[i]; }
-        run_offsets[sl.nReads] = acc;
-        if (runs) {
-            if (acc > runs_cap) return gs_fail(GS_ERR_LIMIT, "%llu contig runs, capacity %llu", (unsigned long long)acc, (unsigned long long)runs_cap);
-            // runs of read i sit at dRuns[kmerOff[i] .. + count): copy the dense prefix region back, then compact
-            std::vector<gs_run> tmp((size_t)sl.totalKmers);
-            if (sl.totalKmers) CU(cudaMemcpy(tmp.data(), sl.dRuns, (size_t)sl.totalKmers * sizeof(gs_run), cudaMemcpyDeviceToHost));
-            for (u32 i = 0; i < sl.nReads; i++)
-                if (sl.hRunCounts[i]) memcpy(runs + run_offsets[i], tmp.data() + sl.hKmerOff[i], (size_t)sl.hRunCounts[i] * sizeof(gs_run));
-        }
-    }
+    if (s->cfg.want_runs && run_offsets) return collect_runs(sl, run_offsets, runs, runs_cap);
     return GS_OK;
 }
 

@@ -532,6 +532,33 @@ FastqKMerMatcher::~FastqKMerMatcher() {}
 
 static void appendInt(std::string& s, long long v) { s += std::to_string(v); }
 
+// writeMatchDetails + printKrakenStyleOut (C/match/FastqKMerMatcher.java:597-611, 723-756) for one read
+void FastqKMerMatcher::writeKrakenLine(OutputSink& krakenOut, const gs_read_result& r, const uint8_t* d, size_t dl, int64_t L, const gs_run* runs,
+                                       size_t nRuns, int entry, std::string& line) {
+    if (nRuns > 0) entryBufferUsed_[entry] = true;  // printKrakenStyleOut allocated the pooled entry's buffer
+    if (!((cfg_.writeAll || r.class_vidx >= 0) && entryBufferUsed_[entry])) return;
+    line.clear();
+    line += r.class_vidx >= 0 ? "C\t" : "U\t";
+    size_t sp = dl;
+    for (size_t j = 1; j < dl; j++) if (d[j] == ' ') { sp = j; break; }
+    if (sp > 1) line.append((const char*)d + 1, sp - 1);
+    line.push_back('\t');
+    if (r.class_vidx >= 0) line += meta_.taxid[(size_t)r.class_vidx]; else line.push_back('0');
+    line.push_back('\t');
+    appendInt(line, L);
+    line.push_back('\t');
+    for (size_t j = 0; j < nRuns; j++) {
+        if (j > 0) line.push_back(' ');
+        if (runs[j].label == GS_RUN_INVALID) line.push_back('A');
+        else if (runs[j].label == GS_RUN_MISS) line.push_back('0');
+        else line += meta_.taxid[runs[j].label];
+        line.push_back(':');
+        appendInt(line, runs[j].len);
+    }
+    line.push_back('\n');
+    krakenOut.write(line.data(), line.size());
+}
+
 void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
                                     std::vector<uint64_t>& bestKey) {
     const int V = meta_.nValues;
@@ -570,31 +597,7 @@ void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, 
             const uint8_t* p = b.probs(i, pl);
             writeRead(*filtered, d, dl, b.bases + a, (size_t)L, p, pl, b.hasProbs[i] != 0, scratch);
         }
-        if (krakenOut) {
-            if (runOff[i + 1] > runOff[i]) entryBufferUsed_[b.entry[i]] = true;  // printKrakenStyleOut allocated the buffer
-            if ((cfg_.writeAll || r.class_vidx >= 0) && entryBufferUsed_[b.entry[i]]) {  // writeMatchDetails (:723-756)
-                line.clear();
-                line += r.class_vidx >= 0 ? "C\t" : "U\t";
-                size_t sp = dl;
-                for (size_t j = 1; j < dl; j++) if (d[j] == ' ') { sp = j; break; }
-                if (sp > 1) line.append((const char*)d + 1, sp - 1);
-                line.push_back('\t');
-                if (r.class_vidx >= 0) line += meta_.taxid[(size_t)r.class_vidx]; else line.push_back('0');
-                line.push_back('\t');
-                appendInt(line, L);
-                line.push_back('\t');
-                for (uint64_t j = runOff[i]; j < runOff[i + 1]; j++) {  // printKrakenStyleOut (:597-611)
-                    if (j > runOff[i]) line.push_back(' ');
-                    if (runs[j].label == GS_RUN_INVALID) line.push_back('A');
-                    else if (runs[j].label == GS_RUN_MISS) line.push_back('0');
-                    else line += meta_.taxid[runs[j].label];
-                    line.push_back(':');
-                    appendInt(line, runs[j].len);
-                }
-                line.push_back('\n');
-                krakenOut->write(line.data(), line.size());
-            }
-        }
+        if (krakenOut) writeKrakenLine(*krakenOut, r, d, dl, L, runs.data() + runOff[i], (size_t)(runOff[i + 1] - runOff[i]), b.entry[i], line);
         // classified-read statistics: the four double sums in read order (:511-526)
         if (r.flags & GS_READ_ACCEPTED) {
             CountsPerTaxid& st = stats[(size_t)r.class_vidx];
@@ -610,10 +613,15 @@ void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, 
 
 // A batch that went to the device as raw FASTQ text: descriptors, bases and qualities are read from the (pinned) text through
 // the record table the device returns; same bookkeeping as processBatch.
-void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filtered, std::vector<CountsPerTaxid>& stats, std::vector<uint64_t>& bestKey) {
+void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
+                                        std::vector<uint64_t>& bestKey) {
     const gs_read_result* res = nullptr; const gs_maxcontig_event* ev = nullptr; const uint32_t* evHdr = nullptr; const gs_fastq_rec* recs = nullptr;
     uint32_t n = 0, nEv = 0;
-    check(gs_match_collect_fastq(s, b.ticket, &res, &n, &ev, &evHdr, &nEv, &recs), "gs_match_collect_fastq");
+    std::vector<uint64_t> runOff;
+    std::vector<gs_run> runs;
+    if (krakenOut) { runOff.assign((size_t)b.n + 1, 0); runs.resize((size_t)std::max<uint64_t>(b.totalKmers, 1)); }
+    check(gs_match_collect_fastq(s, b.ticket, &res, &n, &ev, &evHdr, &nEv, &recs, krakenOut ? runOff.data() : nullptr,
+                                 krakenOut ? runs.data() : nullptr, b.totalKmers), "gs_match_collect_fastq");
     for (uint32_t e = 0; e < nEv; e++) {  // maxContigDescriptor (FastqKMerMatcher.java:402-409)
         const gs_maxcontig_event& x = ev[e];
         const uint64_t key = ((uint64_t)x.contig_len << 40) | ((((uint64_t)1 << 40) - 1) - x.read_no);
@@ -626,7 +634,7 @@ void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filter
         dst.clear();
         for (size_t j = 1; j < dl && j < (size_t)cfg_.initialReadSizeBytes && d[j] != ' '; j++) dst.push_back((char)d[j]);
     }
-    std::string scratch;
+    std::string scratch, line;
     const int k = meta_.k;
     for (uint32_t i = 0; i < n; i++) {
         const gs_read_result& r = res[i];
@@ -636,6 +644,9 @@ void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filter
         if ((r.flags & GS_READ_FOUND) && filtered)  // afterMatch (:304-315)
             writeRead(*filtered, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), b.text + rc.seq_start, (size_t)L,
                       b.text + rc.qual_start, (size_t)(recs[i + 1].hdr_start - 1 - rc.qual_start), cfg_.withProbs, scratch);
+        if (krakenOut)  // FASTQ records always travel in the first pooled ReadEntry at threads = 0 (AbstractFastqReader.java:447-455)
+            writeKrakenLine(*krakenOut, r, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), L, runs.data() + runOff[i],
+                            (size_t)(runOff[i + 1] - runOff[i]), 0, line);
         if (r.flags & GS_READ_ACCEPTED) {  // the four double sums in read order (:511-526)
             CountsPerTaxid& st = stats[(size_t)r.class_vidx];
             const double err = ((double)(int32_t)r.tax_err) / (double)max;
@@ -678,7 +689,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
     cur->reset(ordinal);
     auto collectOldest = [&]() {
         Batch* b = inflight.front(); inflight.pop_front();
-        if (b->isText) processTextBatch(s, *b, filtered, stats, bestKey);
+        if (b->isText) processTextBatch(s, *b, filtered, krakenOut, stats, bestKey);
         else processBatch(s, *b, filtered, krakenOut, stats, bestKey);
         freeList.push_back(b);
     };
@@ -699,7 +710,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
         ordinal++;
     };
     for (const Input& in : fastqs) {   // processFastqStreams (C/fastq/AbstractLoggingFastqStreamer.java:95-131)
-        if (!cfg_.gpuParse || in.fasta || krakenOut) {
+        if (!cfg_.gpuParse || in.fasta) {
             reader.readFastq(in, onRecord);
             totalReads += reader.reads; totalKMers += reader.kMers; totalBPs += reader.readBPs;
             continue;
@@ -715,7 +726,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
                 check(gs_match_submit_fastq(s, b->text, cut, ordinal, &info, &t), "gs_match_submit_fastq");
                 textChunks++;
                 if (info.status) return false;
-                b->ticket = t; b->n = info.n_reads; b->firstOrdinal = ordinal;
+                b->ticket = t; b->n = info.n_reads; b->firstOrdinal = ordinal; b->totalKmers = info.total_kmers;
                 ordinal += info.n_reads;
                 totalReads += info.n_reads; totalKMers += (int64_t)info.total_kmers; totalBPs += (int64_t)info.total_bps;
                 inflight.push_back(cur);

@@ -51,7 +51,7 @@ struct MatchConfig {  // the config keys the path reads (C/GSConfigKey.java:302-
     int layout = GS_LAYOUT_TABLE;
     uint32_t batchReads = 1u << 20;       // reads per pinned batch
     size_t batchBytes = (size_t)256 << 20;  // bases per pinned batch
-    // FASTQ inputs (not FASTA, no kraken-style output): raw text chunks go to the GPU, which splits the records
+    // FASTQ inputs (not FASTA): raw text chunks go to the GPU, which splits the records
     // (gs_match_submit_fastq); the first chunk the device refuses switches the rest of that input to the sequential parser
     bool gpuParse = true;
     size_t textChunkBytes = (size_t)64 << 20;
@@ -114,7 +114,10 @@ class FastqKMerMatcher {
     struct Batch;
     void processBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
                       std::vector<uint64_t>& bestKey);
-    void processTextBatch(gs_sess* s, Batch& b, OutputSink* filtered, std::vector<CountsPerTaxid>& stats, std::vector<uint64_t>& bestKey);
+    void processTextBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
+                          std::vector<uint64_t>& bestKey);
+    void writeKrakenLine(OutputSink& krakenOut, const gs_read_result& r, const uint8_t* desc, size_t descLen, int64_t L, const gs_run* runs,
+                         size_t nRuns, int entry, std::string& line);
 
    public:
     uint64_t textChunks = 0, textChunksRefused = 0;  // chunks split on the GPU / handed back to the sequential parser

@@ -86,6 +86,7 @@ int gs_match_kernel_occupancy(int mode);
 void gs_launch_text_split(const uint8_t* text, u64 n, u32* blockCounts, u32* lineEnd, u32 lineCap, u32* meta, gs_fastq_rec* recs, u32* lens,
                           int k, unsigned long long* totals, cudaStream_t st);
 void gs_launch_text_compact(const uint8_t* text, const gs_fastq_rec* recs, const u32* lens, u32 n, u64* tileSums, u64* offsets, uint8_t* bases, cudaStream_t st);
+void gs_launch_text_kmer_offsets(const u32* lens, u32 n, int k, u32* klens, u64* tileSums, u64* kmerOff, cudaStream_t st);
 void gs_launch_text_event_headers(const gs_maxcontig_event* ev, const u32* nEv, u32 evCap, const gs_fastq_rec* recs, u64 firstReadNo, u32 n, u32* hdr, cudaStream_t st);
 
 // database update phase

@@ -211,6 +211,18 @@ void gs_launch_text_compact(const uint8_t* text, const gs_fastq_rec* recs, const
     gs_scan_apply_kernel<<<nTiles, 256, 0, st>>>(lens, n, tileSums, offsets);
     gs_text_gather_kernel<<<148 * 8, 256, 0, st>>>(text, recs, offsets, n, bases);
 }
+// k-mer offsets of the reads (exclusive prefix sums of max(0, L - k + 1)): where each read's contig runs go (want_runs)
+__global__ void gs_text_klens_kernel(const u32* __restrict__ lens, u32 n, int k, u32* klens) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) klens[i] = lens[i] >= (u32)k ? lens[i] - (u32)k + 1u : 0u;
+}
+void gs_launch_text_kmer_offsets(const u32* lens, u32 n, int k, u32* klens, u64* tileSums, u64* kmerOff, cudaStream_t st) {
+    if (n == 0) { cudaMemsetAsync(kmerOff, 0, sizeof(u64), st); return; }
+    const u32 nTiles = (n + GS_SCAN_TILE - 1) / GS_SCAN_TILE;
+    gs_text_klens_kernel<<<148 * 4, 256, 0, st>>>(lens, n, k, klens);
+    gs_scan_tile_sums_kernel<<<nTiles, 256, 0, st>>>(klens, n, tileSums);
+    gs_scan_top_kernel<<<1, 1024, 0, st>>>(tileSums, nTiles);
+    gs_scan_apply_kernel<<<nTiles, 256, 0, st>>>(klens, n, tileSums, kmerOff);
+}
 // header offsets of the reads named by the max-contig events of a batch (the host copies the descriptor from its text)
 __global__ void gs_text_event_headers_kernel(const gs_maxcontig_event* __restrict__ ev, const u32* __restrict__ nEv, u32 evCap, const gs_fastq_rec* __restrict__ recs,
                                              u64 firstReadNo, u32 n, u32* hdr) {

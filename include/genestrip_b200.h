@@ -179,7 +179,7 @@ int gs_match_submit(gs_sess*, const uint8_t* bases, const uint64_t* offsets, uin
  * under the reference parser's rules (no NUL byte, third line starts with '+', quality at least as long as the sequence,
  * line count a multiple of 4).  If it is not, info->status holds GS_FASTQ_* bits, *ticket is 0, nothing is pending, and the
  * caller parses this chunk with the sequential parser (gs_match_submit) -- results never depend on the fast path.
- * Otherwise the batch runs exactly like gs_match_submit of the same reads.  n_bytes < 2^32 - 256; not with want_runs. */
+ * Otherwise the batch runs exactly like gs_match_submit of the same reads.  n_bytes < 2^32 - 256. */
 typedef struct gs_fastq_info {
     uint32_t n_reads;
     uint32_t status;       /* 0 = strict 4-line FASTQ, batch submitted */
@@ -199,10 +199,11 @@ typedef struct gs_fastq_rec {
 int gs_match_submit_fastq(gs_sess*, const uint8_t* text, uint64_t n_bytes, uint64_t first_read_no, gs_fastq_info* info,
                           gs_ticket* ticket);
 /* Zero-copy views (valid like gs_match_collect_view's): out[n_reads], recs[n_reads + 1] (the last entry marks the end of
- * the text), events[n_events] with event_hdr_start[e] = header offset of the read that caused event e. */
+ * the text), events[n_events] with event_hdr_start[e] = header offset of the read that caused event e.  With want_runs:
+ * run_offsets[n_reads + 1] / runs[runs_cap] as in gs_match_collect (runs_cap >= info.total_kmers always suffices); else NULL. */
 int gs_match_collect_fastq(gs_sess*, gs_ticket, const gs_read_result** out, uint32_t* n_reads,
                            const gs_maxcontig_event** events, const uint32_t** event_hdr_start, uint32_t* n_events,
-                           const gs_fastq_rec** recs);
+                           const gs_fastq_rec** recs, uint64_t* run_offsets, gs_run* runs, uint64_t runs_cap);
 /* Wait for a ticket.  out[n_reads]; events[ev_cap] / n_events may be NULL.  If want_runs: run_offsets
  * [n_reads+1] and runs[runs_cap] receive the contig runs (GS_ERR_LIMIT if runs_cap is too small). */
 int gs_match_collect(gs_sess*, gs_ticket, gs_read_result* out, gs_maxcontig_event* events, uint32_t ev_cap,

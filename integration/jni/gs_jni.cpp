@@ -145,7 +145,7 @@ JNIEXPORT jlongArray JNICALL J(matchSubmitFastq)(JNIEnv* env, jclass, jlong s, j
 // [0] results, [1] max-contig events, [2] header offset per event (u32), [3] record table (nReads + 1) x gs_fastq_rec
 JNIEXPORT jobjectArray JNICALL J(matchCollectFastq)(JNIEnv* env, jclass, jlong s, jlong ticket) {
     const gs_read_result* out; const gs_maxcontig_event* ev; const uint32_t* eh; const gs_fastq_rec* recs; uint32_t n = 0, nev = 0;
-    if (gs_match_collect_fastq((gs_sess*)s, (gs_ticket)ticket, &out, &n, &ev, &eh, &nev, &recs) != GS_OK) { throwLast(env); return nullptr; }
+    if (gs_match_collect_fastq((gs_sess*)s, (gs_ticket)ticket, &out, &n, &ev, &eh, &nev, &recs, nullptr, nullptr, 0) != GS_OK) { throwLast(env); return nullptr; }
     jobjectArray arr = env->NewObjectArray(4, env->FindClass("java/nio/ByteBuffer"), nullptr);
     env->SetObjectArrayElement(arr, 0, env->NewDirectByteBuffer((void*)out, (jlong)n * (jlong)sizeof(gs_read_result)));
     env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer((void*)ev, (jlong)nev * (jlong)sizeof(gs_maxcontig_event)));

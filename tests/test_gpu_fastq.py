@@ -107,6 +107,27 @@ def test_fastq_text_parity(project, oracle, native, variant):
             assert orun.desc[v] == hdr[1:].split(b" ")[0]
 
 
+def test_fastq_text_contig_runs(project, oracle, native):
+    """want_runs through the text path: the per-read contig runs (printKrakenStyleOut, C/match/FastqKMerMatcher.java:597-611)
+    equal those of the host-parsed path for the same reads."""
+    odb, gdb, genomes = project
+    bases, offsets, src = synth.sample_reads([g for _, g in genomes], 1200, 150, seed=31, frac_db=0.8, sub_rate=0.02, n_rate=0.004, len_jitter=80)
+    fq = synth.fastq_bytes(bases, offsets, src)
+    _, _, _, _, runs_ref, _ = util.gpu_match(native, gdb, bases, offsets, batch=len(offsets) - 1, want_runs=1)
+    ro_ref, ru_ref = runs_ref[0]
+    sess = native.MatchSession(gdb, native.default_match_cfg(want_runs=1))
+    try:
+        t, info = sess.submit_fastq(np.frombuffer(fq, dtype=np.uint8))
+        assert t and info.status == 0
+        res, ev, eh, recs, ro, ru = sess.collect_fastq(t)
+        sess.finish()
+    finally:
+        sess.close()
+    np.testing.assert_array_equal(ro, ro_ref)
+    np.testing.assert_array_equal(ru, ru_ref)
+    assert len(ru) > len(res)
+
+
 def test_fastq_text_refuses_non_strict_input(project, native):
     _, gdb, genomes = project
     g0 = genomes[0][1]

@@ -192,15 +192,17 @@ def test_match_goal_gpu_fastq_feeder(project, oracle, host, tmp_path, with_probs
     p2 = str(tmp_path / "b.fastq.gz")
     with gzip.open(p2, "wb") as f:
         f.write(f2)
-    ocfg = oracle.match_cfg(k=K, write_filtered=True, with_probs=with_probs)
+    ocfg = oracle.match_cfg(k=K, write_filtered=True, write_kraken=True, with_probs=with_probs)
     orun = odb.match_files(ocfg, [f1, f2])
     p1 = str(tmp_path / "a.fastq")   # plain file: parallel pread() straight into the pinned chunks
     open(p1, "wb").write(f1)
     for chunk in (30000, 1 << 20):
-        res = host.match_goal(gdb, meta, [f1 if chunk == 30000 else p1, p2], write_filtered=True, with_probs=int(with_probs), text_chunk_bytes=chunk)
+        res = host.match_goal(gdb, meta, [f1 if chunk == 30000 else p1, p2], write_filtered=True, write_kraken=True, with_probs=int(with_probs),
+                              text_chunk_bytes=chunk)
         assert res.text_chunks_refused == 0 and res.text_chunks >= (40 if chunk == 30000 else 2)
         assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
         assert res.filtered == orun.filtered
+        assert res.kraken == orun.kraken   # kraken-style lines from the contig runs of text batches
         for i in range(4):
             np.testing.assert_array_equal(res.dsums[i], orun.dstats[i])
         _assert_csv_equal(res.csv, orun.csv)
