@@ -926,7 +926,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
             CU(dgrow(&D.redoList, &D.redoCap, (size_t)P.nReads));
         }
         P.redoList = D.redoList; P.redoCount = D.overflowCount + 3; P.groupCounter = D.overflowCount + 4;
-        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 4, ((u64)P.nReads + 127) / 128), D.sCompute);
+        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 7, ((u64)P.nReads + 127) / 128), D.sCompute);
         CU(cudaGetLastError());
         s->launches += 1;
     }

@@ -481,19 +481,24 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
 
 // ---- K2T: reduce kernel for short reads, one THREAD per read.  A 150-base read has 120 labels: a warp per read spends
 // most of its instructions on per-read set-up and warp-wide bookkeeping, a thread per read just walks its labels.  A warp
-// takes 32 consecutive reads; their labels are staged 32 positions at a time through a [32][33] shared-memory tile (row i =
-// read i: coalesced 128-byte global loads, conflict-free transposed reads), so global traffic is one pass over the labels.
+// takes 32 consecutive reads; their labels are staged GS_T_POS positions at a time through a [32][GS_T_POS + 1] shared-memory
+// tile (row i = read i: coalesced global reads, conflict-free transposed reads), so global traffic is one pass over the labels.
 // The contig statistics are accumulated per (read, taxon) in a small per-thread table and applied once at the end of the read
 // (sums and maxima: same result as the reference's per-contig updates, FastqKMerMatcher.java:396-410), so a read that turns
 // out to need more than GS_T_CAP table entries has had no side effects yet and is handed to the warp-per-read kernel.
 #define GS_T_CAP 8
 #define GS_T_THREADS 128
 #define GS_T_MAX_LEN 2047  // cnt (11 bits) | contigs (10 bits) | maxlen (11 bits) share one word
-__global__ void __launch_bounds__(GS_T_THREADS) gs_reduce_thread_kernel(const GsMatchParams P) {
+#ifndef GS_T_POS
+#define GS_T_POS 16        // label positions per staging round: tile = [32 reads][GS_T_POS + 1] words, two of them per warp
+#endif
+#define GS_T_ROW (GS_T_POS + 1)
+#define GS_T_BLOCKS (GS_T_POS == 16 ? 7 : 4)   // resident CTAs per SM the shared memory allows (31.2 KB / 47.6 KB per CTA)
+__global__ void __launch_bounds__(GS_T_THREADS, GS_T_BLOCKS) gs_reduce_thread_kernel(const GsMatchParams P) {
     __shared__ u32 s_vi[GS_T_CAP][GS_T_THREADS];
     __shared__ u32 s_pk[GS_T_CAP][GS_T_THREADS];   // cnt << 21 | contigs << 11 | maxlen
     __shared__ u32 s_sq[GS_T_CAP][GS_T_THREADS];
-    __shared__ u32 s_tile[GS_T_THREADS / 32][2 * 32 * 33];
+    __shared__ u32 s_tile[GS_T_THREADS / 32][2 * 32 * GS_T_ROW];
     __shared__ u64 s_fs[GS_T_THREADS / 32][32];
     __shared__ int s_max[GS_T_THREADS / 32][32];
     const GsDbView& db = P.db;
@@ -533,31 +538,47 @@ __global__ void __launch_bounds__(GS_T_THREADS) gs_reduce_thread_kernel(const Gs
         // ---- stage positions [b, b + 32) of the warp's 32 reads with 4-byte cp.async (global -> shared without registers),
         // double-buffered: the copies of round b + 32 are in flight while round b is walked
         auto stage = [&](int b, u32* dst) {
-            const int p = b + lane;
+            // a cp.async instruction moves GS_T_POS positions of 32 / GS_T_POS reads: lane = (read parity, position)
+            const int sub = lane / GS_T_POS, pos = lane % GS_T_POS;
+            const int p = b + pos;
 #pragma unroll 8
-            for (int i = 0; i < 32; i++) {
+            for (int i0 = 0; i0 < 32; i0 += 32 / GS_T_POS) {
+                const int i = i0 + sub;
                 if (p < s_max[warp][i]) {
-                    const u32 sa = (u32)__cvta_generic_to_shared(dst + i * 33 + lane);
+                    const u32 sa = (u32)__cvta_generic_to_shared(dst + i * GS_T_ROW + pos);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(P.labels + s_fs[warp][i] + p) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if (wmax > 0) stage(0, tile);
-        for (int b = 0; b < wmax; b += 32) {
-            u32* cur = tile + ((b >> 5) & 1) * (32 * 33);
-            if (b + 32 < wmax) {
-                stage(b + 32, tile + (((b >> 5) & 1) ^ 1) * (32 * 33));
+        for (int b = 0; b < wmax; b += GS_T_POS) {
+            u32* cur = tile + ((b / GS_T_POS) & 1) * (32 * GS_T_ROW);
+            if (b + GS_T_POS < wmax) {
+                stage(b + GS_T_POS, tile + (((b / GS_T_POS) & 1) ^ 1) * (32 * GS_T_ROW));
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncwarp();
             if (walk) {
-                const int n = min(32, max + 1 - b);  // position `max` is the terminator that flushes the last run
-                for (int i = 0; i < n; i++) {
-                    const u32 lab = b + i == max ? GS_LABEL_END : cur[lane * 33 + i];
-                    if (lab == prev) { len++; continue; }
+                const int n = min(GS_T_POS, max + 1 - b);  // position `max` is the terminator that flushes the last run
+                // run boundaries of this round as a bit mask (all loads first, no branch per label) ...
+                u32 m = 0, pl = prev;
+#pragma unroll
+                for (int i = 0; i < GS_T_POS; i++) {
+                    const u32 l = b + i == max ? GS_LABEL_END : cur[lane * GS_T_ROW + i];
+                    m |= (u32)(l != pl) << i;
+                    pl = l;
+                }
+                m &= (1u << n) - 1u;
+                // ... then one step per boundary
+                int cursor = 0;
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    len += i - cursor;
+                    cursor = i;
                     if (prev < GS_LABEL_INVALID && len > 0) {  // a contig of taxon `prev` ends (:396-410, 458-471)
                         int j = 0;
                         while (j < nTab && s_vi[j][t] != prev) j++;
@@ -580,11 +601,12 @@ __global__ void __launch_bounds__(GS_T_THREADS) gs_reduce_thread_kernel(const Gs
                     } else if (prev == GS_LABEL_INVALID) {
                         sawInvalid = true;
                     }
-                    prev = lab;
-                    len = 1;
+                    prev = b + i == max ? GS_LABEL_END : cur[lane * GS_T_ROW + i];
+                    len = 0;
                 }
+                len += n - cursor;
                 if (overflow) { P.redoList[atomicAdd(P.redoCount, 1u)] = r; walk = false; }
-                else if (b + 32 > max) walk = false;  // terminator consumed: the read is complete
+                else if (b + GS_T_POS > max) walk = false;  // terminator consumed: the read is complete
             }
             __syncwarp();
         }
