@@ -169,6 +169,7 @@ struct gs_db {
     int mzBits = 0;  // log2 of the minimizer prefilter's size in bits; 0 = none
     bool mzWide = false;  // minimizers ordered by a 64-bit hash (stores whose filter would use most of the 32-bit hash space)
     bool seenLeased = false;  // the table's in-line seen bits belong to at most one unique-counting session at a time
+    int openSessions = 0;     // match sessions that read this database (gs_db_update needs none)
     // radix source staging
     std::vector<std::pair<u64, int16_t>> radixItems;
     u64 bytes = 0;
@@ -551,7 +552,7 @@ extern "C" gs_db* gs_db_load_file(gs_ctx* ctx, const char* path) {
 extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, const uint64_t* region_offsets, const int32_t* region_vidx,
                             uint32_t n_regions, int upper_case, uint64_t* n_changed) {
     if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
-    if (db->seenLeased) return gs_fail(GS_ERR_STATE, "a match session holds the probe table's seen bits: close it before updating");
+    if (db->seenLeased || db->openSessions > 0) return gs_fail(GS_ERR_STATE, "%d match session(s) are open on this database: close them before updating", db->openSessions);
     if (n_changed) *n_changed = 0;
     if (n_regions == 0 || n_bytes == 0) return GS_OK;
     if (!seq || !region_offsets || !region_vidx) return gs_fail(GS_ERR_ARG, "null argument");
@@ -830,6 +831,7 @@ extern "C" void gs_match_close(gs_sess* s) {
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
     }
     if (s->inlineSeen) s->db->seenLeased = false;
+    if (s->db->openSessions > 0) s->db->openSessions--;
     delete s;
 }
 
@@ -845,6 +847,7 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
     if (c.layout != GS_LAYOUT_TABLE && c.layout != GS_LAYOUT_CLASSIC) { gs_fail(GS_ERR_ARG, "unknown layout %d", c.layout); return nullptr; }
     gs_sess* s = new gs_sess();
     s->db = db; s->cfg = c;
+    db->openSessions++;
     s->layout = c.layout;
     s->nPos = c.layout == GS_LAYOUT_TABLE ? ((u64)GS_TAB_SLOT_STRIDE << db->tbits) : db->n;
     if (c.layout == GS_LAYOUT_TABLE && c.count_unique_kmers && !db->seenLeased) { s->inlineSeen = true; db->seenLeased = true; }
