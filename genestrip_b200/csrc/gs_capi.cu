@@ -724,6 +724,7 @@ struct DevSess {
     u32* labels = nullptr; size_t labelsCap = 0;
     u32* validBits = nullptr; size_t validCap = 0;
     u32* startBits = nullptr; size_t startCap = 0;
+    u32* bmask = nullptr; size_t bmaskCap = 0;
     u32* redoList = nullptr; size_t redoCap = 0;
     std::vector<cudaEvent_t> timingEv;  // gs_match_set_timing: 3 events per batch (before label, after label, after reduce)
     MatchSlot slots[GS_MAX_INFLIGHT];
@@ -823,7 +824,7 @@ extern "C" void gs_match_close(gs_sess* s) {
         }
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
-        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList);
+        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList); cudaFree(D.bmask);
         for (cudaEvent_t e : D.timingEv) cudaEventDestroy(e);
         D.timingEv.clear();
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
@@ -912,6 +913,16 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     CU(cudaMemsetAsync(D.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
     gs_launch_mark_starts(P, D.sCompute);
     CU(cudaGetLastError());
+    // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
+    const bool threadPath = !s->cfg.want_runs && nBytes / P.nReads <= 512;
+    if (!threadPath && !getenv("GS_DEBUG_NO_BMASK")) {  // long reads / contig runs: the label kernel also marks the run boundaries
+        const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
+        if (words > D.bmaskCap) {
+            CU(cudaStreamSynchronize(D.sCompute));
+            CU(dgrow(&D.bmask, &D.bmaskCap, words));
+        }
+        P.bmask = D.bmask;
+    }
     const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)D.labelBlocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
     cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
     if (s->timing) {
@@ -921,8 +932,6 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     gs_launch_label(P, false, labelBlocks, D.sCompute);
     CU(cudaGetLastError());
     if (s->timing) CU(cudaEventRecord(tev[1], D.sCompute));
-    // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
-    const bool threadPath = !s->cfg.want_runs && nBytes / P.nReads <= 512;
     if (threadPath) {
         if (P.nReads > D.redoCap) {
             CU(cudaStreamSynchronize(D.sCompute));

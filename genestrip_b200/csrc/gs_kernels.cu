@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
 
         // ---- chunks
         u64 fwdN = gs_extract(cw, lane, k), rcN = gs_revcomp(fwdN, k);
+        u32 carryLab = 0;  // label of the last position of the previous chunk (run-boundary masks)
         MzT hN = 0, preN = 0;
         if (mz) { hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcN & mmask) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask); preN = gs_seg_prefix_min(hN, lane); }
 #pragma unroll 1
@@ -239,6 +240,16 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
             }
             __syncwarp();  // reconverge here, not at the compiler's leisure: the shuffles of the next chunk need the full warp
             if (f < P.flatLen) P.labels[f] = lab;
+            if (P.bmask) {
+                // run-boundary mask for the warp-per-read reduce kernel: bit = this position's label differs from its
+                // predecessor's.  The predecessor of a segment's first position belongs to another warp: that bit is set
+                // unconditionally and verified by the reader.
+                u32 pv = __shfl_up_sync(FULL, lab, 1);
+                if (lane == 0) pv = carryLab;
+                const u32 bm = __ballot_sync(FULL, lab != pv || (c == 0 && lane == 0));
+                if (lane == 0) P.bmask[(u64)seg * GS_SEG_CHUNKS + c] = bm;
+                carryLab = __shfl_sync(FULL, lab, 31);
+            }
         }
     }
 }
@@ -249,8 +260,9 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
 // (table in global scratch sized nValues; contig statistics were already applied by the fast path, only reads1KMer
 // beyond the first GS_TABLE_CAP taxa and the classification are done here).
 // DUMP: additionally write the per-position labels / positions in k-mer order (parity tests).
-template <int MODE, bool DUMP>
+template <int MODE, bool DUMP, bool MASKED>
 __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_reduce_kernel(const GsMatchParams P) {
+    __shared__ uint16_t s_bpos[MASKED ? GS_WARPS_PER_BLOCK : 1][MASKED ? 1024 : 1];  // run boundaries of 1024 positions, per warp
     __shared__ u32 s_tabVi[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
     __shared__ u32 s_tabCnt[MODE == 0 ? GS_WARPS_PER_BLOCK : 1][MODE == 0 ? GS_TABLE_CAP : 1];
     __shared__ u32 s_cand[GS_WARPS_PER_BLOCK][GS_MAX_PATHS];
@@ -306,6 +318,75 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
         u32 carryLabel = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
         u64 runCursor = 0;               // want_runs: next free slot of this read's run list
 
+        if (MASKED) {
+            // ---- long reads: walk the run BOUNDARIES the label kernel marked (one bit per position) instead of the labels.
+            // 32 mask words = 1024 positions per round; their set bits are spread out into a per-warp list, then 32 boundaries
+            // at a time are handled like the starts of the label loop below: the run that ends at boundary p has label
+            // labels[p - 1] and length p - (previous boundary).
+            const u64 fEnd = fs + (u64)max;      // terminator position: flushes the last run
+            u64 prevB = fs;
+            uint16_t* bp = s_bpos[warp];
+            for (u64 w0 = fs >> 5; w0 * 32 <= fEnd; w0 += 32) {
+                const u64 w = w0 + lane, p0 = w * 32;
+                u32 mw = 0;
+                if (p0 <= fEnd && p0 + 32 > fs) {
+                    mw = P.bmask[w];
+                    if ((w % GS_SEG_CHUNKS) == 0 && (mw & 1u) && p0 > fs && p0 < fEnd && P.labels[p0] == P.labels[p0 - 1]) mw &= ~1u;  // segment start: verify
+                    const int lo = fs > p0 ? (int)(fs - p0) : 0;
+                    const int hi = fEnd - p0 >= 32 ? 32 : (int)(fEnd - p0);
+                    mw &= (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    if (fs >= p0) mw |= 1u << lo;                                  // the read's first position starts a run
+                    if (fEnd >= p0 && fEnd - p0 < 32) mw |= 1u << (int)(fEnd - p0);  // terminator
+                }
+                const int cnt = __popc(mw);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+                const int total = __shfl_sync(FULL, incl, 31);
+                int slot = incl - cnt;
+                while (mw) { const int b = __ffs(mw) - 1; mw &= mw - 1; bp[slot++] = (uint16_t)(lane * 32 + b); }
+                __syncwarp();
+                for (int g = 0; g < total; g += 32) {
+                    const int idx = g + lane;
+                    const bool act = idx < total;
+                    const u64 p = w0 * 32 + (u64)bp[act ? idx : total - 1];
+                    u64 pp = __shfl_up_sync(FULL, p, 1);
+                    if (lane == 0) pp = prevB;
+                    const int runLen = act ? (int)(p - pp) : 0;
+                    const u32 prev = runLen > 0 ? __ldg(P.labels + p - 1) : GS_LABEL_END;  // label of the run that ends at p
+                    if (P.classify) misses += __reduce_add_sync(FULL, prev == GS_LABEL_MISS ? runLen : 0);
+                    sawInvalid |= __any_sync(FULL, prev == GS_LABEL_INVALID);
+                    const bool flushTax = prev < GS_LABEL_INVALID && runLen > 0;
+                    if (flushTax) {  // :396-410 (contig boundary) and :458-471 (final contig)
+                        atomicAdd((u64*)(P.counters + 0 * (size_t)V + prev), (u64)runLen);
+                        atomicAdd((u64*)(P.counters + 1 * (size_t)V + prev), 1ULL);
+                        atomicAdd((u64*)(P.counters + 2 * (size_t)V + prev), (u64)runLen * (u64)runLen);
+                        atomicMax(P.maxcontig + prev, ((u64)runLen << GS_MAXCONTIG_SHIFT) | (GS_ORDINAL_MASK - (ordinal & GS_ORDINAL_MASK)));
+                    }
+                    if (P.runs) {  // printKrakenStyleOut (:597-611): every finished run incl. '0' and 'A'
+                        const bool flushAny = runLen > 0;
+                        const u32 FA = __ballot_sync(FULL, flushAny);
+                        if (flushAny) {
+                            u64 slotR = P.runOffsets[r] + runCursor + (u64)__popc(FA & ((1u << lane) - 1u));
+                            if (slotR < P.runsCap) P.runs[slotR] = gs_run{prev, (u32)runLen};
+                        }
+                        runCursor += (u64)__popc(FA);
+                    }
+                    u32 F = __ballot_sync(FULL, flushTax);
+                    while (F) {
+                        const int src = __ffs(F) - 1;
+                        F &= F - 1;
+                        const u32 v = __shfl_sync(FULL, prev, src);
+                        const u32 n = (u32)__shfl_sync(FULL, runLen, src);
+                        if (!overflow) {
+                            if (!gs_table_add(T, nTab, v, n, lane, P.counters + 3 * (size_t)V, 0)) overflow = true;
+                        }
+                    }
+                    prevB = __shfl_sync(FULL, p, min(31, total - g - 1));
+                }
+                __syncwarp();
+            }
+        } else {
 #pragma unroll 1
         for (int c0 = 0; c0 <= max; c0 += 32) {  // position `max` is the terminator that flushes the last run
             const int p = c0 + lane;
@@ -356,6 +437,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
             }
             if (S) carryLen = 32 - (31 - __clz(S)); else carryLen += 32;
             carryLabel = __shfl_sync(FULL, lab, 31);
+        }
         }
         if (MODE == 0 && P.runs && lane == 0) P.runCounts[r] = (u32)runCursor;
 
@@ -750,10 +832,11 @@ void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t
 void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
     const int threads = GS_WARPS_PER_BLOCK * 32;
     if (mode == 0) {
-        if (dump) gs_reduce_kernel<0, true><<<blocks, threads, 0, st>>>(P);
-        else gs_reduce_kernel<0, false><<<blocks, threads, 0, st>>>(P);
+        if (dump) gs_reduce_kernel<0, true, false><<<blocks, threads, 0, st>>>(P);
+        else if (P.bmask) gs_reduce_kernel<0, false, true><<<blocks, threads, 0, st>>>(P);
+        else gs_reduce_kernel<0, false, false><<<blocks, threads, 0, st>>>(P);
     } else {
-        gs_reduce_kernel<1, false><<<blocks, threads, 0, st>>>(P);
+        gs_reduce_kernel<1, false, false><<<blocks, threads, 0, st>>>(P);
     }
 }
 
@@ -1038,8 +1121,8 @@ void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st) {
 
 int gs_match_kernel_occupancy(int mode) {
     int nb = 0;
-    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<0, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<0, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);

@@ -29,6 +29,7 @@ struct GsMatchParams {
     u32* labels;            // [flatLen] label of the k-mer starting at each flat position
     u32* validBits;         // [segments * 31 (+pad)] bit f = base f is one of CGAT
     u32* startBits;         // same size: bit f = a read starts at f
+    u32* bmask;             // same size, or NULL: bit f = the label at f differs from the label at f - 1 (long-read reduce)
     u32* segCounter;        // next unclaimed segment of the label kernel
     u32* redoList;          // reads the thread-per-read reduce kernel hands to the warp-per-read kernel (NULL: warp kernel takes all reads)
     u32* redoCount;
