@@ -915,7 +915,8 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     CU(cudaGetLastError());
     // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
     const bool threadPath = !s->cfg.want_runs && nBytes / P.nReads <= 512;
-    if (!threadPath && !getenv("GS_DEBUG_NO_BMASK")) {  // long reads / contig runs: the label kernel also marks the run boundaries
+    static const bool noMask = getenv("GS_DEBUG_NO_BMASK") != nullptr;   // A/B: reduce kernels that walk every label
+    if (!noMask) {  // the label kernel also marks the run boundaries: the reduce kernels visit boundaries, not labels
         const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
         if (words > D.bmaskCap) {
             CU(cudaStreamSynchronize(D.sCompute));
@@ -938,7 +939,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
             CU(dgrow(&D.redoList, &D.redoCap, (size_t)P.nReads));
         }
         P.redoList = D.redoList; P.redoCount = D.overflowCount + 3; P.groupCounter = D.overflowCount + 4;
-        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 7, ((u64)P.nReads + 127) / 128), D.sCompute);
+        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 8, ((u64)P.nReads + 127) / 128), D.sCompute);
         CU(cudaGetLastError());
         s->launches += 1;
     }

@@ -576,13 +576,20 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_MIN_BLOCKS) gs_red
 #endif
 #define GS_T_ROW (GS_T_POS + 1)
 #define GS_T_BLOCKS (GS_T_POS == 16 ? 7 : 4)   // resident CTAs per SM the shared memory allows (31.2 KB / 47.6 KB per CTA)
-__global__ void __launch_bounds__(GS_T_THREADS, GS_T_BLOCKS) gs_reduce_thread_kernel(const GsMatchParams P) {
+#define GS_T_MAXB 16       // MASKED: run boundaries per read handled by the thread (more: warp-per-read kernel)
+// MASKED = the label kernel wrote run-boundary masks (P.bmask): a thread then reads the few mask words of its read, collects
+// the boundary positions, fetches the labels of the runs that end there with independent loads and never touches the other
+// labels -- no staging tile at all.
+template <bool MASKED>
+__global__ void __launch_bounds__(GS_T_THREADS, MASKED ? 8 : GS_T_BLOCKS) gs_reduce_thread_kernel(const GsMatchParams P) {
     __shared__ u32 s_vi[GS_T_CAP][GS_T_THREADS];
     __shared__ u32 s_pk[GS_T_CAP][GS_T_THREADS];   // cnt << 21 | contigs << 11 | maxlen
     __shared__ u32 s_sq[GS_T_CAP][GS_T_THREADS];
-    __shared__ u32 s_tile[GS_T_THREADS / 32][2 * 32 * GS_T_ROW];
-    __shared__ u64 s_fs[GS_T_THREADS / 32][32];
-    __shared__ int s_max[GS_T_THREADS / 32][32];
+    __shared__ u32 s_tile[GS_T_THREADS / 32][MASKED ? GS_T_CAP * 32 : 2 * 32 * GS_T_ROW];
+    __shared__ u64 s_fs[MASKED ? 1 : GS_T_THREADS / 32][MASKED ? 1 : 32];
+    __shared__ int s_max[MASKED ? 1 : GS_T_THREADS / 32][MASKED ? 1 : 32];
+    __shared__ uint16_t s_bp[MASKED ? GS_T_MAXB : 1][MASKED ? GS_T_THREADS : 1];  // boundary positions relative to the read's first position
+    __shared__ u32 s_bl[MASKED ? GS_T_MAXB : 1][MASKED ? GS_T_THREADS : 1];       // label of the run that ends at the boundary
     const GsDbView& db = P.db;
     const int k = db.k, V = db.nValues, t = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32* tile = s_tile[warp];
@@ -609,14 +616,72 @@ __global__ void __launch_bounds__(GS_T_THREADS, GS_T_BLOCKS) gs_reduce_thread_ke
         bool walk = have && max > 0;
         if (have && max <= 0) P.out[r] = gs_read_result{classV, readKmers, taxErr, flags};
         if (walk && L > GS_T_MAX_LEN) { P.redoList[atomicAdd(P.redoCount, 1u)] = r; walk = false; }
+        int nTab = 0, misses = 0, len = 0;
+        bool overflow = false, sawInvalid = false;
+        u32 prev = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
+        // one contig / miss run / invalid run ends: the body of the reference's run handling (:390-421, 455-473)
+        auto endRun = [&](u32 lab, int rl) {
+            if (lab < GS_LABEL_INVALID && rl > 0) {
+                int j = 0;
+                while (j < nTab && s_vi[j][t] != lab) j++;
+                if (j < nTab) {
+                    const u32 pk = s_pk[j][t];
+                    const u32 ml = pk & 0x7FFu;
+                    s_pk[j][t] = (((pk >> 21) + (u32)rl) << 21) | ((((pk >> 11) & 0x3FFu) + 1u) << 11) | ((u32)rl > ml ? (u32)rl : ml);
+                    s_sq[j][t] += (u32)rl * (u32)rl;
+                } else if (nTab < GS_T_CAP) {
+                    s_vi[nTab][t] = lab;
+                    s_pk[nTab][t] = ((u32)rl << 21) | (1u << 11) | (u32)rl;
+                    s_sq[nTab][t] = (u32)rl * (u32)rl;
+                    nTab++;
+                } else {
+                    overflow = true;
+                }
+            } else if (lab == GS_LABEL_MISS) {
+                misses += rl;
+            } else if (lab == GS_LABEL_INVALID) {
+                sawInvalid = true;
+            }
+        };
+        if (MASKED) {
+            if (walk) {
+                // ---- boundaries of the read from its mask words (forced at the first position and at the terminator)
+                const u64 fEnd = fs + (u64)max;
+                int nb = 0;
+                for (u64 w = fs >> 5; w * 32 <= fEnd && nb <= GS_T_MAXB; w++) {
+                    const u64 p0 = w * 32;
+                    u32 mw = __ldg(P.bmask + w);
+                    if ((w % GS_SEG_CHUNKS) == 0 && (mw & 1u) && p0 > fs && p0 < fEnd && P.labels[p0] == P.labels[p0 - 1]) mw &= ~1u;  // segment start: verify
+                    const int lo = fs > p0 ? (int)(fs - p0) : 0;
+                    const int hi = fEnd - p0 >= 32 ? 32 : (int)(fEnd - p0);
+                    mw &= (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                    if (fs >= p0) mw &= ~(1u << lo);                                  // the read's first position: no run ends there
+                    if (fEnd - p0 < 32) mw |= 1u << (int)(fEnd - p0);                 // terminator
+                    while (mw && nb <= GS_T_MAXB) {
+                        const int bit = __ffs(mw) - 1;
+                        mw &= mw - 1;
+                        if (nb < GS_T_MAXB) s_bp[nb][t] = (uint16_t)(p0 + (u64)bit - fs);
+                        nb++;
+                    }
+                }
+                if (nb > GS_T_MAXB) { overflow = true; }
+                else {
+                    for (int j = 0; j < nb; j++) s_bl[j][t] = __ldg(P.labels + fs + (u64)s_bp[j][t] - 1);   // independent loads
+                    int pb = 0;
+                    for (int j = 0; j < nb && !overflow; j++) {
+                        const int q = (int)s_bp[j][t];
+                        endRun(s_bl[j][t], q - pb);
+                        pb = q;
+                    }
+                }
+                if (overflow) { P.redoList[atomicAdd(P.redoCount, 1u)] = r; }
+            }
+        } else {
         __syncwarp();
         s_fs[warp][lane] = fs;
         s_max[warp][lane] = walk ? max : 0;
         const int wmax = __reduce_max_sync(FULL, walk ? max + 1 : 0);  // + the terminator position that flushes the last run
         __syncwarp();
-        int nTab = 0, misses = 0, len = 0;
-        bool overflow = false, sawInvalid = false;
-        u32 prev = GS_LABEL_MISS;  // lastTaxid = null (FastqKMerMatcher.java:336)
         // ---- stage positions [b, b + 32) of the warp's 32 reads with 4-byte cp.async (global -> shared without registers),
         // double-buffered: the copies of round b + 32 are in flight while round b is walked
         auto stage = [&](int b, u32* dst) {
@@ -691,6 +756,7 @@ __global__ void __launch_bounds__(GS_T_THREADS, GS_T_BLOCKS) gs_reduce_thread_ke
                 else if (b + GS_T_POS > max) walk = false;  // terminator consumed: the read is complete
             }
             __syncwarp();
+        }
         }
         if (!have || max <= 0 || overflow || L > GS_T_MAX_LEN) continue;
         // ---- apply the read's contig statistics
@@ -812,7 +878,8 @@ __global__ void __launch_bounds__(GS_T_THREADS, GS_T_BLOCKS) gs_reduce_thread_ke
     }
 }
 void gs_launch_reduce_thread(const GsMatchParams& P, int blocks, cudaStream_t st) {
-    gs_reduce_thread_kernel<<<blocks, GS_T_THREADS, 0, st>>>(P);
+    if (P.bmask) gs_reduce_thread_kernel<true><<<blocks, GS_T_THREADS, 0, st>>>(P);
+    else gs_reduce_thread_kernel<false><<<blocks, GS_T_THREADS, 0, st>>>(P);
 }
 
 void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st) {

@@ -451,6 +451,13 @@ def test_thread_kernel_hand_over_paths(oracle, native, gpu_ctx):
         for i in range(60):                        # 9 .. 20 taxa in one read (40 bases = 10 k-mers of each): warp kernel
             parts = [genomes[int(s)][1][int(a):int(a) + 40] for s, a in zip(rng.choice(n_sp, size=int(rng.integers(9, 21)), replace=False), rng.integers(0, 2900, size=20))]
             reads.append(b"".join(parts))
+        for i in range(120):                       # 2 .. 8 taxa, 3 .. 17 run boundaries, some with an N: both sides of the
+            n = 2 + i % 7                          # thread kernel's limit of 16 boundaries per read
+            parts = [genomes[int(s)][1][int(a):int(a) + 40] for s, a in zip(rng.choice(n_sp, size=n, replace=False), rng.integers(0, 2900, size=n))]
+            r = bytearray(b"".join(parts))
+            if i % 3 == 0:
+                r[int(rng.integers(0, len(r)))] = ord("N")
+            reads.append(bytes(r))
         for i in range(3):                         # more than 128 taxa: slow path (vote table in global memory)
             parts = [genomes[int(s)][1][int(a):int(a) + 32] for s, a in zip(rng.permutation(n_sp)[:150], rng.integers(0, 2900, size=150))]
             reads.append(b"".join(parts))
