@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <stdexcept>
 #include <thread>
 
@@ -372,6 +373,148 @@ static size_t lastRecordStart(const uint8_t* text, size_t len) {
 }
 
 
+// Block gzip (BGZF, the `bgzip` format of htslib): an ordinary multi-member gzip file -- java.util.zip.GZIPInputStream and
+// zlib's gzread inflate it member by member like any other -- whose members are independent deflate streams of at most
+// 64 KB and carry their own compressed size in a 'BC' extra subfield (RFC 1952 2.3.1.1).  The block boundaries are
+// therefore known without inflating anything, and the blocks a text chunk needs are inflated by several threads straight
+// into the pinned chunk (the reference inflates on its single producer thread).  Every block is checked
+// like gzread checks it (CRC-32 and ISIZE); a member without the subfield ends the fast path at that byte (`foreignAt`),
+// where the caller goes on with zlib's sequential reader, so the text never depends on which path produced it.
+class BgzfReader {
+public:
+    // true if the file's first member is a BGZF block
+    static bool probe(int fd) {
+        uint8_t h[18];
+        if (pread(fd, h, sizeof(h), 0) != (ssize_t)sizeof(h)) return false;
+        size_t hdr = 0, total = 0;
+        return parseHeader(h, sizeof(h), hdr, total) == 1;
+    }
+    explicit BgzfReader(int fd) : fd_(fd) {
+        const char* e = getenv("GS_INFLATE_THREADS");
+        const long v = e ? atol(e) : 0;
+        threads_ = (unsigned)(v > 0 ? v : std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+    }
+    bool eof() const { return eof_ && carryPos_ == carry_.size(); }
+    bool foreign() const { return foreign_ && carryPos_ == carry_.size(); }   // a non-BGZF member follows at foreignAt()
+    size_t foreignAt() const { return cpos_; }   // compressed offset of the first block that has not been inflated yet
+    void drainCarry(std::vector<uint8_t>& out) { out.insert(out.end(), carry_.begin() + (long)carryPos_, carry_.end()); carryPos_ = carry_.size(); }
+    // up to `want` bytes of inflated text into dst; fewer only at the end of the file or in front of a foreign member
+    size_t read(uint8_t* dst, size_t want) {
+        size_t done = 0;
+        while (done < want) {
+            if (carryPos_ < carry_.size()) {
+                const size_t take = std::min(want - done, carry_.size() - carryPos_);
+                memcpy(dst + done, carry_.data() + carryPos_, take);
+                carryPos_ += take; done += take;
+                continue;
+            }
+            if (eof_ || foreign_) break;
+            done += round(dst + done, want - done);
+        }
+        return done;
+    }
+
+private:
+    struct Block { size_t off, hdr, total; uint32_t isize; size_t out; };
+    // 1 = BGZF block header (hdr = header bytes, total = member bytes), 0 = some other gzip member / not gzip, -1 = need more bytes
+    static int parseHeader(const uint8_t* h, size_t n, size_t& hdr, size_t& total) {
+        if (n < 12) return -1;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4) return 0;   // BGZF: deflate, FLG = FEXTRA only
+        const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+        if (n < 12 + xlen) return -1;
+        for (size_t p = 12; p + 4 <= 12 + xlen;) {
+            const size_t slen = (size_t)h[p + 2] | ((size_t)h[p + 3] << 8);
+            if (h[p] == 'B' && h[p + 1] == 'C' && slen == 2 && p + 6 <= 12 + xlen) {
+                hdr = 12 + xlen;
+                total = ((size_t)h[p + 4] | ((size_t)h[p + 5] << 8)) + 1;
+                return total >= hdr + 8 ? 1 : 0;
+            }
+            p += 4 + slen;
+        }
+        return 0;
+    }
+    // one window of compressed bytes: list its whole blocks, inflate those that fit into dst in parallel (the first one
+    // that does not fit goes through the carry buffer)
+    size_t round(uint8_t* dst, size_t room) {
+        const size_t window = std::max<size_t>((size_t)1 << 16, std::min<size_t>(room / 2 + ((size_t)1 << 17), (size_t)64 << 20));
+        cbuf_.resize(window);
+        size_t got = 0;
+        while (got < window) {
+            const ssize_t r = pread(fd_, cbuf_.data() + got, window - got, (off_t)(cpos_ + got));
+            if (r < 0) fail("read error");
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        if (got == 0) { eof_ = true; return 0; }
+        std::vector<Block> blocks;
+        size_t off = 0, out = 0;
+        bool toCarry = false;
+        while (off < got) {
+            size_t hdr = 0, total = 0;
+            const uint8_t* h = cbuf_.data() + off;
+            if ((got - off >= 1 && h[0] != 0x1f) || (got - off >= 2 && h[1] != 0x8b)) {
+                // bytes behind the last member that are no gzip header: ignored, as by zlib's gzread and GZIPInputStream
+                if (blocks.empty()) { eof_ = true; return 0; }
+                break;
+            }
+            const int rc = parseHeader(h, got - off, hdr, total);
+            if (rc == 0) { if (blocks.empty()) { foreign_ = true; return 0; } break; }
+            if (rc < 0 || off + total > got) {
+                if (blocks.empty() && got < window) fail("read error");   // the file ends inside a block (gzread: unexpected end of file)
+                break;
+            }
+            const uint8_t* t = cbuf_.data() + off + total - 4;
+            const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            if (isize > (1u << 16)) { if (blocks.empty()) { foreign_ = true; return 0; } break; }   // not a BGZF block after all
+            if (out + isize > room) {
+                if (!blocks.empty()) break;
+                toCarry = true;                                           // the only block of this round: through the carry buffer
+            }
+            blocks.push_back(Block{off, hdr, total, isize, out});
+            off += total; out += isize;
+            if (toCarry) break;
+        }
+        if (blocks.empty()) fail("read error");
+        uint8_t* target = dst;
+        if (toCarry) { carry_.resize(blocks[0].isize); carryPos_ = 0; target = carry_.data(); }
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, blocks.size() / 8 + 1));
+        std::vector<int> bad(nt, 0);
+        auto work = [&](unsigned t) {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
+            for (size_t i = blocks.size() * t / nt; i < blocks.size() * (t + 1) / nt; i++) {
+                const Block& b = blocks[i];
+                const uint8_t* src = cbuf_.data() + b.off;
+                zs.next_in = (Bytef*)(src + b.hdr); zs.avail_in = (uInt)(b.total - b.hdr - 8);
+                zs.next_out = (Bytef*)(target + b.out); zs.avail_out = (uInt)b.isize;
+                uint8_t none;
+                if (b.isize == 0) { zs.next_out = &none; zs.avail_out = 0; }
+                const int rc = inflate(&zs, Z_FINISH);
+                const uint8_t* c = src + b.total - 8;
+                const uint32_t crc = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+                if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)(target + b.out), (uInt)b.isize) != crc) { bad[t] = 1; break; }
+                if (inflateReset(&zs) != Z_OK) { bad[t] = 1; break; }
+            }
+            inflateEnd(&zs);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        for (unsigned t = 0; t < nt; t++)
+            if (bad[t]) fail("read error");   // corrupt block (gzread: data error / incorrect data check)
+        cpos_ += off;
+        return toCarry ? 0 : out;
+    }
+    int fd_;
+    unsigned threads_ = 1;
+    size_t cpos_ = 0;
+    bool eof_ = false, foreign_ = false;
+    std::vector<uint8_t> cbuf_, carry_;
+    size_t carryPos_ = 0;
+};
+
 // The GPU feeder's host side, shared by the match and filter drivers: stream one FASTQ input as pinned text chunks that end
 // at a record boundary.  cur() = the batch to fill, next() = the batch cur() will yield after the next successful submit (the
 // read-ahead target); submit(batch, cut) hands text[0, cut) to the device and returns true if the device took it (the driver
@@ -382,20 +525,27 @@ template <typename CurFn, typename NextFn, typename SubmitFn, typename SeqFn>
 static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextFn&& next, SubmitFn&& submit, SeqFn&& sequential) {
     gzFile gz = nullptr;
     int fd = -1;        // uncompressed files are read with parallel pread() straight into the pinned chunk
+    int zfd = -1;       // block-gzip files: the descriptor the BgzfReader reads from
+    std::unique_ptr<BgzfReader> bgzf;
     size_t filePos = 0;
     if (!in.path.empty()) {
         fd = open(in.path.c_str(), O_RDONLY);
         if (fd < 0) fail("cannot open " + in.path);
         unsigned char magic[2] = {0, 0};
         const ssize_t m = pread(fd, magic, 2, 0);
-        if (m == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {   // gzip: zlib inflates on this thread
-            close(fd); fd = -1;
-            gz = gzopen(in.path.c_str(), "rb");
-            if (!gz) fail("cannot open " + in.path);
-            gzbuffer(gz, 1 << 20);
+        if (m == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            if (BgzfReader::probe(fd) && !getenv("GS_NO_BGZF")) {   // block gzip: the blocks are inflated in parallel
+                bgzf.reset(new BgzfReader(fd));
+                zfd = fd; fd = -1;
+            } else {                                                // gzip: zlib inflates on this thread
+                close(fd); fd = -1;
+                gz = gzopen(in.path.c_str(), "rb");
+                if (!gz) fail("cannot open " + in.path);
+                gzbuffer(gz, 1 << 20);
+            }
         }
     }
-    struct Closer { gzFile& g; int& f; ~Closer() { if (g) gzclose(g); if (f >= 0) close(f); } } closer{gz, fd};
+    struct Closer { gzFile& g; int& f; int& z; ~Closer() { if (g) gzclose(g); if (f >= 0) close(f); if (z >= 0) close(z); } } closer{gz, fd, zfd};
     auto readPlain = [&](uint8_t* dst, size_t want) -> size_t {
         const size_t slice = (size_t)4 << 20;
         static const size_t maxThreads = [] { const char* e = getenv("GS_FEEDER_THREADS"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 8); }();
@@ -432,7 +582,18 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextF
     // bytes [len, target) of a chunk buffer from the stream / file / caller's memory; sets eof at the end of the input
     auto fill = [&](uint8_t* text, size_t& len, size_t target) {
         while (!eof && len < target) {
-            if (gz) {
+            if (bgzf) {
+                len += bgzf->read(text + len, target - len);
+                if (bgzf->eof()) eof = true;
+                else if (bgzf->foreign()) {   // an ordinary gzip member follows: zlib's sequential reader takes over from there
+                    if (lseek(zfd, (off_t)bgzf->foreignAt(), SEEK_SET) < 0) fail("seek error");
+                    gz = gzdopen(zfd, "rb");
+                    if (!gz) fail("cannot open " + in.path);
+                    zfd = -1;                 // owned by gz now
+                    gzbuffer(gz, 1 << 20);
+                    bgzf.reset();
+                }
+            } else if (gz) {
                 const int got = gzread(gz, text + len, (unsigned)std::min<size_t>(target - len, 1u << 30));
                 if (got < 0) fail("read error");
                 if (got == 0) eof = true;
@@ -507,7 +668,17 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextF
                 if (!gz) fail("cannot open " + in.path);
                 gzbuffer(gz, 1 << 20);
                 if (gzseek(gz, (z_off_t)filePos, SEEK_SET) < 0) fail("seek error");
-            } else if (!gz) {
+            } else if (bgzf) {   // block gzip: what the reader still holds, then zlib's sequential reader from the next block on
+                bgzf->drainCarry(pending);
+                if (!bgzf->eof()) {
+                    if (lseek(zfd, (off_t)bgzf->foreignAt(), SEEK_SET) < 0) fail("seek error");
+                    gz = gzdopen(zfd, "rb");
+                    if (!gz) fail("cannot open " + in.path);
+                    zfd = -1;
+                    gzbuffer(gz, 1 << 20);
+                }
+                bgzf.reset();
+            } else if (!gz && in.path.empty()) {
                 pending.insert(pending.end(), in.data + memPos, in.data + in.len);   // in-memory input: the rest follows in memory
             }
             LineReader lr(gz, pending.data(), pending.size());
@@ -1126,6 +1297,29 @@ gsh_result* gsh_parse_only(int k, int with_probs, const uint8_t* const* data, co
             r->totals[0] += reader.reads; r->totals[1] += reader.kMers; r->totals[2] += reader.readBPs;
         }
     } catch (const std::exception& e) { r->error = e.what(); }
+    return r;
+}
+
+// The feeder's block-gzip reader alone (no GPU): the inflated text of a BGZF file, read in requests of `request` bytes;
+// an ordinary gzip member in the middle ends the text there (*foreign_at = its compressed offset, else -1).
+gsh_result* gsh_bgzf_read_all(const char* path, size_t request, int64_t* foreign_at) {
+    gsh_result* r = new gsh_result();
+    *foreign_at = -1;
+    int fd = -1;
+    try {
+        fd = open(path, O_RDONLY);
+        if (fd < 0) fail(std::string("cannot open ") + path);
+        if (!BgzfReader::probe(fd)) fail("not a block-gzip file");
+        BgzfReader rd(fd);
+        std::vector<uint8_t> buf(std::max<size_t>(request, 1));
+        for (;;) {
+            const size_t got = rd.read(buf.data(), buf.size());
+            r->rest.append((const char*)buf.data(), got);
+            if (rd.foreign()) { *foreign_at = (int64_t)rd.foreignAt(); break; }
+            if (got < buf.size()) break;
+        }
+    } catch (const std::exception& e) { r->error = e.what(); }
+    if (fd >= 0) close(fd);
     return r;
 }
 

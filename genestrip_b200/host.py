@@ -51,6 +51,8 @@ def _lib():
         L.gsh_last_record_start.restype = C.c_size_t
         L.gsh_last_record_start.argtypes = [_P, C.c_size_t]
         L.gsh_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        L.gsh_bgzf_read_all.restype = _P
+        L.gsh_bgzf_read_all.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]
         _ready = True
     return L
 
@@ -158,6 +160,14 @@ def last_record_start(text):
     """Where the GPU feeder would cut a text chunk: offset of the last record start (0 = no boundary found)."""
     b = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, dtype=np.uint8)
     return int(_lib().gsh_last_record_start(b.ctypes.data, len(text)))
+
+
+def bgzf_read_all(path, request=1 << 20):
+    """The feeder's block-gzip reader alone (no GPU): (inflated text, compressed offset of a non-BGZF member that ended the
+    fast path or -1), reading `request` bytes at a time."""
+    foreign = C.c_int64(-1)
+    res = GoalResult(_lib().gsh_bgzf_read_all(str(path).encode(), int(request), C.byref(foreign)))
+    return res.rest, int(foreign.value)
 
 
 def java_double_to_string(v):

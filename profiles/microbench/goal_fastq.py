@@ -62,6 +62,36 @@ for name, kw in (("gpu_feeder", dict(gpu_parse=True, text_chunk_bytes=chunk_mb <
     res[name] = {"seconds": best, "reads_per_s": n_reads / best, "kmers_per_s": r.total_kmers / best, "file_GB_per_s": size / best / 1e9,
                  "text_chunks": r.text_chunks, "csv_rows": r.csv.count(b"\n")}
     res[name + "_csv_md5"] = __import__("hashlib").md5(r.csv).hexdigest()
+if os.environ.get("GS_BGZF"):
+    # the same text as a block-gzip file: blocks inflated by the feeder's threads vs zlib's sequential gzread (GS_NO_BGZF)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from concurrent.futures import ProcessPoolExecutor
+    gz_path = path + ".gz"
+    piece = 0xff00 * 256
+    with open(path, "rb") as f, open(gz_path, "wb") as g, ProcessPoolExecutor(max_workers=os.cpu_count()) as pool:
+        parts = []
+        while True:
+            buf = f.read(piece)
+            if not buf:
+                break
+            parts.append(pool.submit(util.bgzf_bytes, buf, 0xff00, 1, False))
+        for fu in parts:
+            g.write(fu.result())
+        g.write(util.bgzf_bytes(b""))
+    res["bgzf_file_bytes"] = os.path.getsize(gz_path)
+    for name, env in (("gpu_feeder_bgzf", None), ("gpu_feeder_gzread", "1")):
+        if env:
+            os.environ["GS_NO_BGZF"] = env
+        t0 = time.perf_counter()
+        r = host.match_goal(db, meta, [gz_path], gpu_parse=True, text_chunk_bytes=chunk_mb << 20)
+        dt = time.perf_counter() - t0
+        os.environ.pop("GS_NO_BGZF", None)
+        assert r.total_reads == n_reads
+        res[name] = {"seconds": dt, "reads_per_s": n_reads / dt, "kmers_per_s": r.total_kmers / dt, "text_GB_per_s": size / dt / 1e9,
+                     "text_chunks": r.text_chunks, "same_csv_as_plain_file": __import__("hashlib").md5(r.csv).hexdigest() == res["gpu_feeder_csv_md5"]}
+    res["inflate_threads"] = int(os.environ.get("GS_INFLATE_THREADS", "0")) or min(32, os.cpu_count())
+    os.remove(gz_path)
 res["same_csv"] = res["gpu_feeder_csv_md5"] == res.get("host_parser_csv_md5")
 res["chunk_mb"] = chunk_mb
 res["file_bytes"] = size

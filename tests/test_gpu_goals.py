@@ -243,6 +243,37 @@ def test_match_goal_gpu_fastq_feeder_falls_back(project, oracle, host, tmp_path)
         _assert_csv_equal(res.csv, orun.csv)
 
 
+def test_match_goal_block_gzip_input(project, oracle, host, tmp_path):
+    """Block-gzip (BGZF) FASTQ files: the feeder inflates the blocks with several host threads (BgzfReader, gs_host.cpp) and
+    the records are split on the GPU.  Same results as the oracle's sequential reader over the same text -- also when an
+    ordinary gzip member follows the blocks (zlib takes over there) and when a chunk is refused in the middle of the file
+    (the sequential parser continues behind the inflated bytes)."""
+    import util
+    odb, gdb, meta, genomes = project
+    g = genomes[1][1]
+    b1, o1, s1 = _reads(genomes, 6000, 21)
+    b2, o2, s2 = _reads(genomes, 900, 22, len_jitter=40)
+    t1, t2 = synth.fastq_bytes(b1, o1, s1), synth.fastq_bytes(b2, o2, s2, prefix="q")
+    odd = b"@b\n" + g[300:360] + b"\n" + g[360:420] + b"\n+b\n" + b"J" * 100 + b"\n" + b"J" * 20 + b"\n"   # multi-line record
+    cases = (("blocks only", t1 + t2, util.bgzf_bytes(t1 + t2), 0),
+             ("small blocks, no end-of-file block", t1, util.bgzf_bytes(t1, block=5000, eof_block=False), 0),
+             ("blocks, then an ordinary gzip member", t1 + t2, util.bgzf_bytes(t1, eof_block=False) + gzip.compress(t2), 0),
+             ("refused chunk in the middle", t1 + odd + t2, util.bgzf_bytes(t1 + odd + t2, block=20000), 1))
+    for name, text, packed, refused in cases:
+        assert gzip.decompress(packed) == text
+        orun = odb.match_files(oracle.match_cfg(k=K, write_filtered=True, write_kraken=True, with_probs=True), [text])
+        path = str(tmp_path / "in.fastq.gz")
+        open(path, "wb").write(packed)
+        for chunk in (100000, 1 << 22):
+            res = host.match_goal(gdb, meta, [path], write_filtered=True, write_kraken=True, with_probs=1, text_chunk_bytes=chunk)
+            assert res.text_chunks_refused == refused, name
+            assert res.text_chunks - res.text_chunks_refused >= 1, name
+            assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps), name
+            assert res.filtered == orun.filtered, name
+            assert res.kraken == orun.kraken, name
+            _assert_csv_equal(res.csv, orun.csv)
+
+
 def test_filter_goal_gpu_fastq_feeder(project, oracle, native, gpu_ctx, host):
     """`filter` with the GPU FASTQ feeder: accepted / rejected FASTQ byte-identical with the oracle (ReadEntry.write,
     C/fastq/AbstractFastqReader.java:570-584), with and without qualities, incl. the fall-back on a non-strict tail."""

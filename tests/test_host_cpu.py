@@ -1,6 +1,9 @@
 """CPU-side checks of the C++ host layer that need no GPU: FASTQ/FASTA parsing against the oracle, Double.toString."""
 import math
 
+import numpy as np
+import pytest
+
 
 def test_java_double_to_string_matches_oracle_and_known_values(native, oracle):
     from genestrip_b200 import host
@@ -97,3 +100,47 @@ def test_feeder_record_boundary_search(native):
     assert host.last_record_start(b"") == 0
     assert host.last_record_start(b"no newline at all") == 0
     assert host.last_record_start(b"ACGT\nACGT\nACGT\nACGT\n" * 30) == 0     # no '@' header anywhere
+
+
+def test_block_gzip_reader(native, tmp_path):
+    """The feeder inflates block-gzip (BGZF) input with several threads (BgzfReader in gs_host.cpp).  The text
+    must be what gzip / java.util.zip.GZIPInputStream give for the same file (a multi-member gzip file,
+    C/fastq/AbstractFastqReader.java:224 via StreamProvider), for any request size; bytes behind the last member are
+    ignored; an ordinary gzip member ends the fast path exactly there; a corrupt block is an error."""
+    import gzip
+    import util
+    from genestrip_b200 import host
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(4000):
+        n = int(rng.integers(30, 400))
+        seq = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n, p=[0.24, 0.25, 0.25, 0.25, 0.01]).tobytes()
+        recs.append(b"@r%d some text\n" % i + seq + b"\n+\n" + bytes(rng.integers(33, 74, size=n, dtype=np.uint8)) + b"\n")
+    text = b"".join(recs)
+    p = tmp_path / "reads.fastq.gz"
+    for block in (0xff00, 7001, 100):
+        sub = text if block > 100 else text[:20000]
+        p.write_bytes(util.bgzf_bytes(sub, block=block))
+        assert gzip.decompress(p.read_bytes()) == sub             # the fixture is an ordinary gzip file
+        for request in (1 << 20, 65536, 65537, 4096, 1):
+            if request == 1 and len(sub) > 20000:
+                continue
+            got, foreign = host.bgzf_read_all(p, request)
+            assert foreign == -1 and got == sub, (block, request)
+    # no end-of-file block, empty blocks in the middle, trailing bytes that are no gzip header
+    body = util.bgzf_bytes(text[:50000], eof_block=False) + util.bgzf_bytes(b"", eof_block=True) + util.bgzf_bytes(text[50000:90000], eof_block=False)
+    p.write_bytes(body + b"\0\0\0garbage")
+    assert host.bgzf_read_all(p, 30000) == (text[:90000], -1)
+    # an ordinary gzip member in the middle: the block reader stops exactly in front of it
+    head = util.bgzf_bytes(text[:70000], eof_block=False)
+    p.write_bytes(head + gzip.compress(text[70000:80000]))
+    assert host.bgzf_read_all(p, 1 << 16) == (text[:70000], len(head))
+    # corrupt data / truncated file: an error, as from gzread / GZIPInputStream
+    bad = bytearray(util.bgzf_bytes(text[:70000]))
+    bad[40] ^= 0x55
+    p.write_bytes(bytes(bad))
+    with pytest.raises(Exception):
+        host.bgzf_read_all(p, 1 << 16)
+    p.write_bytes(util.bgzf_bytes(text[:70000])[:-40])
+    with pytest.raises(Exception):
+        host.bgzf_read_all(p, 1 << 16)

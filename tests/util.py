@@ -116,3 +116,20 @@ def host_meta(host, odb):
     """DbMeta of the C++ host layer from the oracle database's metadata (names, ranks, tree, db k-mer counts)."""
     parent, depth, position, has_node = odb.tree()
     return host.DbMeta(odb.k, odb.n_kmers, odb.taxids(), odb.node_names(), odb.node_ranks(), parent, position, depth, has_node, odb.db_kmers())
+
+
+def bgzf_bytes(data, block=0xff00, level=6, eof_block=True):
+    """`data` as block gzip (BGZF, what htslib's bgzip writes): gzip members of at most `block` input bytes, each with the
+    'BC' extra subfield that holds the member's size - 1, and the empty end-of-file block."""
+    import struct
+    import zlib
+    out = bytearray()
+    pieces = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_block else [])
+    for piece in pieces:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(piece) + co.flush()
+        total = 18 + len(body) + 8
+        assert total <= 0x10000
+        out += struct.pack("<4BI2BH2BHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, total - 1)
+        out += body + struct.pack("<II", zlib.crc32(piece) & 0xffffffff, len(piece))
+    return bytes(out)
