@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgenestrip_b200.so")
-SOURCES = ["gs_kernels.cu", "gs_text.cu", "gs_capi.cu", "gs_host.cpp"]
+SOURCES = ["gs_kernels.cu", "gs_text.cu", "gs_inflate.cu", "gs_capi.cu", "gs_host.cpp"]
 HEADERS = ["gs_kernels.cuh", "gs_device.cuh", "gs_host.hpp", os.path.join("..", "..", "include", "genestrip_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread", "-shared"]

@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 3
+GS_ABI_VERSION = 4
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -44,7 +44,8 @@ EVENT_DTYPE = np.dtype([("vidx", "<u4"), ("contig_len", "<u4"), ("read_no", "<u8
 TAXON_COUNTS_DTYPE = np.dtype([("kmers", "<i8"), ("contigs", "<i8"), ("contig_len_squared_sum", "<i8"), ("reads_1kmer", "<i8"),
                                ("reads", "<i8"), ("reads_kmers", "<i8"), ("reads_bps", "<i8"), ("unique_kmers", "<i8"),
                                ("max_contig_len", "<i4"), ("touched", "<i4"), ("max_contig_read_no", "<u8")])
-assert READ_RESULT_DTYPE.itemsize == 16 and TAXON_COUNTS_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 16
+DEFLATE_BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4"), ("crc32", "<u4"), ("status", "<u4")])
+assert READ_RESULT_DTYPE.itemsize == 16 and TAXON_COUNTS_DTYPE.itemsize == 80 and EVENT_DTYPE.itemsize == 16 and DEFLATE_BLOCK_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -106,6 +107,9 @@ _SIGS = {
     "gs_filter_sync": (C.c_int, [_P]),
     "gs_filter_stream": (_P, [_P]),
     "gs_filter_close": (None, [_P]),
+    "gs_inflate_blocks": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint32, _P, C.c_uint64]),
+    "gs_db_context": (_P, [_P]),
+    "gs_filter_context": (_P, [_P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -160,10 +164,45 @@ class Context:
     def n_devices(self):
         return lib().gs_ctx_n_devices(self.h)
 
+    def inflate_blocks(self, comp, blocks, out_bytes):
+        """gs_inflate_blocks: the raw-deflate members described by `blocks` (DEFLATE_BLOCK_DTYPE; see bgzf_blocks) of the
+        block-gzip bytes `comp` -> text, inflated and checked (size, CRC-32) on the device.  Returns (text, blocks)."""
+        comp = np.ascontiguousarray(np.frombuffer(comp, dtype=np.uint8))
+        blocks = np.ascontiguousarray(blocks, dtype=DEFLATE_BLOCK_DTYPE).copy()
+        out = np.empty(max(int(out_bytes), 1), dtype=np.uint8)
+        rc = lib().gs_inflate_blocks(self.h, _ptr(comp), comp.size, _ptr(blocks), len(blocks), _ptr(out), int(out_bytes))
+        self.last_inflate_blocks = blocks
+        _check(rc)
+        return out[:int(out_bytes)], blocks
+
     def close(self):
         if self.h:
             lib().gs_ctx_destroy(self.h)
             self.h = None
+
+
+def bgzf_blocks(comp):
+    """Member table of a block-gzip (BGZF) byte string for Context.inflate_blocks: one entry per member, from the 'BC' extra
+    subfield (member size - 1) and the trailer (CRC-32, ISIZE).  Returns (blocks, total inflated bytes)."""
+    import struct
+    rows, off, out = [], 0, 0
+    while off < len(comp):
+        if comp[off:off + 4] != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a block-gzip member at byte %d" % off)
+        xlen = struct.unpack_from("<H", comp, off + 10)[0]
+        p, total = off + 12, None
+        while p + 4 <= off + 12 + xlen:
+            si1, si2, slen = struct.unpack_from("<BBH", comp, p)
+            if (si1, si2, slen) == (66, 67, 2):
+                total = struct.unpack_from("<H", comp, p + 4)[0] + 1
+            p += 4 + slen
+        if total is None:
+            raise ValueError("member at byte %d has no BC subfield" % off)
+        crc, isize = struct.unpack_from("<II", comp, off + total - 8)
+        rows.append((off + 12 + xlen, out, total - 12 - xlen - 8, isize, crc, 0))
+        off += total
+        out += isize
+    return np.array(rows, dtype=DEFLATE_BLOCK_DTYPE), out
 
 
 class PinnedBuffer:

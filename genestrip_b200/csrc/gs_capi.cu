@@ -80,6 +80,19 @@ static u64 magic_for(u64 d) { return d ? (~0ULL) / d : 0; }
 struct gs_ctx {
     std::vector<int> devs;
     std::vector<int> sms;
+    // gs_inflate_blocks: scratch on device 0, one call at a time
+    std::mutex infMutex;
+    cudaStream_t infStream = nullptr;
+    uint8_t* infComp = nullptr; size_t infCompCap = 0;
+    uint8_t* infText = nullptr; size_t infTextCap = 0;
+    gs_deflate_block* infBlocks = nullptr; size_t infBlocksCap = 0;
+    ~gs_ctx() {
+        if (infStream || infComp || infText || infBlocks) {
+            cudaSetDevice(devs.empty() ? 0 : devs[0]);
+            cudaFree(infComp); cudaFree(infText); cudaFree(infBlocks);
+            if (infStream) cudaStreamDestroy(infStream);
+        }
+    }
 };
 
 extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
@@ -123,6 +136,36 @@ extern "C" gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices) {
 }
 extern "C" void gs_ctx_destroy(gs_ctx* c) { delete c; }
 extern "C" int gs_ctx_n_devices(const gs_ctx* c) { return c ? (int)c->devs.size() : 0; }
+
+// Block-gzip members -> text on the device (gs_inflate.cu), see genestrip_b200.h
+extern "C" int gs_inflate_blocks(gs_ctx* c, const uint8_t* comp, uint64_t comp_bytes, gs_deflate_block* blocks, uint32_t n_blocks,
+                                 uint8_t* out, uint64_t out_bytes) {
+    if (!c) return gs_fail(GS_ERR_STATE, "null context");
+    if (n_blocks == 0) return GS_OK;
+    if (!comp || !blocks || (!out && out_bytes)) return gs_fail(GS_ERR_ARG, "null argument");
+    for (uint32_t i = 0; i < n_blocks; i++) {
+        const gs_deflate_block& b = blocks[i];
+        if (b.in_off > comp_bytes || b.in_len > comp_bytes - b.in_off || b.out_off > out_bytes || b.out_len > out_bytes - b.out_off)
+            return gs_fail(GS_ERR_ARG, "deflate block %u lies outside the buffers", i);
+    }
+    std::lock_guard<std::mutex> lock(c->infMutex);
+    CU(cudaSetDevice(c->devs[0]));
+    if (!c->infStream) CU(cudaStreamCreateWithFlags(&c->infStream, cudaStreamNonBlocking));
+    CU(dgrow(&c->infComp, &c->infCompCap, (size_t)comp_bytes + 16));
+    CU(dgrow(&c->infText, &c->infTextCap, (size_t)out_bytes + 16));
+    CU(dgrow(&c->infBlocks, &c->infBlocksCap, (size_t)n_blocks));
+    CU(cudaMemcpyAsync(c->infComp, comp, comp_bytes, cudaMemcpyHostToDevice, c->infStream));
+    CU(cudaMemcpyAsync(c->infBlocks, blocks, (size_t)n_blocks * sizeof(gs_deflate_block), cudaMemcpyHostToDevice, c->infStream));
+    gs_launch_inflate_blocks(c->infComp, c->infText, c->infBlocks, n_blocks, c->infStream);
+    CU(cudaGetLastError());
+    if (out_bytes) CU(cudaMemcpyAsync(out, c->infText, out_bytes, cudaMemcpyDeviceToHost, c->infStream));
+    CU(cudaMemcpyAsync(blocks, c->infBlocks, (size_t)n_blocks * sizeof(gs_deflate_block), cudaMemcpyDeviceToHost, c->infStream));
+    CU(cudaStreamSynchronize(c->infStream));
+    for (uint32_t i = 0; i < n_blocks; i++)
+        if (blocks[i].status) return gs_fail(GS_ERR_DATA, "block-gzip member %u is corrupt (%s)", i,
+                                             blocks[i].status == 1 ? "malformed deflate stream" : blocks[i].status == 2 ? "size mismatch" : "CRC-32 mismatch");
+    return GS_OK;
+}
 
 extern "C" void* gs_alloc_pinned(size_t bytes) {
     void* p = nullptr;
@@ -654,6 +697,7 @@ extern "C" void gs_db_destroy(gs_db* db) {
     delete db;
 }
 
+extern "C" gs_ctx* gs_db_context(gs_db* db) { return db ? db->ctx : nullptr; }
 extern "C" uint64_t gs_db_device_bytes(const gs_db* db) { return db ? db->bytes : 0; }
 extern "C" int gs_db_n_devices(const gs_db* db) { return db ? (int)db->d.size() : 0; }
 
@@ -1479,6 +1523,7 @@ extern "C" void gs_filter_destroy(gs_filter* f) {
 }
 
 extern "C" int gs_filter_n_devices(const gs_filter* f) { return f ? (int)f->d.size() : 0; }
+extern "C" gs_ctx* gs_filter_context(gs_filter* f) { return f ? f->ctx : nullptr; }
 
 extern "C" gs_filter* gs_filter_create(gs_ctx* ctx, int kind, int64_t p0, int64_t p1, const int64_t* factors,
                                        const int64_t* words, uint64_t n_words) {

@@ -5,6 +5,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -380,6 +381,8 @@ static size_t lastRecordStart(const uint8_t* text, size_t len) {
 // into the pinned chunk (the reference inflates on its single producer thread).  Every block is checked
 // like gzread checks it (CRC-32 and ISIZE); a member without the subfield ends the fast path at that byte (`foreignAt`),
 // where the caller goes on with zlib's sequential reader, so the text never depends on which path produced it.
+static std::atomic<uint64_t> g_deviceInflatedBlocks{0};   // block-gzip members inflated on the device by this process (tests, benchmarks)
+
 class BgzfReader {
 public:
     // true if the file's first member is a BGZF block
@@ -389,11 +392,17 @@ public:
         size_t hdr = 0, total = 0;
         return parseHeader(h, sizeof(h), hdr, total) == 1;
     }
-    explicit BgzfReader(int fd) : fd_(fd) {
+    // ctx != nullptr: the blocks are inflated on the device (gs_inflate_blocks; GS_GPU_INFLATE=0 keeps the host threads)
+    explicit BgzfReader(int fd, gs_ctx* ctx = nullptr) : fd_(fd) {
         const char* e = getenv("GS_INFLATE_THREADS");
         const long v = e ? atol(e) : 0;
         threads_ = (unsigned)(v > 0 ? v : std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
+        const char* g = getenv("GS_GPU_INFLATE");
+        if (ctx && !(g && g[0] == '0')) ctx_ = ctx;
     }
+    ~BgzfReader() { if (cpin_) gs_free_pinned(cpin_); }
+    BgzfReader(const BgzfReader&) = delete;
+    BgzfReader& operator=(const BgzfReader&) = delete;
     bool eof() const { return eof_ && carryPos_ == carry_.size(); }
     bool foreign() const { return foreign_ && carryPos_ == carry_.size(); }   // a non-BGZF member follows at foreignAt()
     size_t foreignAt() const { return cpos_; }   // compressed offset of the first block that has not been inflated yet
@@ -436,11 +445,12 @@ private:
     // one window of compressed bytes: list its whole blocks, inflate those that fit into dst in parallel (the first one
     // that does not fit goes through the carry buffer)
     size_t round(uint8_t* dst, size_t room) {
-        const size_t window = std::max<size_t>((size_t)1 << 16, std::min<size_t>(room / 2 + ((size_t)1 << 17), (size_t)64 << 20));
-        cbuf_.resize(window);
+        // compressed bytes this round will need, from the ratio the previous rounds saw (a short window only costs another round)
+        const size_t window = std::max<size_t>((size_t)1 << 16, std::min<size_t>((size_t)((double)room / ratio_ * 1.1) + ((size_t)1 << 17), (size_t)64 << 20));
+        uint8_t* cbuf = compBuffer(window);
         size_t got = 0;
         while (got < window) {
-            const ssize_t r = pread(fd_, cbuf_.data() + got, window - got, (off_t)(cpos_ + got));
+            const ssize_t r = pread(fd_, cbuf + got, window - got, (off_t)(cpos_ + got));
             if (r < 0) fail("read error");
             if (r == 0) break;
             got += (size_t)r;
@@ -451,7 +461,7 @@ private:
         bool toCarry = false;
         while (off < got) {
             size_t hdr = 0, total = 0;
-            const uint8_t* h = cbuf_.data() + off;
+            const uint8_t* h = cbuf + off;
             if ((got - off >= 1 && h[0] != 0x1f) || (got - off >= 2 && h[1] != 0x8b)) {
                 // bytes behind the last member that are no gzip header: ignored, as by zlib's gzread and GZIPInputStream
                 if (blocks.empty()) { eof_ = true; return 0; }
@@ -463,7 +473,7 @@ private:
                 if (blocks.empty() && got < window) fail("read error");   // the file ends inside a block (gzread: unexpected end of file)
                 break;
             }
-            const uint8_t* t = cbuf_.data() + off + total - 4;
+            const uint8_t* t = cbuf + off + total - 4;
             const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
             if (isize > (1u << 16)) { if (blocks.empty()) { foreign_ = true; return 0; } break; }   // not a BGZF block after all
             if (out + isize > room) {
@@ -477,6 +487,23 @@ private:
         if (blocks.empty()) fail("read error");
         uint8_t* target = dst;
         if (toCarry) { carry_.resize(blocks[0].isize); carryPos_ = 0; target = carry_.data(); }
+        if (ctx_ && !toCarry && blocks.size() >= 32) {
+            // on the device: one thread per block, size and CRC-32 checked there (gs_inflate.cu)
+            std::vector<gs_deflate_block> tab(blocks.size());
+            for (size_t i = 0; i < blocks.size(); i++) {
+                const Block& b = blocks[i];
+                const uint8_t* c = cbuf + b.off + b.total - 8;
+                tab[i] = gs_deflate_block{b.off + b.hdr, b.out, (uint32_t)(b.total - b.hdr - 8), b.isize,
+                                          (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24), 0u};
+            }
+            const int rc = gs_inflate_blocks(ctx_, cbuf, off, tab.data(), (uint32_t)tab.size(), target, out);
+            if (rc == GS_ERR_DATA) fail("read error");   // corrupt block (gzread: data error / incorrect data check)
+            if (rc != GS_OK) fail(std::string("gs_inflate_blocks: ") + gs_last_error());
+            g_deviceInflatedBlocks += blocks.size();
+            cpos_ += off;
+            if (off > 0 && out > 0) ratio_ = std::max(1.0, (double)out / (double)off);
+            return out;
+        }
         const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads_, blocks.size() / 8 + 1));
         std::vector<int> bad(nt, 0);
         auto work = [&](unsigned t) {
@@ -485,7 +512,7 @@ private:
             if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
             for (size_t i = blocks.size() * t / nt; i < blocks.size() * (t + 1) / nt; i++) {
                 const Block& b = blocks[i];
-                const uint8_t* src = cbuf_.data() + b.off;
+                const uint8_t* src = cbuf + b.off;
                 zs.next_in = (Bytef*)(src + b.hdr); zs.avail_in = (uInt)(b.total - b.hdr - 8);
                 zs.next_out = (Bytef*)(target + b.out); zs.avail_out = (uInt)b.isize;
                 uint8_t none;
@@ -505,14 +532,29 @@ private:
         for (unsigned t = 0; t < nt; t++)
             if (bad[t]) fail("read error");   // corrupt block (gzread: data error / incorrect data check)
         cpos_ += off;
+        if (off > 0 && out > 0) ratio_ = std::max(1.0, (double)out / (double)off);
         return toCarry ? 0 : out;
     }
+    // the window of compressed bytes: pinned when it goes to the device
+    uint8_t* compBuffer(size_t bytes) {
+        if (!ctx_) { cbuf_.resize(bytes); return cbuf_.data(); }
+        if (bytes > cpinCap_) {
+            if (cpin_) gs_free_pinned(cpin_);
+            cpinCap_ = bytes + bytes / 4;
+            cpin_ = (uint8_t*)gs_alloc_pinned(cpinCap_);
+            if (!cpin_) { cpinCap_ = 0; fail(std::string("pinned allocation failed: ") + gs_last_error()); }
+        }
+        return cpin_;
+    }
+    gs_ctx* ctx_ = nullptr;
+    uint8_t* cpin_ = nullptr; size_t cpinCap_ = 0;
     int fd_;
     unsigned threads_ = 1;
     size_t cpos_ = 0;
     bool eof_ = false, foreign_ = false;
     std::vector<uint8_t> cbuf_, carry_;
     size_t carryPos_ = 0;
+    double ratio_ = 3.0;   // inflated / compressed bytes of the last round
 };
 
 // The GPU feeder's host side, shared by the match and filter drivers: stream one FASTQ input as pinned text chunks that end
@@ -522,7 +564,7 @@ private:
 // FASTQ); from the first refusal on, the rest of the input -- the refused chunk included -- goes through the sequential
 // parser (`sequential(LineReader&)`), so the results never depend on this fast path.
 template <typename CurFn, typename NextFn, typename SubmitFn, typename SeqFn>
-static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextFn&& next, SubmitFn&& submit, SeqFn&& sequential) {
+static void feedFastqText(gs_ctx* ctx, const Input& in, size_t chunkBytes, CurFn&& cur, NextFn&& next, SubmitFn&& submit, SeqFn&& sequential) {
     gzFile gz = nullptr;
     int fd = -1;        // uncompressed files are read with parallel pread() straight into the pinned chunk
     int zfd = -1;       // block-gzip files: the descriptor the BgzfReader reads from
@@ -535,7 +577,7 @@ static void feedFastqText(const Input& in, size_t chunkBytes, CurFn&& cur, NextF
         const ssize_t m = pread(fd, magic, 2, 0);
         if (m == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
             if (BgzfReader::probe(fd) && !getenv("GS_NO_BGZF")) {   // block gzip: the blocks are inflated in parallel
-                bgzf.reset(new BgzfReader(fd));
+                bgzf.reset(new BgzfReader(fd, ctx));
                 zfd = fd; fd = -1;
             } else {                                                // gzip: zlib inflates on this thread
                 close(fd); fd = -1;
@@ -888,7 +930,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
         }
         // ---- GPU feeder: text chunks cut at record boundaries; `cur` is the batch being filled
         flush();  // host-parsed reads of an earlier input keep their place in the order
-        feedFastqText(in, cfg_.textChunkBytes,
+        feedFastqText(gs_db_context(db_), in, cfg_.textChunkBytes,
             [&]() -> HostBatch* { return cur; },
             [&]() -> HostBatch* { return freeList.front(); },
             [&](HostBatch* b, size_t cut) -> bool {
@@ -1141,7 +1183,7 @@ void FastqBloomFilter::runFilter(const std::vector<Input>& fastqs, OutputSink* f
             continue;
         }
         flush();
-        feedFastqText(in, textChunkBytes,
+        feedFastqText(gs_filter_context(f_), in, textChunkBytes,
             [&]() -> HostBatch* { return cur; },
             [&]() -> HostBatch* { return freeList.front(); },
             [&](HostBatch* b, size_t cut) -> bool {
@@ -1322,6 +1364,8 @@ gsh_result* gsh_bgzf_read_all(const char* path, size_t request, int64_t* foreign
     if (fd >= 0) close(fd);
     return r;
 }
+
+uint64_t gsh_device_inflated_blocks(void) { return g_deviceInflatedBlocks.load(); }
 
 // The feeder's record-boundary search alone (no GPU): offset of the last record start in text[0, len), 0 = none in sight.
 size_t gsh_last_record_start(const uint8_t* text, size_t len) { return lastRecordStart(text, len); }

@@ -95,3 +95,6 @@ void gs_launch_db_update(const GsDbView& db, const u32* labels, const long long*
                          u32 nRegions, uint16_t* vals, unsigned long long* nChanged, cudaStream_t st);
 void gs_launch_cgat_upper(uint8_t* buf, u64 n, cudaStream_t st);
 void gs_launch_values_to_raw(const uint16_t* vals, u64 n, int16_t* raw, cudaStream_t st);
+
+// gs_inflate.cu: one thread per raw-deflate block (block-gzip input), status per block
+void gs_launch_inflate_blocks(const uint8_t* comp, uint8_t* text, gs_deflate_block* blocks, uint32_t nBlocks, cudaStream_t st);

@@ -51,6 +51,8 @@ def _lib():
         L.gsh_last_record_start.restype = C.c_size_t
         L.gsh_last_record_start.argtypes = [_P, C.c_size_t]
         L.gsh_java_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        L.gsh_device_inflated_blocks.restype = C.c_uint64
+        L.gsh_device_inflated_blocks.argtypes = []
         L.gsh_bgzf_read_all.restype = _P
         L.gsh_bgzf_read_all.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]
         _ready = True
@@ -160,6 +162,11 @@ def last_record_start(text):
     """Where the GPU feeder would cut a text chunk: offset of the last record start (0 = no boundary found)."""
     b = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, dtype=np.uint8)
     return int(_lib().gsh_last_record_start(b.ctypes.data, len(text)))
+
+
+def device_inflated_blocks():
+    """Block-gzip members this process has inflated on the device so far (gs_inflate_blocks through the feeder)."""
+    return int(_lib().gsh_device_inflated_blocks())
 
 
 def bgzf_read_all(path, request=1 << 20):

@@ -21,14 +21,15 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 3
+#define GS_ABI_VERSION 4
 
 typedef enum gs_status {
     GS_OK = 0,
     GS_ERR_ARG = -1,     /* bad argument / call order */
     GS_ERR_CUDA = -2,    /* CUDA runtime error (incl. no device) */
     GS_ERR_STATE = -3,   /* object not finalized / ticket not pending */
-    GS_ERR_LIMIT = -4    /* a documented size limit was exceeded */
+    GS_ERR_LIMIT = -4,   /* a documented size limit was exceeded */
+    GS_ERR_DATA = -5     /* corrupt input data (block-gzip: malformed deflate stream, size or CRC-32 mismatch) */
 } gs_status;
 
 typedef struct gs_ctx gs_ctx;       /* one per process: the set of GPUs used */
@@ -275,6 +276,26 @@ int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_of
 int gs_filter_sync(gs_fsess*);
 void* gs_filter_stream(gs_fsess*);
 void gs_filter_close(gs_fsess*);
+
+/* ---- block-gzip input ---------------------------------------------------------------------------
+ * Replaces: java.util.zip.GZIPInputStream in front of the FASTQ reader (B/io/StreamProvider via
+ * C/fastq/AbstractFastqReader.java:224) for block-gzip (BGZF) files -- multi-member gzip files whose members are
+ * independent raw-deflate streams of at most 64 KB.  The caller finds the members from their headers (the 'BC' extra
+ * subfield holds the member size) and describes them here; the device inflates them, one thread per block, and checks
+ * each against its trailer like gzread / GZIPInputStream do (exactly out_len bytes, CRC-32).
+ * comp[comp_bytes] and out[out_bytes] are host buffers (pinned ones copy faster); blocks[i] = deflate data at
+ * comp + in_off (in_len bytes, gzip header and trailer excluded) -> out + out_off (out_len = ISIZE bytes, crc32 = the
+ * trailer's CRC-32).  Returns GS_ERR_DATA if a block is corrupt (blocks[i].status != 0 marks it); nothing of `out` is
+ * valid then.  Calls on one context are serialized. */
+typedef struct gs_deflate_block {
+    uint64_t in_off, out_off;
+    uint32_t in_len, out_len, crc32, status;
+} gs_deflate_block;
+int gs_inflate_blocks(gs_ctx*, const uint8_t* comp, uint64_t comp_bytes, gs_deflate_block* blocks, uint32_t n_blocks,
+                      uint8_t* out, uint64_t out_bytes);
+/* the context a database / filter index lives on (for callers that only hold the object) */
+gs_ctx* gs_db_context(gs_db*);
+gs_ctx* gs_filter_context(gs_filter*);
 
 #ifdef __cplusplus
 }
