@@ -2,12 +2,16 @@
 //
 // The reference inflates on its single producer thread (java.util.zip.GZIPInputStream in front of
 // C/fastq/AbstractFastqReader.java:224).  A BGZF file is a multi-member gzip file whose members are
-// independent deflate streams of at most 64 KB, and a batch of reads holds thousands of them, so the device gives every
-// block its own thread: the 32 lanes of a warp decode 32 blocks side by side (canonical Huffman decoding by code length,
-// the tables in thread-local memory), and the parallelism that hides the latency of the serial bit stream comes from the
-// number of blocks in flight, not from inside a block.  Every block is checked like gzread / GZIPInputStream check it:
-// the stream must end exactly at ISIZE bytes and the CRC-32 of the output must match the member's trailer.
-// No loop runs longer than the block's input bits plus its output bytes, whatever the input holds.
+// independent deflate streams of at most 64 KB, and a batch of reads holds thousands of them.  A deflate stream is serial
+// (every code starts where the previous one ended), so the parallelism comes from the number of blocks in flight: every
+// block gets its own warp, whose first lane walks the bit stream (lanes that decode different blocks side by side diverge
+// at every symbol and end up serialized -- measured: 32 blocks per warp took 32 x as long as one).  What keeps the walk
+// short is that a symbol costs no dependent memory loads to find its length: the canonical code's left-justified
+// first-code limits of the 15 code lengths sit in registers, the code length is the number of limits the next 15 bits
+// reach (15 independent compares), and one table load yields the symbol.
+// Every block is checked like gzread / GZIPInputStream check it: the stream must end exactly at ISIZE bytes and the
+// CRC-32 (slicing-by-4, tables in shared memory) must match the member's trailer.  No loop runs longer than the block's
+// input bits plus its output bytes, whatever the input holds.
 #include "gs_kernels.cuh"
 
 #include <cuda_runtime.h>
@@ -15,7 +19,7 @@
 typedef unsigned char u8;
 typedef unsigned short u16;
 
-#define GS_INF_THREADS 32
+#define GS_INF_WARPS 4        // blocks per CTA: one warp each
 #define GS_INF_MAXBITS 15
 #define GS_INF_MAXL 288
 #define GS_INF_MAXD 30
@@ -28,7 +32,20 @@ struct BitReader {
     u64 buf;
     int cnt;  // valid bits in buf; negative = the stream was read past its end
     __device__ __forceinline__ void refill() {
-        while (cnt <= 56 && pos < end) { buf |= (u64)in[pos++] << cnt; cnt += 8; }
+        if (pos + 8 <= end) {
+            // eight independent byte loads; the bits above cnt are the stream's next bits and are ORed in again, unchanged,
+            // by the next refill
+            u64 w = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) w |= (u64)in[pos + j] << (8 * j);
+            buf |= w << cnt;
+            const int adv = (63 - cnt) >> 3;
+            pos += (u32)adv; cnt += adv * 8;
+        } else {
+            // tail of the input: the speculative bits above cnt must go, the bytes below are added exactly
+            buf &= cnt > 0 ? (~0ULL >> (64 - cnt)) : 0ULL;
+            while (cnt <= 56 && pos < end) { buf |= (u64)in[pos++] << cnt; cnt += 8; }
+        }
     }
     __device__ __forceinline__ u32 take(int n) {
         const u32 v = (u32)buf & ((1u << n) - 1u);
@@ -37,43 +54,45 @@ struct BitReader {
     }
 };
 
-// canonical Huffman code of n symbols from their code lengths (count[len] = symbols of that length, symbol[] = symbols
-// ordered by code): 0 = complete, > 0 = incomplete, < 0 = over-subscribed
-__device__ int gs_inf_construct(u16* count, u16* symbol, const u8* length, int n) {
-    u16 offs[GS_INF_MAXBITS + 1];
+// Canonical Huffman code of n symbols from their code lengths: symbol[] = the symbols ordered by code, limit[l] = the
+// left-justified (15-bit) first code beyond length l, base[l] = index of length l's first symbol minus its first code.
+// 0 = complete, > 0 = incomplete, < 0 = over-subscribed; coded = symbols that have a code.  limit[] is indexed by
+// constants only (registers).
+__device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1], int* base, u16* symbol, const u8* length, int n, int& coded) {
+    u16 count[GS_INF_MAXBITS + 1], offs[GS_INF_MAXBITS + 1];
     for (int l = 0; l <= GS_INF_MAXBITS; l++) count[l] = 0;
     for (int s = 0; s < n; s++) count[length[s]]++;
-    if (count[0] == n) return 0;
     int left = 1;
+    u32 first = 0, index = 0;
+    bool over = false;
+#pragma unroll
     for (int l = 1; l <= GS_INF_MAXBITS; l++) {
-        left <<= 1;
-        left -= (int)count[l];
-        if (left < 0) return left;
+        const u32 c = count[l];
+        left = (left << 1) - (int)c;
+        over |= left < 0;
+        offs[l] = (u16)index;
+        base[l] = (int)index - (int)first;
+        index += c;
+        first += c;
+        limit[l] = over ? 0u : first << (GS_INF_MAXBITS - l);
+        first <<= 1;
     }
-    offs[1] = 0;
-    for (int l = 1; l < GS_INF_MAXBITS; l++) offs[l + 1] = offs[l] + count[l];
+    coded = n - (int)count[0];
+    if (over) return -1;
     for (int s = 0; s < n; s++)
         if (length[s] != 0) symbol[offs[length[s]]++] = (u16)s;
-    return left;
+    return coded == 0 ? 0 : left;
 }
 
-// one symbol: walk the code lengths, one bit each (the caller refilled: at least 48 bits are there unless the input ends)
-__device__ __forceinline__ int gs_inf_decode(BitReader& br, const u16* count, const u16* symbol) {
-    int code = 0, first = 0, index = 0;
-    u64 b = br.buf;
-#pragma unroll 1
-    for (int len = 1; len <= GS_INF_MAXBITS; len++) {
-        code |= (int)(b & 1u);
-        b >>= 1;
-        const int c = (int)count[len];
-        if (code - c < first) {
-            br.buf = b; br.cnt -= len;
-            return (int)symbol[index + (code - first)];
-        }
-        index += c; first += c;
-        first <<= 1; code <<= 1;
-    }
-    return -1;
+// one symbol (the caller refilled: at least 48 bits are there unless the input ends): -1 = no such code
+__device__ __forceinline__ int gs_inf_decode(BitReader& br, const u32 (&limit)[GS_INF_MAXBITS + 1], const int* base, const u16* symbol) {
+    const u32 code = __brev((u32)br.buf) >> 17;   // the next 15 bits, first bit on top
+    int len = 1;
+#pragma unroll
+    for (int l = 1; l <= GS_INF_MAXBITS; l++) len += code >= limit[l];
+    if (len > GS_INF_MAXBITS) return -1;
+    br.buf >>= len; br.cnt -= len;
+    return (int)symbol[base[len] + (int)(code >> (GS_INF_MAXBITS - len))];
 }
 
 }  // namespace
@@ -83,12 +102,12 @@ __device__ __forceinline__ int gs_inf_decode(BitReader& br, const u16* count, co
 #define GS_INF_ERR_SIZE 2u     // output does not have exactly ISIZE bytes
 #define GS_INF_ERR_CRC 3u      // CRC-32 mismatch
 
-__global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const u8* __restrict__ comp, u8* __restrict__ text, gs_deflate_block* blocks,
-                                                                          u32 nBlocks) {
+__global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(const u8* __restrict__ comp, u8* __restrict__ text, gs_deflate_block* blocks,
+                                                                             u32 nBlocks) {
     __shared__ u16 s_lbase[29], s_dbase[30];
     __shared__ u8 s_lext[29], s_dext[30], s_order[19];
-    __shared__ u32 s_crc[256];
-    {   // RFC 1951 3.2.5 / 3.2.7 tables and the CRC-32 table (polynomial 0xEDB88320, RFC 1952 8), built once per CTA
+    __shared__ u32 s_crc[4][256];
+    {   // RFC 1951 3.2.5 / 3.2.7 tables and the CRC-32 tables (polynomial 0xEDB88320, RFC 1952 8; slicing by 4), once per CTA
         const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
         const u8 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
         const u16 dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -100,18 +119,25 @@ __global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
             u32 c = i;
             for (int j = 0; j < 8; j++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            s_crc[i] = c;
+            s_crc[0][i] = c;
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+            u32 c = s_crc[0][i];
+            for (int t = 1; t < 4; t++) { c = (c >> 8) ^ s_crc[0][c & 0xFFu]; s_crc[t][i] = c; }
         }
     }
     __syncthreads();
-    const u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= nBlocks) return;
+    const u32 bi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one block per warp
+    if (bi >= nBlocks || (threadIdx.x & 31) != 0) return;                 // the bit stream is walked by the warp's first lane
     const gs_deflate_block B = blocks[bi];
     u8* out = text + B.out_off;
     const u32 outLen = B.out_len;
     u32 o = 0;
     BitReader br{comp + B.in_off, 0u, B.in_len, 0ULL, 0};
-    u16 lcount[GS_INF_MAXBITS + 1], lsym[GS_INF_MAXL], dcount[GS_INF_MAXBITS + 1], dsym[GS_INF_MAXD];
+    u32 llimit[GS_INF_MAXBITS + 1], dlimit[GS_INF_MAXBITS + 1];   // registers
+    int lidx[GS_INF_MAXBITS + 1], didx[GS_INF_MAXBITS + 1];
+    u16 lsym[GS_INF_MAXL], dsym[GS_INF_MAXD];
     u8 lengths[GS_INF_MAXL + GS_INF_MAXD + 2];
     u32 err = 0;
     bool last = false;
@@ -135,24 +161,26 @@ __global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const
             continue;
         }
         if (type == 3) { err = GS_INF_ERR_STREAM; break; }
+        int coded = 0;
         if (type == 1) {   // fixed codes (RFC 1951 3.2.6)
             for (int s = 0; s < 144; s++) lengths[s] = 8;
             for (int s = 144; s < 256; s++) lengths[s] = 9;
             for (int s = 256; s < 280; s++) lengths[s] = 7;
             for (int s = 280; s < GS_INF_MAXL; s++) lengths[s] = 8;
-            gs_inf_construct(lcount, lsym, lengths, GS_INF_MAXL);
+            gs_inf_construct(llimit, lidx, lsym, lengths, GS_INF_MAXL, coded);
             for (int s = 0; s < GS_INF_MAXD; s++) lengths[s] = 5;
-            gs_inf_construct(dcount, dsym, lengths, GS_INF_MAXD);
+            gs_inf_construct(dlimit, didx, dsym, lengths, GS_INF_MAXD, coded);
         } else {           // dynamic codes (RFC 1951 3.2.7)
             const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
             if (br.cnt < 0 || nlen > 286 || ndist > GS_INF_MAXD) { err = GS_INF_ERR_STREAM; break; }
             for (int i = 0; i < 19; i++) lengths[i] = 0;
             for (int i = 0; i < ncode; i++) { br.refill(); lengths[s_order[i]] = (u8)br.take(3); }
-            if (br.cnt < 0 || gs_inf_construct(lcount, lsym, lengths, 19) != 0) { err = GS_INF_ERR_STREAM; break; }
+            // the code-length code lives in the distance code's tables until those are built
+            if (br.cnt < 0 || gs_inf_construct(dlimit, didx, dsym, lengths, 19, coded) != 0) { err = GS_INF_ERR_STREAM; break; }
             int idx = 0;
             while (idx < nlen + ndist) {
                 br.refill();
-                int sym = gs_inf_decode(br, lcount, lsym);
+                const int sym = gs_inf_decode(br, dlimit, didx, dsym);
                 if (sym < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
                 if (sym < 16) { lengths[idx++] = (u8)sym; continue; }
                 int rep, val = 0;
@@ -167,15 +195,15 @@ __global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const
             }
             if (err) break;
             if (lengths[256] == 0) { err = GS_INF_ERR_STREAM; break; }
-            int e = gs_inf_construct(lcount, lsym, lengths, nlen);
-            if (e < 0 || (e > 0 && nlen - (int)lcount[0] != 1)) { err = GS_INF_ERR_STREAM; break; }
-            e = gs_inf_construct(dcount, dsym, lengths + nlen, ndist);
-            if (e < 0 || (e > 0 && ndist - (int)dcount[0] != 1)) { err = GS_INF_ERR_STREAM; break; }
+            int e = gs_inf_construct(llimit, lidx, lsym, lengths, nlen, coded);
+            if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
+            e = gs_inf_construct(dlimit, didx, dsym, lengths + nlen, ndist, coded);
+            if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
         }
         // literals and matches until the end-of-block symbol
         for (;;) {
-            br.refill();
-            int sym = gs_inf_decode(br, lcount, lsym);
+            if (br.cnt < 48) br.refill();   // a length/distance pair takes at most 15 + 5 + 15 + 13 = 48 bits
+            int sym = gs_inf_decode(br, llimit, lidx, lsym);
             if (sym < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
             if (sym < 256) {
                 if (o >= outLen) { err = GS_INF_ERR_SIZE; break; }
@@ -186,20 +214,35 @@ __global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const
             sym -= 257;
             if (sym >= 29) { err = GS_INF_ERR_STREAM; break; }
             const u32 len = (u32)s_lbase[sym] + br.take(s_lext[sym]);
-            const int ds = gs_inf_decode(br, dcount, dsym);
+            const int ds = gs_inf_decode(br, dlimit, didx, dsym);
             if (ds < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
             const u32 dist = (u32)s_dbase[ds] + br.take(s_dext[ds]);
             if (br.cnt < 0 || dist > o) { err = GS_INF_ERR_STREAM; break; }
             if (o + len > outLen) { err = GS_INF_ERR_SIZE; break; }
             const u8* from = out + o - dist;
-            for (u32 i = 0; i < len; i++) out[o + i] = from[i];   // byte by byte: the ranges overlap when dist < len
+            u32 i = 0;
+            if (dist >= 8) {   // source and destination of eight bytes do not overlap: the loads need not wait for the stores
+                for (; i + 8 <= len; i += 8) {
+                    u8 t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) t[j] = from[i + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) out[o + i + j] = t[j];
+                }
+            }
+            for (; i < len; i++) out[o + i] = from[i];   // byte by byte: the ranges overlap when dist < len
             o += len;
         }
     }
     if (!err && o != outLen) err = GS_INF_ERR_SIZE;
     if (!err) {
-        u32 crc = 0xFFFFFFFFu;
-        for (u32 i = 0; i < outLen; i++) crc = s_crc[(crc ^ out[i]) & 0xFFu] ^ (crc >> 8);
+        u32 crc = 0xFFFFFFFFu, i = 0;
+        for (; i < outLen && ((size_t)(out + i) & 3u); i++) crc = s_crc[0][(crc ^ out[i]) & 0xFFu] ^ (crc >> 8);
+        for (; i + 4 <= outLen; i += 4) {
+            crc ^= *(const u32*)(out + i);
+            crc = s_crc[3][crc & 0xFFu] ^ s_crc[2][(crc >> 8) & 0xFFu] ^ s_crc[1][(crc >> 16) & 0xFFu] ^ s_crc[0][crc >> 24];
+        }
+        for (; i < outLen; i++) crc = s_crc[0][(crc ^ out[i]) & 0xFFu] ^ (crc >> 8);
         if ((crc ^ 0xFFFFFFFFu) != B.crc32) err = GS_INF_ERR_CRC;
     }
     blocks[bi].status = err;
@@ -207,5 +250,5 @@ __global__ void __launch_bounds__(GS_INF_THREADS) gs_inflate_blocks_kernel(const
 
 void gs_launch_inflate_blocks(const uint8_t* comp, uint8_t* text, gs_deflate_block* blocks, uint32_t nBlocks, cudaStream_t st) {
     if (nBlocks == 0) return;
-    gs_inflate_blocks_kernel<<<(nBlocks + GS_INF_THREADS - 1) / GS_INF_THREADS, GS_INF_THREADS, 0, st>>>(comp, text, blocks, nBlocks);
+    gs_inflate_blocks_kernel<<<(nBlocks + GS_INF_WARPS - 1) / GS_INF_WARPS, GS_INF_WARPS * 32, 0, st>>>(comp, text, blocks, nBlocks);
 }

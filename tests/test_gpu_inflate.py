@@ -63,7 +63,7 @@ def test_inflate_blocks_detects_corruption(native, gpu_ctx):
         assert st[b] != 0 and not np.delete(st, b).any()
     for field, delta in (("in_len", -5), ("out_len", -5), ("crc32", 1)):
         b2 = blocks.copy()
-        b2[field][0] += delta
+        b2[field][0] = int(b2[field][0]) + delta
         with pytest.raises(native.GenestripError):
             gpu_ctx.inflate_blocks(comp, b2, n)
     with pytest.raises(native.GenestripError) as e:                    # a block outside the buffers is refused up front
