@@ -6,9 +6,11 @@
 // (every code starts where the previous one ended), so the parallelism comes from the number of blocks in flight: every
 // block gets its own warp, whose first lane walks the bit stream (lanes that decode different blocks side by side diverge
 // at every symbol and end up serialized -- measured: 32 blocks per warp took 32 x as long as one).  What keeps the walk
-// short is that a symbol costs no dependent memory loads to find its length: the canonical code's left-justified
-// first-code limits of the 15 code lengths sit in registers, the code length is the number of limits the next 15 bits
-// reach (15 independent compares), and one table load yields the symbol.
+// short: a symbol whose code has at most 10 bits (8 for distances) is one shared-memory load from a per-warp look-up
+// table indexed by the next bits of the stream; longer codes need no dependent loads to find their length either -- the
+// canonical code's left-justified first-code limits of the 15 code lengths sit in registers and the code length is the
+// number of limits the next 15 bits reach (15 independent compares).  Matches are copied eight bytes at a time, runs
+// (distance below 8) from a register that holds the period.
 // Every block is checked like gzread / GZIPInputStream check it: the stream must end exactly at ISIZE bytes and the
 // CRC-32 (slicing-by-4, tables in shared memory) must match the member's trailer.  No loop runs longer than the block's
 // input bits plus its output bytes, whatever the input holds.
@@ -23,6 +25,8 @@ typedef unsigned short u16;
 #define GS_INF_MAXBITS 15
 #define GS_INF_MAXL 288
 #define GS_INF_MAXD 30
+#define GS_INF_LBITS 10       // look-up tables: literal/length codes up to 10 bits, distance codes up to 8 bits in one load
+#define GS_INF_DBITS 8
 
 namespace {
 
@@ -58,7 +62,9 @@ struct BitReader {
 // left-justified (15-bit) first code beyond length l, base[l] = index of length l's first symbol minus its first code.
 // 0 = complete, > 0 = incomplete, < 0 = over-subscribed; coded = symbols that have a code.  limit[] is indexed by
 // constants only (registers).
-__device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1], int* base, u16* symbol, const u8* length, int n, int& coded) {
+// tab (or nullptr): direct look-up by the next tabBits bits of the stream: symbol | code length << 9, 0 = the code is longer.
+__device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1], int* base, u16* symbol, const u8* length, int n, int& coded,
+                                                u16* tab = nullptr, int tabBits = 0) {
     u16 count[GS_INF_MAXBITS + 1], offs[GS_INF_MAXBITS + 1];
     for (int l = 0; l <= GS_INF_MAXBITS; l++) count[l] = 0;
     for (int s = 0; s < n; s++) count[length[s]]++;
@@ -81,6 +87,20 @@ __device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1]
     if (over) return -1;
     for (int s = 0; s < n; s++)
         if (length[s] != 0) symbol[offs[length[s]]++] = (u16)s;
+    if (tab) {
+        // codes are packed first bit first into a stream that is read lowest bit first: entry index = the code's bits
+        // reversed, repeated for every value of the bits that follow it
+        for (int i = 0; i < (1 << tabBits); i++) tab[i] = 0;
+        u32 code = 0;
+        int si = 0;
+        for (int l = 1; l <= tabBits; l++) {
+            for (u32 c = 0; c < count[l]; c++, si++, code++) {
+                const u16 e = (u16)(symbol[si] | (l << 9));
+                for (u32 k = __brev(code) >> (32 - l); k < (1u << tabBits); k += 1u << l) tab[k] = e;
+            }
+            code <<= 1;
+        }
+    }
     return coded == 0 ? 0 : left;
 }
 
@@ -95,6 +115,16 @@ __device__ __forceinline__ int gs_inf_decode(BitReader& br, const u32 (&limit)[G
     return (int)symbol[base[len] + (int)(code >> (GS_INF_MAXBITS - len))];
 }
 
+// the same through the look-up table: one shared-memory load for codes of at most tabBits bits
+__device__ __forceinline__ int gs_inf_decode_tab(BitReader& br, const u16* tab, u32 tabMask, const u32 (&limit)[GS_INF_MAXBITS + 1], const int* base,
+                                                 const u16* symbol) {
+    const u32 e = tab[(u32)br.buf & tabMask];
+    if (e == 0) return gs_inf_decode(br, limit, base, symbol);
+    const int len = (int)(e >> 9);
+    br.buf >>= len; br.cnt -= len;
+    return (int)(e & 0x1FFu);
+}
+
 }  // namespace
 
 // status written per block: 0 = ok, else the first reason the block is not what its trailer says
@@ -107,6 +137,7 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
     __shared__ u16 s_lbase[29], s_dbase[30];
     __shared__ u8 s_lext[29], s_dext[30], s_order[19];
     __shared__ u32 s_crc[4][256];
+    __shared__ u16 s_ltab[GS_INF_WARPS][1 << GS_INF_LBITS], s_dtab[GS_INF_WARPS][1 << GS_INF_DBITS];
     {   // RFC 1951 3.2.5 / 3.2.7 tables and the CRC-32 tables (polynomial 0xEDB88320, RFC 1952 8; slicing by 4), once per CTA
         const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
         const u8 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -133,6 +164,8 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
     const gs_deflate_block B = blocks[bi];
     u8* out = text + B.out_off;
     const u32 outLen = B.out_len;
+    u16* ltab = s_ltab[threadIdx.x >> 5];
+    u16* dtab = s_dtab[threadIdx.x >> 5];
     u32 o = 0;
     BitReader br{comp + B.in_off, 0u, B.in_len, 0ULL, 0};
     u32 llimit[GS_INF_MAXBITS + 1], dlimit[GS_INF_MAXBITS + 1];   // registers
@@ -167,9 +200,9 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             for (int s = 144; s < 256; s++) lengths[s] = 9;
             for (int s = 256; s < 280; s++) lengths[s] = 7;
             for (int s = 280; s < GS_INF_MAXL; s++) lengths[s] = 8;
-            gs_inf_construct(llimit, lidx, lsym, lengths, GS_INF_MAXL, coded);
+            gs_inf_construct(llimit, lidx, lsym, lengths, GS_INF_MAXL, coded, ltab, GS_INF_LBITS);
             for (int s = 0; s < GS_INF_MAXD; s++) lengths[s] = 5;
-            gs_inf_construct(dlimit, didx, dsym, lengths, GS_INF_MAXD, coded);
+            gs_inf_construct(dlimit, didx, dsym, lengths, GS_INF_MAXD, coded, dtab, GS_INF_DBITS);
         } else {           // dynamic codes (RFC 1951 3.2.7)
             const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
             if (br.cnt < 0 || nlen > 286 || ndist > GS_INF_MAXD) { err = GS_INF_ERR_STREAM; break; }
@@ -195,15 +228,15 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             }
             if (err) break;
             if (lengths[256] == 0) { err = GS_INF_ERR_STREAM; break; }
-            int e = gs_inf_construct(llimit, lidx, lsym, lengths, nlen, coded);
+            int e = gs_inf_construct(llimit, lidx, lsym, lengths, nlen, coded, ltab, GS_INF_LBITS);
             if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
-            e = gs_inf_construct(dlimit, didx, dsym, lengths + nlen, ndist, coded);
+            e = gs_inf_construct(dlimit, didx, dsym, lengths + nlen, ndist, coded, dtab, GS_INF_DBITS);
             if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
         }
         // literals and matches until the end-of-block symbol
         for (;;) {
             if (br.cnt < 48) br.refill();   // a length/distance pair takes at most 15 + 5 + 15 + 13 = 48 bits
-            int sym = gs_inf_decode(br, llimit, lidx, lsym);
+            int sym = gs_inf_decode_tab(br, ltab, (1u << GS_INF_LBITS) - 1u, llimit, lidx, lsym);
             if (sym < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
             if (sym < 256) {
                 if (o >= outLen) { err = GS_INF_ERR_SIZE; break; }
@@ -214,23 +247,34 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             sym -= 257;
             if (sym >= 29) { err = GS_INF_ERR_STREAM; break; }
             const u32 len = (u32)s_lbase[sym] + br.take(s_lext[sym]);
-            const int ds = gs_inf_decode(br, dlimit, didx, dsym);
+            const int ds = gs_inf_decode_tab(br, dtab, (1u << GS_INF_DBITS) - 1u, dlimit, didx, dsym);
             if (ds < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
             const u32 dist = (u32)s_dbase[ds] + br.take(s_dext[ds]);
             if (br.cnt < 0 || dist > o) { err = GS_INF_ERR_STREAM; break; }
             if (o + len > outLen) { err = GS_INF_ERR_SIZE; break; }
             const u8* from = out + o - dist;
-            u32 i = 0;
-            if (dist >= 8) {   // source and destination of eight bytes do not overlap: the loads need not wait for the stores
-                for (; i + 8 <= len; i += 8) {
-                    u8 t[8];
+            if (dist >= 8) {
+                // eight bytes at a time: source and destination of a group do not overlap, so the loads are independent of
+                // the stores (a byte-by-byte copy waits for a full load latency per byte: the compiler must keep the order)
+                for (u32 i = 0; i < len; i += 8) {
+                    const u32 n = len - i;
+                    u64 t = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) t[j] = from[i + j];
+                    for (u32 j = 0; j < 8; j++) if (j < n) t |= (u64)from[i + j] << (8 * j);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) out[o + i + j] = t[j];
+                    for (u32 j = 0; j < 8; j++) if (j < n) out[o + i + j] = (u8)(t >> (8 * j));
+                }
+            } else {
+                // the match overlaps its own output (runs, short periods): the period goes into a register once
+                u64 pat = 0;
+#pragma unroll
+                for (u32 j = 0; j < 7; j++) if (j < dist) pat |= (u64)from[j] << (8 * j);
+                u32 j = 0;
+                for (u32 i = 0; i < len; i++) {
+                    out[o + i] = (u8)(pat >> (8 * j));
+                    j = j + 1 == dist ? 0 : j + 1;
                 }
             }
-            for (; i < len; i++) out[o + i] = from[i];   // byte by byte: the ranges overlap when dist < len
             o += len;
         }
     }

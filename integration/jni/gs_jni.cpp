@@ -169,6 +169,13 @@ JNIEXPORT jobjectArray JNICALL J(filterCollectFastq)(JNIEnv* env, jclass, jlong 
     env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer((void*)recs, ((jlong)n + 1) * (jlong)sizeof(gs_fastq_rec)));
     return arr;
 }
+// ---- block-gzip input: comp / out = direct buffers over pinned memory, blocks = direct buffer of gs_deflate_block[nBlocks]
+// (filled by the Java reader from the members' headers and trailers); throws on a corrupt member like GZIPInputStream does
+JNIEXPORT void JNICALL J(inflateBlocks)(JNIEnv* env, jclass, jlong ctx, jobject comp, jlong compBytes, jobject blocks, jint nBlocks, jobject out, jlong outBytes) {
+    CHECK(gs_inflate_blocks((gs_ctx*)ctx, (const uint8_t*)env->GetDirectBufferAddress(comp), (uint64_t)compBytes,
+                            (gs_deflate_block*)env->GetDirectBufferAddress(blocks), (uint32_t)nBlocks,
+                            (uint8_t*)env->GetDirectBufferAddress(out), (uint64_t)outBytes));
+}
 // ---- db goal, update phase (DBGoal.MyFastaReader.handleStore): the regions of one FASTA batch, line ends stripped
 JNIEXPORT jlong JNICALL J(dbUpdate)(JNIEnv* env, jclass, jlong db, jobject seq, jlong nBytes, jlongArray regionOffsets, jintArray regionValueIndex, jboolean upperCase) {
     const jsize nr = env->GetArrayLength(regionValueIndex);

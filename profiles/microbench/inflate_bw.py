@@ -22,9 +22,11 @@ for d in range(9):
     rec[:, 2 + d] = idx // 10 ** (8 - d) % 10 + 48
 rec[:, 10] = 10; rec[:, 11:11 + L] = seq; rec[:, 11 + L] = 10; rec[:, 12 + L] = ord("+"); rec[:, 13 + L] = 10
 rec[:, 14 + L:14 + 2 * L] = qual; rec[:, -1] = 10
-text_all = rec.tobytes()
+text_binned = rec.tobytes()
+rec[:, 14 + L:14 + 2 * L] = ord("I")                                             # constant qualities: long runs (overlapping matches)
+text_runs = rec.tobytes()
 ctx = capi.Context([0])
-for mb in sizes:
+for mb, (kind, text_all) in [(m, kt) for kt in (("binned random qualities", text_binned), ("constant qualities", text_runs)) for m in sizes]:
     text = text_all[:mb << 20]
     piece = 0xff00 * 64
     with ProcessPoolExecutor(max_workers=os.cpu_count()) as pool:
@@ -44,5 +46,5 @@ for mb in sizes:
         assert rc == 0
         best = dt if best is None else min(best, dt)
     assert obuf.array[:total].tobytes() == text
-    print(json.dumps({"text_MB": mb, "blocks": len(blocks), "compressed_MB": round(len(comp) / 2 ** 20, 1), "ratio": round(total / len(comp), 2),
+    print(json.dumps({"data": kind, "text_MB": mb, "blocks": len(blocks), "compressed_MB": round(len(comp) / 2 ** 20, 1), "ratio": round(total / len(comp), 2),
                       "seconds_incl_h2d_d2h": best, "text_GB_per_s": total / best / 1e9}))

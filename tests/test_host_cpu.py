@@ -144,3 +144,67 @@ def test_block_gzip_reader(native, tmp_path):
     p.write_bytes(util.bgzf_bytes(text[:70000])[:-40])
     with pytest.raises(Exception):
         host.bgzf_read_all(p, 1 << 16)
+
+
+def test_device_inflate_decoder_logic_on_the_host(native, tmp_path):
+    """The deflate decoder of gs_inflate.cu (block-gzip members inflated on the device), compiled as plain C++ by
+    tests/inflate_host_harness.cpp and run thread by thread: stored / fixed / dynamic blocks at every compression level and
+    block size against zlib, and every flipped bit detected (size or CRC-32), as gzread / GZIPInputStream would
+    (C/fastq/AbstractFastqReader.java:224 reads through them).  The GPU run of the same kernel is tests/test_gpu_inflate.py."""
+    import ctypes
+    import os
+    import subprocess
+    import zlib
+    import util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "genestrip_b200", "csrc", "gs_inflate.cu")).read()
+    body = src.replace('#include "gs_kernels.cuh"', "").replace("#include <cuda_runtime.h>", "")
+    body = body[:body.index("void gs_launch_inflate_blocks")]
+    inc = tmp_path / "inflate_body.inc"
+    inc.write_text(body)
+    so = tmp_path / "libinflate_harness.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-shared", "-fPIC",
+                    "-DGS_INFLATE_BODY=\"%s\"" % inc, "-o", str(so), os.path.join(root, "tests", "inflate_host_harness.cpp")], check=True)
+    L = ctypes.CDLL(str(so))
+
+    def inflate(comp, blocks, n_out):
+        comp = np.frombuffer(comp, dtype=np.uint8).copy()
+        out = np.zeros(max(n_out, 1), dtype=np.uint8)
+        blocks = blocks.copy()
+        L.gs_inflate_harness_run(comp.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), blocks.ctypes.data_as(ctypes.c_void_p), len(blocks))
+        return out[:n_out].tobytes(), blocks
+
+    rng = np.random.default_rng(1)
+    recs = []
+    for i in range(1500):
+        n = int(rng.integers(30, 300))
+        seq = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n, p=[0.24, 0.25, 0.25, 0.25, 0.01]).tobytes()
+        qual = bytes(rng.integers(33, 74, size=n, dtype=np.uint8)) if i % 3 else b"I" * n
+        recs.append(b"@r%d x\n" % i + seq + b"\n+\n" + qual + b"\n")
+    fastq = b"".join(recs)
+    cases = {"fastq": fastq, "random": bytes(rng.integers(0, 256, size=70000, dtype=np.uint8)), "zeros": b"\0" * 100000, "short": b"A", "empty": b"",
+             "text": b"the quick brown fox " * 3000, "skewed": bytes(np.minimum(rng.geometric(0.08, size=60000), 255).astype(np.uint8))}
+    for name, data in cases.items():
+        for level in (0, 1, 6, 9):
+            for block in (0xff00, 1000, 37):
+                d = data[:8000] if block < 1000 else data
+                comp = util.bgzf_bytes(d, block=block, level=level)
+                blocks, n = native.bgzf_blocks(comp)
+                out, b = inflate(comp, blocks, n)
+                assert n == len(d) and out == d and not b["status"].any(), (name, level, block)
+    d = fastq[:60000]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)      # fixed Huffman codes
+    body = co.compress(d) + co.flush()
+    out, b = inflate(body, np.array([(0, 0, len(body), len(d), zlib.crc32(d), 0)], dtype=native.DEFLATE_BLOCK_DTYPE), len(d))
+    assert out == d and not b["status"].any()
+    comp = util.bgzf_bytes(fastq[:150000])
+    blocks, n = native.bgzf_blocks(comp)
+    for trial in range(120):                                            # any flipped bit is detected
+        c = bytearray(comp)
+        c[int(rng.integers(18, len(c) - 8 - 28))] ^= 1 << int(rng.integers(0, 8))
+        out, b = inflate(bytes(c), blocks, n)
+        assert b["status"].any() or out == fastq[:150000]
+    for field, delta, want in (("in_len", -5, 1), ("out_len", -5, 2), ("crc32", 1, 3)):
+        b2 = blocks.copy()
+        b2[field][0] = int(b2[field][0]) + delta
+        assert inflate(comp, b2, n)[1]["status"][0] == want
