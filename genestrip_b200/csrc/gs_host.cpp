@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -381,6 +382,7 @@ static size_t lastRecordStart(const uint8_t* text, size_t len) {
 // into the pinned chunk (the reference inflates on its single producer thread).  Every block is checked
 // like gzread checks it (CRC-32 and ISIZE); a member without the subfield ends the fast path at that byte (`foreignAt`),
 // where the caller goes on with zlib's sequential reader, so the text never depends on which path produced it.
+static std::atomic<uint64_t> g_deviceInflateNanos{0}, g_deviceInflateCalls{0}, g_bgzfReadNanos{0};
 static std::atomic<uint64_t> g_deviceInflatedBlocks{0};   // block-gzip members inflated on the device by this process (tests, benchmarks)
 
 class BgzfReader {
@@ -409,6 +411,8 @@ public:
     void drainCarry(std::vector<uint8_t>& out) { out.insert(out.end(), carry_.begin() + (long)carryPos_, carry_.end()); carryPos_ = carry_.size(); }
     // up to `want` bytes of inflated text into dst; fewer only at the end of the file or in front of a foreign member
     size_t read(uint8_t* dst, size_t want) {
+        struct Timer { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+                       ~Timer() { g_bgzfReadNanos += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } } timer;
         size_t done = 0;
         while (done < want) {
             if (carryPos_ < carry_.size()) {
@@ -496,7 +500,10 @@ private:
                 tab[i] = gs_deflate_block{b.off + b.hdr, b.out, (uint32_t)(b.total - b.hdr - 8), b.isize,
                                           (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24), 0u};
             }
+            const auto t0 = std::chrono::steady_clock::now();
             const int rc = gs_inflate_blocks(ctx_, cbuf, off, tab.data(), (uint32_t)tab.size(), target, out);
+            g_deviceInflateNanos += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+            g_deviceInflateCalls += 1;
             if (rc == GS_ERR_DATA) fail("read error");   // corrupt block (gzread: data error / incorrect data check)
             if (rc != GS_OK) fail(std::string("gs_inflate_blocks: ") + gs_last_error());
             g_deviceInflatedBlocks += blocks.size();
@@ -1366,6 +1373,8 @@ gsh_result* gsh_bgzf_read_all(const char* path, size_t request, int64_t* foreign
 }
 
 uint64_t gsh_device_inflated_blocks(void) { return g_deviceInflatedBlocks.load(); }
+// [0] seconds inside gs_inflate_blocks, [1] calls, [2] seconds inside BgzfReader::read (either inflater), since the process started
+void gsh_bgzf_timers(double* out) { out[0] = g_deviceInflateNanos.load() * 1e-9; out[1] = (double)g_deviceInflateCalls.load(); out[2] = g_bgzfReadNanos.load() * 1e-9; }
 
 // The feeder's record-boundary search alone (no GPU): offset of the last record start in text[0, len), 0 = none in sight.
 size_t gsh_last_record_start(const uint8_t* text, size_t len) { return lastRecordStart(text, len); }

@@ -62,7 +62,8 @@ struct BitReader {
 // left-justified (15-bit) first code beyond length l, base[l] = index of length l's first symbol minus its first code.
 // 0 = complete, > 0 = incomplete, < 0 = over-subscribed; coded = symbols that have a code.  limit[] is indexed by
 // constants only (registers).
-// tab (or nullptr): direct look-up by the next tabBits bits of the stream: symbol | code length << 9, 0 = the code is longer.
+// tab (or nullptr): direct look-up by the next tabBits bits of the stream: symbol | code length << 9 | (symbol < 256) << 15,
+// 0 = the code is longer.
 __device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1], int* base, u16* symbol, const u8* length, int n, int& coded,
                                                 u16* tab = nullptr, int tabBits = 0) {
     u16 count[GS_INF_MAXBITS + 1], offs[GS_INF_MAXBITS + 1];
@@ -95,7 +96,7 @@ __device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1]
         int si = 0;
         for (int l = 1; l <= tabBits; l++) {
             for (u32 c = 0; c < count[l]; c++, si++, code++) {
-                const u16 e = (u16)(symbol[si] | (l << 9));
+                const u16 e = (u16)(symbol[si] | (l << 9) | (symbol[si] < 256 ? 0x8000 : 0));   // bit 15: a literal (or a distance symbol: not looked at)
                 for (u32 k = __brev(code) >> (32 - l); k < (1u << tabBits); k += 1u << l) tab[k] = e;
             }
             code <<= 1;
@@ -120,7 +121,7 @@ __device__ __forceinline__ int gs_inf_decode_tab(BitReader& br, const u16* tab, 
                                                  const u16* symbol) {
     const u32 e = tab[(u32)br.buf & tabMask];
     if (e == 0) return gs_inf_decode(br, limit, base, symbol);
-    const int len = (int)(e >> 9);
+    const int len = (int)(e >> 9) & 15;
     br.buf >>= len; br.cnt -= len;
     return (int)(e & 0x1FFu);
 }
@@ -236,6 +237,16 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
         // literals and matches until the end-of-block symbol
         for (;;) {
             if (br.cnt < 48) br.refill();   // a length/distance pair takes at most 15 + 5 + 15 + 13 = 48 bits
+            // literals whose code the table holds take the short way round: one load, one store, one shift.  (Bits read
+            // past the end of the input are zeros and are noticed below or at the end of the block: cnt < 0.)
+            u32 e = ltab[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
+            while ((e & 0x8000u) && o < outLen) {
+                out[o++] = (u8)e;
+                const int l = (int)(e >> 9) & 15;
+                br.buf >>= l; br.cnt -= l;
+                if (br.cnt < 48) br.refill();
+                e = ltab[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
+            }
             int sym = gs_inf_decode_tab(br, ltab, (1u << GS_INF_LBITS) - 1u, llimit, lidx, lsym);
             if (sym < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
             if (sym < 256) {

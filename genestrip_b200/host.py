@@ -169,6 +169,13 @@ def device_inflated_blocks():
     return int(_lib().gsh_device_inflated_blocks())
 
 
+def bgzf_timers():
+    """(seconds inside gs_inflate_blocks, calls, seconds inside the block-gzip reader) of this process so far."""
+    out = (C.c_double * 3)()
+    _lib().gsh_bgzf_timers(out)
+    return float(out[0]), int(out[1]), float(out[2])
+
+
 def bgzf_read_all(path, request=1 << 20):
     """The feeder's block-gzip reader alone (no GPU): (inflated text, compressed offset of a non-BGZF member that ended the
     fast path or -1), reading `request` bytes at a time."""

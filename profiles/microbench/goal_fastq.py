@@ -84,6 +84,7 @@ if os.environ.get("GS_BGZF"):
         if env:
             os.environ[env.split("=")[0]] = env.split("=")[1]
         dt = None
+        tm0 = host.bgzf_timers()
         for rep in range(1 if env and "NO_BGZF" in env else 2):
             t0 = time.perf_counter()
             r = host.match_goal(db, meta, [gz_path], gpu_parse=True, text_chunk_bytes=chunk_mb << 20)
@@ -93,6 +94,8 @@ if os.environ.get("GS_BGZF"):
             os.environ.pop(env.split("=")[0], None)
         assert r.total_reads == n_reads
         res[name] = {"seconds": dt, "reads_per_s": n_reads / dt, "kmers_per_s": r.total_kmers / dt, "text_GB_per_s": size / dt / 1e9,
+                     "inflate_call_s_all_reps": host.bgzf_timers()[0] - tm0[0], "inflate_calls_all_reps": host.bgzf_timers()[1] - tm0[1],
+                     "bgzf_reader_s_all_reps": host.bgzf_timers()[2] - tm0[2],
                      "text_chunks": r.text_chunks, "same_csv_as_plain_file": __import__("hashlib").md5(r.csv).hexdigest() == res["gpu_feeder_csv_md5"]}
     res["inflate_threads"] = int(os.environ.get("GS_INFLATE_THREADS", "0")) or min(32, os.cpu_count())
     res["device_inflated_blocks"] = host.device_inflated_blocks()
