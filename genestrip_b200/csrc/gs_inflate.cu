@@ -7,7 +7,7 @@
 // block gets its own warp, whose first lane walks the bit stream (lanes that decode different blocks side by side diverge
 // at every symbol and end up serialized -- measured: 32 blocks per warp took 32 x as long as one).  What keeps the walk
 // short: a symbol whose code has at most 10 bits (8 for distances) is one shared-memory load from a per-warp look-up
-// table indexed by the next bits of the stream; longer codes need no dependent loads to find their length either -- the
+// table indexed by the next bits of the stream, two literals whose codes fit those bits together are one load as well; longer codes need no dependent loads to find their length either -- the
 // canonical code's left-justified first-code limits of the 15 code lengths sit in registers and the code length is the
 // number of limits the next 15 bits reach (15 independent compares).  Matches are copied eight bytes at a time, runs
 // (distance below 8) from a register that holds the period.
@@ -37,12 +37,15 @@ struct BitReader {
     int cnt;  // valid bits in buf; negative = the stream was read past its end
     __device__ __forceinline__ void refill() {
         if (pos + 8 <= end) {
-            // eight independent byte loads; the bits above cnt are the stream's next bits and are ORed in again, unchanged,
-            // by the next refill
-            u64 w = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) w |= (u64)in[pos + j] << (8 * j);
-            buf |= w << cnt;
+            // the next eight bytes from three aligned 32-bit loads (the stream starts at any byte of the buffer); the bits
+            // above cnt are the stream's next bits and are ORed in again, unchanged, by the next refill
+            const size_t a = (size_t)(in + pos);
+            const u32* w = (const u32*)(a & ~(size_t)3);
+            const u32 sh = (u32)(a & 3u) * 8u;
+            const u32 w0 = w[0], w1 = w[1], w2 = sh ? w[2] : 0u;
+            const u64 lo = ((u64)w1 << 32) | w0;
+            const u64 v = sh ? (lo >> sh) | ((u64)w2 << (64u - sh)) : lo;
+            buf |= v << cnt;
             const int adv = (63 - cnt) >> 3;
             pos += (u32)adv; cnt += adv * 8;
         } else {
@@ -63,9 +66,9 @@ struct BitReader {
 // 0 = complete, > 0 = incomplete, < 0 = over-subscribed; coded = symbols that have a code.  limit[] is indexed by
 // constants only (registers).
 // tab (or nullptr): direct look-up by the next tabBits bits of the stream: symbol | code length << 9 | (symbol < 256) << 15,
-// 0 = the code is longer.
+// 0 = the code is longer; pairs (or nullptr): see below.
 __device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1], int* base, u16* symbol, const u8* length, int n, int& coded,
-                                                u16* tab = nullptr, int tabBits = 0) {
+                                                u16* tab = nullptr, int tabBits = 0, u32* pairs = nullptr) {
     u16 count[GS_INF_MAXBITS + 1], offs[GS_INF_MAXBITS + 1];
     for (int l = 0; l <= GS_INF_MAXBITS; l++) count[l] = 0;
     for (int s = 0; s < n; s++) count[length[s]]++;
@@ -101,6 +104,21 @@ __device__ __forceinline__ int gs_inf_construct(u32 (&limit)[GS_INF_MAXBITS + 1]
             }
             code <<= 1;
         }
+        if (pairs) {
+            // two literals in one look-up where the table's bits hold both codes (bases are 2-bit codes in FASTQ text):
+            // first | second << 8 | bits of both << 16, 0 = no such pair
+            for (u32 i = 0; i < (1u << tabBits); i++) {
+                const u32 e1 = tab[i];
+                u32 p = 0;
+                if (e1 & 0x8000u) {
+                    const u32 l1 = (e1 >> 9) & 15u;
+                    const u32 e2 = tab[i >> l1];
+                    const u32 l2 = (e2 >> 9) & 15u;
+                    if ((e2 & 0x8000u) && l1 + l2 <= (u32)tabBits) p = (e1 & 0xFFu) | ((e2 & 0xFFu) << 8) | ((l1 + l2) << 16);
+                }
+                pairs[i] = p;
+            }
+        }
     }
     return coded == 0 ? 0 : left;
 }
@@ -135,18 +153,19 @@ __device__ __forceinline__ int gs_inf_decode_tab(BitReader& br, const u16* tab, 
 
 __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(const u8* __restrict__ comp, u8* __restrict__ text, gs_deflate_block* blocks,
                                                                              u32 nBlocks) {
-    __shared__ u16 s_lbase[29], s_dbase[30];
-    __shared__ u8 s_lext[29], s_dext[30], s_order[19];
+    __shared__ u32 s_ltab2[29], s_dtab2[30];   // base | extra bits << 16
+    __shared__ u8 s_order[19];
     __shared__ u32 s_crc[4][256];
     __shared__ u16 s_ltab[GS_INF_WARPS][1 << GS_INF_LBITS], s_dtab[GS_INF_WARPS][1 << GS_INF_DBITS];
+    __shared__ u32 s_lpair[GS_INF_WARPS][1 << GS_INF_LBITS];
     {   // RFC 1951 3.2.5 / 3.2.7 tables and the CRC-32 tables (polynomial 0xEDB88320, RFC 1952 8; slicing by 4), once per CTA
         const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
         const u8 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
         const u16 dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
         const u8 dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
         const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-        if (threadIdx.x < 29) { s_lbase[threadIdx.x] = lbase[threadIdx.x]; s_lext[threadIdx.x] = lext[threadIdx.x]; }
-        if (threadIdx.x < 30) { s_dbase[threadIdx.x] = dbase[threadIdx.x]; s_dext[threadIdx.x] = dext[threadIdx.x]; }
+        if (threadIdx.x < 29) s_ltab2[threadIdx.x] = (u32)lbase[threadIdx.x] | ((u32)lext[threadIdx.x] << 16);
+        if (threadIdx.x < 30) s_dtab2[threadIdx.x] = (u32)dbase[threadIdx.x] | ((u32)dext[threadIdx.x] << 16);
         if (threadIdx.x < 19) s_order[threadIdx.x] = order[threadIdx.x];
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
             u32 c = i;
@@ -167,6 +186,7 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
     const u32 outLen = B.out_len;
     u16* ltab = s_ltab[threadIdx.x >> 5];
     u16* dtab = s_dtab[threadIdx.x >> 5];
+    u32* lpair = s_lpair[threadIdx.x >> 5];
     u32 o = 0;
     BitReader br{comp + B.in_off, 0u, B.in_len, 0ULL, 0};
     u32 llimit[GS_INF_MAXBITS + 1], dlimit[GS_INF_MAXBITS + 1];   // registers
@@ -201,7 +221,7 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             for (int s = 144; s < 256; s++) lengths[s] = 9;
             for (int s = 256; s < 280; s++) lengths[s] = 7;
             for (int s = 280; s < GS_INF_MAXL; s++) lengths[s] = 8;
-            gs_inf_construct(llimit, lidx, lsym, lengths, GS_INF_MAXL, coded, ltab, GS_INF_LBITS);
+            gs_inf_construct(llimit, lidx, lsym, lengths, GS_INF_MAXL, coded, ltab, GS_INF_LBITS, lpair);
             for (int s = 0; s < GS_INF_MAXD; s++) lengths[s] = 5;
             gs_inf_construct(dlimit, didx, dsym, lengths, GS_INF_MAXD, coded, dtab, GS_INF_DBITS);
         } else {           // dynamic codes (RFC 1951 3.2.7)
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             }
             if (err) break;
             if (lengths[256] == 0) { err = GS_INF_ERR_STREAM; break; }
-            int e = gs_inf_construct(llimit, lidx, lsym, lengths, nlen, coded, ltab, GS_INF_LBITS);
+            int e = gs_inf_construct(llimit, lidx, lsym, lengths, nlen, coded, ltab, GS_INF_LBITS, lpair);
             if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
             e = gs_inf_construct(dlimit, didx, dsym, lengths + nlen, ndist, coded, dtab, GS_INF_DBITS);
             if (e < 0 || (e > 0 && coded != 1)) { err = GS_INF_ERR_STREAM; break; }
@@ -239,13 +259,21 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             if (br.cnt < 48) br.refill();   // a length/distance pair takes at most 15 + 5 + 15 + 13 = 48 bits
             // literals whose code the table holds take the short way round: one load, one store, one shift.  (Bits read
             // past the end of the input are zeros and are noticed below or at the end of the block: cnt < 0.)
+            u32 pe = lpair[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
+            while (pe != 0 && o + 2 <= outLen) {   // two literals at once
+                out[o] = (u8)pe; out[o + 1] = (u8)(pe >> 8);
+                o += 2;
+                const int l = (int)(pe >> 16);
+                br.buf >>= l; br.cnt -= l;
+                if (br.cnt < 48) br.refill();
+                pe = lpair[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
+            }
             u32 e = ltab[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
-            while ((e & 0x8000u) && o < outLen) {
+            if ((e & 0x8000u) && o < outLen) {     // one literal, then pairs again
                 out[o++] = (u8)e;
                 const int l = (int)(e >> 9) & 15;
                 br.buf >>= l; br.cnt -= l;
-                if (br.cnt < 48) br.refill();
-                e = ltab[(u32)br.buf & ((1u << GS_INF_LBITS) - 1u)];
+                continue;
             }
             int sym = gs_inf_decode_tab(br, ltab, (1u << GS_INF_LBITS) - 1u, llimit, lidx, lsym);
             if (sym < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
@@ -257,23 +285,37 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             if (sym == 256) break;
             sym -= 257;
             if (sym >= 29) { err = GS_INF_ERR_STREAM; break; }
-            const u32 len = (u32)s_lbase[sym] + br.take(s_lext[sym]);
+            const u32 lt = s_ltab2[sym];
+            const u32 len = (lt & 0xFFFFu) + br.take((int)(lt >> 16));
             const int ds = gs_inf_decode_tab(br, dtab, (1u << GS_INF_DBITS) - 1u, dlimit, didx, dsym);
             if (ds < 0 || br.cnt < 0) { err = GS_INF_ERR_STREAM; break; }
-            const u32 dist = (u32)s_dbase[ds] + br.take(s_dext[ds]);
+            const u32 dt = s_dtab2[ds];
+            const u32 dist = (dt & 0xFFFFu) + br.take((int)(dt >> 16));
             if (br.cnt < 0 || dist > o) { err = GS_INF_ERR_STREAM; break; }
             if (o + len > outLen) { err = GS_INF_ERR_SIZE; break; }
             const u8* from = out + o - dist;
             if (dist >= 8) {
                 // eight bytes at a time: source and destination of a group do not overlap, so the loads are independent of
-                // the stores (a byte-by-byte copy waits for a full load latency per byte: the compiler must keep the order)
-                for (u32 i = 0; i < len; i += 8) {
-                    const u32 n = len - i;
-                    u64 t = 0;
+                // the stores (a byte-by-byte copy waits for a full load latency per byte: the compiler must keep the order).
+                // While there is room, whole groups are written: the bytes beyond the match are overwritten by what follows.
+                const u32 groups = (len + 7u) & ~7u;
+                if (o + groups <= outLen) {
+                    for (u32 i = 0; i < groups; i += 8) {
+                        u8 t[8];
 #pragma unroll
-                    for (u32 j = 0; j < 8; j++) if (j < n) t |= (u64)from[i + j] << (8 * j);
+                        for (u32 j = 0; j < 8; j++) t[j] = from[i + j];
 #pragma unroll
-                    for (u32 j = 0; j < 8; j++) if (j < n) out[o + i + j] = (u8)(t >> (8 * j));
+                        for (u32 j = 0; j < 8; j++) out[o + i + j] = t[j];
+                    }
+                } else {
+                    for (u32 i = 0; i < len; i += 8) {
+                        const u32 n = len - i;
+                        u64 t = 0;
+#pragma unroll
+                        for (u32 j = 0; j < 8; j++) if (j < n) t |= (u64)from[i + j] << (8 * j);
+#pragma unroll
+                        for (u32 j = 0; j < 8; j++) if (j < n) out[o + i + j] = (u8)(t >> (8 * j));
+                    }
                 }
             } else {
                 // the match overlaps its own output (runs, short periods): the period goes into a register once
