@@ -319,6 +319,18 @@ def test_filter_goal_gpu_fastq_feeder(project, oracle, native, gpu_ctx, host):
                 np.testing.assert_array_equal(res.accept, orun.accept)
                 assert res.filtered == orun.filtered and res.rest == orun.rest
                 assert (res.total_reads, res.total_kmers, res.total_bps) == (orun.total_reads, orun.total_kmers, orun.total_bps)
+        # the same text as a block-gzip file: inflated on the device the filter index lives on (gs_filter_context)
+        import tempfile
+        orun = oracle.filter_files(flt_o, K, [fq + tail], min_pos_count=1, pos_ratio=0.2, with_probs=True)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "in.fastq.gz")
+            open(path, "wb").write(util.bgzf_bytes(fq + tail, block=4000))
+            before = host.device_inflated_blocks()
+            res = host.filter_goal(gflt, K, [path], with_probs=True, text_chunk_bytes=400000, batch_reads=900)
+            assert host.device_inflated_blocks() - before >= 64
+        assert res.text_chunks_refused == 1
+        np.testing.assert_array_equal(res.accept, orun.accept)
+        assert res.filtered == orun.filtered and res.rest == orun.rest
     finally:
         gflt.close()
 
