@@ -12,7 +12,8 @@
 // number of limits the next 15 bits reach (15 independent compares).  Matches are copied eight bytes at a time, runs
 // (distance below 8) from a register that holds the period.
 // Every block is checked like gzread / GZIPInputStream check it: the stream must end exactly at ISIZE bytes and the
-// CRC-32 (slicing-by-4, tables in shared memory) must match the member's trailer.  No loop runs longer than the block's
+// CRC-32 (all 32 lanes: a slice each by slicing-by-4 from shared tables, combined like zlib's crc32_combine) must match
+// the member's trailer.  No loop runs longer than the block's
 // input bits plus its output bytes, whatever the input holds.
 #include "gs_kernels.cuh"
 
@@ -144,6 +145,35 @@ __device__ __forceinline__ int gs_inf_decode_tab(BitReader& br, const u16* tab, 
     return (int)(e & 0x1FFu);
 }
 
+// ---- CRC-32 (RFC 1952 8) of a block by the whole warp: every lane takes a slice, the slices' CRCs are combined with
+// crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B)  (polynomials in the reflected representation, as zlib's crc32_combine)
+__device__ __forceinline__ u32 gs_crc_bytes(const u8* p, u32 n, const u32 (*T)[256]) {
+    u32 crc = 0xFFFFFFFFu, i = 0;
+    for (; i < n && ((size_t)(p + i) & 3u); i++) crc = T[0][(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+    for (; i + 4 <= n; i += 4) {   // slicing by four
+        crc ^= *(const u32*)(p + i);
+        crc = T[3][crc & 0xFFu] ^ T[2][(crc >> 8) & 0xFFu] ^ T[1][(crc >> 16) & 0xFFu] ^ T[0][crc >> 24];
+    }
+    for (; i < n; i++) crc = T[0][(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+    return crc ^ 0xFFFFFFFFu;
+}
+__device__ __forceinline__ u32 gs_crc_mul(u32 a, u32 b) {   // a * b mod P
+    u32 p = 0;
+    for (u32 m = 1u << 31; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+__device__ __forceinline__ u32 gs_crc_xpow8(u32 n) {        // x^(8 n) mod P
+    u32 r = 1u << 31, base = 1u << 23;                       // x^0, x^8
+    for (; n; n >>= 1) {
+        if (n & 1u) r = gs_crc_mul(r, base);
+        base = gs_crc_mul(base, base);
+    }
+    return r;
+}
+
 }  // namespace
 
 // status written per block: 0 = ok, else the first reason the block is not what its trailer says
@@ -180,7 +210,8 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
     }
     __syncthreads();
     const u32 bi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one block per warp
-    if (bi >= nBlocks || (threadIdx.x & 31) != 0) return;                 // the bit stream is walked by the warp's first lane
+    if (bi >= nBlocks) return;
+    const u32 lane = threadIdx.x & 31u;
     const gs_deflate_block B = blocks[bi];
     u8* out = text + B.out_off;
     const u32 outLen = B.out_len;
@@ -194,7 +225,7 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
     u16 lsym[GS_INF_MAXL], dsym[GS_INF_MAXD];
     u8 lengths[GS_INF_MAXL + GS_INF_MAXD + 2];
     u32 err = 0;
-    bool last = false;
+    bool last = lane != 0;   // the bit stream is walked by the warp's first lane; the others join again for the CRC
     while (!last && !err) {
         br.refill();
         last = br.take(1) != 0;
@@ -331,17 +362,35 @@ __global__ void __launch_bounds__(GS_INF_WARPS * 32) gs_inflate_blocks_kernel(co
             o += len;
         }
     }
-    if (!err && o != outLen) err = GS_INF_ERR_SIZE;
-    if (!err) {
-        u32 crc = 0xFFFFFFFFu, i = 0;
-        for (; i < outLen && ((size_t)(out + i) & 3u); i++) crc = s_crc[0][(crc ^ out[i]) & 0xFFu] ^ (crc >> 8);
-        for (; i + 4 <= outLen; i += 4) {
-            crc ^= *(const u32*)(out + i);
-            crc = s_crc[3][crc & 0xFFu] ^ s_crc[2][(crc >> 8) & 0xFFu] ^ s_crc[1][(crc >> 16) & 0xFFu] ^ s_crc[0][crc >> 24];
+    if (lane == 0 && !err && o != outLen) err = GS_INF_ERR_SIZE;
+    // ---- CRC-32 of the output: a slice per lane, combined in slice order
+    const u32 slice = (((outLen + 31u) / 32u) + 3u) & ~3u;
+    u32 acc = 0;
+#ifdef GS_INFLATE_HOST_HARNESS
+    if (!err) {   // (the host harness runs one lane: it walks the 32 slices itself)
+        const u32 mSlice = gs_crc_xpow8(slice);
+        for (u32 i = 0; i < 32; i++) {
+            const u32 start = i * slice < outLen ? i * slice : outLen, n = outLen - start < slice ? outLen - start : slice;
+            const u32 ci = gs_crc_bytes(out + start, n, s_crc);
+            if (n) acc = i == 0 ? ci : gs_crc_mul(n == slice ? mSlice : gs_crc_xpow8(n), acc) ^ ci;
         }
-        for (; i < outLen; i++) crc = s_crc[0][(crc ^ out[i]) & 0xFFu] ^ (crc >> 8);
-        if ((crc ^ 0xFFFFFFFFu) != B.crc32) err = GS_INF_ERR_CRC;
     }
+#else
+    __syncwarp();
+    err = __shfl_sync(0xFFFFFFFFu, err, 0);
+    if (!err) {
+        const u32 myStart = lane * slice < outLen ? lane * slice : outLen, myN = outLen - myStart < slice ? outLen - myStart : slice;
+        const u32 c = gs_crc_bytes(out + myStart, myN, s_crc);
+        const u32 mSlice = gs_crc_xpow8(slice);
+        for (u32 i = 0; i < 32; i++) {
+            const u32 start = i * slice < outLen ? i * slice : outLen, n = outLen - start < slice ? outLen - start : slice;
+            const u32 ci = __shfl_sync(0xFFFFFFFFu, c, (int)i);
+            if (n) acc = i == 0 ? ci : gs_crc_mul(n == slice ? mSlice : gs_crc_xpow8(n), acc) ^ ci;
+        }
+    }
+    if (lane != 0) return;
+#endif
+    if (!err && acc != B.crc32) err = GS_INF_ERR_CRC;
     blocks[bi].status = err;
 }
 

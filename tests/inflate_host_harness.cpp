@@ -22,6 +22,7 @@ static inline uint32_t __brev(uint32_t v) {
     return r;
 }
 struct gs_deflate_block { uint64_t in_off, out_off; uint32_t in_len, out_len, crc32, status; };
+#define GS_INFLATE_HOST_HARNESS 1
 #include GS_INFLATE_BODY
 
 extern "C" int gs_inflate_harness_run(const uint8_t* comp, uint8_t* text, gs_deflate_block* blocks, uint32_t n) {
