@@ -44,6 +44,9 @@ final class GsNative {
     // db goal, update phase (DBGoal.MyFastaReader): value = LCA(value, region node) for the stored k-mers of the regions
     static native long dbUpdate(long db, ByteBuffer seq, long nBytes, long[] regionOffsets, int[] regionValueIndex, boolean upperCase);
     static native void dbGetValues(long db, long offset, short[] vals, int n);
+    // block-gzip input: blocks = nBlocks x {long inOff, long outOff, int inLen, int outLen, int crc32, int status} (little endian),
+    // filled from the members' headers ('BC' subfield) and trailers; throws when a member is corrupt, like GZIPInputStream
+    static native void inflateBlocks(long ctx, ByteBuffer comp, long compBytes, ByteBuffer blocks, int nBlocks, ByteBuffer out, long outBytes);
 }
 
 /**
