@@ -137,6 +137,7 @@ extern "C" gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices) {
 extern "C" void gs_ctx_destroy(gs_ctx* c) { delete c; }
 extern "C" int gs_ctx_n_devices(const gs_ctx* c) { return c ? (int)c->devs.size() : 0; }
 
+static_assert(sizeof(gs_deflate_block) == 32, "gs_deflate_block is part of the ABI: 2 x u64 + 4 x u32");
 // Block-gzip members -> text on the device (gs_inflate.cu), see genestrip_b200.h
 extern "C" int gs_inflate_blocks(gs_ctx* c, const uint8_t* comp, uint64_t comp_bytes, gs_deflate_block* blocks, uint32_t n_blocks,
                                  uint8_t* out, uint64_t out_bytes) {

@@ -31,6 +31,7 @@ def test_struct_layouts(native):
     assert native.RUN_DTYPE.itemsize == 8
     assert native.EVENT_DTYPE.itemsize == 16
     assert native.TAXON_COUNTS_DTYPE.itemsize == 80
+    assert native.DEFLATE_BLOCK_DTYPE.itemsize == 32 and native.FASTQ_REC_DTYPE.itemsize == 16
     cfg = native.default_match_cfg()
     # defaults of C/GSConfigKey.java:302-350
     assert (cfg.classify_reads, cfg.count_unique_kmers, cfg.max_kmer_res_counts, cfg.use_bloom_filter) == (1, 1, 0, 1)
