@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 4
+GS_ABI_VERSION = 5
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -84,6 +84,13 @@ _SIGS = {
     "gs_match_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P),
                                         _P, _P, C.c_uint64]),
     "gs_match_finish": (C.c_int, [_P, _P, _P]),
+    "gs_comm_unique_id": (C.c_int, [_P]),
+    "gs_comm_create": (_P, [_P, _P, C.c_int, C.c_int]),
+    "gs_comm_world": (C.c_int, [_P]),
+    "gs_comm_rank": (C.c_int, [_P]),
+    "gs_comm_destroy": (None, [_P]),
+    "gs_match_finish_comm": (C.c_int, [_P, _P, _P, _P]),
+    "gs_match_merge_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "gs_match_close": (None, [_P]),
     "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
     "gs_match_sync": (C.c_int, [_P]),
@@ -178,6 +185,29 @@ class Context:
     def close(self):
         if self.h:
             lib().gs_ctx_destroy(self.h)
+            self.h = None
+
+
+class Comm:
+    """gs_comm: this process' GPU as rank `rank` of `world` (one process per GPU); NCCL underneath, loaded at run time."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().gs_comm_unique_id(C.cast(buf, _P)))
+        return bytes(buf)
+
+    def __init__(self, ctx, unique_id, world, rank):
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self.h = lib().gs_comm_create(ctx.h, C.cast(buf, _P), int(world), int(rank))
+        if not self.h:
+            raise GenestripError(-2, lib().gs_last_error().decode())
+        self.world, self.rank = int(world), int(rank)
+
+    def close(self):
+        if self.h:
+            lib().gs_comm_destroy(self.h)
             self.h = None
 
 
@@ -436,14 +466,24 @@ class MatchSession:
             res = res + (run_off, runs[:int(run_off[n_reads])])
         return res
 
-    def finish(self):
+    def finish(self, comm=None):
+        """End of the run.  With `comm` (one process per GPU): the collective merge over all ranks, gs_match_finish_comm."""
         V = self.db.n_values
         counts = np.zeros(max(V, 1), dtype=TAXON_COUNTS_DTYPE)
         top = None
         if self.cfg.count_unique_kmers and self.cfg.max_kmer_res_counts > 0:
             top = np.zeros((V + 1, self.cfg.max_kmer_res_counts), dtype=np.int16)
-        _check(lib().gs_match_finish(self.h, _ptr(counts), _ptr(top)))
+        if comm is None:
+            _check(lib().gs_match_finish(self.h, _ptr(counts), _ptr(top)))
+        else:
+            _check(lib().gs_match_finish_comm(self.h, comm.h, _ptr(counts), _ptr(top)))
         return counts[:V], top
+
+    def merge_stats(self):
+        """(total_ms, bitset_ms, bytes read from the other ranks, path) of the last multi-GPU merge; path 1 = peer mappings, 2 = NCCL."""
+        a, b, n, p = C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_int(0)
+        _check(lib().gs_match_merge_stats(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(p)))
+        return a.value, b.value, n.value, p.value
 
     # ---- device-resident variants (bench kernel-only number, NCCL reduction of raw state)
     def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, first_read_no, d_out_ptr):

@@ -2,6 +2,8 @@
 // double-buffered batches on side streams, end-of-run merge.  No CPU fallback: every compute entry point needs a
 // CUDA device and fails with GS_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the functions are resolved with dlopen (gs_nccl), the library does not link against NCCL
 
 #include <algorithm>
 #include <cstdarg>
@@ -75,11 +77,61 @@ static cudaError_t hgrow(T** p, size_t* cap, size_t need) {
 static u64 magic_for(u64 d) { return d ? (~0ULL) / d : 0; }
 
 // ---------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time: "libnccl.so.2" is the copy the host process already loaded (torch's, the JVM's) or the system's.
+// Only the end-of-run merge across GPUs needs it; everything else works without.
+// ---------------------------------------------------------------------------------------------------------
+struct GsNccl {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+static GsNccl* gs_nccl() {
+    static GsNccl N;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("GS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            N.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (N.handle) break;
+        }
+        if (!N.handle) { N.error = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found") + "; set GS_NCCL_LIB"; return; }
+        bool ok = true;
+        auto sym = [&](const char* name) { void* p = dlsym(N.handle, name); if (!p) { ok = false; N.error = std::string("NCCL symbol missing: ") + name; } return p; };
+        *(void**)&N.GetUniqueId = sym("ncclGetUniqueId"); *(void**)&N.CommInitRank = sym("ncclCommInitRank"); *(void**)&N.CommInitAll = sym("ncclCommInitAll");
+        *(void**)&N.CommDestroy = sym("ncclCommDestroy"); *(void**)&N.AllReduce = sym("ncclAllReduce"); *(void**)&N.AllGather = sym("ncclAllGather");
+        *(void**)&N.Send = sym("ncclSend"); *(void**)&N.Recv = sym("ncclRecv"); *(void**)&N.GroupStart = sym("ncclGroupStart"); *(void**)&N.GroupEnd = sym("ncclGroupEnd");
+        *(void**)&N.GetErrorString = sym("ncclGetErrorString");
+        if (!ok) { dlclose(N.handle); N.handle = nullptr; }
+    });
+    return N.handle ? &N : nullptr;
+}
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return gs_fail(GS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, gs_nccl()->GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------
+struct gs_comm;
 struct gs_ctx {
     std::vector<int> devs;
     std::vector<int> sms;
+    bool peerAll = true;            // every device of the context can map every other one's memory
+    gs_comm* allComm = nullptr;     // communicator over the context's own devices (gs_match_finish with n_devices > 1), made on first use
     // gs_inflate_blocks: scratch on device 0, one call at a time
     std::mutex infMutex;
     cudaStream_t infStream = nullptr;
@@ -121,6 +173,7 @@ extern "C" gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices) {
             int can = 0;
             cudaDeviceCanAccessPeer(&can, c->devs[i], c->devs[j]);
             if (can) { cudaSetDevice(c->devs[i]); cudaDeviceEnablePeerAccess(c->devs[j], 0); cudaGetLastError(); }
+            else c->peerAll = false;
         }
     // The path is random 8-byte probes into multi-GB arrays: keep the L2 from promoting every 32-byte sector miss to a
     // 64/128-byte DRAM fetch (measured with ncu: 2.5 DRAM sectors per missed sector at the default granularity).
@@ -134,7 +187,11 @@ extern "C" gs_ctx* gs_ctx_create(const int* device_ordinals, int n_devices) {
     cudaSetDevice(c->devs[0]);
     return c;
 }
-extern "C" void gs_ctx_destroy(gs_ctx* c) { delete c; }
+extern "C" void gs_comm_destroy(gs_comm*);
+extern "C" void gs_ctx_destroy(gs_ctx* c) {
+    if (c && c->allComm) { gs_comm_destroy(c->allComm); c->allComm = nullptr; }
+    delete c;
+}
 extern "C" int gs_ctx_n_devices(const gs_ctx* c) { return c ? (int)c->devs.size() : 0; }
 
 static_assert(sizeof(gs_deflate_block) == 32, "gs_deflate_block is part of the ABI: 2 x u64 + 4 x u32");
@@ -210,6 +267,7 @@ struct gs_db {
     u64 nBuckets = 0;
     // probe table
     int tbits = 0, rbits = 0;
+    u64 tabBuckets = 0;       // 2^tbits + GS_TAB_PAD_BUCKETS
     int mzBits = 0;  // log2 of the minimizer prefilter's size in bits; 0 = none
     bool mzWide = false;  // minimizers ordered by a 64-bit hash (stores whose filter would use most of the 32-bit hash space)
     bool seenLeased = false;  // the table's in-line seen bits belong to at most one unique-counting session at a time
@@ -360,6 +418,28 @@ extern "C" int gs_db_build_bloom_blocked(gs_db* db, int64_t* words_out, uint64_t
     return GS_OK;
 }
 
+// Probe table of device 0 from its sorted keys / converted values: deterministic placement (gs_kernels.cu "probe table build").
+static int build_table(gs_db* db) {
+    DevDb& d0 = db->d[0];
+    const u64 nB = db->tabBuckets;
+    const u64 nBlocks = gs_table_scan_blocks(nB);
+    u32 *counts = nullptr, *delta = nullptr, *blockIn = nullptr, *bad = nullptr;
+    long long* agg = nullptr;
+    struct Scratch { u32 **a, **b, **c, **d; long long** e; ~Scratch() { cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*d); cudaFree(*e); } } guard{&counts, &delta, &blockIn, &bad, &agg};
+    if (!d0.tab) CU(dmalloc(&d0.tab, nB * 4));
+    CU(dmalloc(&counts, nB)); CU(dmalloc(&delta, nB + 1)); CU(dmalloc(&blockIn, nBlocks)); CU(dmalloc(&agg, nBlocks * 2)); CU(dmalloc(&bad, 1));
+    CU(cudaMemset(d0.tab, 0, nB * 32));
+    CU(cudaMemset(counts, 0, nB * sizeof(u32)));
+    CU(cudaMemset(bad, 0, sizeof(u32)));
+    gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, delta, agg, blockIn, bad, nB, db->rbits, 0);
+    CU(cudaGetLastError());
+    u32 tail = 0, hbad = 0;
+    CU(cudaMemcpy(&tail, delta + nB, sizeof(u32), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&hbad, bad, sizeof(u32), cudaMemcpyDeviceToHost));
+    if (tail != 0 || hbad != 0) return gs_fail(GS_ERR_LIMIT, "probe table: a collision chain does not fit (%s)", hbad ? "a bucket with 2^16 or more keys" : "ran past the pad buckets");
+    return GS_OK;
+}
+
 extern "C" int gs_db_finalize(gs_db* db) {
     if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
     DevDb& d0 = db->d[0];
@@ -418,16 +498,9 @@ extern "C" int gs_db_finalize(gs_db* db) {
         int tb = GS_TAB_MIN_BITS;
         while ((2ULL << tb) < db->n) tb++;
         db->tbits = tb; db->rbits = 62 - tb;
-        const u64 nB = 1ULL << tb;
-        u32* counts = nullptr;
-        CU(dmalloc(&d0.tab, nB * 4));
-        CU(dmalloc(&counts, nB));
-        CU(cudaMemset(d0.tab, 0, nB * 32));
-        CU(cudaMemset(counts, 0, nB * sizeof(u32)));
-        gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, db->tbits, db->rbits, 0);
-        CU(cudaGetLastError());
-        CU(cudaDeviceSynchronize());
-        CU(cudaFree(counts));
+        db->tabBuckets = (1ULL << tb) + GS_TAB_PAD_BUCKETS;
+        rc = build_table(db);
+        if (rc) return rc;
     }
     // tree
     CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));
@@ -445,8 +518,8 @@ extern "C" int gs_db_finalize(gs_db* db) {
         CU(cudaMemcpyPeer(di.keys, di.dev, d0.keys, d0.dev, (db->n + 1) * sizeof(u64)));
         CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
         CU(cudaMemcpyPeer(di.bstart, di.dev, d0.bstart, d0.dev, (db->nBuckets + 1) * sizeof(u32)));
-        CU(dmalloc(&di.tab, (4ULL << db->tbits)));
-        CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (32ULL << db->tbits)));
+        CU(dmalloc(&di.tab, db->tabBuckets * 4));
+        CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, db->tabBuckets * 32));
         CU(cudaMemcpyPeer(di.parent, di.dev, d0.parent, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.depth, di.dev, d0.depth, d0.dev, (size_t)V * sizeof(int)));
         CU(cudaMemcpyPeer(di.pre, di.dev, d0.pre, d0.dev, (size_t)V * sizeof(int)));
@@ -466,11 +539,11 @@ extern "C" int gs_db_finalize(gs_db* db) {
         v.keys = d.keys; v.vals = d.vals; v.n = db->n; v.bstart = d.bstart; v.bshift = db->bshift; v.nBuckets = db->nBuckets;
         v.k = db->k; v.bloom = d.bloom; v.bloomBuckets = db->bloomBuckets; v.bloomMagic = magic_for(db->bloomBuckets);
         v.bloomSeed = db->bloomSeed; v.hasBloom = db->hasBloom ? 1 : 0;
-        v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits;
+        v.tab = d.tab; v.tbits = db->tbits; v.rbits = db->rbits; v.tabSlots = db->tabBuckets * GS_TAB_SLOT_STRIDE;
         v.mzFilter = d.mzFilter; v.mzMask = db->mzBits ? (u32)((1ULL << db->mzBits) - 1) : 0u; v.mzWide = db->mzWide ? 1 : 0;
         v.parent = d.parent; v.depth = d.depth; v.pre = d.pre; v.last = d.last; v.nValues = V;
     }
-    db->bytes = (32ULL << db->tbits) + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16 + (db->mzBits ? (1ULL << (db->mzBits - 3)) : 0);
+    db->bytes = db->tabBuckets * 32 + (db->n + 1) * 8 + db->n * 2 + (db->nBuckets + 1) * 4 + (db->hasBloom ? db->bloomWords * 8 : 0) + (u64)V * 16 + (db->mzBits ? (1ULL << (db->mzBits - 3)) : 0);
     CU(cudaSetDevice(d0.dev));
     db->finalized = true;
     return GS_OK;
@@ -653,19 +726,13 @@ extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, con
     if (n_changed) *n_changed = changed;
     cudaFree(dSeq); cudaFree(dOff); cudaFree(dNode); cudaFree(dLab); cudaFree(dPos); cudaFree(dValid); cudaFree(dStart); cudaFree(dChanged); cudaFree(dCtr);
     if (changed) {  // the probe table carries the values in its entries: rebuild it, then refresh the replicas
-        const u64 nB = 1ULL << db->tbits;
-        u32* counts = nullptr;
-        CU(dmalloc(&counts, nB));
-        CU(cudaMemset(d0.tab, 0, nB * 32));
-        CU(cudaMemset(counts, 0, nB * sizeof(u32)));
-        gs_launch_table_build(d0.keys, d0.vals, db->n, d0.tab, counts, db->tbits, db->rbits, 0);
-        CU(cudaGetLastError());
+        int rcb = build_table(db);
+        if (rcb) return rcb;
         CU(cudaDeviceSynchronize());
-        CU(cudaFree(counts));
         for (size_t i = 1; i < db->d.size(); i++) {
             DevDb& di = db->d[i];
             CU(cudaMemcpyPeer(di.vals, di.dev, d0.vals, d0.dev, db->n * sizeof(uint16_t)));
-            CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, (32ULL << db->tbits)));
+            CU(cudaMemcpyPeer(di.tab, di.dev, d0.tab, d0.dev, db->tabBuckets * 32));
         }
         CU(cudaDeviceSynchronize());
     }
@@ -786,6 +853,11 @@ struct gs_sess {
     int layout = GS_LAYOUT_TABLE;
     bool inlineSeen = false;  // unique k-mer bits are kept in the probe-table lines (leased from the database)
     u64 nPos = 0;  // "storage positions" addressed by the unique-k-mer bitset: table slot ids or sorted-array indices
+    // end-of-run merge across GPUs (merge_state)
+    bool merged = false;
+    double mergeMs = 0, mergeBitsetMs = 0;   // CUDA events on device 0's compute stream: whole merge / bitset part
+    u64 mergeBytes = 0;                      // bitset bytes this rank fetched from the other ranks
+    int mergePath = 0;                       // 1 = peer mappings read in place, 2 = ncclSend/ncclRecv slice exchange
 };
 
 extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
@@ -895,7 +967,7 @@ extern "C" gs_sess* gs_match_open(gs_db* db, const gs_match_cfg* cfg) {
     s->db = db; s->cfg = c;
     db->openSessions++;
     s->layout = c.layout;
-    s->nPos = c.layout == GS_LAYOUT_TABLE ? ((u64)GS_TAB_SLOT_STRIDE << db->tbits) : db->n;
+    s->nPos = c.layout == GS_LAYOUT_TABLE ? db->tabBuckets * GS_TAB_SLOT_STRIDE : db->n;
     if (c.layout == GS_LAYOUT_TABLE && c.count_unique_kmers && !db->seenLeased) { s->inlineSeen = true; db->seenLeased = true; }
     s->devs.resize(db->d.size());
     for (size_t i = 0; i < db->d.size(); i++) {
@@ -1413,58 +1485,295 @@ static void update_max_counts(int16_t count, int16_t* target, int n) {
     }
 }
 
-extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top_counts) {
-    if (!s) return gs_fail(GS_ERR_STATE, "null session");
-    for (DevSess& D : s->devs)
-        for (MatchSlot& sl : D.slots)
-            if (sl.pending) return gs_fail(GS_ERR_STATE, "ticket %llu still pending", (unsigned long long)sl.ticket);
-    int rc = gs_match_sync(s);
-    if (rc) return rc;
-    const int V = s->db->V;
-    const u64 n = s->nPos;
-    DevSess& D0 = s->devs[0];
-    std::vector<long long> acc((size_t)7 * V, 0), tmp((size_t)7 * V);
-    std::vector<u64> mc((size_t)V, 0), mtmp((size_t)V);
-    // per-device accumulators -> host sums / maxima; bitsets and hit counters are merged into device 0
-    for (DevSess& D : s->devs) {
-        CU(cudaSetDevice(D.dev));
-        CU(cudaMemcpy(tmp.data(), D.counters, (size_t)7 * V * sizeof(long long), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(mtmp.data(), D.maxcontig, (size_t)V * sizeof(u64), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < acc.size(); i++) acc[i] += tmp[i];
-        for (int v = 0; v < V; v++) mc[v] = std::max(mc[v], mtmp[v]);
+// ---------------------------------------------------------------------------------------------------------
+// end-of-run merge across GPUs (the only exchange step of the path).  Stands in for the tail of
+// FastqKMerMatcher.runMatcher (C/match/FastqKMerMatcher.java:199-234), where ONE statsIndex / KMerUniqueCounterBits has seen
+// all reads: here every GPU has its share, so
+//   counters  int64[7][V]  ncclAllReduce(sum)        maxcontig  uint64[V]  ncclAllReduce(max)  (ties -> lowest read ordinal)
+//   bitset    rank r owns words [r * per, (r + 1) * per): one kernel ORs that slice of every rank's bitset -- read in place over
+//             NVLink through peer mappings (same process: cudaDeviceEnablePeerAccess; other processes: cudaIpc handles), or,
+//             where no mapping is possible, after an ncclSend/ncclRecv slice exchange -- and counts the merged words per value
+//             index (KMerUniqueCounterBits.getUniqueKmerCounts :146-163); then ncclAllReduce(sum) of unique[V].
+//   hit counters (maxKMerResCounts > 0): summed per slice the same way, then the merged slices are passed round so that every
+//             rank holds the whole merged bitset and counters for getMaxCountsCounts (:173-199).
+// Every rank ends up with the complete result.
+// ---------------------------------------------------------------------------------------------------------
+struct gs_comm {
+    gs_ctx* ctx = nullptr;
+    int world = 0;
+    std::vector<ncclComm_t> comms;  // one per device of the context
+    std::vector<int> ranks;
+};
+
+extern "C" int gs_comm_unique_id(uint8_t* id) {
+    if (!id) return gs_fail(GS_ERR_ARG, "null argument");
+    GsNccl* N = gs_nccl();
+    if (!N) return gs_fail(GS_ERR_STATE, "NCCL is not available (libnccl.so.2 could not be loaded; set GS_NCCL_LIB)");
+    static_assert(GS_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "gs_comm_unique_id hands out an ncclUniqueId");
+    ncclUniqueId u;
+    NC(N->GetUniqueId(&u));
+    memcpy(id, u.internal, GS_COMM_ID_BYTES);
+    return GS_OK;
+}
+
+extern "C" void gs_comm_destroy(gs_comm* cm) {
+    if (!cm) return;
+    GsNccl* N = gs_nccl();
+    for (size_t i = 0; i < cm->comms.size(); i++)
+        if (N && cm->comms[i]) { cudaSetDevice(cm->ctx->devs[i]); N->CommDestroy(cm->comms[i]); }
+    delete cm;
+}
+
+extern "C" gs_comm* gs_comm_create(gs_ctx* ctx, const uint8_t* id, int world, int rank) {
+    if (!ctx || !id) { gs_fail(GS_ERR_ARG, "null argument"); return nullptr; }
+    if (ctx->devs.size() != 1) { gs_fail(GS_ERR_ARG, "gs_comm_create joins ONE GPU per process to a job (context has %zu devices; their merge needs no communicator)", ctx->devs.size()); return nullptr; }
+    if (world < 1 || world > GS_MAX_RANKS || rank < 0 || rank >= world) { gs_fail(GS_ERR_ARG, "rank %d of %d (at most %d ranks)", rank, world, GS_MAX_RANKS); return nullptr; }
+    GsNccl* N = gs_nccl();
+    if (!N) { gs_fail(GS_ERR_STATE, "NCCL is not available (libnccl.so.2 could not be loaded; set GS_NCCL_LIB)"); return nullptr; }
+    CUP(cudaSetDevice(ctx->devs[0]));
+    ncclUniqueId u;
+    memcpy(u.internal, id, GS_COMM_ID_BYTES);
+    ncclComm_t c = nullptr;
+    ncclResult_t r = N->CommInitRank(&c, world, u, rank);
+    if (r != ncclSuccess) { gs_fail(GS_ERR_CUDA, "ncclCommInitRank failed: %s", N->GetErrorString(r)); return nullptr; }
+    gs_comm* cm = new gs_comm();
+    cm->ctx = ctx; cm->world = world; cm->comms.push_back(c); cm->ranks.push_back(rank);
+    return cm;
+}
+extern "C" int gs_comm_world(const gs_comm* cm) { return cm ? cm->world : 0; }
+extern "C" int gs_comm_rank(const gs_comm* cm) { return cm && cm->ranks.size() == 1 ? cm->ranks[0] : -1; }
+
+// communicator over the devices of a multi-GPU context (one process drives them all)
+static gs_comm* ctx_all_comm(gs_ctx* ctx) {
+    if (ctx->allComm) return ctx->allComm;
+    GsNccl* N = gs_nccl();
+    if (!N) { gs_fail(GS_ERR_STATE, "NCCL is not available (libnccl.so.2 could not be loaded; set GS_NCCL_LIB): a context with %zu devices needs it for the end-of-run merge", ctx->devs.size()); return nullptr; }
+    if (ctx->devs.size() > GS_MAX_RANKS) { gs_fail(GS_ERR_LIMIT, "more than %d devices", GS_MAX_RANKS); return nullptr; }
+    gs_comm* cm = new gs_comm();
+    cm->ctx = ctx; cm->world = (int)ctx->devs.size();
+    cm->comms.assign(ctx->devs.size(), nullptr);
+    ncclResult_t r = N->CommInitAll(cm->comms.data(), (int)ctx->devs.size(), ctx->devs.data());
+    if (r != ncclSuccess) { gs_fail(GS_ERR_CUDA, "ncclCommInitAll failed: %s", N->GetErrorString(r)); delete cm; return nullptr; }
+    for (size_t i = 0; i < ctx->devs.size(); i++) cm->ranks.push_back((int)i);
+    ctx->allComm = cm;
+    return cm;
+}
+
+static void merge_slice(u64 n, int world, int rank, u64* per, u64* lo, u64* hi) {
+    u64 p = (n + (u64)world - 1) / (u64)world;
+    p = (p + 63) & ~63ULL;   // slices start at multiples of 64 words: 128-bit loads and 512-byte aligned exchanges
+    *per = p;
+    *lo = std::min(n, (u64)rank * p);
+    *hi = std::min(n, *lo + p);
+}
+
+// peer mappings of one array of every rank (IPC handles exchanged over the communicator); closes them on destruction
+struct IpcPeers {
+    std::vector<void*> opened;
+    ~IpcPeers() { for (void* p : opened) if (p) cudaIpcCloseMemHandle(p); }
+};
+// ptrs[q] = rank q's `mine` as seen from this process; *ok = 0 if a mapping failed somewhere (every rank gets the same verdict)
+static int ipc_exchange(GsNccl* N, gs_comm* cm, cudaStream_t st, void* mine, void** ptrs, IpcPeers& keep, int* ok) {
+    const int W = cm->world, r = cm->ranks[0];
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    int good = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    uint8_t* dH = nullptr;
+    int* dOk = nullptr;
+    CU(dmalloc(&dH, sizeof(h) * (size_t)W)); CU(dmalloc(&dOk, 1));
+    struct Free { void *a, *b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dH, dOk};
+    CU(cudaMemcpyAsync(dH + sizeof(h) * (size_t)r, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    NC(N->AllGather(dH + sizeof(h) * (size_t)r, dH, sizeof(h), ncclUint8, cm->comms[0], st));
+    std::vector<cudaIpcMemHandle_t> all((size_t)W);
+    CU(cudaMemcpyAsync(all.data(), dH, sizeof(h) * (size_t)W, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int q = 0; q < W && good; q++) {
+        if (q == r) { ptrs[q] = mine; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+        keep.opened.push_back(p);
+        ptrs[q] = p;
     }
-    std::vector<long long> uniq((size_t)V, 0);
-    if (s->cfg.count_unique_kmers)
-        for (DevSess& D : s->devs) { rc = materialize_bitset(s, D); if (rc) return rc; }
-    if (D0.bitset) {
+    CU(cudaMemcpyAsync(dOk, &good, sizeof(int), cudaMemcpyHostToDevice, st));
+    NC(N->AllReduce(dOk, dOk, 1, ncclInt32, ncclMin, cm->comms[0], st));
+    CU(cudaMemcpyAsync(&good, dOk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *ok = good;
+    return GS_OK;
+}
+
+static int merge_state(gs_sess* s, gs_comm* cm) {
+    GsNccl* N = gs_nccl();
+    if (!N) return gs_fail(GS_ERR_STATE, "NCCL is not available");
+    if (cm->ctx != s->db->ctx || cm->comms.size() != s->devs.size()) return gs_fail(GS_ERR_ARG, "communicator and session belong to different contexts");
+    const int V = s->db->V, W = cm->world, L = (int)s->devs.size();
+    const bool uniq = s->cfg.count_unique_kmers != 0;
+    int rc;
+    if (uniq) for (DevSess& D : s->devs) { rc = materialize_bitset(s, D); if (rc) return rc; }
+    DevSess& D0 = s->devs[0];
+    CU(cudaSetDevice(D0.dev));
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+    struct Ev { cudaEvent_t a, b, c; ~Ev() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); } } evs{e0, e1, e2};
+    CU(cudaEventRecord(e0, D0.sCompute));
+    // ---- counters and max-contigs
+    NC(N->GroupStart());
+    for (int l = 0; l < L; l++) {
+        DevSess& D = s->devs[l];
+        NC(N->AllReduce(D.counters, D.counters, (size_t)7 * V, ncclInt64, ncclSum, cm->comms[l], D.sCompute));
+        NC(N->AllReduce(D.maxcontig, D.maxcontig, (size_t)V, ncclUint64, ncclMax, cm->comms[l], D.sCompute));
+    }
+    NC(N->GroupEnd());
+    s->mergeBytes = 0; s->mergePath = 0;
+    if (uniq && D0.bitset) {
         CU(cudaSetDevice(D0.dev));
-        if (s->devs.size() > 1 && !s->finished) {
-            u64* peerBits = nullptr; uint16_t* peerCnt = nullptr;
-            CU(dmalloc(&peerBits, D0.bitsetWords));
-            if (D0.hitCounts) CU(dmalloc(&peerCnt, n + 2));
-            for (size_t i = 1; i < s->devs.size(); i++) {
-                CU(cudaMemcpyPeer(peerBits, D0.dev, s->devs[i].bitset, s->devs[i].dev, D0.bitsetWords * sizeof(u64)));
-                gs_launch_or_words(D0.bitset, peerBits, D0.bitsetWords, D0.sCompute);
-                CU(cudaGetLastError());
-                if (D0.hitCounts) {
-                    CU(cudaMemcpyPeer(peerCnt, D0.dev, s->devs[i].hitCounts, s->devs[i].dev, (n + 2) * sizeof(uint16_t)));
-                    gs_launch_add_u16(D0.hitCounts, peerCnt, n, D0.sCompute);
-                    CU(cudaGetLastError());
-                }
-                CU(cudaStreamSynchronize(D0.sCompute));
-                s->launches += D0.hitCounts ? 2 : 1;
+        CU(cudaEventRecord(e1, D0.sCompute));
+        const u64 words = D0.bitsetWords;
+        // ---- where do the other ranks' bitsets come from?
+        const char* force = getenv("GS_MERGE_PATH");   // "nccl": slice exchange even where peer mappings exist (A/B measurements)
+        bool peer = !(force && strcmp(force, "nccl") == 0);
+        std::vector<std::vector<void*>> bitPtr((size_t)L, std::vector<void*>((size_t)W, nullptr)), hitPtr = bitPtr;
+        IpcPeers keep;
+        if (peer) {
+            if (L == W) {   // one process: every device's arrays are directly addressable
+                peer = cm->ctx->peerAll;
+                for (int l = 0; l < L && peer; l++) for (int q = 0; q < W; q++) { bitPtr[l][q] = s->devs[q].bitset; hitPtr[l][q] = s->devs[q].hitCounts; }
+            } else {        // one process per GPU: map the other ranks' arrays through IPC handles
+                int ok = 0;
+                rc = ipc_exchange(N, cm, D0.sCompute, D0.bitset, bitPtr[0].data(), keep, &ok);
+                if (rc) return rc;
+                if (ok && D0.hitCounts) { rc = ipc_exchange(N, cm, D0.sCompute, D0.hitCounts, hitPtr[0].data(), keep, &ok); if (rc) return rc; }
+                peer = ok != 0;
             }
-            CU(cudaFree(peerBits));
-            if (peerCnt) CU(cudaFree(peerCnt));
         }
-        CU(cudaMemsetAsync(D0.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D0.sCompute));
-        gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].view, s->layout, D0.unique, D0.sms * 8, D0.sCompute);
-        CU(cudaGetLastError());
-        s->launches += 1;
-        CU(cudaStreamSynchronize(D0.sCompute));
+        s->mergePath = peer ? 1 : 2;
+        // ---- bitset: OR of the own slice over all ranks + per-taxon popcount, then the sum of the slices' counts
+        std::vector<u64*> recv((size_t)L, nullptr);
+        struct FreeAll { std::vector<u64*>& v; std::vector<DevSess>& d; ~FreeAll() { for (size_t i = 0; i < v.size(); i++) if (v[i]) { cudaSetDevice(d[i].dev); cudaFree(v[i]); } } } fr{recv, s->devs};
+        u64 per = 0, lo = 0, hi = 0;
+        if (!peer) {
+            for (int l = 0; l < L; l++) {
+                merge_slice(words, W, cm->ranks[l], &per, &lo, &hi);
+                CU(cudaSetDevice(s->devs[l].dev));
+                CU(dmalloc(&recv[l], per * (u64)W));
+            }
+            NC(N->GroupStart());
+            for (int l = 0; l < L; l++) {
+                DevSess& D = s->devs[l];
+                merge_slice(words, W, cm->ranks[l], &per, &lo, &hi);
+                for (int q = 0; q < W; q++) {
+                    u64 pq, loq, hiq;
+                    merge_slice(words, W, q, &pq, &loq, &hiq);
+                    if (hiq > loq) NC(N->Send(D.bitset + loq, (size_t)(hiq - loq), ncclUint64, q, cm->comms[l], D.sCompute));
+                    if (hi > lo) NC(N->Recv(recv[l] + (u64)q * per, (size_t)(hi - lo), ncclUint64, q, cm->comms[l], D.sCompute));
+                }
+            }
+            NC(N->GroupEnd());
+        }
+        for (int l = 0; l < L; l++) {
+            DevSess& D = s->devs[l];
+            merge_slice(words, W, cm->ranks[l], &per, &lo, &hi);
+            CU(cudaSetDevice(D.dev));
+            GsPeerPtrs src;
+            memset(&src, 0, sizeof(src));
+            for (int q = 0; q < W; q++) src.p[q] = peer ? (const u64*)bitPtr[l][q] : recv[l] + (u64)q * per - lo;
+            CU(cudaMemsetAsync(D.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D.sCompute));
+            gs_launch_merge_or_popcount(src, W, D.bitset, lo, hi, s->db->d[D.devIndex].view, s->layout, D.unique, D.sms * 8, D.sCompute);
+            CU(cudaGetLastError());
+            s->launches += 1;
+            if (l == 0) s->mergeBytes += (hi - lo) * 8 * (u64)(W - 1);
+        }
+        NC(N->GroupStart());
+        for (int l = 0; l < L; l++) NC(N->AllReduce(s->devs[l].unique, s->devs[l].unique, (size_t)V, ncclInt64, ncclSum, cm->comms[l], s->devs[l].sCompute));
+        NC(N->GroupEnd());
+        // ---- per-position hit counters: slice sums, then every rank collects the merged slices of bitset and counters
+        if (D0.hitCounts) {
+            std::vector<uint16_t*> hrecv((size_t)L, nullptr);
+            struct FreeH { std::vector<uint16_t*>& v; std::vector<DevSess>& d; ~FreeH() { for (size_t i = 0; i < v.size(); i++) if (v[i]) { cudaSetDevice(d[i].dev); cudaFree(v[i]); } } } frh{hrecv, s->devs};
+            const u64 nPos = s->nPos;
+            auto posSlice = [&](int rank, u64* a, u64* b) { u64 p, l0, h0; merge_slice(words, W, rank, &p, &l0, &h0); *a = std::min(nPos, l0 * 64); *b = std::min(nPos, h0 * 64); };
+            u64 a = 0, b = 0;
+            if (!peer) {
+                for (int l = 0; l < L; l++) { CU(cudaSetDevice(s->devs[l].dev)); CU(dmalloc(&hrecv[l], per * 64 * (u64)W)); }
+                NC(N->GroupStart());
+                for (int l = 0; l < L; l++) {
+                    DevSess& D = s->devs[l];
+                    posSlice(cm->ranks[l], &a, &b);
+                    for (int q = 0; q < W; q++) {
+                        u64 aq, bq;
+                        posSlice(q, &aq, &bq);
+                        if (bq > aq) NC(N->Send(D.hitCounts + aq, (size_t)(bq - aq) * 2, ncclUint8, q, cm->comms[l], D.sCompute));
+                        if (b > a) NC(N->Recv(hrecv[l] + (u64)q * per * 64, (size_t)(b - a) * 2, ncclUint8, q, cm->comms[l], D.sCompute));
+                    }
+                }
+                NC(N->GroupEnd());
+            }
+            for (int l = 0; l < L; l++) {
+                DevSess& D = s->devs[l];
+                posSlice(cm->ranks[l], &a, &b);
+                CU(cudaSetDevice(D.dev));
+                GsPeerPtrs src;
+                memset(&src, 0, sizeof(src));
+                for (int q = 0; q < W; q++) src.p[q] = peer ? (const u64*)hitPtr[l][q] : (const u64*)(hrecv[l] + (u64)q * per * 64 - a);
+                gs_launch_merge_add_u16(src, W, D.hitCounts, a, b, D.sCompute);
+                CU(cudaGetLastError());
+                s->launches += 1;
+            }
+            // (rank q's kernels above have read every other rank's slice q before q sends its merged slice: stream order)
+            NC(N->GroupStart());
+            for (int l = 0; l < L; l++) {
+                DevSess& D = s->devs[l];
+                merge_slice(words, W, cm->ranks[l], &per, &lo, &hi);
+                posSlice(cm->ranks[l], &a, &b);
+                for (int q = 0; q < W; q++) {
+                    if (q == cm->ranks[l]) continue;
+                    u64 pq, loq, hiq, aq, bq;
+                    merge_slice(words, W, q, &pq, &loq, &hiq);
+                    posSlice(q, &aq, &bq);
+                    if (hi > lo) NC(N->Send(D.bitset + lo, (size_t)(hi - lo), ncclUint64, q, cm->comms[l], D.sCompute));
+                    if (hiq > loq) NC(N->Recv(D.bitset + loq, (size_t)(hiq - loq), ncclUint64, q, cm->comms[l], D.sCompute));
+                    if (b > a) NC(N->Send(D.hitCounts + a, (size_t)(b - a) * 2, ncclUint8, q, cm->comms[l], D.sCompute));
+                    if (bq > aq) NC(N->Recv(D.hitCounts + aq, (size_t)(bq - aq) * 2, ncclUint8, q, cm->comms[l], D.sCompute));
+                }
+            }
+            NC(N->GroupEnd());
+        }
+    }
+    CU(cudaSetDevice(D0.dev));
+    if (!(uniq && D0.bitset)) CU(cudaEventRecord(e1, D0.sCompute));
+    CU(cudaEventRecord(e2, D0.sCompute));
+    // Once these streams have drained nobody reads this rank's arrays any more: the all-reduce of `unique` (or the last slice
+    // exchange) on rank q sits behind q's merge kernels in stream order, and it cannot complete here before q has reached it.
+    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); CU(cudaStreamSynchronize(D.sCompute)); }
+    float msAll = 0, msBits = 0;
+    CU(cudaSetDevice(D0.dev));
+    CU(cudaEventElapsedTime(&msAll, e0, e2));
+    CU(cudaEventElapsedTime(&msBits, e1, e2));
+    s->mergeMs = msAll; s->mergeBitsetMs = msBits;
+    s->merged = true;
+    return GS_OK;
+}
+
+// results of the finished run from device 0 (after the merge every device holds the same totals)
+static int read_out(gs_sess* s, gs_taxon_counts* counts, int16_t* top_counts, bool popcountLocal) {
+    const int V = s->db->V;
+    DevSess& D0 = s->devs[0];
+    CU(cudaSetDevice(D0.dev));
+    std::vector<long long> acc((size_t)7 * V, 0), uniq((size_t)V, 0);
+    std::vector<u64> mc((size_t)V, 0);
+    CU(cudaMemcpy(acc.data(), D0.counters, (size_t)7 * V * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(mc.data(), D0.maxcontig, (size_t)V * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (D0.bitset) {
+        if (popcountLocal) {
+            CU(cudaMemsetAsync(D0.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D0.sCompute));
+            gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].view, s->layout, D0.unique, D0.sms * 8, D0.sCompute);
+            CU(cudaGetLastError());
+            s->launches += 1;
+            CU(cudaStreamSynchronize(D0.sCompute));
+        }
         CU(cudaMemcpy(uniq.data(), D0.unique, (size_t)V * sizeof(long long), cudaMemcpyDeviceToHost));
     }
-    s->finished = true;
     if (counts) {
         for (int v = 0; v < V; v++) {
             gs_taxon_counts& c = counts[v];
@@ -1484,6 +1793,7 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
         for (int v = 0; v < V; v++) total += (u64)uniq[v];
         u32* dHits = nullptr; unsigned long long* dN = nullptr;
         CU(dmalloc(&dHits, (size_t)total)); CU(dmalloc(&dN, 1));
+        struct Free { void *a, *b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dHits, dN};
         CU(cudaMemsetAsync(dN, 0, sizeof(unsigned long long), D0.sCompute));
         gs_launch_collect_hits(D0.bitset, D0.bitsetWords, D0.hitCounts, s->db->d[0].view, s->layout, dHits, dN, total, D0.sCompute);
         CU(cudaGetLastError());
@@ -1494,12 +1804,54 @@ extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top
         if (got != total) return gs_fail(GS_ERR_STATE, "hit list holds %llu entries, expected %llu", got, (unsigned long long)total);
         std::vector<u32> hits((size_t)total);
         if (total) CU(cudaMemcpy(hits.data(), dHits, (size_t)total * sizeof(u32), cudaMemcpyDeviceToHost));
-        CU(cudaFree(dHits)); CU(cudaFree(dN));
         for (u32 hcv : hits) {  // the n largest counters per row: independent of the visiting order
             update_max_counts((int16_t)(hcv & 0xFFFF), top_counts + (size_t)(hcv >> 16) * nTop, nTop);
             update_max_counts((int16_t)(hcv & 0xFFFF), top_counts + (size_t)V * nTop, nTop);
         }
     }
+    return GS_OK;
+}
+
+static int finish_checks(gs_sess* s) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    for (DevSess& D : s->devs)
+        for (MatchSlot& sl : D.slots)
+            if (sl.pending) return gs_fail(GS_ERR_STATE, "ticket %llu still pending", (unsigned long long)sl.ticket);
+    return gs_match_sync(s);
+}
+
+extern "C" int gs_match_finish(gs_sess* s, gs_taxon_counts* counts, int16_t* top_counts) {
+    int rc = finish_checks(s);
+    if (rc) return rc;
+    if (s->devs.size() > 1 && !s->merged) {   // one process, several GPUs: merge over the context's own communicator
+        gs_comm* cm = ctx_all_comm(s->db->ctx);
+        if (!cm) return GS_ERR_STATE;
+        rc = merge_state(s, cm);
+        if (rc) return rc;
+    } else if (s->cfg.count_unique_kmers && !s->merged) {
+        rc = materialize_bitset(s, s->devs[0]);
+        if (rc) return rc;
+    }
+    s->finished = true;
+    return read_out(s, counts, top_counts, !s->merged);
+}
+
+extern "C" int gs_match_finish_comm(gs_sess* s, gs_comm* cm, gs_taxon_counts* counts, int16_t* top_counts) {
+    if (!cm) return gs_match_finish(s, counts, top_counts);
+    int rc = finish_checks(s);
+    if (rc) return rc;
+    if (s->devs.size() != 1) return gs_fail(GS_ERR_ARG, "gs_match_finish_comm: one GPU per process (the session spans %zu devices)", s->devs.size());
+    if (!s->merged) { rc = merge_state(s, cm); if (rc) return rc; }
+    s->finished = true;
+    return read_out(s, counts, top_counts, false);
+}
+
+extern "C" int gs_match_merge_stats(const gs_sess* s, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path) {
+    if (!s) return gs_fail(GS_ERR_ARG, "null session");
+    if (total_ms) *total_ms = s->mergeMs;
+    if (bitset_ms) *bitset_ms = s->mergeBitsetMs;
+    if (bytes_from_peers) *bytes_from_peers = s->mergeBytes;
+    if (path) *path = s->mergePath;
     return GS_OK;
 }
 

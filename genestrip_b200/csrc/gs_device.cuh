@@ -65,6 +65,7 @@ struct GsDbView {
     // answers hit/miss and yields the value and the position's seen bit (see "probe table" below)
     const u64* tab;
     int tbits, rbits;       // bucket = mix62(key) >> rbits, remainder = low rbits bits, rbits = 62 - tbits
+    u64 tabSlots;           // 4 * (2^tbits + GS_TAB_PAD_BUCKETS): slots incl. the landing zone behind the last home bucket
     // minimizer prefilter (see "minimizer prefilter" below): bit gs_mz_index(h, mzMask) of mzFilter is set for the hash h of the
     // minimizer of every stored k-mer; NULL = no prefilter (k too small)
     const u64* mzFilter;
@@ -188,8 +189,14 @@ __device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBl
 // bucket = mix62(key) >> rbits, remainder = low rbits bits (mix62 is a bijection, so bucket + remainder identify the key);
 // `spill` (slot 0 only) = a key of this bucket was pushed to a following bucket; `seen` = unique-k-mer bit of the session
 // that leases it (KMerUniqueCounterBits), so counting a k-mer as seen needs no second memory request.
+// The placement is a pure function of the key set (gs_kernels.cu "probe table build"): the keys of home bucket b occupy the
+// consecutive slots [4b + delta_b, 4b + delta_b + c_b) in ascending remainder order, delta_0 = 0,
+// delta_{b+1} = max(0, delta_b + c_b - 4) -- sorted linear probing at slot granularity.  Every process that builds the table
+// from the same store therefore gets the same slot ids, which is what lets per-GPU unique-k-mer bitsets (bit = slot id) be
+// OR-merged across ranks.  Chains run forward without wrap-around into GS_TAB_PAD_BUCKETS spare buckets behind the last one.
 #define GS_TAB_SLOTS 4
 #define GS_TAB_SLOT_STRIDE 4    // slot id = bucket * 4 + j: the "storage position" used for unique k-mer counting
+#define GS_TAB_PAD_BUCKETS 64   // landing zone behind bucket 2^tbits - 1 (the build fails if a chain would run past it)
 #define GS_TAB_MIN_BITS 17      // rbits <= 45 so that remainder + value + 3 flag bits fit 64 bits
 #define GS_TAB_SEEN 1ULL
 #define GS_TAB_OCC 2ULL
@@ -238,7 +245,7 @@ __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBuc
             break;
         }
         if (!(bk.e[0] & GS_TAB_SPILL)) break;  // nothing spilled past this bucket
-        b = (b + 1) & ((1ULL << db.tbits) - 1);
+        b = b + 1;                             // no wrap-around: the pad buckets end every chain
         bk = gs_load_bucket(db.tab, b);
     }
     return lab;
@@ -258,10 +265,10 @@ __device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& 
     return j;
 }
 // (scalars instead of the view: a reference to the kernel parameter block would force a local copy of it)
-static __device__ __noinline__ u32 gs_table_chain(const u64* tab, int tbits, int rbits, u64 h, u64 b, u64* posOut, u32* seenOut) {
+static __device__ __noinline__ u32 gs_table_chain(const u64* tab, int rbits, u64 h, u64 b, u64* posOut, u32* seenOut) {
     u32 lab = GS_LABEL_MISS;
     for (;;) {
-        b = (b + 1) & ((1ULL << tbits) - 1);
+        b = b + 1;
         const GsBucket bk = gs_load_bucket(tab, b);
         u64 e;
         const int j = gs_table_match(rbits, h, bk, e);
@@ -385,7 +392,7 @@ __device__ __forceinline__ T gs_window_min(T sufCur, T preCur, T preNxt, int lan
 // value stored at a "storage position" of the unique-k-mer bitset: sorted-array index (classic) or table slot id
 __device__ __forceinline__ u32 gs_value_at(const GsDbView& db, int layout, u64 pos) {
     if (layout == GS_LAYOUT_TABLE) {
-        if ((pos / GS_TAB_SLOT_STRIDE) >> db.tbits) return GS_VAL_NONODE;
+        if (pos >= db.tabSlots) return GS_VAL_NONODE;
         const u64 e = __ldcg(db.tab + pos);
         return (e & GS_TAB_OCC) ? (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu : GS_VAL_NONODE;
     }

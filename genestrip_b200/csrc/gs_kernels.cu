@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                         seen = e & GS_TAB_SEEN;
                         if (more) {  // rare: the key was pushed to a following bucket
                             u32 sn = 0;
-                            lab = gs_table_chain(db.tab, db.tbits, db.rbits, h, b0, &pos, &sn);
+                            lab = gs_table_chain(db.tab, db.rbits, h, b0, &pos, &sn);
                             seen = sn != 0;
                         }
                     }
@@ -971,27 +971,119 @@ void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCoun
     gs_collect_hits_kernel<<<148 * 8, 256, 0, st>>>(bits, nWords, hitCounts, db, layout, out, nOut, cap);
 }
 
-// ---- probe table build: every key claims a slot of its home bucket; keys of full buckets go to the next bucket with
-// room and the buckets they pass are flagged (phase 2, after all entries are in place)
-__global__ void gs_table_insert_kernel(const u64* __restrict__ keys, const uint16_t* __restrict__ vals, u64 n, u64* tab, u32* counts, int tbits, int rbits) {
+// ---- probe table build.  The layout is a pure function of the key set (no dependence on thread arrival order), so that
+// every rank of a multi-GPU job -- each builds its own replica -- addresses the same k-mer by the same slot id:
+//   1. count:  c_b = number of keys whose home bucket is b                                  (gs_table_count_kernel)
+//   2. scan:   delta_0 = 0, delta_{b+1} = max(0, delta_b + c_b - 4)                         (gs_table_scan_kernel, three passes)
+//              -- the keys of bucket b occupy the slots [4b + delta_b, 4b + delta_b + c_b): sorted linear probing
+//   3. place:  every key takes a slot of its bucket's range (arrival order)                 (gs_table_place_kernel)
+//   4. sort:   every range is sorted by entry = by remainder (distinct within a bucket)     (gs_table_sort_kernel)
+//   5. flags:  bucket b is flagged `spill` iff delta_{b+1} > 0, i.e. a key whose home is <= b sits behind bucket b
+// The recurrence of step 2 composes as functions d -> max(d + s, t): a block of buckets is summarised by (s, t), blocks are
+// combined left to right (gs_lq_combine), and delta at a block's first bucket is its prefix applied to 0.
+struct GsLq { long long s, t; };   // d -> max(d + s, t)
+__device__ __forceinline__ GsLq gs_lq_combine(GsLq a, GsLq b) {  // first a, then b
+    GsLq r;
+    r.s = a.s + b.s;
+    r.t = max(a.t + b.s, b.t);
+    return r;
+}
+#define GS_TB_THREADS 256
+#define GS_TB_PER_THREAD 8
+#define GS_TB_BLOCK (GS_TB_THREADS * GS_TB_PER_THREAD)
+
+__global__ void gs_table_count_kernel(const u64* __restrict__ keys, u64 n, u32* counts, int rbits) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    const u64 bmask = (1ULL << tbits) - 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(counts + (gs_mix62(keys[i]) >> rbits), 1u);
+}
+// PHASE 0: (s, t) of every block of GS_TB_BLOCK buckets -> agg[block].  PHASE 1: delta of every bucket from blockIn[block].
+template <int PHASE>
+__global__ void __launch_bounds__(GS_TB_THREADS) gs_table_scan_kernel(const u32* __restrict__ counts, u64 nBuckets, GsLq* agg, const u32* __restrict__ blockIn, u32* delta, u32* bad) {
+    __shared__ GsLq sh[GS_TB_THREADS];
+    const u64 b0 = (u64)blockIdx.x * GS_TB_BLOCK + (u64)threadIdx.x * GS_TB_PER_THREAD;
+    GsLq mine = {0, -(1LL << 60)};  // identity
+    u32 c[GS_TB_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < GS_TB_PER_THREAD; i++) {
+        const u32 raw = b0 + i < nBuckets ? counts[b0 + i] : 4u;      // buckets past the end: neutral (x = 0)
+        if (PHASE == 0 && raw > 0xFFFFu) atomicOr(bad, 1u);           // the place kernel keeps its fill cursor in the upper half
+        c[i] = raw & 0xFFFFu;
+        mine = gs_lq_combine(mine, GsLq{(long long)c[i] - 4, 0});
+    }
+    sh[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 1; d < GS_TB_THREADS; d <<= 1) {   // inclusive scan, left operand first
+        GsLq v = sh[threadIdx.x];
+        if ((int)threadIdx.x >= d) v = gs_lq_combine(sh[threadIdx.x - d], v);
+        __syncthreads();
+        sh[threadIdx.x] = v;
+        __syncthreads();
+    }
+    if (PHASE == 0) {
+        if (threadIdx.x == GS_TB_THREADS - 1) agg[blockIdx.x] = sh[threadIdx.x];
+    } else {
+        long long d = (long long)blockIn[blockIdx.x];
+        if (threadIdx.x > 0) { const GsLq p = sh[threadIdx.x - 1]; d = max(d + p.s, p.t); }
+#pragma unroll
+        for (int i = 0; i < GS_TB_PER_THREAD; i++) {
+            if (b0 + i < nBuckets) delta[b0 + i] = (u32)d;
+            d = max(0LL, d + (long long)c[i] - 4);
+        }
+        if (b0 + GS_TB_PER_THREAD >= nBuckets && b0 < nBuckets) delta[nBuckets] = (u32)d;  // written by the thread that owns the last bucket
+    }
+}
+// one block: blockIn[j] = delta at the first bucket of block j (sequential over a thread's share, scan across the threads)
+__global__ void __launch_bounds__(1024) gs_table_scan_blocks_kernel(const GsLq* __restrict__ agg, u64 nBlocks, u32* blockIn) {
+    __shared__ GsLq sh[1024];
+    const u64 per = (nBlocks + 1023) / 1024;
+    const u64 j0 = (u64)threadIdx.x * per, j1 = min(nBlocks, j0 + per);
+    GsLq mine = {0, -(1LL << 60)};
+    for (u64 j = j0; j < j1; j++) mine = gs_lq_combine(mine, agg[j]);
+    sh[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        GsLq v = sh[threadIdx.x];
+        if ((int)threadIdx.x >= d) v = gs_lq_combine(sh[threadIdx.x - d], v);
+        __syncthreads();
+        sh[threadIdx.x] = v;
+        __syncthreads();
+    }
+    long long d = 0;
+    if (threadIdx.x > 0) { const GsLq p = sh[threadIdx.x - 1]; d = max(0LL + p.s, p.t); d = max(d, 0LL); }
+    for (u64 j = j0; j < j1; j++) {
+        blockIn[j] = (u32)d;
+        const GsLq a = agg[j];
+        d = max(d + a.s, a.t);
+    }
+}
+__global__ void gs_table_place_kernel(const u64* __restrict__ keys, const uint16_t* __restrict__ vals, u64 n, u64* tab, u32* counts, const u32* __restrict__ delta, int rbits) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const u64 h = gs_mix62(keys[i]);
-        u64 b = h >> rbits;
+        const u64 b = h >> rbits;
         const u64 entry = ((h & ((1ULL << rbits) - 1)) << GS_TAB_REM_SHIFT) | ((u64)vals[i] << GS_TAB_VAL_SHIFT) | GS_TAB_OCC;
-        for (;;) {
-            const u32 idx = atomicAdd(counts + b, 1u) & 0x7FFFFFFFu;
-            if (idx < GS_TAB_SLOTS) { tab[b * 4 + idx] = entry; break; }
-            atomicOr(counts + b, 0x80000000u);  // something spilled past this bucket
-            b = (b + 1) & bmask;
+        const u32 idx = atomicAdd(counts + b, 0x10000u) >> 16;   // fill cursor in the upper half, the count stays below
+        tab[b * 4 + delta[b] + idx] = entry;
+    }
+}
+__global__ void gs_table_sort_kernel(u64* tab, const u32* __restrict__ counts, const u32* __restrict__ delta, u64 nBuckets) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride) {
+        const u32 c = counts[b] & 0xFFFFu;
+        if (c < 2) continue;
+        u64* g = tab + b * 4 + delta[b];
+        for (u32 i = 1; i < c; i++) {  // insertion sort: the ranges hold a handful of entries
+            const u64 e = g[i];
+            u32 j = i;
+            while (j > 0 && g[j - 1] > e) { g[j] = g[j - 1]; j--; }
+            g[j] = e;
         }
     }
 }
-__global__ void gs_table_finalize_kernel(u64* tab, const u32* __restrict__ counts, u64 nBuckets) {
+__global__ void gs_table_flags_kernel(u64* tab, const u32* __restrict__ delta, u64 nBuckets) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride)
-        if (counts[b] & 0x80000000u) tab[b * 4] |= GS_TAB_SPILL;
+        if (delta[b + 1] > 0) tab[b * 4] |= GS_TAB_SPILL;
 }
 // seen bits of all entries -> 0 (a session leases them), and seen bits -> compact bitset (bit = slot id)
 __global__ void gs_table_clear_seen_kernel(u64* tab, u64 nSlots) {
@@ -1024,22 +1116,78 @@ __global__ void gs_mz_build_kernel(const u64* __restrict__ keys, u64 n, int k, u
 void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, int wide, cudaStream_t st) { gs_mz_build_kernel<<<148 * 8, 256, 0, st>>>(keys, n, k, filter, mask, wide); }
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st) { gs_table_clear_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots); }
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st) { gs_table_extract_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots, out); }
-void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st) {
-    gs_table_insert_kernel<<<148 * 8, 256, 0, st>>>(keys, vals, n, tab, counts, tbits, rbits);
-    gs_table_finalize_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, 1ULL << tbits);
+// nBuckets = 2^tbits + GS_TAB_PAD_BUCKETS; counts[nBuckets], delta[nBuckets + 1], agg / blockIn[gs_table_scan_blocks(nBuckets)]
+// are scratch (counts and *bad zeroed by the caller).  Afterwards delta[nBuckets] must be 0 (nothing ran past the pad buckets)
+// and *bad must be 0 (no bucket with 2^16 or more keys).
+u64 gs_table_scan_blocks(u64 nBuckets) { return (nBuckets + GS_TB_BLOCK - 1) / GS_TB_BLOCK; }
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, u32* delta, void* agg, u32* blockIn,
+                           u32* bad, u64 nBuckets, int rbits, cudaStream_t st) {
+    const u64 nBlocks = gs_table_scan_blocks(nBuckets);
+    gs_table_count_kernel<<<148 * 8, 256, 0, st>>>(keys, n, counts, rbits);
+    gs_table_scan_kernel<0><<<(unsigned)nBlocks, GS_TB_THREADS, 0, st>>>(counts, nBuckets, (GsLq*)agg, nullptr, nullptr, bad);
+    gs_table_scan_blocks_kernel<<<1, 1024, 0, st>>>((const GsLq*)agg, nBlocks, blockIn);
+    gs_table_scan_kernel<1><<<(unsigned)nBlocks, GS_TB_THREADS, 0, st>>>(counts, nBuckets, nullptr, blockIn, delta, bad);
+    gs_table_place_kernel<<<148 * 8, 256, 0, st>>>(keys, vals, n, tab, counts, delta, rbits);
+    gs_table_sort_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, delta, nBuckets);
+    gs_table_flags_kernel<<<148 * 8, 256, 0, st>>>(tab, delta, nBuckets);
 }
 
-// end-of-run merge of per-device unique-k-mer state (one process driving several GPUs): dst |= src, dst += src
-__global__ void gs_or_words_kernel(u64* __restrict__ dst, const u64* __restrict__ src, u64 n) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] |= src[i];
+// ---- end-of-run merge of the per-GPU unique-k-mer state (KMerUniqueCounterBits is ONE bitset in the reference,
+// C/store/KMerUniqueCounterBits.java:117-163; here every GPU has set bits for its share of the reads).
+// Rank r owns the words [wordBegin, wordEnd) of the bitset.  src.p[q][w] is rank q's word w -- either q's bitset itself,
+// read over NVLink through a peer mapping (no staging copy: the transfer IS the kernel's loads), or the slice q sent into a
+// local receive buffer (pointer pre-offset by -wordBegin).  One pass ORs the nSrc copies with 128-bit loads, writes the merged
+// words into the own bitset and counts them per value index (getUniqueKmerCounts :146-163); the counts of the slices are
+// then summed over the ranks.
+__global__ void __launch_bounds__(256) gs_merge_or_popcount_kernel(const GsPeerPtrs src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd,
+                                                                   const GsDbView db, int layout, long long* unique) {
+    const u64 stride = (u64)gridDim.x * blockDim.x * 2;
+    for (u64 w0 = wordBegin + (u64)blockIdx.x * blockDim.x * 2; w0 < wordEnd; w0 += stride) {  // warp-uniform trip count
+        const u64 w = w0 + (u64)threadIdx.x * 2;   // wordBegin is even (slices are cut at even word indices), so w is 16-byte aligned
+        u64 m[2] = {0, 0};
+        if (w + 1 < wordEnd) {
+            for (int q = 0; q < nSrc; q++) {
+                const ulonglong2 v = *(const ulonglong2*)(src.p[q] + w);
+                m[0] |= v.x; m[1] |= v.y;
+            }
+            *(ulonglong2*)(own + w) = make_ulonglong2(m[0], m[1]);
+        } else if (w < wordEnd) {
+            for (int q = 0; q < nSrc; q++) m[0] |= src.p[q][w];
+            own[w] = m[0];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 word = m[h];
+            while (__any_sync(FULL, word != 0)) {
+                int v = -1;
+                if (word) {
+                    const int b = __ffsll((long long)word) - 1;
+                    word &= word - 1;
+                    const u32 vv = gs_value_at(db, layout, (w + h) * 64 + (u64)b);
+                    if (vv != GS_VAL_NONODE) v = (int)vv;
+                }
+                const u32 peers = __match_any_sync(FULL, v);
+                if (v >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd((u64*)(unique + v), (u64)__popc(peers));
+            }
+        }
+    }
 }
-void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st) { gs_or_words_kernel<<<148 * 8, 256, 0, st>>>(dst, src, n); }
-__global__ void gs_add_u16_kernel(uint16_t* __restrict__ dst, const uint16_t* __restrict__ src, u64 n) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (uint16_t)(dst[i] + src[i]);  // Java short wrap-around
+void gs_launch_merge_or_popcount(const GsPeerPtrs& src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout,
+                                 long long* unique, int blocks, cudaStream_t st) {
+    if (wordEnd > wordBegin) gs_merge_or_popcount_kernel<<<blocks, 256, 0, st>>>(src, nSrc, own, wordBegin, wordEnd, db, layout, unique);
 }
-void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st) { gs_add_u16_kernel<<<148 * 8, 256, 0, st>>>(dst, src, n); }
+// per-position hit counters (maxKMerResCounts > 0): own[i] = sum over the ranks, Java short wrap-around (:134-140)
+__global__ void gs_merge_add_u16_kernel(const GsPeerPtrs src, int nSrc, uint16_t* own, u64 begin, u64 end) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+        u32 acc = 0;
+        for (int q = 0; q < nSrc; q++) acc += ((const uint16_t*)src.p[q])[i];
+        own[i] = (uint16_t)acc;
+    }
+}
+void gs_launch_merge_add_u16(const GsPeerPtrs& src, int nSrc, uint16_t* own, u64 begin, u64 end, cudaStream_t st) {
+    if (end > begin) gs_merge_add_u16_kernel<<<148 * 8, 256, 0, st>>>(src, nSrc, own, begin, end);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // database build helpers

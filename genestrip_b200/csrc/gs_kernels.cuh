@@ -69,10 +69,16 @@ void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, cons
 void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st);
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st);
-void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, int tbits, int rbits, cudaStream_t st);
+u64 gs_table_scan_blocks(u64 nBuckets);
+void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, u32* delta, void* agg, u32* blockIn,
+                           u32* bad, u64 nBuckets, int rbits, cudaStream_t st);
 void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, int wide, cudaStream_t st);
-void gs_launch_or_words(u64* dst, const u64* src, u64 n, cudaStream_t st);
-void gs_launch_add_u16(uint16_t* dst, const uint16_t* src, u64 n, cudaStream_t st);
+// end-of-run merge across GPUs: per-rank source pointers (peer mappings or receive buffers), see gs_merge_or_popcount_kernel
+#define GS_MAX_RANKS 64
+struct GsPeerPtrs { const u64* p[GS_MAX_RANKS]; };
+void gs_launch_merge_or_popcount(const GsPeerPtrs& src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout,
+                                 long long* unique, int blocks, cudaStream_t st);
+void gs_launch_merge_add_u16(const GsPeerPtrs& src, int nSrc, uint16_t* own, u64 begin, u64 end, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);
 void gs_launch_bloom_build(const u64* keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed, cudaStream_t st);
 void gs_launch_convert_values(const int16_t* raw, const int* hasNode, u64 n, int V, uint16_t* vals, u32* bad, cudaStream_t st);

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 4
+#define GS_ABI_VERSION 5
 
 typedef enum gs_status {
     GS_OK = 0,
@@ -220,6 +220,30 @@ int gs_match_collect_view(gs_sess*, gs_ticket, const gs_read_result** out, uint3
 int gs_match_finish(gs_sess*, gs_taxon_counts* counts, int16_t* top_counts);
 void gs_match_close(gs_sess*);
 
+/* ---- several GPUs: the end-of-run merge ------------------------------------------------------------
+ * Reads shard over GPUs with the database replicated; nothing is exchanged while matching.  At the end the per-GPU state has to
+ * become what ONE FastqKMerMatcher would hold after all reads (the tail of runMatcher, C/match/FastqKMerMatcher.java:199-234;
+ * KMerUniqueCounterBits.getUniqueKmerCounts, C/store/KMerUniqueCounterBits.java:146-163): counters by ncclAllReduce(sum),
+ * max-contigs by ncclAllReduce(max) on (len << 40 | ~ordinal), unique-k-mer bitsets OR-merged slice-wise by a kernel that reads
+ * the other GPUs' bitsets over NVLink (peer mappings; ncclSend/ncclRecv exchange where none can be made) and counts the merged
+ * bits per value index, then ncclAllReduce(sum) of the counts.  NCCL is loaded at run time ("libnccl.so.2", or $GS_NCCL_LIB).
+ *  - one process, several GPUs (gs_ctx_create with n devices): gs_match_finish does all of this by itself;
+ *  - one process per GPU: rank 0 calls gs_comm_unique_id and hands the 128 bytes to the other processes by whatever channel the
+ *    host has (the Java host: its own RPC; bench.py: torch.distributed broadcast); every process calls gs_comm_create and, at
+ *    the end of the run, gs_match_finish_comm (collective: all ranks, same configuration).  Every rank receives the full result.
+ * The database must have been built from the same store on every rank (the probe table's slot ids are a function of the key set). */
+typedef struct gs_comm gs_comm;
+#define GS_COMM_ID_BYTES 128
+int gs_comm_unique_id(uint8_t* id /* [GS_COMM_ID_BYTES] */);
+gs_comm* gs_comm_create(gs_ctx*, const uint8_t* id, int world, int rank); /* the context must hold exactly one device */
+int gs_comm_world(const gs_comm*);
+int gs_comm_rank(const gs_comm*);
+void gs_comm_destroy(gs_comm*);
+int gs_match_finish_comm(gs_sess*, gs_comm*, gs_taxon_counts* counts, int16_t* top_counts);
+/* Measurement of the last merge of this session: CUDA-event time of the whole merge and of its bitset part (ms, on the
+ * session's compute stream), bitset bytes this rank read from the other ranks, path (1 = peer mappings, 2 = NCCL exchange). */
+int gs_match_merge_stats(const gs_sess*, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path);
+
 /* Device-resident variants (inputs already in HBM; used by bench.py's kernel-only number and by a host that
  * decodes on the GPU).  d_bases must be 16-byte aligned and readable 32 bytes past the last base; d_offsets[0] == 0 and
  * d_offsets[n_reads] == n_bases (checked on the device).  Runs on the session's device 0, asynchronously on the session's
@@ -227,7 +251,7 @@ void gs_match_close(gs_sess*);
 int gs_match_run_device(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                         uint64_t n_bases, uint64_t first_read_no, gs_read_result* d_out);
 int gs_match_sync(gs_sess*);
-/* Raw device state for cross-process reduction over NCCL (one process per GPU, DESIGN.md "Multi-GPU"):
+/* Raw device state (tests; before ABI 5 also the hook for a reduction outside the library -- see gs_match_finish_comm):
  * counters = int64[7][n_values] (kmers, contigs, sqsum, reads1, reads, readsKmers, readsBPs),
  * maxcontig = uint64[n_values] packed (len << 40 | ~ordinal), bitset = uint64[bitset_words] or NULL, one bit per
  * storage position of the session's layout (table slot id or sorted-array index). */

@@ -1,4 +1,6 @@
-"""world_size-2 (and 3) gloo tests of the end-of-job merge used by bench.py --gpus N (no GPU needed)."""
+"""world_size-2 (and 3) gloo tests of the multi-rank host logic (no GPU needed): the communicator id reaches every rank, the
+slice geometry covers the bitset, and the merge semantics the library implements on the GPUs (gs_match_finish_comm) are pinned
+by their plain torch.distributed statement."""
 import os
 import socket
 import sys
@@ -43,7 +45,9 @@ def _worker(rank, world, port, V, n_pos, vals, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from genestrip_b200.dist import merge_match_state
+    from genestrip_b200.dist import merge_match_state_reference as merge_match_state, broadcast_unique_id
+    uid = broadcast_unique_id(dist, lambda: bytes(range(128)))
+    assert uid == bytes(range(128))
     counters, maxcontig, bits = _rank_state(rank, V, n_pos)
     t_c, t_m, t_b = torch.from_numpy(counters.copy()), torch.from_numpy(maxcontig.copy()), torch.from_numpy(_pack(bits).copy())
 
@@ -94,11 +98,11 @@ def test_merge_match_state_gloo(world, n_pos):
 
 def test_slice_bounds_cover_everything():
     from genestrip_b200.dist import slice_bounds
-    for n_words in (0, 1, 7, 64, 1000):
+    for n_words in (0, 1, 7, 64, 1000, 8191, 1 << 20):
         for world in (1, 2, 3, 8):
             covered = []
             for r in range(world):
                 per, lo, hi = slice_bounds(n_words, world, r)
                 covered.extend(range(lo, hi))
-                assert hi - lo <= per
+                assert hi - lo <= per and (lo % 64 == 0 or lo == hi)
             assert covered == list(range(n_words))
