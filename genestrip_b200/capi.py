@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 5
+GS_ABI_VERSION = 6
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -29,7 +29,7 @@ class MatchCfg(C.Structure):
     _fields_ = [("classify_reads", C.c_int), ("count_unique_kmers", C.c_int), ("max_kmer_res_counts", C.c_int),
                 ("use_bloom_filter", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
                 ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
-                ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int)]
+                ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int), ("host_pack_threads", C.c_int)]
 
 
 class FastqInfo(C.Structure):
@@ -90,6 +90,9 @@ _SIGS = {
     "gs_comm_rank": (C.c_int, [_P]),
     "gs_comm_destroy": (None, [_P]),
     "gs_match_finish_comm": (C.c_int, [_P, _P, _P, _P]),
+    "gs_pack_bases": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int]),
+    "gs_pack_isa": (C.c_char_p, []),
+    "gs_match_pack_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gs_match_merge_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "gs_match_close": (None, [_P]),
     "gs_match_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P]),
@@ -209,6 +212,16 @@ class Comm:
         if self.h:
             lib().gs_comm_destroy(self.h)
             self.h = None
+
+
+def pack_bases(bases, threads=1):
+    """gs_pack_bases: ASCII bases -> (codes uint64[ceil(n/32)], valid uint32[ceil(n/32)]), the form host_pack_threads puts on the link."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    words = (len(bases) + 31) // 32
+    codes = np.empty(words, dtype=np.uint64)
+    valid = np.empty(words, dtype=np.uint32)
+    _check(lib().gs_pack_bases(_ptr(bases), len(bases), _ptr(codes), _ptr(valid), int(threads)))
+    return codes, valid
 
 
 def bgzf_blocks(comp):
@@ -478,6 +491,12 @@ class MatchSession:
         else:
             _check(lib().gs_match_finish_comm(self.h, comm.h, _ptr(counts), _ptr(top)))
         return counts[:V], top
+
+    def pack_stats(self):
+        """(threads, host seconds spent packing, bases packed, base bytes put on the link) of this session's submits."""
+        t, sec, n, b = C.c_int(0), C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().gs_match_pack_stats(self.h, C.byref(t), C.byref(sec), C.byref(n), C.byref(b)))
+        return t.value, sec.value, n.value, b.value
 
     def merge_stats(self):
         """(total_ms, bitset_ms, bytes read from the other ranks, path) of the last multi-GPU merge; path 1 = peer mappings, 2 = NCCL."""

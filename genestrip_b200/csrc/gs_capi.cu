@@ -6,6 +6,7 @@
 #include <nccl.h>   // types only: the functions are resolved with dlopen (gs_nccl), the library does not link against NCCL
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "gs_kernels.cuh"
+#include "gs_pack.hpp"
 
 // ---------------------------------------------------------------------------------------------------------
 // error plumbing
@@ -817,6 +819,11 @@ struct MatchSlot {
     u64* dTileSums = nullptr; size_t tileSumsCap = 0;
     u32* dEvHdr = nullptr; u32* hEvHdr = nullptr;
     bool isText = false;
+    // bases packed on the host (gs_match_cfg.host_pack_threads != 0): pinned staging + device copies of codes / validity words
+    u64* hCodes = nullptr; size_t hCodesCap = 0;
+    u32* hValid = nullptr; size_t hValidCap = 0;
+    u64* dCodes = nullptr; size_t dCodesCap = 0;
+    u32* dValid = nullptr; size_t dValidCap = 0;
     cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
 };
 
@@ -858,6 +865,9 @@ struct gs_sess {
     double mergeMs = 0, mergeBitsetMs = 0;   // CUDA events on device 0's compute stream: whole merge / bitset part
     u64 mergeBytes = 0;                      // bitset bytes this rank fetched from the other ranks
     int mergePath = 0;                       // 1 = peer mappings read in place, 2 = ncclSend/ncclRecv slice exchange
+    gsp::Packer* packer = nullptr;           // host_pack_threads != 0: made on the first gs_match_submit
+    double packSeconds = 0;                  // host time spent packing (gs_match_pack_stats)
+    u64 packBytes = 0, h2dBytes = 0;         // bases packed / bytes of base data put on the link
 };
 
 extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
@@ -874,6 +884,7 @@ extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
     c->want_runs = 0;
     c->layout = GS_LAYOUT_TABLE;
     c->prefilter = 1;
+    c->host_pack_threads = -1;
 }
 
 static int sess_alloc_dev(gs_sess* s, DevSess& D) {
@@ -929,6 +940,9 @@ extern "C" void gs_match_close(gs_sess* s) {
         for (MatchSlot& sl : D.slots) {
             cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dOut); cudaFree(sl.dEv); cudaFree(sl.dNEv);
             cudaFree(sl.dKmerOff); cudaFree(sl.dRuns); cudaFree(sl.dRunCounts);
+            cudaFree(sl.dCodes); cudaFree(sl.dValid);
+            if (sl.hCodes) cudaFreeHost(sl.hCodes);
+            if (sl.hValid) cudaFreeHost(sl.hValid);
             if (sl.hOut) cudaFreeHost(sl.hOut);
             if (sl.hEv) cudaFreeHost(sl.hEv);
             if (sl.hNEv) cudaFreeHost(sl.hNEv);
@@ -950,6 +964,7 @@ extern "C" void gs_match_close(gs_sess* s) {
     }
     if (s->inlineSeen) s->db->seenLeased = false;
     if (s->db->openSessions > 0) s->db->openSessions--;
+    delete s->packer;
     delete s;
 }
 
@@ -998,7 +1013,7 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
 // flat geometry of a batch whose bases cover byte offsets [off0, off0 + nBytes) of P.bases; grows the hand-over buffers
 static int prepare_flat(DevSess& D, GsMatchParams& P, u64 off0, u64 nBytes) {
     P.off0 = off0;
-    P.lead = (u32)((uintptr_t)(P.bases + off0) & 15);
+    P.lead = P.packCodes ? 0u : (u32)((uintptr_t)(P.bases + off0) & 15);   // packed words start at the batch's first base
     P.flatLen = (u64)P.lead + nBytes;
     const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
     const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
@@ -1097,15 +1112,38 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
             if (L >= (u64)k) totalKmers += L - k + 1;
         }
     CU(cudaSetDevice(D.dev));
-    CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
     CU(dgrow(&sl.dOffsets, &sl.offCap, (size_t)n_reads + 1));
     CU(dgrow(&sl.dOut, &sl.outCap, (size_t)n_reads));
     CU(hgrow(&sl.hOut, &sl.hOutCap, (size_t)n_reads));
-    // inputs: host -> device on the copy-in stream (cudaMemcpyAsync; truly asynchronous for pinned buffers)
-    if (nBytes) CU(cudaMemcpyAsync(sl.dBases, bases + base0, nBytes, cudaMemcpyHostToDevice, D.sCopyIn));
-    CU(cudaMemcpyAsync(sl.dOffsets, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
     GsMatchParams P;
     fill_params(s, D, P);
+    // inputs: host -> device on the copy-in stream (cudaMemcpyAsync; truly asynchronous for pinned buffers)
+    const bool packed = s->cfg.host_pack_threads != 0 && nBytes > 0;
+    if (packed) {
+        // 0.375 instead of 1 byte per base on the link: the host threads write the two streams the label kernel stages anyway
+        // (gs_pack.hpp).  The kernel reads 32 words per segment of 31: room for that behind the last packed word, zeroed.
+        if (!s->packer) s->packer = new gsp::Packer(s->cfg.host_pack_threads);
+        const size_t words = (size_t)((nBytes + 31) / 32);
+        const size_t devWords = (size_t)((nBytes + GS_SEG_POS - 1) / GS_SEG_POS) * GS_SEG_CHUNKS + 64;
+        CU(hgrow(&sl.hCodes, &sl.hCodesCap, words));
+        CU(hgrow(&sl.hValid, &sl.hValidCap, words));
+        CU(dgrow(&sl.dCodes, &sl.dCodesCap, devWords));
+        CU(dgrow(&sl.dValid, &sl.dValidCap, devWords));
+        const auto t0 = std::chrono::steady_clock::now();
+        s->packer->pack(bases + base0, nBytes, (uint64_t*)sl.hCodes, sl.hValid);
+        s->packSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        s->packBytes += nBytes; s->h2dBytes += words * 12;
+        CU(cudaMemcpyAsync(sl.dCodes, sl.hCodes, words * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
+        CU(cudaMemcpyAsync(sl.dValid, sl.hValid, words * sizeof(u32), cudaMemcpyHostToDevice, D.sCopyIn));
+        CU(cudaMemsetAsync(sl.dCodes + words, 0, (devWords - words) * sizeof(u64), D.sCopyIn));
+        CU(cudaMemsetAsync(sl.dValid + words, 0, (devWords - words) * sizeof(u32), D.sCopyIn));
+        P.packCodes = sl.dCodes; P.packValid = sl.dValid;
+    } else {
+        CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
+        if (nBytes) CU(cudaMemcpyAsync(sl.dBases, bases + base0, nBytes, cudaMemcpyHostToDevice, D.sCopyIn));
+        s->h2dBytes += nBytes;
+    }
+    CU(cudaMemcpyAsync(sl.dOffsets, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
     if (s->cfg.want_runs) {
         CU(hgrow(&sl.hKmerOff, &sl.hKmerOffCap, (size_t)n_reads + 1));
         u64 acc = 0;
@@ -1125,10 +1163,10 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     }
     CU(cudaEventRecord(sl.evH2D, D.sCopyIn));
     CU(cudaStreamWaitEvent(D.sCompute, sl.evH2D, 0));
-    P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
+    P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
     // offsets are relative to bases + offsets[0] on the device: the kernel subtracts nothing, so rebase here
     // (the device copy of the base stream starts at host offset base0)
-    P.bases = sl.dBases - base0;
+    P.bases = packed ? nullptr : sl.dBases - base0;
     int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, base0, nBytes);
     if (rc) return rc;
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
@@ -1844,6 +1882,24 @@ extern "C" int gs_match_finish_comm(gs_sess* s, gs_comm* cm, gs_taxon_counts* co
     if (!s->merged) { rc = merge_state(s, cm); if (rc) return rc; }
     s->finished = true;
     return read_out(s, counts, top_counts, false);
+}
+
+extern "C" int gs_pack_bases(const uint8_t* bases, uint64_t n, uint64_t* codes, uint32_t* valid, int threads) {
+    if ((!bases && n) || !codes || !valid) return gs_fail(GS_ERR_ARG, "null argument");
+    if (threads == 1) { gsp::pack_range(bases, n, codes, valid); return GS_OK; }
+    gsp::Packer pk(threads);
+    pk.pack(bases, n, codes, valid);
+    return GS_OK;
+}
+extern "C" const char* gs_pack_isa(void) { return gsp::pack_isa(); }
+
+extern "C" int gs_match_pack_stats(const gs_sess* s, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes) {
+    if (!s) return gs_fail(GS_ERR_ARG, "null session");
+    if (threads) *threads = s->packer ? s->packer->threads() : 0;
+    if (pack_seconds) *pack_seconds = s->packSeconds;
+    if (bases_packed) *bases_packed = s->packBytes;
+    if (h2d_base_bytes) *h2d_base_bytes = s->h2dBytes;
+    return GS_OK;
 }
 
 extern "C" int gs_match_merge_stats(const gs_sess* s, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path) {

@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
         __syncwarp();
         // ---- stage: ASCII -> packed 2-bit codes + validity bits (C/util/CGAT.java:60-69)
         const uint4* ap = (const uint4*)(fb + f0);
+        if (P.packCodes) {  // the host packed the batch: the two streams arrive ready-made, one coalesced load each
+            cw[lane] = __ldg(P.packCodes + (u64)seg * GS_SEG_CHUNKS + lane);
+            vw[lane] = __ldg(P.packValid + (u64)seg * GS_SEG_CHUNKS + lane);
+        } else
 #pragma unroll
         for (int j = lane; j < GS_SEG_BASES / 16; j += 32) {
             u32 code = 0, valid = 0;

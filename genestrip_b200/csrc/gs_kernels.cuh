@@ -6,6 +6,8 @@
 struct GsMatchParams {
     GsDbView db;
     const uint8_t* bases;   // reads back to back, ASCII
+    const u64* packCodes;   // or (gs_pack.hpp) the same bases packed by the host: 2-bit codes, 32 per word, first base on top ...
+    const u32* packValid;   // ... and a validity bit per base; flat position 0 = the batch's first base (lead = 0)
     const u64* offsets;     // [nReads + 1]
     u32 nReads;
     u64 firstReadNo;

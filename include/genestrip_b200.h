@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 5
+#define GS_ABI_VERSION 6
 
 typedef enum gs_status {
     GS_OK = 0,
@@ -124,6 +124,10 @@ typedef struct gs_match_cfg {
     int layout;                        /* device index: GS_LAYOUT_TABLE (default) or GS_LAYOUT_CLASSIC; same results  */
     int prefilter;                     /* 1 (default): skip the probe table for k-mers whose minimizer is in no stored k-mer
                                           (L2-resident bit filter built by gs_db_finalize; same results, k >= 24 only)   */
+    int host_pack_threads;             /* how gs_match_submit moves the bases to the device.  0: as they are, 1 byte per base.
+                                          n > 0: n host threads (the caller included) first pack them to 2-bit codes + a
+                                          validity bit, 0.375 bytes per base on the link; -1 (default): n = the CPUs this
+                                          process may run on, at most 32.  Same results either way.                      */
 } gs_match_cfg;
 #define GS_LAYOUT_TABLE 0   /* 128-byte probe table built from the store's arrays: one DRAM line touch per k-mer      */
 #define GS_LAYOUT_CLASSIC 1 /* the reference's own structures: blocked Bloom filter + binary search of the sorted array */
@@ -240,6 +244,14 @@ int gs_comm_world(const gs_comm*);
 int gs_comm_rank(const gs_comm*);
 void gs_comm_destroy(gs_comm*);
 int gs_match_finish_comm(gs_sess*, gs_comm*, gs_taxon_counts* counts, int16_t* top_counts);
+/* The packer itself (host only, no device needed): n ASCII bases -> codes[ceil(n/32)] (2-bit codes C=0 G=1 A=2 T=3,
+ * C/util/CGAT.java:66-69, 32 per word, first base in the top two bits) and valid[ceil(n/32)] (bit i = base 32w+i is one of the
+ * upper-case letters CGAT, CGAT.java:60-69).  threads as in gs_match_cfg.host_pack_threads (1 = the calling thread alone). */
+int gs_pack_bases(const uint8_t* bases, uint64_t n, uint64_t* codes, uint32_t* valid, int threads);
+const char* gs_pack_isa(void); /* "avx512", "avx2" or "scalar": the body chosen on this CPU */
+/* Host-side packing of this session so far (gs_match_cfg.host_pack_threads): threads of the pool (0 = none was needed), host
+ * seconds spent packing inside gs_match_submit, bases packed, and the bytes of base data all submits put on the link. */
+int gs_match_pack_stats(const gs_sess*, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes);
 /* Measurement of the last merge of this session: CUDA-event time of the whole merge and of its bitset part (ms, on the
  * session's compute stream), bitset bytes this rank read from the other ranks, path (1 = peer mappings, 2 = NCCL exchange). */
 int gs_match_merge_stats(const gs_sess*, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path);

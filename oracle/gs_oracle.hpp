@@ -215,6 +215,16 @@ struct BlockedKMerBloomFilter : KMerProbFilter {
         data[(size_t)start] |= m1;
         data[(size_t)(start + 1 + jushr(h, 60))] |= m2;
     }
+    // putLong from several threads at once (bench-scale database construction only): same bits, OR-ed atomically
+    void putLongShared(jlong key) {
+        jlong h = hash(key);
+        jlong start = reduce(h);
+        h = h ^ jrotl(h, 32);
+        jlong m1 = jshl(1, (int)h) | jshl(1, (int)jshr(h, 6));
+        jlong m2 = jshl(1, (int)jshr(h, 12)) | jshl(1, (int)jshr(h, 18));
+        __atomic_fetch_or(&data[(size_t)start], m1, __ATOMIC_RELAXED);
+        __atomic_fetch_or(&data[(size_t)(start + 1 + jushr(h, 60))], m2, __ATOMIC_RELAXED);
+    }
     bool containsLong(jlong key) const override {  // :181-198
         jlong h = seed ^ key;
         jlong start = reduce(h);

@@ -91,6 +91,10 @@ def lib():
         L.gso_bloom_words.argtypes = [_P]
         L.gso_bloom_factors.restype = _P
         L.gso_bloom_factors.argtypes = [_P]
+        L.gso_bloom_from_words.restype = _P
+        L.gso_bloom_from_words.argtypes = [C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int64]
+        L.gso_filter_reads_mt.restype = C.c_int64
+        L.gso_filter_reads_mt.argtypes = [_P, C.c_int, C.c_int, C.c_double, _P, _P, C.c_int64, C.c_int, _P]
         L.gso_match_files.restype = _P
         L.gso_match_files.argtypes = [_P, C.POINTER(MatchCfg), _P, _P, _P, C.c_int]
         L.gso_filter_files.restype = _P
@@ -150,6 +154,23 @@ class Bloom:
     def __init__(self, handle=None, kind=0, fpp=0.01, owned=True):
         self.h = handle if handle is not None else lib().gso_bloom_new(kind, fpp)
         self.owned = owned and handle is None
+
+    @classmethod
+    def from_words(cls, kind, bits, hashes, factors, words):
+        """A hashed (XOR = 1 / Murmur = 2) filter from its serialized state: bit count, hash factors, bit vector words."""
+        factors = np.ascontiguousarray(factors, dtype=np.int64)
+        words = np.ascontiguousarray(words, dtype=np.int64)
+        f = cls(handle=lib().gso_bloom_from_words(kind, bits, hashes, _ptr(factors), _ptr(words), len(words)))
+        f.owned = True
+        return f
+
+    def accept_reads_mt(self, k, bases, offsets, threads, min_pos_count=1, pos_ratio=0.2):
+        """FastqBloomFilter.isAcceptRead over pre-parsed reads on `threads` threads; returns (k-mers of the reads, accept uint8[n])."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        acc = np.zeros(len(offsets) - 1, dtype=np.uint8)
+        n = lib().gso_filter_reads_mt(self.h, k, min_pos_count, pos_ratio, _ptr(bases), _ptr(offsets), len(offsets) - 1, threads, _ptr(acc))
+        return n, acc
 
     def ensure(self, n):
         return lib().gso_bloom_ensure(self.h, n)

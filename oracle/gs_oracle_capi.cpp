@@ -95,6 +95,17 @@ void* gso_bloom_new(int kind, double fpp) {
     if (kind == 0) return new BlockedKMerBloomFilter();
     return new HashedKMerBloomFilter(fpp, kind == 1);
 }
+// A hashed filter as LoadIndexGoal would deserialize it (C/goals/LoadIndexGoal.java:92-104): the serialized bit count, hash
+// factors and bit vector words are authoritative (AbstractKMerBloomFilter.java:104-110 regenerates factors only on growth).
+void* gso_bloom_from_words(int kind, int64_t bits, int hashes, const int64_t* factors, const int64_t* words, int64_t nWords) {
+    auto* f = new HashedKMerBloomFilter(1e-8, kind == 1);
+    f->bits = bits;
+    f->hashes = hashes;
+    f->hashFactors.assign(factors, factors + hashes);
+    f->bitVector.size = nWords;
+    f->bitVector.bits.assign(words, words + nWords);
+    return f;
+}
 void gso_bloom_free(void* f) { delete (KMerProbFilter*)f; }
 int64_t gso_bloom_ensure(void* f, int64_t n) { return ((KMerProbFilter*)f)->ensureExpectedSize(n, false); }
 void gso_bloom_put(void* f, const int64_t* keys, int64_t n) { for (int64_t i = 0; i < n; i++) ((KMerProbFilter*)f)->putLong(keys[i]); }
@@ -235,7 +246,20 @@ gso_db* gso_db_from_arrays(int k, const int64_t* keys, const int16_t* vals, int6
     for (int v = 0; v < nValues; v++) sa->getAddValueIndex(std::to_string(v + 1));
     sa->sorted = true;
     sa->filter = sa->createOptimizedFilter();
-    if (sa->filter) for (int64_t i = 0; i < n; i++) sa->filter->putLong(keys[i]);
+    if (sa->filter) {
+        // the store's filter over all keys (KMerSortedArray.java:409-422); several threads for the 1e8..2e9-key bench databases
+        auto* bf = dynamic_cast<BlockedKMerBloomFilter*>(sa->filter.get());
+        const int T = bf ? (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency())) : 1;
+        if (T > 1 && n > (1 << 20)) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; t++)
+                th.emplace_back([=] { for (int64_t i = n * t / T, e = n * (t + 1) / T; i < e; i++) bf->putLongShared(keys[i]); });
+            for (auto& x : th) x.join();
+            bf->entries = n;
+        } else {
+            for (int64_t i = 0; i < n; i++) sa->filter->putLong(keys[i]);
+        }
+    }
     attachStore(d, std::unique_ptr<KMerStoreBase>(sa));
     d->db.fix();
     d->db.convert();
@@ -464,6 +488,35 @@ int64_t gso_match_reads_mt(gso_db* d, const gso_match_cfg* c, const uint8_t* bas
             kmersPerVidxOut[v] = s;
         }
     }
+    return total.load();
+}
+
+// FastqBloomFilter.isAcceptRead (C/bloom/FastqBloomFilter.java:120-161) over pre-parsed reads, `threads` consumer threads
+// (the reference's consumers each run isAcceptRead on whole reads).  accept[i] = 0/1.  Returns the number of k-mers of the reads.
+int64_t gso_filter_reads_mt(void* filter, int k, int minPosCount, double posRatio, const uint8_t* bases, const uint64_t* offsets,
+                            int64_t nReads, int threads, uint8_t* accept) {
+    KMerProbFilter* f = (KMerProbFilter*)filter;
+    if (threads < 1) threads = 1;
+    std::atomic<int64_t> next(0), total(0);
+    auto worker = [&]() {
+        int64_t mine = 0;
+        const int64_t CH = 1024;
+        for (;;) {
+            int64_t b = next.fetch_add(CH);
+            if (b >= nReads) break;
+            int64_t en = std::min(nReads, b + CH);
+            for (int64_t i = b; i < en; i++) {
+                const int len = (int)(offsets[i + 1] - offsets[i]);
+                accept[i] = isAcceptRead(*f, k, minPosCount, posRatio, bases + offsets[i], len) ? 1 : 0;
+                if (len >= k) mine += len - k + 1;
+            }
+        }
+        total += mine;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(worker);
+    worker();
+    for (auto& x : th) x.join();
     return total.load();
 }
 

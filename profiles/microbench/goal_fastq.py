@@ -12,7 +12,7 @@ n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 8_000_000
 out_dir = sys.argv[2] if len(sys.argv) > 2 else "/dev/shm"
 wl = dict(bench.WORKLOADS["viral"])
 dev = torch.device("cuda", 0)
-keys, vals_raw, parent, codes = bench.make_database(torch, dev, wl, seed=43)
+keys, vals_raw, parent, codes = bench.make_database(torch, dev, bench.DATABASES[wl["db"]], seed=43)
 V = len(parent)
 ctx = capi.Context([0])
 db = capi.Database.from_pointers(ctx, bench.K, keys.data_ptr(), vals_raw.data_ptr(), keys.numel(), V, parent, build_bloom=True)

@@ -115,6 +115,11 @@ CONFIGS = [
     dict(layout=1),
     dict(layout=1, use_bloom_filter=0),
     dict(layout=1, max_kmer_res_counts=4),
+    # how the bases cross the link (gs_match_cfg.host_pack_threads; the default -1 packs them with every available CPU)
+    dict(host_pack_threads=0),
+    dict(host_pack_threads=1),
+    dict(host_pack_threads=3, max_kmer_res_counts=4),
+    dict(host_pack_threads=0, layout=1),
 ]
 
 
@@ -212,8 +217,9 @@ def _fastq(reads):
     return b"".join(b"@r%d x\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(reads))
 
 
-@pytest.mark.parametrize("cfg", [dict(), dict(max_read_tax_error_count=0.5), dict(want_runs=1), dict(min_kmers_for_class=3), dict(layout=1)],
-                         ids=["default", "taxerr", "runs", "threshold", "classic"])
+@pytest.mark.parametrize("cfg", [dict(), dict(max_read_tax_error_count=0.5), dict(want_runs=1), dict(min_kmers_for_class=3), dict(layout=1),
+                                 dict(host_pack_threads=0), dict(host_pack_threads=0, want_runs=1)],
+                         ids=["default", "taxerr", "runs", "threshold", "classic", "ascii-link", "ascii-link-runs"])
 def test_edge_case_reads(project, oracle, native, cfg):
     odb, gdb, genomes = project
     rng = np.random.default_rng(99)

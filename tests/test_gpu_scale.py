@@ -20,7 +20,7 @@ def viral(native, gpu_ctx):
     import bench
     dev = torch.device("cuda:0")
     wl = dict(bench.WORKLOADS["viral"])
-    keys, vals_raw, parent, codes = bench.make_database(torch, dev, wl, seed=43)
+    keys, vals_raw, parent, codes = bench.make_database(torch, dev, bench.DATABASES[wl["db"]], seed=43)
     db = native.Database.from_pointers(gpu_ctx, K, keys.data_ptr(), vals_raw.data_ptr(), keys.numel(), len(parent), parent, build_bloom=True)
     R = 300_000
     bases, offsets = bench.make_reads(torch, dev, wl, codes, R, seed=99)

@@ -208,3 +208,45 @@ def test_device_inflate_decoder_logic_on_the_host(native, tmp_path):
         b2 = blocks.copy()
         b2[field][0] = int(b2[field][0]) + delta
         assert inflate(comp, b2, n)[1]["status"][0] == want
+
+
+def _pack_reference(b):
+    """Plain numpy statement of gs_pack.hpp: C=0 G=1 A=2 T=3 (C/util/CGAT.java:66-69), anything else invalid (:60-69)."""
+    n = len(b)
+    words = (n + 31) // 32
+    code = np.zeros(words * 32, dtype=np.uint64)
+    ok = np.zeros(words * 32, dtype=bool)
+    for ch, c in ((ord("C"), 0), (ord("G"), 1), (ord("A"), 2), (ord("T"), 3)):
+        m = b == ch
+        code[:n][m] = c
+        ok[:n] |= m
+    shifts = (62 - 2 * np.arange(32, dtype=np.uint64)).astype(np.uint64)
+    codes = np.bitwise_or.reduce(code.reshape(words, 32) << shifts[None, :], axis=1) if words else np.zeros(0, dtype=np.uint64)
+    valid = (ok.reshape(words, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32) if words else np.zeros(0, dtype=np.uint32)
+    return codes.astype(np.uint64), valid
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_packer_matches_numpy_statement(native, threads):
+    """The 2-bit packer behind gs_match_cfg.host_pack_threads (no GPU needed): every byte value, ragged tails, empty input,
+    several pool threads over a batch larger than one claim."""
+    rng = np.random.default_rng(7)
+    assert native.lib().gs_pack_isa() in (b"avx512", b"avx2", b"scalar")
+    cases = [np.zeros(0, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.frombuffer(b"ACGTacgtNn\r\n" * 11, dtype=np.uint8)]
+    for n in (1, 31, 32, 33, 63, 64, 65, 1000, 4097, 700_001):
+        b = np.frombuffer(b"CGAT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        bad = rng.random(n) < 0.01
+        b[bad] = rng.integers(0, 256, int(bad.sum()), dtype=np.uint8)
+        cases.append(b)
+    for b in cases:
+        codes, valid = native.pack_bases(b, threads=threads)
+        rc, rv = _pack_reference(b)
+        np.testing.assert_array_equal(valid, rv)
+        np.testing.assert_array_equal(codes, rc)
+    # unaligned source pointer
+    b = np.frombuffer(b"CGAT", dtype=np.uint8)[rng.integers(0, 4, 5003)].copy()
+    for sh in (1, 7, 13):
+        codes, valid = native.pack_bases(b[sh:], threads=threads)
+        rc, rv = _pack_reference(b[sh:])
+        np.testing.assert_array_equal(codes, rc)
+        np.testing.assert_array_equal(valid, rv)
