@@ -409,6 +409,8 @@ def run_match(E, name, wl, want_fastq, want_cpu):
     cfg.host_pack_threads = args.pack_threads if args.pack_threads >= 0 else max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     native_options = {"layout": args.layout, "minimizer_prefilter": bool(cfg.prefilter) and args.layout == "table", "host_pack_threads": int(cfg.host_pack_threads)}
     sess = capi.MatchSession(db, cfg)
+    if E.comm:
+        sess.prepare_merge(E.comm)   # set-up, not part of the job: peer mappings of the bitsets, merge kernel loaded
     stream = torch.cuda.ExternalStream(sess.stream, device=dev)
     d_out = torch.zeros(R * 16, dtype=torch.uint8, device=dev)
     steps_done = args.warmup + args.steps
@@ -441,7 +443,6 @@ def run_match(E, name, wl, want_fastq, want_cpu):
 
     # ---------------- end of job: the merge across the ranks, inside the library (the only exchange step of the path)
     E.barrier()
-    bitset_words = sess.device_state()[3] if E.comm else 0
     counts, _ = sess.finish(E.comm)
     launches = sess.kernel_launches - launches0
     merge_ms, merge_bits_ms, merge_bytes, merge_path = sess.merge_stats() if E.comm else (0.0, 0.0, 0, 0)
@@ -456,6 +457,7 @@ def run_match(E, name, wl, want_fastq, want_cpu):
             chk = capi.MatchSession(db, cfg)
             for r in range(world):
                 bb = batches if r == 0 else [make_reads(torch, dev, wl, codes, R, seed=4343 + 1000 * r + b) for b in range(n_batches)]
+                torch.cuda.synchronize()   # the session's stream does not wait for torch's: the reads must exist before the kernels start
                 for i in range(steps_done):
                     device_step(chk, i, bb)
                 chk.sync()
@@ -465,6 +467,8 @@ def run_match(E, name, wl, want_fastq, want_cpu):
             fields = ("kmers", "contigs", "contig_len_squared_sum", "reads_1kmer", "reads", "reads_kmers", "reads_bps", "unique_kmers", "max_contig_len", "max_contig_read_no")
             bad = [f for f in fields if not np.array_equal(c1[f], counts[f])]
             merge_parity = not bad
+            for f in bad:
+                log("  %s: merged sum %d, single-GPU sum %d, %d of %d entries differ" % (f, int(counts[f].astype(np.int64).sum()), int(c1[f].astype(np.int64).sum()), int((counts[f] != c1[f]).sum()), len(c1[f])))
             if bad:
                 log("MERGE PARITY FAILURE (%s): fields %s differ between the %d-GPU merge and the single-GPU pass" % (name, bad, world))
             torch.cuda.empty_cache()
@@ -604,7 +608,7 @@ def run_match(E, name, wl, want_fastq, want_cpu):
                "end_of_job_reduce_ms": merge_ms_max, "hits_total": total_hits, "unique_kmers_total": unique_total}
         if E.comm:
             rec["merge"] = {"where": "gs_match_finish_comm (library, NCCL loaded at run time)", "total_ms": merge_ms_max, "bitset_ms": merge_bits_ms,
-                            "bitset_bytes_read_from_peers_per_rank": int(merge_bytes), "bitset_bytes_per_rank": int(bitset_words) * 8,
+                            "bitset_bytes_read_from_peers_per_rank": int(merge_bytes), "bitset_bytes_per_rank": int(merge_bytes) * world // max(1, world - 1),
                             "path": {1: "peer mappings (cudaIpc) read in place by the OR/popcount kernel", 2: "ncclSend/ncclRecv slice exchange"}.get(merge_path, "none"),
                             "merge_parity": merge_parity,
                             "merge_parity_what": "merged counters, unique k-mers and max-contigs of the %d ranks == one GPU processing every rank's %d batches" % (world, steps_done)}

@@ -89,6 +89,7 @@ _SIGS = {
     "gs_comm_world": (C.c_int, [_P]),
     "gs_comm_rank": (C.c_int, [_P]),
     "gs_comm_destroy": (None, [_P]),
+    "gs_match_prepare_merge": (C.c_int, [_P, _P]),
     "gs_match_finish_comm": (C.c_int, [_P, _P, _P, _P]),
     "gs_pack_bases": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int]),
     "gs_pack_isa": (C.c_char_p, []),
@@ -478,6 +479,10 @@ class MatchSession:
         if runs is not None:
             res = res + (run_off, runs[:int(run_off[n_reads])])
         return res
+
+    def prepare_merge(self, comm):
+        """gs_match_prepare_merge (collective): peer mappings and merge kernel set up ahead of the run."""
+        _check(lib().gs_match_prepare_merge(self.h, comm.h))
 
     def finish(self, comm=None):
         """End of the run.  With `comm` (one process per GPU): the collective merge over all ranks, gs_match_finish_comm."""

@@ -298,7 +298,7 @@ extern "C" gs_db* gs_db_create(gs_ctx* ctx, int k, uint64_t n_kmers, int n_value
 
 extern "C" int gs_db_put_keys(gs_db* db, uint64_t offset, const int64_t* keys, uint64_t n) {
     if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
-    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "key segment [%llu,%llu) exceeds n_kmers=%llu", (unsigned long long)offset, (unsigned long long)(offset + n), (unsigned long long)db->n);
+    if (offset > db->n || n > db->n - offset) return gs_fail(GS_ERR_ARG, "key segment [%llu,%llu) exceeds n_kmers=%llu", (unsigned long long)offset, (unsigned long long)(offset + n), (unsigned long long)db->n);
     CU(cudaSetDevice(db->d[0].dev));
     CU(cudaMemcpy(db->d[0].keys + offset, keys, n * sizeof(u64), cudaMemcpyDefault));  // host or device source
     return GS_OK;
@@ -306,7 +306,7 @@ extern "C" int gs_db_put_keys(gs_db* db, uint64_t offset, const int64_t* keys, u
 
 extern "C" int gs_db_put_values(gs_db* db, uint64_t offset, const int16_t* vidx_raw, uint64_t n) {
     if (!db || db->finalized) return gs_fail(GS_ERR_STATE, "database missing or already finalized");
-    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "value segment exceeds n_kmers");
+    if (offset > db->n || n > db->n - offset) return gs_fail(GS_ERR_ARG, "value segment exceeds n_kmers");
     CU(cudaSetDevice(db->d[0].dev));
     CU(cudaMemcpy(db->rawVals + offset, vidx_raw, n * sizeof(int16_t), cudaMemcpyDefault));
     return GS_OK;
@@ -473,7 +473,11 @@ extern "C" int gs_db_finalize(gs_db* db) {
     CU(cudaFree(dHas));
     CU(cudaFree(dBad));
     if (bad) return gs_fail(GS_ERR_ARG, "%u stored values have an index >= n_values", bad);
-    CU(cudaFree(db->rawVals)); db->rawVals = nullptr;
+    // Values whose tax id has no tree node were collapsed to GS_VAL_NONODE above; their original indices are only needed again
+    // by gs_db_get_values / gs_db_save_file, so the raw shorts are kept exactly when such values exist.
+    bool allNodes = true;
+    for (int v = 0; v < V; v++) allNodes = allNodes && db->hHasNode[(size_t)v] != 0;
+    if (allNodes) { CU(cudaFree(db->rawVals)); db->rawVals = nullptr; }
     // bucket index over the top key bits: ~4 keys per bucket on average
     int lg = 0;
     while ((1ULL << (lg + 1)) <= std::max<u64>(db->n, 1)) lg++;
@@ -621,13 +625,35 @@ extern "C" int gs_db_save_file(gs_db* db, const char* path) {
     return GS_OK;
 }
 
+static gs_db* db_load_file(gs_ctx* ctx, const char* path);
 extern "C" gs_db* gs_db_load_file(gs_ctx* ctx, const char* path) {
+    // nothing may unwind through the C boundary (a JVM sits on the other side): a file whose header asks for absurd sizes
+    // ends as an error code, not as std::bad_alloc
+    try {
+        return db_load_file(ctx, path);
+    } catch (const std::exception& e) {
+        gs_fail(GS_ERR_ARG, "%s: %s", path ? path : "(null)", e.what());
+        return nullptr;
+    }
+}
+static gs_db* db_load_file(gs_ctx* ctx, const char* path) {
     if (!ctx || !path) { gs_fail(GS_ERR_ARG, "null argument"); return nullptr; }
     FILE* f = fopen(path, "rb");
     if (!f) { gs_fail(GS_ERR_ARG, "cannot open %s", path); return nullptr; }
     struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
     GsbHeader h;
     if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "GSB1\0\0\0\0", 8) != 0 || h.version != 1) { gs_fail(GS_ERR_ARG, "%s is not a GSB1 database file", path); return nullptr; }
+    {   // the header's sizes must add up to the file's size before anything is allocated from them
+        const long at = ftell(f);
+        if (fseek(f, 0, SEEK_END) != 0) { gs_fail(GS_ERR_ARG, "%s: cannot seek", path); return nullptr; }
+        const u64 fileBytes = (u64)ftell(f);
+        fseek(f, at, SEEK_SET);
+        const bool bloom = (h.flags & 1u) != 0;
+        const bool sane = h.k >= 1 && h.k <= 31 && h.n_values <= 65536 && h.n_kmers <= fileBytes / 10 &&
+                          (!bloom || (h.bloom_words == h.bloom_buckets + 17 && h.bloom_words <= fileBytes / 8));
+        const u64 want = sizeof(GsbHeader) + h.n_kmers * 8 + ((h.n_kmers * 2 + 7) & ~7ULL) + (((u64)h.n_values * 8 + 7) & ~7ULL) + (bloom ? h.bloom_words * 8 : 0);
+        if (!sane || want != fileBytes) { gs_fail(GS_ERR_ARG, "%s: header does not match the file (%llu bytes, header implies %llu)", path, (unsigned long long)fileBytes, (unsigned long long)want); return nullptr; }
+    }
     gs_db* db = gs_db_create(ctx, (int)h.k, h.n_kmers, (int)h.n_values);
     if (!db) return nullptr;
     auto bail = [&](const char* what) -> gs_db* { std::string msg = gs_last_error(); gs_db_destroy(db); gs_fail(GS_ERR_ARG, "%s: %s %s", path, what, msg.c_str()); return nullptr; };
@@ -743,16 +769,16 @@ extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, con
 
 extern "C" int gs_db_get_values(gs_db* db, uint64_t offset, int16_t* vidx_raw, uint64_t n) {
     if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
-    if (offset + n > db->n) return gs_fail(GS_ERR_ARG, "range beyond the %llu stored k-mers", (unsigned long long)db->n);
+    if (offset > db->n || n > db->n - offset) return gs_fail(GS_ERR_ARG, "range beyond the %llu stored k-mers", (unsigned long long)db->n);
     if (n == 0) return GS_OK;
     if (!vidx_raw) return gs_fail(GS_ERR_ARG, "null argument");
     CU(cudaSetDevice(db->d[0].dev));
     int16_t* dRaw = nullptr;
     CU(dmalloc(&dRaw, (size_t)n));
-    gs_launch_values_to_raw(db->d[0].vals + offset, n, dRaw, 0);
+    struct Free { void* p; ~Free() { cudaFree(p); } } fr{dRaw};
+    gs_launch_values_to_raw(db->d[0].vals + offset, db->rawVals ? db->rawVals + offset : nullptr, n, dRaw, 0);
     CU(cudaGetLastError());
     CU(cudaMemcpy(vidx_raw, dRaw, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
-    CU(cudaFree(dRaw));
     return GS_OK;
 }
 
@@ -835,6 +861,7 @@ struct DevSess {
     u64* bitset = nullptr; u64 bitsetWords = 0;
     uint16_t* hitCounts = nullptr;
     long long* unique = nullptr;    // [V]
+    u32* popPartial = nullptr; size_t popPartialCap = 0;   // per-CTA count tables of the popcount kernel
     u32* overflowList = nullptr; size_t ovCap = 0;
     u32* overflowCount = nullptr;
     u32* slowTable = nullptr;
@@ -865,6 +892,11 @@ struct gs_sess {
     double mergeMs = 0, mergeBitsetMs = 0;   // CUDA events on device 0's compute stream: whole merge / bitset part
     u64 mergeBytes = 0;                      // bitset bytes this rank fetched from the other ranks
     int mergePath = 0;                       // 1 = peer mappings read in place, 2 = ncclSend/ncclRecv slice exchange
+    // gs_match_prepare_merge: peer mappings of the other ranks' bitsets / hit counters made ahead of the merge
+    gs_comm* prepComm = nullptr;
+    bool prepPeer = false;
+    std::vector<void*> prepBits, prepHits;   // [world]
+    std::vector<void*> prepOpened;           // mappings to close (cudaIpcCloseMemHandle)
     gsp::Packer* packer = nullptr;           // host_pack_threads != 0: made on the first gs_match_submit
     double packSeconds = 0;                  // host time spent packing (gs_match_pack_stats)
     u64 packBytes = 0, h2dBytes = 0;         // bases packed / bytes of base data put on the link
@@ -953,7 +985,7 @@ extern "C" void gs_match_close(gs_sess* s) {
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
         }
-        cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique);
+        cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique); cudaFree(D.popPartial);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
         cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList); cudaFree(D.bmask);
         for (cudaEvent_t e : D.timingEv) cudaEventDestroy(e);
@@ -964,6 +996,7 @@ extern "C" void gs_match_close(gs_sess* s) {
     }
     if (s->inlineSeen) s->db->seenLeased = false;
     if (s->db->openSessions > 0) s->db->openSessions--;
+    for (void* p : s->prepOpened) if (p) cudaIpcCloseMemHandle(p);
     delete s->packer;
     delete s;
 }
@@ -1430,7 +1463,8 @@ extern "C" int gs_match_unique_popcount(gs_sess* s, const uint64_t* d_bitset, ui
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     DevSess& D = s->devs[0];
     CU(cudaSetDevice(D.dev));
-    gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].view, s->layout, (long long*)d_unique, D.sms * 8, D.sCompute);
+    CU(dgrow(&D.popPartial, &D.popPartialCap, (size_t)gs_popcount_scratch_words(D.sms, s->db->V)));
+    gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].view, s->layout, (long long*)d_unique, D.popPartial, D.sms, D.sCompute);
     CU(cudaGetLastError());
     s->launches += 1;
     return GS_OK;
@@ -1562,6 +1596,7 @@ extern "C" void gs_comm_destroy(gs_comm* cm) {
     delete cm;
 }
 
+static void comm_warm_up_peers(gs_comm* cm);
 extern "C" gs_comm* gs_comm_create(gs_ctx* ctx, const uint8_t* id, int world, int rank) {
     if (!ctx || !id) { gs_fail(GS_ERR_ARG, "null argument"); return nullptr; }
     if (ctx->devs.size() != 1) { gs_fail(GS_ERR_ARG, "gs_comm_create joins ONE GPU per process to a job (context has %zu devices; their merge needs no communicator)", ctx->devs.size()); return nullptr; }
@@ -1576,6 +1611,23 @@ extern "C" gs_comm* gs_comm_create(gs_ctx* ctx, const uint8_t* id, int world, in
     if (r != ncclSuccess) { gs_fail(GS_ERR_CUDA, "ncclCommInitRank failed: %s", N->GetErrorString(r)); return nullptr; }
     gs_comm* cm = new gs_comm();
     cm->ctx = ctx; cm->world = world; cm->comms.push_back(c); cm->ranks.push_back(rank);
+    // NCCL connects lazily: the first collective of every kind pays for the channel set-up (270 ms measured).  That belongs to
+    // creating the communicator, not to the first merge.
+    {
+        long long* w = nullptr;
+        if (dmalloc(&w, (size_t)world * 2) == cudaSuccess) {
+            cudaMemset(w, 0, (size_t)world * 2 * sizeof(long long));
+            N->AllReduce(w, w, (size_t)world, ncclInt64, ncclSum, c, 0);
+            N->AllReduce(w, w, (size_t)world, ncclUint64, ncclMax, c, 0);
+            N->AllGather(w + rank, w, 1, ncclInt64, c, 0);
+            N->GroupStart();
+            for (int q = 0; q < world; q++) { N->Send(w + q, 1, ncclInt64, q, c, 0); N->Recv(w + world + q, 1, ncclInt64, q, c, 0); }
+            N->GroupEnd();
+            cudaStreamSynchronize(0);
+            cudaFree(w);
+        }
+    }
+    comm_warm_up_peers(cm);
     return cm;
 }
 extern "C" int gs_comm_world(const gs_comm* cm) { return cm ? cm->world : 0; }
@@ -1641,6 +1693,72 @@ static int ipc_exchange(GsNccl* N, gs_comm* cm, cudaStream_t st, void* mine, voi
     return GS_OK;
 }
 
+// The first peer mapping between two processes enables peer access between their contexts (74 ms measured); that is
+// communicator set-up too.  A throw-away exchange of a small buffer pays for it here.
+static void comm_warm_up_peers(gs_comm* cm) {
+    GsNccl* N = gs_nccl();
+    if (!N || cm->world < 2 || cm->comms.size() != 1) return;
+    void* buf = nullptr;
+    if (cudaMalloc(&buf, 256) != cudaSuccess) { cudaGetLastError(); return; }
+    std::vector<void*> ptrs((size_t)cm->world, nullptr);
+    int ok = 0;
+    {
+        IpcPeers keep;
+        ipc_exchange(N, cm, 0, buf, ptrs.data(), keep, &ok);
+    }
+    // every rank has closed its mappings before anybody frees: one more collective as the barrier
+    int* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(int)) == cudaSuccess) {
+        cudaMemset(d, 0, sizeof(int));
+        N->AllReduce(d, d, 1, ncclInt32, ncclSum, cm->comms[0], 0);
+        cudaStreamSynchronize(0);
+        cudaFree(d);
+    }
+    cudaFree(buf);
+}
+
+static int materialize_bitset(gs_sess* s, DevSess& D);
+extern "C" int gs_match_prepare_merge(gs_sess* s, gs_comm* cm) {
+    if (!s || !cm) return gs_fail(GS_ERR_ARG, "null argument");
+    if (s->finished || s->merged) return gs_fail(GS_ERR_STATE, "session already finished");
+    if (s->devs.size() != 1 || cm->comms.size() != 1) return GS_OK;   // one process, several GPUs: the devices address each other directly
+    if (cm->ctx != s->db->ctx) return gs_fail(GS_ERR_ARG, "communicator and session belong to different contexts");
+    if (s->prepComm == cm) return GS_OK;
+    GsNccl* N = gs_nccl();
+    if (!N) return gs_fail(GS_ERR_STATE, "NCCL is not available");
+    DevSess& D = s->devs[0];
+    CU(cudaSetDevice(D.dev));
+    const int W = cm->world;
+    s->prepBits.assign((size_t)W, nullptr); s->prepHits.assign((size_t)W, nullptr);
+    s->prepPeer = false;
+    if (s->cfg.count_unique_kmers) {
+        if (!D.bitset) {   // in-line seen bits: the compact bitset only exists from the end of the run on, but its address can be handed out now
+            CU(dmalloc(&D.bitset, D.bitsetWords));
+            CU(cudaMemsetAsync(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64), D.sCompute));
+        }
+        const char* force = getenv("GS_MERGE_PATH");
+        if (!(force && strcmp(force, "nccl") == 0)) {
+            IpcPeers keep;
+            int ok = 0;
+            int rc = ipc_exchange(N, cm, D.sCompute, D.bitset, s->prepBits.data(), keep, &ok);
+            if (rc) return rc;
+            if (ok && D.hitCounts) { rc = ipc_exchange(N, cm, D.sCompute, D.hitCounts, s->prepHits.data(), keep, &ok); if (rc) return rc; }
+            s->prepPeer = ok != 0;
+            s->prepOpened.swap(keep.opened);   // the session keeps the mappings until the merge is over
+            if (!s->prepPeer) { for (void* p : s->prepOpened) if (p) cudaIpcCloseMemHandle(p); s->prepOpened.clear(); }
+        }
+        // the merge kernel: scratch allocated and the function loaded (an empty slice) before the run, not at its end
+        CU(dgrow(&D.popPartial, &D.popPartialCap, (size_t)gs_popcount_scratch_words(D.sms, s->db->V)));
+        GsPeerPtrs none;
+        memset(&none, 0, sizeof(none));
+        gs_launch_merge_or_popcount(none, 0, D.bitset, 0, 0, s->db->d[D.devIndex].view, s->layout, D.unique, D.popPartial, 1, D.sCompute);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(D.sCompute));
+    }
+    s->prepComm = cm;
+    return GS_OK;
+}
+
 static int merge_state(gs_sess* s, gs_comm* cm) {
     GsNccl* N = gs_nccl();
     if (!N) return gs_fail(GS_ERR_STATE, "NCCL is not available");
@@ -1648,13 +1766,26 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
     const int V = s->db->V, W = cm->world, L = (int)s->devs.size();
     const bool uniq = s->cfg.count_unique_kmers != 0;
     int rc;
-    if (uniq) for (DevSess& D : s->devs) { rc = materialize_bitset(s, D); if (rc) return rc; }
     DevSess& D0 = s->devs[0];
     CU(cudaSetDevice(D0.dev));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     struct Ev { cudaEvent_t a, b, c; ~Ev() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); } } evs{e0, e1, e2};
     CU(cudaEventRecord(e0, D0.sCompute));
+    static const bool dbgMerge = getenv("GS_DEBUG_MERGE") != nullptr;   // phase times on stderr (each phase drained: not for timing runs)
+    auto tPrev = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (!dbgMerge) return;
+        cudaStreamSynchronize(D0.sCompute);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gs merge rank %d] %-28s %8.3f ms\n", cm->ranks[0], what, std::chrono::duration<double, std::milli>(now - tPrev).count());
+        tPrev = now;
+    };
+    stamp("drain before merge");
+    // in-line seen bits (probe table entries) -> compact bitset: part of the end-of-run work, so inside the measured span
+    if (uniq) for (DevSess& D : s->devs) { rc = materialize_bitset(s, D); if (rc) return rc; }
+    CU(cudaSetDevice(D0.dev));
+    stamp("seen bits -> bitset");
     // ---- counters and max-contigs
     NC(N->GroupStart());
     for (int l = 0; l < L; l++) {
@@ -1663,6 +1794,7 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
         NC(N->AllReduce(D.maxcontig, D.maxcontig, (size_t)V, ncclUint64, ncclMax, cm->comms[l], D.sCompute));
     }
     NC(N->GroupEnd());
+    stamp("all-reduce counters/maxcontig");
     s->mergeBytes = 0; s->mergePath = 0;
     if (uniq && D0.bitset) {
         CU(cudaSetDevice(D0.dev));
@@ -1677,6 +1809,9 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
             if (L == W) {   // one process: every device's arrays are directly addressable
                 peer = cm->ctx->peerAll;
                 for (int l = 0; l < L && peer; l++) for (int q = 0; q < W; q++) { bitPtr[l][q] = s->devs[q].bitset; hitPtr[l][q] = s->devs[q].hitCounts; }
+            } else if (s->prepComm == cm) {   // mapped ahead of the run (gs_match_prepare_merge)
+                peer = s->prepPeer;
+                for (int q = 0; q < W; q++) { bitPtr[0][q] = s->prepBits[(size_t)q]; hitPtr[0][q] = s->prepHits[(size_t)q]; }
             } else {        // one process per GPU: map the other ranks' arrays through IPC handles
                 int ok = 0;
                 rc = ipc_exchange(N, cm, D0.sCompute, D0.bitset, bitPtr[0].data(), keep, &ok);
@@ -1686,6 +1821,7 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
             }
         }
         s->mergePath = peer ? 1 : 2;
+        stamp("peer mappings");
         // ---- bitset: OR of the own slice over all ranks + per-taxon popcount, then the sum of the slices' counts
         std::vector<u64*> recv((size_t)L, nullptr);
         struct FreeAll { std::vector<u64*>& v; std::vector<DevSess>& d; ~FreeAll() { for (size_t i = 0; i < v.size(); i++) if (v[i]) { cudaSetDevice(d[i].dev); cudaFree(v[i]); } } } fr{recv, s->devs};
@@ -1717,14 +1853,17 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
             memset(&src, 0, sizeof(src));
             for (int q = 0; q < W; q++) src.p[q] = peer ? (const u64*)bitPtr[l][q] : recv[l] + (u64)q * per - lo;
             CU(cudaMemsetAsync(D.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D.sCompute));
-            gs_launch_merge_or_popcount(src, W, D.bitset, lo, hi, s->db->d[D.devIndex].view, s->layout, D.unique, D.sms * 8, D.sCompute);
+            CU(dgrow(&D.popPartial, &D.popPartialCap, (size_t)gs_popcount_scratch_words(D.sms, V)));
+            gs_launch_merge_or_popcount(src, W, D.bitset, lo, hi, s->db->d[D.devIndex].view, s->layout, D.unique, D.popPartial, D.sms, D.sCompute);
             CU(cudaGetLastError());
             s->launches += 1;
             if (l == 0) s->mergeBytes += (hi - lo) * 8 * (u64)(W - 1);
         }
+        stamp("OR + popcount kernel");
         NC(N->GroupStart());
         for (int l = 0; l < L; l++) NC(N->AllReduce(s->devs[l].unique, s->devs[l].unique, (size_t)V, ncclInt64, ncclSum, cm->comms[l], s->devs[l].sCompute));
         NC(N->GroupEnd());
+        stamp("all-reduce unique");
         // ---- per-position hit counters: slice sums, then every rank collects the merged slices of bitset and counters
         if (D0.hitCounts) {
             std::vector<uint16_t*> hrecv((size_t)L, nullptr);
@@ -1790,6 +1929,8 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
     CU(cudaEventElapsedTime(&msBits, e1, e2));
     s->mergeMs = msAll; s->mergeBitsetMs = msBits;
     s->merged = true;
+    for (void* p : s->prepOpened) if (p) cudaIpcCloseMemHandle(p);
+    s->prepOpened.clear(); s->prepComm = nullptr;
     return GS_OK;
 }
 
@@ -1805,7 +1946,8 @@ static int read_out(gs_sess* s, gs_taxon_counts* counts, int16_t* top_counts, bo
     if (D0.bitset) {
         if (popcountLocal) {
             CU(cudaMemsetAsync(D0.unique, 0, std::max<size_t>(V, 1) * sizeof(long long), D0.sCompute));
-            gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].view, s->layout, D0.unique, D0.sms * 8, D0.sCompute);
+            CU(dgrow(&D0.popPartial, &D0.popPartialCap, (size_t)gs_popcount_scratch_words(D0.sms, V)));
+            gs_launch_unique_popcount(D0.bitset, 0, D0.bitsetWords, s->db->d[0].view, s->layout, D0.unique, D0.popPartial, D0.sms, D0.sCompute);
             CU(cudaGetLastError());
             s->launches += 1;
             CU(cudaStreamSynchronize(D0.sCompute));

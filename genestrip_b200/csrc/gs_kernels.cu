@@ -19,6 +19,8 @@
 //  * mergeReadTaxidPath (:568-586) is idempotent per node, so only first occurrences of distinct taxa matter.
 #include "gs_kernels.cuh"
 
+#include <algorithm>
+#include <cstring>
 #include <type_traits>
 
 #define FULL 0xFFFFFFFFu
@@ -928,30 +930,93 @@ void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u3
     gs_maxcontig_events_kernel<<<(V + 255) / 256, 256, 0, st>>>(maxcontig, V, firstReadNo, nReads, ev, nEv);
 }
 
-// KMerUniqueCounterBits.getUniqueKmerCounts (C/store/KMerUniqueCounterBits.java:146-163): per value index, the
-// number of set bits among its storage positions.  One thread per 64-bit bitset word; equal value indices of a
-// warp's current bits are pre-aggregated with match_any before the atomic.
-__global__ void gs_unique_popcount_kernel(const u64* __restrict__ bits, u64 wordBegin, u64 wordEnd, GsDbView db, int layout, long long* unique) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 w0 = wordBegin + (u64)blockIdx.x * blockDim.x; w0 < wordEnd; w0 += stride) {  // warp-uniform trip count
-        const u64 w = w0 + threadIdx.x;
-        u64 word = w < wordEnd ? __ldg(bits + w) : 0ULL;
-        while (__any_sync(FULL, word != 0)) {
-            int v = -1;
-            if (word) {
-                const int b = __ffsll((long long)word) - 1;
-                word &= word - 1;
-                const u64 pos = w * 64 + (u64)b;
-                const u32 vv = gs_value_at(db, layout, pos);
-                if (vv != GS_VAL_NONODE) v = (int)vv;
+// KMerUniqueCounterBits.getUniqueKmerCounts (C/store/KMerUniqueCounterBits.java:146-163): per value index, the number of
+// set bits among its storage positions -- and, across GPUs, the OR-merge that makes ONE bitset out of the per-GPU ones first
+// (KMerUniqueCounterBits is one object in the reference, :117-163; here every GPU has set bits for its share of the reads).
+//
+// A rank owns the words [wordBegin, wordEnd) of the bitset.  src.p[q][w] is rank q's word w -- either q's bitset itself, read
+// over NVLink through a peer mapping (no staging copy: the transfer IS the kernel's loads), or the slice q sent into a local
+// receive buffer (pointer pre-offset by -wordBegin).  nSrc == 0: no merge, count the own words.
+// Shape: the storage positions of a word are 64 consecutive table slots (or sorted-array indices), so the values are streamed,
+// not looked up: a warp ORs 32 words (one coalesced load per source), then walks its non-zero words with every lane owning two
+// positions -- one 16-byte load of the two table entries where a bit is set.  Counts go to a per-CTA table in shared memory
+// (value indices are spread evenly over the positions: global atomics on [V] counters were the whole cost of the first
+// version, 44 ms for the 2e9-k-mer store on 2 GPUs); every CTA writes its table to `partial`, gs_sum_partials_kernel adds them up.
+#define GS_POP_THREADS 1024
+#define GS_POP_VCHUNK 57344u   // value indices counted per pass: 224 KB of u32 counters in shared memory
+__global__ void __launch_bounds__(GS_POP_THREADS, 1) gs_merge_or_popcount_kernel(const GsPeerPtrs src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd,
+                                                                                const GsDbView db, int layout, u32 vLo, u32 vCnt, u32* __restrict__ partial) {
+    extern __shared__ u32 s_cnt[];
+    for (u32 i = threadIdx.x; i < vCnt; i += GS_POP_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 stride = (u64)gridDim.x * (GS_POP_THREADS / 32) * 32;
+    for (u64 g = wordBegin + ((u64)blockIdx.x * (GS_POP_THREADS / 32) + warp) * 32; g < wordEnd; g += stride) {
+        const u64 w = g + lane;
+        u64 m = 0;
+        if (w < wordEnd) {
+            if (nSrc > 0) {
+                for (int q = 0; q < nSrc; q++) m |= src.p[q][w];
+                own[w] = m;
+            } else {
+                m = own[w];
             }
-            const u32 peers = __match_any_sync(FULL, v);
-            if (v >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd((u64*)(unique + v), (u64)__popc(peers));
+        }
+        u32 nz = __ballot_sync(FULL, m != 0);
+        while (nz) {
+            const int j = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const u64 word = __shfl_sync(FULL, m, j);
+            const u32 b2 = (u32)(word >> (2 * lane)) & 3u;
+            if (b2) {
+                const u64 pos = (g + (u64)j) * 64 + 2 * (u64)lane;   // two neighbouring storage positions per lane
+                u32 v0 = GS_VAL_NONODE, v1 = GS_VAL_NONODE;
+                if (layout == GS_LAYOUT_TABLE) {
+                    if (pos + 1 < db.tabSlots) {
+                        u64 e0, e1;
+                        asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(e0), "=l"(e1) : "l"(db.tab + pos));
+                        if (e0 & GS_TAB_OCC) v0 = (u32)(e0 >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
+                        if (e1 & GS_TAB_OCC) v1 = (u32)(e1 >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
+                    }
+                } else {
+                    if (pos < db.n) v0 = __ldg(db.vals + pos);
+                    if (pos + 1 < db.n) v1 = __ldg(db.vals + pos + 1);
+                }
+                if ((b2 & 1u) && v0 != GS_VAL_NONODE && v0 - vLo < vCnt) atomicAdd(&s_cnt[v0 - vLo], 1u);
+                if ((b2 & 2u) && v1 != GS_VAL_NONODE && v1 - vLo < vCnt) atomicAdd(&s_cnt[v1 - vLo], 1u);
+            }
         }
     }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < vCnt; i += GS_POP_THREADS) partial[(u64)blockIdx.x * vCnt + i] = s_cnt[i];
 }
-void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st) {
-    if (wordEnd > wordBegin) gs_unique_popcount_kernel<<<blocks, 256, 0, st>>>(bits, wordBegin, wordEnd, db, layout, unique);
+__global__ void gs_sum_partials_kernel(const u32* __restrict__ partial, int nBlocks, u32 vCnt, long long* unique) {
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= vCnt) return;
+    long long acc = 0;
+    for (int b = 0; b < nBlocks; b++) acc += partial[(u64)b * vCnt + v];
+    unique[v] += acc;
+}
+// partial = scratch of gs_popcount_scratch_words(blocks, nValues) u32.  unique[v] += set bits of value index v in the words.
+u64 gs_popcount_scratch_words(int blocks, int nValues) { return (u64)blocks * std::min<u64>((u64)std::max(nValues, 1), GS_POP_VCHUNK); }
+void gs_launch_merge_or_popcount(const GsPeerPtrs& src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout,
+                                 long long* unique, u32* partial, int blocks, cudaStream_t st) {
+    if (wordEnd < wordBegin) return;   // an empty range still launches (one block): loads the function ahead of the merge
+    const u64 groups = (wordEnd - wordBegin + GS_POP_THREADS - 1) / GS_POP_THREADS;
+    blocks = (int)std::max<u64>(1, std::min<u64>((u64)blocks, groups));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gs_merge_or_popcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GS_POP_VCHUNK * sizeof(u32))); attr = true; }
+    const u32 V = (u32)std::max(db.nValues, 1);
+    for (u32 vLo = 0; vLo < V; vLo += GS_POP_VCHUNK) {   // one pass unless there are more than GS_POP_VCHUNK value indices
+        const u32 vCnt = std::min(GS_POP_VCHUNK, V - vLo);
+        gs_merge_or_popcount_kernel<<<blocks, GS_POP_THREADS, vCnt * sizeof(u32), st>>>(src, vLo == 0 ? nSrc : 0, own, wordBegin, wordEnd, db, layout, vLo, vCnt, partial);
+        gs_sum_partials_kernel<<<(vCnt + 255) / 256, 256, 0, st>>>(partial, blocks, vCnt, unique + vLo);
+    }
+}
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, u32* partial, int blocks, cudaStream_t st) {
+    GsPeerPtrs none;
+    memset(&none, 0, sizeof(none));
+    gs_launch_merge_or_popcount(none, 0, const_cast<u64*>(bits), wordBegin, wordEnd, db, layout, unique, partial, blocks, st);
 }
 
 // (value index, hit counter) of every set position, for getMaxCountsCounts (C/store/KMerUniqueCounterBits.java:173-199)
@@ -1136,50 +1201,7 @@ void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* ta
     gs_table_flags_kernel<<<148 * 8, 256, 0, st>>>(tab, delta, nBuckets);
 }
 
-// ---- end-of-run merge of the per-GPU unique-k-mer state (KMerUniqueCounterBits is ONE bitset in the reference,
-// C/store/KMerUniqueCounterBits.java:117-163; here every GPU has set bits for its share of the reads).
-// Rank r owns the words [wordBegin, wordEnd) of the bitset.  src.p[q][w] is rank q's word w -- either q's bitset itself,
-// read over NVLink through a peer mapping (no staging copy: the transfer IS the kernel's loads), or the slice q sent into a
-// local receive buffer (pointer pre-offset by -wordBegin).  One pass ORs the nSrc copies with 128-bit loads, writes the merged
-// words into the own bitset and counts them per value index (getUniqueKmerCounts :146-163); the counts of the slices are
-// then summed over the ranks.
-__global__ void __launch_bounds__(256) gs_merge_or_popcount_kernel(const GsPeerPtrs src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd,
-                                                                   const GsDbView db, int layout, long long* unique) {
-    const u64 stride = (u64)gridDim.x * blockDim.x * 2;
-    for (u64 w0 = wordBegin + (u64)blockIdx.x * blockDim.x * 2; w0 < wordEnd; w0 += stride) {  // warp-uniform trip count
-        const u64 w = w0 + (u64)threadIdx.x * 2;   // wordBegin is even (slices are cut at even word indices), so w is 16-byte aligned
-        u64 m[2] = {0, 0};
-        if (w + 1 < wordEnd) {
-            for (int q = 0; q < nSrc; q++) {
-                const ulonglong2 v = *(const ulonglong2*)(src.p[q] + w);
-                m[0] |= v.x; m[1] |= v.y;
-            }
-            *(ulonglong2*)(own + w) = make_ulonglong2(m[0], m[1]);
-        } else if (w < wordEnd) {
-            for (int q = 0; q < nSrc; q++) m[0] |= src.p[q][w];
-            own[w] = m[0];
-        }
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            u64 word = m[h];
-            while (__any_sync(FULL, word != 0)) {
-                int v = -1;
-                if (word) {
-                    const int b = __ffsll((long long)word) - 1;
-                    word &= word - 1;
-                    const u32 vv = gs_value_at(db, layout, (w + h) * 64 + (u64)b);
-                    if (vv != GS_VAL_NONODE) v = (int)vv;
-                }
-                const u32 peers = __match_any_sync(FULL, v);
-                if (v >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd((u64*)(unique + v), (u64)__popc(peers));
-            }
-        }
-    }
-}
-void gs_launch_merge_or_popcount(const GsPeerPtrs& src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout,
-                                 long long* unique, int blocks, cudaStream_t st) {
-    if (wordEnd > wordBegin) gs_merge_or_popcount_kernel<<<blocks, 256, 0, st>>>(src, nSrc, own, wordBegin, wordEnd, db, layout, unique);
-}
+// ---- end-of-run merge of the per-GPU unique-k-mer state: gs_merge_or_popcount_kernel above; here the hit counters
 // per-position hit counters (maxKMerResCounts > 0): own[i] = sum over the ranks, Java short wrap-around (:134-140)
 __global__ void gs_merge_add_u16_kernel(const GsPeerPtrs src, int nSrc, uint16_t* own, u64 begin, u64 end) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -1394,11 +1416,13 @@ __global__ void gs_cgat_upper_kernel(uint8_t* buf, u64 n) {
     }
 }
 void gs_launch_cgat_upper(uint8_t* buf, u64 n, cudaStream_t st) { gs_cgat_upper_kernel<<<148 * 8, 256, 0, st>>>(buf, n); }
-__global__ void gs_values_to_raw_kernel(const uint16_t* __restrict__ vals, u64 n, int16_t* raw) {
+// `kept` = the shorts as they were uploaded (only there when some value index has no tree node): a position whose value was
+// collapsed to GS_VAL_NONODE gets its original short back, so save -> load round-trips such databases.
+__global__ void gs_values_to_raw_kernel(const uint16_t* __restrict__ vals, const int16_t* __restrict__ kept, u64 n, int16_t* raw) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const u32 v = vals[i];
-        raw[i] = v == GS_VAL_NONODE ? (int16_t)-1 : (int16_t)((int)v - 32768);  // value index + Short.MIN_VALUE (KMerSortedArray.java:348)
+        raw[i] = v == GS_VAL_NONODE ? (kept ? kept[i] : (int16_t)-1) : (int16_t)((int)v - 32768);  // value index + Short.MIN_VALUE (KMerSortedArray.java:348)
     }
 }
-void gs_launch_values_to_raw(const uint16_t* vals, u64 n, int16_t* raw, cudaStream_t st) { gs_values_to_raw_kernel<<<148 * 8, 256, 0, st>>>(vals, n, raw); }
+void gs_launch_values_to_raw(const uint16_t* vals, const int16_t* kept, u64 n, int16_t* raw, cudaStream_t st) { gs_values_to_raw_kernel<<<148 * 8, 256, 0, st>>>(vals, kept, n, raw); }

@@ -67,7 +67,8 @@ void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t
 void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st);
 void gs_launch_reduce_thread(const GsMatchParams& P, int blocks, cudaStream_t st);
 void gs_launch_maxcontig_events(const u64* maxcontig, int V, u64 firstReadNo, u32 nReads, gs_maxcontig_event* ev, u32* nEv, cudaStream_t st);
-void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, int blocks, cudaStream_t st);
+u64 gs_popcount_scratch_words(int blocks, int nValues);
+void gs_launch_unique_popcount(const u64* bits, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout, long long* unique, u32* partial, int blocks, cudaStream_t st);
 void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCounts, const GsDbView& db, int layout, u32* out, unsigned long long* nOut, u64 cap, cudaStream_t st);
 void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st);
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st);
@@ -79,7 +80,7 @@ void gs_launch_mz_build(const u64* keys, u64 n, int k, u64* filter, u32 mask, in
 #define GS_MAX_RANKS 64
 struct GsPeerPtrs { const u64* p[GS_MAX_RANKS]; };
 void gs_launch_merge_or_popcount(const GsPeerPtrs& src, int nSrc, u64* own, u64 wordBegin, u64 wordEnd, const GsDbView& db, int layout,
-                                 long long* unique, int blocks, cudaStream_t st);
+                                 long long* unique, u32* partial, int blocks, cudaStream_t st);
 void gs_launch_merge_add_u16(const GsPeerPtrs& src, int nSrc, uint16_t* own, u64 begin, u64 end, cudaStream_t st);
 void gs_launch_bucket_index(const u64* keys, u64 n, int bshift, u64 nb, u32* bstart, cudaStream_t st);
 void gs_launch_bloom_build(const u64* keys, u64 n, u64* words, u64 buckets, u64 magic, long long seed, cudaStream_t st);
@@ -102,7 +103,7 @@ void gs_launch_text_event_headers(const gs_maxcontig_event* ev, const u32* nEv, 
 void gs_launch_db_update(const GsDbView& db, const u32* labels, const long long* flatPos, u64 flatLen, const u64* offsets, const int* regionNode,
                          u32 nRegions, uint16_t* vals, unsigned long long* nChanged, cudaStream_t st);
 void gs_launch_cgat_upper(uint8_t* buf, u64 n, cudaStream_t st);
-void gs_launch_values_to_raw(const uint16_t* vals, u64 n, int16_t* raw, cudaStream_t st);
+void gs_launch_values_to_raw(const uint16_t* vals, const int16_t* kept, u64 n, int16_t* raw, cudaStream_t st);
 
 // gs_inflate.cu: one thread per raw-deflate block (block-gzip input), status per block
 void gs_launch_inflate_blocks(const uint8_t* comp, uint8_t* text, gs_deflate_block* blocks, uint32_t nBlocks, cudaStream_t st);

@@ -244,6 +244,10 @@ int gs_comm_world(const gs_comm*);
 int gs_comm_rank(const gs_comm*);
 void gs_comm_destroy(gs_comm*);
 int gs_match_finish_comm(gs_sess*, gs_comm*, gs_taxon_counts* counts, int16_t* top_counts);
+/* Optional, collective, any time before gs_match_finish_comm (best right after gs_match_open): exchanges the peer mappings of
+ * the ranks' unique-k-mer bitsets and loads the merge kernel, so that the merge at the end of the run does not pay for them
+ * (5 ms for a 512 MB bitset).  Every rank must call gs_match_finish_comm before any rank closes its session. */
+int gs_match_prepare_merge(gs_sess*, gs_comm*);
 /* The packer itself (host only, no device needed): n ASCII bases -> codes[ceil(n/32)] (2-bit codes C=0 G=1 A=2 T=3,
  * C/util/CGAT.java:66-69, 32 per word, first base in the top two bits) and valid[ceil(n/32)] (bit i = base 32w+i is one of the
  * upper-case letters CGAT, CGAT.java:60-69).  threads as in gs_match_cfg.host_pack_threads (1 = the calling thread alone). */

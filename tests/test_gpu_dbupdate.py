@@ -154,3 +154,39 @@ def test_db_file_round_trip(oracle, native, gpu_ctx, tmp_path):
         g2.close()
         odb_fill.free()
         odb_full.free()
+
+
+def test_db_file_round_trip_keeps_values_without_a_tree_node(native, gpu_ctx, tmp_path):
+    """A stored value whose tax id has no tree node matches like a miss (C/store/Database.java:136-143) but must come back from
+    gs_db_get_values / a saved file with its own index, not as index 32767; and a header that lies about sizes is refused
+    before anything is allocated from it."""
+    rng = np.random.default_rng(11)
+    n, V = 5000, 6
+    keys = np.unique(rng.integers(0, 1 << 62, size=n, dtype=np.int64))
+    vidx = rng.integers(0, V, size=len(keys))
+    vals = (vidx - 32768).astype(np.int16)
+    parent = np.array([-1, 0, 0, 1, -1, 2], dtype=np.int32)
+    has_node = np.array([1, 1, 1, 1, 0, 1], dtype=np.int32)     # value index 4: taxon not in the tree
+    db = native.Database(gpu_ctx, K, keys, vals, V, parent_by_vidx=parent, has_node=has_node, bloom=None, build_bloom=True)
+    path = str(tmp_path / "nonode.gsb")
+    try:
+        np.testing.assert_array_equal(db.values(), vals)
+        v, _ = db.lookup(keys)
+        np.testing.assert_array_equal(v, np.where(vidx == 4, -1, vidx))
+        db.save(path)
+    finally:
+        db.close()
+    g2 = native.Database.load(gpu_ctx, path)
+    try:
+        np.testing.assert_array_equal(g2.values(), vals)
+        v, _ = g2.lookup(keys)
+        np.testing.assert_array_equal(v, np.where(vidx == 4, -1, vidx))
+    finally:
+        g2.close()
+    raw = bytearray(open(path, "rb").read())
+    for field_off, val in ((16, 1 << 40), (24, 70000), (48, 1 << 50)):   # n_kmers, n_values, bloom_words
+        bad = bytearray(raw)
+        bad[field_off:field_off + 8] = int(val).to_bytes(8, "little")
+        open(str(tmp_path / "lie.gsb"), "wb").write(bad)
+        with pytest.raises(native.GenestripError):
+            native.Database.load(gpu_ctx, str(tmp_path / "lie.gsb"))

@@ -52,8 +52,10 @@ def _worker(rank, world, port, merge_path, out):
         n = len(offsets) - 1
         lo, hi = rank * n // world, (rank + 1) * n // world        # this rank's share; read ordinals stay global
         report = []
-        for cfg in CONFIGS:
+        for ci, cfg in enumerate(CONFIGS):
             sess = capi.MatchSession(gdb, capi.default_match_cfg(**cfg))
+            if ci % 2 == 0:   # with and without the set-up done ahead of the run (gs_match_prepare_merge)
+                sess.prepare_merge(comm)
             res = []
             for b0 in range(lo, hi, 700):
                 b1 = min(hi, b0 + 700)
