@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 6
+GS_ABI_VERSION = 7
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -29,7 +29,7 @@ class MatchCfg(C.Structure):
     _fields_ = [("classify_reads", C.c_int), ("count_unique_kmers", C.c_int), ("max_kmer_res_counts", C.c_int),
                 ("use_bloom_filter", C.c_int), ("max_classification_paths", C.c_int), ("min_kmers_for_class", C.c_int),
                 ("max_read_tax_error_count", C.c_double), ("max_read_class_error_count", C.c_double),
-                ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int), ("host_pack_threads", C.c_int)]
+                ("want_runs", C.c_int), ("layout", C.c_int), ("prefilter", C.c_int), ("host_pack_threads", C.c_int), ("host_pack_percent", C.c_int)]
 
 
 class FastqInfo(C.Structure):
@@ -93,6 +93,7 @@ _SIGS = {
     "gs_match_finish_comm": (C.c_int, [_P, _P, _P, _P]),
     "gs_pack_bases": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int]),
     "gs_pack_isa": (C.c_char_p, []),
+    "gs_match_pack_fraction": (C.c_double, [_P]),
     "gs_match_pack_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gs_match_merge_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "gs_match_close": (None, [_P]),
@@ -496,6 +497,10 @@ class MatchSession:
         else:
             _check(lib().gs_match_finish_comm(self.h, comm.h, _ptr(counts), _ptr(top)))
         return counts[:V], top
+
+    @property
+    def pack_fraction(self):
+        return lib().gs_match_pack_fraction(self.h)
 
     def pack_stats(self):
         """(threads, host seconds spent packing, bases packed, base bytes put on the link) of this session's submits."""

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -850,6 +851,10 @@ struct MatchSlot {
     u32* hValid = nullptr; size_t hValidCap = 0;
     u64* dCodes = nullptr; size_t dCodesCap = 0;
     u32* dValid = nullptr; size_t dValidCap = 0;
+    // split of the last submit (adaptive link split, see gs_match_submit): ASCII bytes copied and the events around that copy
+    u64 asciiBytes = 0, packedBases = 0;
+    double packSec = 0;
+    cudaEvent_t evAscii0 = nullptr, evAscii1 = nullptr;
     cudaEvent_t evH2D = nullptr, evCompute = nullptr, evDone = nullptr;
 };
 
@@ -898,6 +903,11 @@ struct gs_sess {
     std::vector<void*> prepBits, prepHits;   // [world]
     std::vector<void*> prepOpened;           // mappings to close (cudaIpcCloseMemHandle)
     gsp::Packer* packer = nullptr;           // host_pack_threads != 0: made on the first gs_match_submit
+    double packFrac = 0.7;                   // share of a batch's bases that goes over the link packed (the rest as ASCII)
+    bool packSeeded = false;                 // packFrac was set once from the first batch's measured costs
+    int packDir = 1, packAcc = 0;            // hill climbing on the time per byte between submits
+    double packAccSec = 0, packAccBytes = 0, packLastCost = 0, packPrevBytes = 0;
+    std::chrono::steady_clock::time_point packPrevSubmit;
     double packSeconds = 0;                  // host time spent packing (gs_match_pack_stats)
     u64 packBytes = 0, h2dBytes = 0;         // bases packed / bytes of base data put on the link
 };
@@ -917,6 +927,7 @@ extern "C" void gs_match_cfg_default(gs_match_cfg* c) {
     c->layout = GS_LAYOUT_TABLE;
     c->prefilter = 1;
     c->host_pack_threads = -1;
+    c->host_pack_percent = -1;
 }
 
 static int sess_alloc_dev(gs_sess* s, DevSess& D) {
@@ -956,6 +967,7 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
         CU(cudaEventCreateWithFlags(&sl.evH2D, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.evDone, cudaEventDisableTiming));
+        CU(cudaEventCreate(&sl.evAscii0)); CU(cudaEventCreate(&sl.evAscii1));
         CU(dmalloc(&sl.dEv, (size_t)std::max(V, 1)));
         CU(dmalloc(&sl.dNEv, 2));
         CU(cudaMallocHost((void**)&sl.hEv, std::max<size_t>(V, 1) * sizeof(gs_maxcontig_event)));
@@ -984,6 +996,8 @@ extern "C" void gs_match_close(gs_sess* s) {
             if (sl.evH2D) cudaEventDestroy(sl.evH2D);
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
+            if (sl.evAscii0) cudaEventDestroy(sl.evAscii0);
+            if (sl.evAscii1) cudaEventDestroy(sl.evAscii1);
         }
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique); cudaFree(D.popPartial);
         cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
@@ -1151,30 +1165,69 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     GsMatchParams P;
     fill_params(s, D, P);
     // inputs: host -> device on the copy-in stream (cudaMemcpyAsync; truly asynchronous for pinned buffers)
-    const bool packed = s->cfg.host_pack_threads != 0 && nBytes > 0;
-    if (packed) {
-        // 0.375 instead of 1 byte per base on the link: the host threads write the two streams the label kernel stages anyway
-        // (gs_pack.hpp).  The kernel reads 32 words per segment of 31: room for that behind the last packed word, zeroed.
+    // Two resources move a batch: the link (1 byte per base as ASCII, no CPU work) and the host's cores (which can pack the
+    // bases to 0.375 bytes each, gs_pack.hpp).  Either alone is the bottleneck somewhere -- the link with one GPU, the cores
+    // (host memory bandwidth, really) with eight -- so a batch is split at a segment boundary: the tail goes out as ASCII
+    // first, its copy runs while the pool packs the head, then the packed words follow.  The label kernel stages a segment
+    // from whichever form holds it.  The split follows the measured cost per byte of the two routes (adaptive unless
+    // host_pack_percent fixes it); results do not depend on it.
+    if (s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && nBytes >= (1u << 22)) {
+        // time per byte from one submit to the next = what the caller sees; every second batch the split takes one step, and
+        // turns round when the last step made things worse.  (A caller that is slower than both routes sees a flat cost: the
+        // split then wanders, harmlessly.)
+        const auto now = std::chrono::steady_clock::now();
+        if (s->packPrevBytes > 0) {
+            s->packAccSec += std::chrono::duration<double>(now - s->packPrevSubmit).count();
+            s->packAccBytes += s->packPrevBytes;
+            if (++s->packAcc == 2) {
+                const double cost = s->packAccSec / s->packAccBytes;
+                if (s->packSeeded) {
+                    if (s->packLastCost > 0 && cost > s->packLastCost * 1.01) s->packDir = -s->packDir;
+                    s->packFrac = std::min(1.0, std::max(0.0, s->packFrac + 0.05 * s->packDir));
+                }
+                s->packLastCost = cost;
+                s->packAcc = 0; s->packAccSec = 0; s->packAccBytes = 0;
+            }
+        }
+        s->packPrevSubmit = now; s->packPrevBytes = (double)nBytes;
+    }
+    const u64 nSegAll = (nBytes + GS_SEG_POS - 1) / GS_SEG_POS;
+    u64 packSegs = 0;
+    if (s->cfg.host_pack_threads != 0 && nBytes > 0) {
+        const double frac = s->cfg.host_pack_percent >= 0 ? std::min(100, s->cfg.host_pack_percent) / 100.0 : s->packFrac;
+        packSegs = std::min<u64>(nSegAll, (u64)llround(frac * (double)nSegAll));
+    }
+    const u64 asciiFrom = std::min<u64>(nBytes, packSegs * GS_SEG_POS);   // first byte that travels as ASCII (a multiple of 16)
+    sl.asciiBytes = nBytes - asciiFrom; sl.packedBases = 0; sl.packSec = 0;
+    if (asciiFrom < nBytes) {
+        CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));   // sized for the whole batch: the split moves, the buffers stay
+        CU(cudaEventRecord(sl.evAscii0, D.sCopyIn));
+        CU(cudaMemcpyAsync(sl.dBases, bases + base0 + asciiFrom, nBytes - asciiFrom, cudaMemcpyHostToDevice, D.sCopyIn));
+        CU(cudaEventRecord(sl.evAscii1, D.sCopyIn));
+        s->h2dBytes += nBytes - asciiFrom;
+        P.bases = sl.dBases - base0 - asciiFrom;   // byte (base0 + f) of the host buffer <-> P.bases + base0 + f, for f >= asciiFrom
+    }
+    if (packSegs) {
+        // the kernel reads 32 words per segment of 31: one word past the last packed segment, zero words behind the batch
         if (!s->packer) s->packer = new gsp::Packer(s->cfg.host_pack_threads);
-        const size_t words = (size_t)((nBytes + 31) / 32);
-        const size_t devWords = (size_t)((nBytes + GS_SEG_POS - 1) / GS_SEG_POS) * GS_SEG_CHUNKS + 64;
-        CU(hgrow(&sl.hCodes, &sl.hCodesCap, words));
-        CU(hgrow(&sl.hValid, &sl.hValidCap, words));
-        CU(dgrow(&sl.dCodes, &sl.dCodesCap, devWords));
-        CU(dgrow(&sl.dValid, &sl.dValidCap, devWords));
+        const u64 wordsAll = (nBytes + 31) / 32;
+        const size_t words = (size_t)std::min<u64>(wordsAll, packSegs * GS_SEG_CHUNKS + 2);
+        const u64 packBases = std::min<u64>(nBytes, (u64)words * 32);
+        CU(hgrow(&sl.hCodes, &sl.hCodesCap, (size_t)wordsAll));
+        CU(hgrow(&sl.hValid, &sl.hValidCap, (size_t)wordsAll));
+        CU(dgrow(&sl.dCodes, &sl.dCodesCap, (size_t)wordsAll + 64));
+        CU(dgrow(&sl.dValid, &sl.dValidCap, (size_t)wordsAll + 64));
         const auto t0 = std::chrono::steady_clock::now();
-        s->packer->pack(bases + base0, nBytes, (uint64_t*)sl.hCodes, sl.hValid);
-        s->packSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        s->packBytes += nBytes; s->h2dBytes += words * 12;
+        s->packer->pack(bases + base0, packBases, (uint64_t*)sl.hCodes, sl.hValid);
+        sl.packSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        sl.packedBases = packBases;
+        s->packSeconds += sl.packSec;
+        s->packBytes += packBases; s->h2dBytes += words * 12;
         CU(cudaMemcpyAsync(sl.dCodes, sl.hCodes, words * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
         CU(cudaMemcpyAsync(sl.dValid, sl.hValid, words * sizeof(u32), cudaMemcpyHostToDevice, D.sCopyIn));
-        CU(cudaMemsetAsync(sl.dCodes + words, 0, (devWords - words) * sizeof(u64), D.sCopyIn));
-        CU(cudaMemsetAsync(sl.dValid + words, 0, (devWords - words) * sizeof(u32), D.sCopyIn));
-        P.packCodes = sl.dCodes; P.packValid = sl.dValid;
-    } else {
-        CU(dgrow(&sl.dBases, &sl.basesCap, (size_t)nBytes + 64));
-        if (nBytes) CU(cudaMemcpyAsync(sl.dBases, bases + base0, nBytes, cudaMemcpyHostToDevice, D.sCopyIn));
-        s->h2dBytes += nBytes;
+        CU(cudaMemsetAsync(sl.dCodes + words, 0, 64 * sizeof(u64), D.sCopyIn));
+        CU(cudaMemsetAsync(sl.dValid + words, 0, 64 * sizeof(u32), D.sCopyIn));
+        P.packCodes = sl.dCodes; P.packValid = sl.dValid; P.packSegs = (u32)std::min<u64>(packSegs, 0xFFFFFFFFu);
     }
     CU(cudaMemcpyAsync(sl.dOffsets, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
     if (s->cfg.want_runs) {
@@ -1199,7 +1252,7 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
     // offsets are relative to bases + offsets[0] on the device: the kernel subtracts nothing, so rebase here
     // (the device copy of the base stream starts at host offset base0)
-    P.bases = packed ? nullptr : sl.dBases - base0;
+    if (!P.bases) P.bases = (const uint8_t*)nullptr - base0;   // nothing travels as ASCII: only the alignment of P.bases + base0 is looked at
     int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, base0, nBytes);
     if (rc) return rc;
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
@@ -1340,6 +1393,19 @@ static int wait_ticket(gs_sess* s, gs_ticket t, DevSess** Dout, MatchSlot** slOu
     CU(cudaEventSynchronize(sl.evDone));
     sl.pending = false;
     *Dout = &D; *slOut = &sl;
+    if (!sl.isText && s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && !s->packSeeded && sl.packedBases >= (1u << 22) && sl.asciiBytes >= (1u << 22)) {
+        // first estimate of the split from the first batch's own costs: packing time p per byte on the cores, copy time a per
+        // byte on the link; cores and link are busy equally long when  p x = a (1 - x) + 0.375 a x.  From there on the split
+        // climbs along the measured time per batch (pack_split_step in gs_match_submit).
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sl.evAscii0, sl.evAscii1) == cudaSuccess && ms > 0) {
+            const double pB = sl.packSec / (double)sl.packedBases, aB = ms * 1e-3 / (double)sl.asciiBytes;
+            s->packFrac = std::min(0.9, std::max(0.1, aB / (pB + 0.625 * aB)));
+            s->packSeeded = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (sl.hNEv[1]) return gs_fail(GS_ERR_ARG, "batch of ticket %llu holds malformed read offsets (descending, or a read longer than 2^31 bases)", (unsigned long long)t);
     return GS_OK;
 }
@@ -2035,6 +2101,7 @@ extern "C" int gs_pack_bases(const uint8_t* bases, uint64_t n, uint64_t* codes, 
 }
 extern "C" const char* gs_pack_isa(void) { return gsp::pack_isa(); }
 
+extern "C" double gs_match_pack_fraction(const gs_sess* s) { return s ? (s->cfg.host_pack_threads == 0 ? 0.0 : s->cfg.host_pack_percent >= 0 ? s->cfg.host_pack_percent / 100.0 : s->packFrac) : 0.0; }
 extern "C" int gs_match_pack_stats(const gs_sess* s, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes) {
     if (!s) return gs_fail(GS_ERR_ARG, "null session");
     if (threads) *threads = s->packer ? s->packer->threads() : 0;

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
         __syncwarp();
         // ---- stage: ASCII -> packed 2-bit codes + validity bits (C/util/CGAT.java:60-69)
         const uint4* ap = (const uint4*)(fb + f0);
-        if (P.packCodes) {  // the host packed the batch: the two streams arrive ready-made, one coalesced load each
+        if (seg < P.packSegs) {  // the host packed this part of the batch: the two streams arrive ready-made, one coalesced load each
             cw[lane] = __ldg(P.packCodes + (u64)seg * GS_SEG_CHUNKS + lane);
             vw[lane] = __ldg(P.packValid + (u64)seg * GS_SEG_CHUNKS + lane);
         } else

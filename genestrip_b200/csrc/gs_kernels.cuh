@@ -8,6 +8,7 @@ struct GsMatchParams {
     const uint8_t* bases;   // reads back to back, ASCII
     const u64* packCodes;   // or (gs_pack.hpp) the same bases packed by the host: 2-bit codes, 32 per word, first base on top ...
     const u32* packValid;   // ... and a validity bit per base; flat position 0 = the batch's first base (lead = 0)
+    u32 packSegs;           // segments [0, packSegs) of the label kernel are staged from the packed words, the others from `bases`
     const u64* offsets;     // [nReads + 1]
     u32 nReads;
     u64 firstReadNo;

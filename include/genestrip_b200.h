@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 6
+#define GS_ABI_VERSION 7
 
 typedef enum gs_status {
     GS_OK = 0,
@@ -128,6 +128,9 @@ typedef struct gs_match_cfg {
                                           n > 0: n host threads (the caller included) first pack them to 2-bit codes + a
                                           validity bit, 0.375 bytes per base on the link; -1 (default): n = the CPUs this
                                           process may run on, at most 32.  Same results either way.                      */
+    int host_pack_percent;             /* with host_pack_threads != 0: the share of every batch that is packed, the rest crosses
+                                          the link as ASCII while the pool packs (link and cores work side by side).
+                                          -1 (default): follows the measured cost of the two routes; 0..100: fixed.       */
 } gs_match_cfg;
 #define GS_LAYOUT_TABLE 0   /* 128-byte probe table built from the store's arrays: one DRAM line touch per k-mer      */
 #define GS_LAYOUT_CLASSIC 1 /* the reference's own structures: blocked Bloom filter + binary search of the sorted array */
@@ -256,6 +259,7 @@ const char* gs_pack_isa(void); /* "avx512", "avx2" or "scalar": the body chosen 
 /* Host-side packing of this session so far (gs_match_cfg.host_pack_threads): threads of the pool (0 = none was needed), host
  * seconds spent packing inside gs_match_submit, bases packed, and the bytes of base data all submits put on the link. */
 int gs_match_pack_stats(const gs_sess*, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes);
+double gs_match_pack_fraction(const gs_sess*); /* the share of a batch that is packed right now (host_pack_percent) */
 /* Measurement of the last merge of this session: CUDA-event time of the whole merge and of its bitset part (ms, on the
  * session's compute stream), bitset bytes this rank read from the other ranks, path (1 = peer mappings, 2 = NCCL exchange). */
 int gs_match_merge_stats(const gs_sess*, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path);

@@ -22,11 +22,11 @@ def test_header_symbols_are_exported(native):
     for name in declared:
         assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
     assert set(native.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.gs_abi_version() == native.GS_ABI_VERSION == 6
+    assert lib.gs_abi_version() == native.GS_ABI_VERSION == 7
 
 
 def test_struct_layouts(native):
-    assert ctypes.sizeof(native.MatchCfg) == 56
+    assert ctypes.sizeof(native.MatchCfg) == 64
     assert native.READ_RESULT_DTYPE.itemsize == 16
     assert native.RUN_DTYPE.itemsize == 8
     assert native.EVENT_DTYPE.itemsize == 16

@@ -120,6 +120,11 @@ CONFIGS = [
     dict(host_pack_threads=1),
     dict(host_pack_threads=3, max_kmer_res_counts=4),
     dict(host_pack_threads=0, layout=1),
+    # the split of a batch between the two routes (default: adaptive, starts at 70 % packed)
+    dict(host_pack_threads=2, host_pack_percent=100),
+    dict(host_pack_threads=2, host_pack_percent=50),
+    dict(host_pack_threads=2, host_pack_percent=3, max_kmer_res_counts=4),
+    dict(host_pack_threads=2, host_pack_percent=0),
 ]
 
 
@@ -218,8 +223,8 @@ def _fastq(reads):
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(max_read_tax_error_count=0.5), dict(want_runs=1), dict(min_kmers_for_class=3), dict(layout=1),
-                                 dict(host_pack_threads=0), dict(host_pack_threads=0, want_runs=1)],
-                         ids=["default", "taxerr", "runs", "threshold", "classic", "ascii-link", "ascii-link-runs"])
+                                 dict(host_pack_threads=0), dict(host_pack_threads=0, want_runs=1), dict(host_pack_percent=100), dict(host_pack_percent=50, want_runs=1)],
+                         ids=["default", "taxerr", "runs", "threshold", "classic", "ascii-link", "ascii-link-runs", "packed-link", "split-link-runs"])
 def test_edge_case_reads(project, oracle, native, cfg):
     odb, gdb, genomes = project
     rng = np.random.default_rng(99)
