@@ -439,7 +439,8 @@ static int build_table(gs_db* db) {
     u32 tail = 0, hbad = 0;
     CU(cudaMemcpy(&tail, delta + nB, sizeof(u32), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&hbad, bad, sizeof(u32), cudaMemcpyDeviceToHost));
-    if (tail != 0 || hbad != 0) return gs_fail(GS_ERR_LIMIT, "probe table: a collision chain does not fit (%s)", hbad ? "a bucket with 2^16 or more keys" : "ran past the pad buckets");
+    if (tail != 0 || hbad != 0)
+        return gs_fail(GS_ERR_LIMIT, "probe table: a collision chain does not fit (%s)", (hbad & 1u) ? "a bucket with 2^16 or more keys" : (hbad & 2u) ? "a key further from its home bucket than an entry can say" : "ran past the pad buckets");
     return GS_OK;
 }
 
@@ -504,10 +505,17 @@ extern "C" int gs_db_finalize(gs_db* db) {
     {
         int tb = GS_TAB_MIN_BITS;
         while ((2ULL << tb) < db->n) tb++;
-        db->tbits = tb; db->rbits = 62 - tb;
-        db->tabBuckets = (1ULL << tb) + GS_TAB_PAD_BUCKETS;
-        rc = build_table(db);
-        if (rc) return rc;
+        if (const char* e = getenv("GS_DEBUG_TAB_BITS")) { const int v = atoi(e); if (v >= GS_TAB_MIN_BITS && v <= 40) tb = v; }   // tests: an overfull table must be refused / doubled
+        for (int attempt = 0;; attempt++) {
+            db->tbits = tb; db->rbits = 62 - tb;
+            db->tabBuckets = (1ULL << tb) + GS_TAB_PAD_BUCKETS;
+            rc = build_table(db);
+            if (rc == GS_OK) break;
+            // a chain that does not fit (possible, if astronomically unlikely, at the default load): same keys, twice the buckets
+            if (rc != GS_ERR_LIMIT || attempt == 2) return rc;
+            CU(cudaFree(d0.tab)); d0.tab = nullptr;
+            tb++;
+        }
     }
     // tree
     CU(dmalloc(&d0.parent, (size_t)V)); CU(dmalloc(&d0.depth, (size_t)V)); CU(dmalloc(&d0.pre, (size_t)V)); CU(dmalloc(&d0.last, (size_t)V));

@@ -185,8 +185,11 @@ __device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBl
 // for the whole GPU whatever their width (8, 16 or 32 bytes per lane) and whether DRAM moves 64 or 128 bytes for them.
 // The reference's structures need Bloom word(s) + bucket index + keys + value = 3-5 requests per k-mer; this table
 // needs one: a bucket is one 32-byte sector of four 8-byte entries, fetched with a single 256-bit load (LDG.E.256).
-//   entry = remainder << 19 | value << 3 | spill << 2 | occupied << 1 | seen
+//   entry = remainder << 24 | displacement << 19 | value << 3 | spill << 2 | occupied << 1 | seen
 // bucket = mix62(key) >> rbits, remainder = low rbits bits (mix62 is a bijection, so bucket + remainder identify the key);
+// `displacement` = how many buckets behind its home bucket the entry sits (0 for ~98 % of the keys): an entry that was
+// pushed into bucket b + t answers only to a lookup that has walked t buckets from ITS home, so a key of another home bucket
+// with the same remainder can never be taken for it -- the match is exact, not exact-up-to-2^-rbits;
 // `spill` (slot 0 only) = a key of this bucket was pushed to a following bucket; `seen` = unique-k-mer bit of the session
 // that leases it (KMerUniqueCounterBits), so counting a k-mer as seen needs no second memory request.
 // The placement is a pure function of the key set (gs_kernels.cu "probe table build"): the keys of home bucket b occupy the
@@ -197,12 +200,14 @@ __device__ __forceinline__ u32 gs_lookup(const GsDbView& db, u64 key, bool useBl
 #define GS_TAB_SLOTS 4
 #define GS_TAB_SLOT_STRIDE 4    // slot id = bucket * 4 + j: the "storage position" used for unique k-mer counting
 #define GS_TAB_PAD_BUCKETS 64   // landing zone behind bucket 2^tbits - 1 (the build fails if a chain would run past it)
-#define GS_TAB_MIN_BITS 17      // rbits <= 45 so that remainder + value + 3 flag bits fit 64 bits
+#define GS_TAB_MIN_BITS 22      // rbits <= 40 so that remainder + displacement + value + 3 flag bits fit 64 bits
 #define GS_TAB_SEEN 1ULL
 #define GS_TAB_OCC 2ULL
 #define GS_TAB_SPILL 4ULL
 #define GS_TAB_VAL_SHIFT 3
-#define GS_TAB_REM_SHIFT 19
+#define GS_TAB_DISP_SHIFT 19
+#define GS_TAB_DISP_MAX 31      // 5 bits; the build fails (and the caller doubles the table) if a key would sit further from home
+#define GS_TAB_REM_SHIFT 24
 #define GS_M62 ((1ULL << 62) - 1)
 
 // bijection on [0, 2^62) (xor-shifts and odd multiplications mod 2^62): equal hashes <=> equal keys
@@ -228,10 +233,10 @@ __device__ __forceinline__ GsBucket gs_load_bucket(const u64* tab, u64 b) {
 // pos = slot id of the match, seen = the slot's seen bit as loaded.
 __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBucket bk, u64& pos, bool& seen) {
     u64 b = h >> db.rbits;
-    const u64 want = ((h & ((1ULL << db.rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;
-    const u64 cmpMask = ~((1ULL << GS_TAB_REM_SHIFT) - 1) | GS_TAB_OCC;
+    u64 want = ((h & ((1ULL << db.rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;   // displacement 0: the home bucket
+    const u64 cmpMask = ~((1ULL << GS_TAB_DISP_SHIFT) - 1) | GS_TAB_OCC;
     u32 lab = GS_LABEL_MISS;
-    for (;;) {  // single exit, slot match by selects: no branch per slot, one structured join for the warp
+    for (int t = 0;; t++) {  // single exit, slot match by selects: no branch per slot, one structured join for the warp
         int j = -1;
         u64 e = 0;
 #pragma unroll
@@ -244,8 +249,9 @@ __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBuc
             lab = v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
             break;
         }
-        if (!(bk.e[0] & GS_TAB_SPILL)) break;  // nothing spilled past this bucket
+        if (!(bk.e[0] & GS_TAB_SPILL) || t == GS_TAB_DISP_MAX) break;  // nothing spilled past this bucket
         b = b + 1;                             // no wrap-around: the pad buckets end every chain
+        want += 1ULL << GS_TAB_DISP_SHIFT;     // an entry of this key there carries the distance walked
         bk = gs_load_bucket(db.tab, b);
     }
     return lab;
@@ -254,9 +260,9 @@ __device__ __forceinline__ u32 gs_table_resolve(const GsDbView& db, u64 h, GsBuc
 // The same split in two for the label kernel: the first bucket is matched without a branch (every lane of the warp runs it,
 // lanes without a pending lookup on bucket 0), the rare continuation into the following buckets is a loop of its own.
 // Returns the slot index of the match in bk (or -1) and the matching entry.
-__device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& bk, u64& e) {
-    const u64 want = ((h & ((1ULL << rbits) - 1)) << GS_TAB_REM_SHIFT) | GS_TAB_OCC;
-    const u64 cmpMask = ~((1ULL << GS_TAB_REM_SHIFT) - 1) | GS_TAB_OCC;
+__device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& bk, u64& e, int t = 0) {
+    const u64 want = ((h & ((1ULL << rbits) - 1)) << GS_TAB_REM_SHIFT) | ((u64)t << GS_TAB_DISP_SHIFT) | GS_TAB_OCC;
+    const u64 cmpMask = ~((1ULL << GS_TAB_DISP_SHIFT) - 1) | GS_TAB_OCC;
     int j = -1;
     e = 0;
 #pragma unroll
@@ -267,11 +273,11 @@ __device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& 
 // (scalars instead of the view: a reference to the kernel parameter block would force a local copy of it)
 static __device__ __noinline__ u32 gs_table_chain(const u64* tab, int rbits, u64 h, u64 b, u64* posOut, u32* seenOut) {
     u32 lab = GS_LABEL_MISS;
-    for (;;) {
+    for (int t = 1; t <= GS_TAB_DISP_MAX; t++) {
         b = b + 1;
         const GsBucket bk = gs_load_bucket(tab, b);
         u64 e;
-        const int j = gs_table_match(rbits, h, bk, e);
+        const int j = gs_table_match(rbits, h, bk, e, t);
         if (j >= 0) {
             *posOut = b * GS_TAB_SLOT_STRIDE + (u64)j;
             *seenOut = (u32)(e & GS_TAB_SEEN);

@@ -1046,7 +1046,8 @@ void gs_launch_collect_hits(const u64* bits, u64 nWords, const uint16_t* hitCoun
 //   2. scan:   delta_0 = 0, delta_{b+1} = max(0, delta_b + c_b - 4)                         (gs_table_scan_kernel, three passes)
 //              -- the keys of bucket b occupy the slots [4b + delta_b, 4b + delta_b + c_b): sorted linear probing
 //   3. place:  every key takes a slot of its bucket's range (arrival order)                 (gs_table_place_kernel)
-//   4. sort:   every range is sorted by entry = by remainder (distinct within a bucket)     (gs_table_sort_kernel)
+//   4. sort:   every range is sorted by entry = by remainder (distinct within a bucket), then every entry is stamped with
+//              its displacement = bucket it sits in - home bucket                           (gs_table_sort_kernel)
 //   5. flags:  bucket b is flagged `spill` iff delta_{b+1} > 0, i.e. a key whose home is <= b sits behind bucket b
 // The recurrence of step 2 composes as functions d -> max(d + s, t): a block of buckets is summarised by (s, t), blocks are
 // combined left to right (gs_lq_combine), and delta at a block's first bucket is its prefix applied to 0.
@@ -1135,18 +1136,21 @@ __global__ void gs_table_place_kernel(const u64* __restrict__ keys, const uint16
         tab[b * 4 + delta[b] + idx] = entry;
     }
 }
-__global__ void gs_table_sort_kernel(u64* tab, const u32* __restrict__ counts, const u32* __restrict__ delta, u64 nBuckets) {
+__global__ void gs_table_sort_kernel(u64* tab, const u32* __restrict__ counts, const u32* __restrict__ delta, u64 nBuckets, u32* bad) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nBuckets; b += stride) {
         const u32 c = counts[b] & 0xFFFFu;
-        if (c < 2) continue;
-        u64* g = tab + b * 4 + delta[b];
+        if (c == 0) continue;
+        const u32 d = delta[b];
+        u64* g = tab + b * 4 + d;
         for (u32 i = 1; i < c; i++) {  // insertion sort: the ranges hold a handful of entries
             const u64 e = g[i];
             u32 j = i;
             while (j > 0 && g[j - 1] > e) { g[j] = g[j - 1]; j--; }
             g[j] = e;
         }
+        if ((d + c - 1) / 4 > GS_TAB_DISP_MAX) { atomicOr(bad, 2u); continue; }   // further from home than the entry format can say
+        for (u32 i = d >= 4 ? 0 : 4 - d; i < c; i++) g[i] |= (u64)((d + i) / 4) << GS_TAB_DISP_SHIFT;
     }
 }
 __global__ void gs_table_flags_kernel(u64* tab, const u32* __restrict__ delta, u64 nBuckets) {
@@ -1187,7 +1191,7 @@ void gs_launch_table_clear_seen(u64* tab, u64 nSlots, cudaStream_t st) { gs_tabl
 void gs_launch_table_extract_seen(const u64* tab, u64 nSlots, u64* out, cudaStream_t st) { gs_table_extract_seen_kernel<<<148 * 8, 256, 0, st>>>(tab, nSlots, out); }
 // nBuckets = 2^tbits + GS_TAB_PAD_BUCKETS; counts[nBuckets], delta[nBuckets + 1], agg / blockIn[gs_table_scan_blocks(nBuckets)]
 // are scratch (counts and *bad zeroed by the caller).  Afterwards delta[nBuckets] must be 0 (nothing ran past the pad buckets)
-// and *bad must be 0 (no bucket with 2^16 or more keys).
+// and *bad must be 0 (bit 0: a bucket with 2^16 or more keys, bit 1: a key more than GS_TAB_DISP_MAX buckets from home).
 u64 gs_table_scan_blocks(u64 nBuckets) { return (nBuckets + GS_TB_BLOCK - 1) / GS_TB_BLOCK; }
 void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* tab, u32* counts, u32* delta, void* agg, u32* blockIn,
                            u32* bad, u64 nBuckets, int rbits, cudaStream_t st) {
@@ -1197,7 +1201,7 @@ void gs_launch_table_build(const u64* keys, const uint16_t* vals, u64 n, u64* ta
     gs_table_scan_blocks_kernel<<<1, 1024, 0, st>>>((const GsLq*)agg, nBlocks, blockIn);
     gs_table_scan_kernel<1><<<(unsigned)nBlocks, GS_TB_THREADS, 0, st>>>(counts, nBuckets, nullptr, blockIn, delta, bad);
     gs_table_place_kernel<<<148 * 8, 256, 0, st>>>(keys, vals, n, tab, counts, delta, rbits);
-    gs_table_sort_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, delta, nBuckets);
+    gs_table_sort_kernel<<<148 * 8, 256, 0, st>>>(tab, counts, delta, nBuckets, bad);
     gs_table_flags_kernel<<<148 * 8, 256, 0, st>>>(tab, delta, nBuckets);
 }
 

@@ -55,3 +55,34 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "gs_oracle" not in text and "oracle/" not in text, "%s references the oracle" % f
+
+
+def _build_c_caller(tmp_path):
+    import subprocess
+    from genestrip_b200.build import LIB_DIR
+    exe = str(tmp_path / "call_order")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "c", "call_order.c"),
+           "-L", LIB_DIR, "-lgenestrip_b200", "-Wl,-rpath," + LIB_DIR, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_plain_c_translation_unit_compiles_and_runs_host_checks(native, tmp_path):
+    """include/genestrip_b200.h is a C header: a C99 translation unit that includes nothing else compiles with -Wall -Werror,
+    links against the library alone and runs the documented call order (integration/c/call_order.c); without a device it stops
+    after the host-only part (ABI version, defaults, packer, error convention)."""
+    import subprocess
+    exe = _build_c_caller(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "call_order:" in res.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_full_call_order_on_the_device(native, gpu_ctx, tmp_path):
+    import subprocess
+    exe = _build_c_caller(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "full call order ok" in res.stdout

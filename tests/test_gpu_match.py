@@ -521,3 +521,46 @@ def test_radix_upload_gives_same_database(project, reads, oracle, native, gpu_ct
         util.assert_match_parity(native, orun, res, counts, top)
     finally:
         g2.close()
+
+
+def _unmix62(h):
+    """Inverse of gs_mix62 (gs_device.cuh): the bijection on [0, 2^62) that spreads the k-mers over the probe table."""
+    M = (1 << 62) - 1
+    x = h
+    x ^= x >> 33
+    x = (x * pow(0x81DADEF4BC2DD44D, -1, 1 << 62)) & M
+    x ^= x >> 27
+    x ^= x >> 54
+    x = (x * pow(0x7FB5D329728EA185, -1, 1 << 62)) & M
+    x ^= x >> 31
+    return x
+
+
+def test_probe_table_is_exact_for_displaced_keys(native, gpu_ctx):
+    """A key pushed out of its full home bucket sits in the next one.  A lookup whose OWN home is that next bucket and whose
+    remainder equals the pushed key's must not take it for its key (a 2^-rbits coincidence at random -- forced here through
+    the inverse of the table's hash), and both keys must be found when both are stored."""
+    tbits, rbits = 22, 40
+    b = 123457
+    rems = [5, 77, 900, 12345, 999999, 1 << 39]      # six keys of home bucket b: the last two land in bucket b + 1
+    mk = lambda bucket, rem: _unmix62((bucket << rbits) | rem)
+    home = [mk(b, r) for r in rems]
+    twin_absent = mk(b + 1, rems[-1])                # home b + 1, remainder of a displaced key: NOT stored
+    twin_stored = mk(b + 1, rems[-2])                # home b + 1, remainder of the other displaced key: stored too
+    far = [mk(b + 1, r) for r in (3, 4)] + [mk(b + 2, r) for r in (8, 9, 10)]   # more pressure: the chain runs on
+    stored = sorted(home + [twin_stored] + far)
+    keys = np.array(stored, dtype=np.int64)
+    vidx = np.arange(len(keys)) % 5
+    vals = (vidx - 32768).astype(np.int16)
+    parent = np.array([-1, 0, 0, 1, 2], dtype=np.int32)
+    db = native.Database(gpu_ctx, K, keys, vals, 5, parent_by_vidx=parent, has_node=None, bloom=None, build_bloom=True)
+    try:
+        v, p = db.lookup(keys)
+        np.testing.assert_array_equal(v, vidx)
+        np.testing.assert_array_equal(p, np.arange(len(keys)))
+        absent = np.array([twin_absent, mk(b + 2, rems[-1]), mk(b + 3, 9), mk(b, 6)], dtype=np.int64)
+        assert not np.isin(absent, keys).any()
+        v, _ = db.lookup(absent, use_bloom=False)
+        np.testing.assert_array_equal(v, -1)          # 0x7FFFFFFF here = the table disagreed with the sorted array
+    finally:
+        db.close()
