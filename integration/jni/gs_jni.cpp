@@ -1,9 +1,10 @@
 // gs_jni.cpp -- the thin JNI shim a Genestrip maintainer adds to bind include/genestrip_b200.h.
 //
-// NOT COMPILED IN THIS REPOSITORY'S BUILD: the image has no JDK (no jni.h).  On a machine with a JDK:
-//   g++ -O2 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include \
-//       gs_jni.cpp -L../../genestrip_b200/_lib -lgenestrip_b200 -o libgsjni.so
-// Java side: integration/java/org/metagene/genestrip/match/GpuFastqKMerMatcher.java (native methods of class GsNative).
+// This image has no JDK (no jni.h): integration/build.sh builds libgsjni.so and the Java classes where one exists, and
+// tests/test_capi_symbols.py compiles this file against tests/jni_stub/jni.h (the subset of the JNI API used here, signatures
+// from the JNI specification) so that it cannot rot unnoticed.  With a JDK:
+//   g++ -O2 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include gs_jni.cpp -L../../genestrip_b200/_lib -lgenestrip_b200 -o libgsjni.so
+// Java side: integration/java/org/metagene/genestrip/gpu/GsNative.java (one native method per function below).
 // Conventions: handles travel as jlong; every failure becomes a RuntimeException carrying gs_last_error(), the same
 // way consumer-thread failures surface in the reference (C/fastq/AbstractFastqReader.java:124-143).
 #include <jni.h>
@@ -12,7 +13,7 @@
 
 static void throwLast(JNIEnv* env) { env->ThrowNew(env->FindClass("java/lang/RuntimeException"), gs_last_error()); }
 #define CHECK(rc) do { if ((rc) != GS_OK) { throwLast(env); return; } } while (0)
-#define J(name) Java_org_metagene_genestrip_match_GsNative_##name
+#define J(name) Java_org_metagene_genestrip_gpu_GsNative_##name
 
 extern "C" {
 
@@ -64,6 +65,9 @@ JNIEXPORT void JNICALL J(dbSetBloomBlocked)(JNIEnv* env, jclass, jlong db, jlong
     env->ReleasePrimitiveArrayCritical(words, p, JNI_ABORT);
     CHECK(rc);
 }
+// the store's optimized filter (KMerSortedArray.optimize, C/store/KMerSortedArray.java:409-422) built on the device: BlockedKMerBloomFilter
+// keeps its words private, and the device-built filter is bit-identical (tests/test_gpu_match.py)
+JNIEXPORT void JNICALL J(dbBuildBloom)(JNIEnv* env, jclass, jlong db) { CHECK(gs_db_build_bloom_blocked((gs_db*)db, nullptr, 0)); }
 JNIEXPORT void JNICALL J(dbFinalize)(JNIEnv* env, jclass, jlong db) { CHECK(gs_db_finalize((gs_db*)db)); }
 JNIEXPORT void JNICALL J(dbDestroy)(JNIEnv*, jclass, jlong db) { gs_db_destroy((gs_db*)db); }
 
@@ -100,6 +104,31 @@ JNIEXPORT jobjectArray JNICALL J(matchCollect)(JNIEnv* env, jclass, jlong s, jlo
     jobjectArray arr = env->NewObjectArray(2, env->FindClass("java/nio/ByteBuffer"), nullptr);
     env->SetObjectArrayElement(arr, 0, env->NewDirectByteBuffer((void*)out, (jlong)n * (jlong)sizeof(gs_read_result)));
     env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer((void*)ev, (jlong)nev * (jlong)sizeof(gs_maxcontig_event)));
+    return arr;
+}
+// Sessions opened with wantRuns (kraken-style output): the per-read contig runs come back too.  Copies into fresh direct
+// buffers: [0] results, [1] events, [2] run offsets (nReads + 1 x u64), [3] runs (label, len).  runsCapacity = the batch's k-mer
+// count (an upper bound of its runs).
+JNIEXPORT jobjectArray JNICALL J(matchCollectRuns)(JNIEnv* env, jclass, jlong s, jlong ticket, jint nReads, jlong runsCapacity) {
+    jclass bb = env->FindClass("java/nio/ByteBuffer");
+    jmethodID alloc = env->GetStaticMethodID(bb, "allocateDirect", "(I)Ljava/nio/ByteBuffer;");
+    const jlong sizes[4] = {(jlong)nReads * (jlong)sizeof(gs_read_result), (jlong)nReads * (jlong)sizeof(gs_maxcontig_event),
+                            ((jlong)nReads + 1) * 8, (runsCapacity > 0 ? runsCapacity : 1) * (jlong)sizeof(gs_run)};
+    jobject bufs[4];
+    void* p[4];
+    for (int i = 0; i < 4; i++) {
+        bufs[i] = env->CallStaticObjectMethod(bb, alloc, (jint)sizes[i]);
+        if (!bufs[i]) return nullptr;
+        p[i] = env->GetDirectBufferAddress(bufs[i]);
+    }
+    uint32_t nev = 0;
+    if (gs_match_collect((gs_sess*)s, (gs_ticket)ticket, (gs_read_result*)p[0], (gs_maxcontig_event*)p[1], (uint32_t)nReads, &nev,
+                         (uint64_t*)p[2], (gs_run*)p[3], (uint64_t)(runsCapacity > 0 ? runsCapacity : 1)) != GS_OK) { throwLast(env); return nullptr; }
+    jobjectArray arr = env->NewObjectArray(4, bb, nullptr);
+    env->SetObjectArrayElement(arr, 0, bufs[0]);
+    env->SetObjectArrayElement(arr, 1, env->NewDirectByteBuffer(p[1], (jlong)nev * (jlong)sizeof(gs_maxcontig_event)));
+    env->SetObjectArrayElement(arr, 2, bufs[2]);
+    env->SetObjectArrayElement(arr, 3, bufs[3]);
     return arr;
 }
 // End of run: nValues x gs_taxon_counts (80 bytes each) into a caller-provided direct buffer.

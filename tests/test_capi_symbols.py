@@ -86,3 +86,30 @@ def test_plain_c_caller_full_call_order_on_the_device(native, gpu_ctx, tmp_path)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "full call order ok" in res.stdout
+
+
+def test_jni_shim_typechecks_and_matches_the_java_natives():
+    """No JDK in this image: the shim (integration/jni/gs_jni.cpp) is type-checked against tests/jni_stub/jni.h, every C entry
+    point it calls is declared in the public header, and its exports and the `native` methods of GsNative.java name the same
+    set of functions (a method without a body on either side would only fail at run time in the JVM)."""
+    import subprocess
+    shim = os.path.join(ROOT, "integration", "jni", "gs_jni.cpp")
+    res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "jni_stub"),
+                          "-I", os.path.join(ROOT, "include"), shim], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    text = open(shim).read()
+    exported = set(re.findall(r"\bJ\((\w+)\)\(", text))
+    java = open(os.path.join(ROOT, "integration", "java", "org", "metagene", "genestrip", "gpu", "GsNative.java")).read()
+    natives = set(re.findall(r"public static native [\w\[\]<>]+ (\w+)\(", java))
+    assert natives == exported, (sorted(natives - exported), sorted(exported - natives))
+    called = set(re.findall(r"\b(gs_[a-z0-9_]+)\(", re.sub(r"//.*", "", text)))
+    assert called <= set(_declared_symbols()), sorted(called - set(_declared_symbols()))
+    # the Java classes only use natives that exist
+    used = set()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "integration", "java")):
+        for f in files:
+            if f.endswith(".java"):
+                used |= set(re.findall(r"GsNative\.(\w+)\(", open(os.path.join(dirpath, f)).read()))
+    assert used <= natives, sorted(used - natives)
+    res = subprocess.run(["bash", os.path.join(ROOT, "integration", "build.sh")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
