@@ -103,19 +103,175 @@ def test_lookup_round_trip_at_full_size(viral, native):
     assert (v[~present] == -1).mean() > 0.9999
 
 
-def test_oracle_spot_check_at_full_size(viral, native, oracle):
+@pytest.fixture(scope="module")
+def viral_oracle(viral, oracle):
+    """The CPU oracle holding the full 1e8-key database (built once for the spot checks below)."""
+    odb = oracle.OracleDb.from_arrays(K, viral["keys"].cpu().numpy(), viral["vals"].cpu().numpy(), len(viral["parent"]), viral["parent"], build_bloom=True)
+    yield odb
+    odb.free()
+
+
+def _fastq(bases, offsets, n):
+    bb = bases.tobytes()
+    o = [int(x) for x in offsets[: n + 1]]
+    return b"".join(b"@r%d x\n%s\n+\n%s\n" % (i, bb[o[i]:o[i + 1]], b"I" * (o[i + 1] - o[i])) for i in range(n))
+
+
+def test_oracle_spot_check_at_full_size(viral, viral_oracle, native, oracle):
     """The CPU oracle on the full 1e8-key database, 20 000 reads: every per-read and per-taxon integer must agree."""
     import util
     n = 20_000
-    keys_h = viral["keys"].cpu().numpy()
-    vals_h = viral["vals"].cpu().numpy()
-    odb = oracle.OracleDb.from_arrays(K, keys_h, vals_h, len(viral["parent"]), viral["parent"], build_bloom=True)
-    try:
-        off = viral["offsets"][: n + 1]
-        bb = viral["bases"][: n * 150].tobytes()
-        fq = b"".join(b"@r%d x\n%s\n+\n%s\n" % (i, bb[i * 150:(i + 1) * 150], b"I" * 150) for i in range(n))
-        orun = odb.match_files(oracle.match_cfg(k=K), [fq])
-        res, c = _run(native, viral["db"], viral["bases"], off)
+    off = viral["offsets"][: n + 1]
+    orun = viral_oracle.match_files(oracle.match_cfg(k=K), [_fastq(viral["bases"], off, n)])
+    for cfg in (dict(), dict(host_pack_threads=0), dict(host_pack_percent=100)):
+        res, c = _run(native, viral["db"], viral["bases"], off, **cfg)
         util.assert_match_parity(native, orun, res, c)
+
+
+def test_long_reads_with_indels_against_the_oracle(viral, viral_oracle, native, oracle):
+    """BASELINE.json configs[4] as SURVEY.md §8d specifies it: 10 kb reads, 90 % from the database, 1 % substitutions and
+    0.2 % single-base insertions / deletions -- 2 000 reads (2e7 k-mers) against the oracle on the full database, per-read
+    classification and the kraken-style runs included."""
+    import torch
+    import bench
+    import util
+    wl = dict(bench.WORKLOADS["longread"])
+    assert wl["indel_rate"] == 0.002 and wl["read_len"] == 10_000
+    dev = torch.device("cuda:0")
+    n = 2_000
+    _, _, _, codes = bench.make_database(torch, dev, bench.DATABASES["viral"], seed=43)   # same seed: the genomes of the fixture's database
+    bases, offsets = bench.make_reads(torch, dev, wl, codes, n, seed=4646)
+    del codes
+    b_h = bases[: n * wl["read_len"]].cpu().numpy()
+    o_h = offsets.cpu().numpy().astype(np.uint64)
+    # the generator really inserts and deletes: a read from the database does not match its genome window position by position
+    cfg = dict(want_runs=1)
+    orun = viral_oracle.match_files(util.oracle_cfg(oracle, K, **cfg), [_fastq(b_h, o_h, n)])
+    sess = native.MatchSession(viral["db"], native.default_match_cfg(**cfg))
+    try:
+        res, ros, rus = [], [], []
+        for a in range(0, n, 500):
+            t = sess.submit(b_h, np.ascontiguousarray(o_h[a:a + 501]), a)
+            r, _, ro, ru = sess.collect(t)
+            res.append(r); ros.append(ro); rus.append(ru)
+        counts, _ = sess.finish()
     finally:
-        odb.free()
+        sess.close()
+    res = np.concatenate(res)
+    util.assert_match_parity(native, orun, res, counts)
+    hit = counts["kmers"].sum() / float(n * (wl["read_len"] - K + 1))
+    assert 0.55 < hit < 0.75, hit                         # 0.9 x 0.99^31 x indel survival ~ 0.62-0.66
+    assert counts["max_contig_len"].max() < wl["read_len"] - K + 1   # no read survives 10 kb without an error
+    taxids = viral_oracle.taxids()
+    lines = orun.kraken.split(b"\n")[:-1]
+    assert len(lines) == n
+    i = 0
+    for ro, ru in zip(ros, rus):
+        for j in range(len(ro) - 1):
+            if i % 97 == 0:
+                assert lines[i].decode().split("\t")[4] == util.kraken_from_runs(taxids, ro, ru, j), "read %d" % i
+            i += 1
+
+
+def test_filter_index_at_full_size_against_the_oracle(viral, native, oracle, gpu_ctx):
+    """BASELINE.json configs[3] at its own size: the XOR Bloom index (fpp 1e-8, 27 hashes) over the 1e8-key database's leaf
+    k-mers, 20 000 reads with ~1 % from the database, accept bits against the oracle's FastqBloomFilter.isAcceptRead over the
+    same index.  The index is built with torch (as bench.py does); the oracle's own hashing pins it: every inserted key must be
+    contained, and the oracle's putLong on a sample must set only bits that are already set."""
+    import torch
+    import bench
+    wl = dict(bench.WORKLOADS["filter"])
+    dev = torch.device("cuda:0")
+    keys, vals = viral["keys"], viral["vals"]
+    dbp = bench.DATABASES["viral"]
+    leaf0 = len(viral["parent"]) - dbp["fanout"] ** dbp["levels"]
+    leaf_keys = keys[(vals.to(torch.int64) + 32768) >= leaf0]
+    bits, hashes, factors, words = bench.build_xor_index(torch, dev, leaf_keys, 1e-8)
+    assert hashes == 27
+    words_h = words.cpu().numpy()
+    oflt = oracle.Bloom.from_words(1, bits, hashes, factors, words_h)
+    sample = leaf_keys[torch.randint(0, leaf_keys.numel(), (50_000,), device=dev)].cpu().numpy()
+    assert oflt.contains(sample).all()
+    probe = oracle.Bloom(kind=1, fpp=1e-8)
+    assert probe.ensure(int(leaf_keys.numel())) == bits          # same sizing rule (AbstractKMerBloomFilter.java:172-185)
+    probe.put(sample[:2000])
+    _, pb, ph, pf, pw = probe.params()
+    assert (pb, ph) == (bits, hashes) and np.array_equal(pf, factors)
+    assert not (pw & ~words_h).any()                             # the oracle's bits for these keys are a subset of the index
+    probe.free()
+    _, _, _, codes = bench.make_database(torch, dev, dbp, seed=43)
+    n = 20_000
+    wl["frac_db"] = 0.05                                         # a few hundred positives in the sample instead of ~200
+    bases, offsets = bench.make_reads(torch, dev, wl, codes, n, seed=4545)
+    del codes
+    b_h = bases[: n * 150].cpu().numpy()
+    o_h = offsets.cpu().numpy().astype(np.uint64)
+    _, acc_o = oflt.accept_reads_mt(K, b_h, o_h, 4)
+    flt = native.Filter(gpu_ctx, native.GS_BLOOM_XOR, bits, hashes, factors, words_h)
+    try:
+        fs = native.FilterSession(flt, K, 1, 0.2)
+        acc_g = fs.collect(fs.submit(b_h, o_h))
+        fs.close()
+        np.testing.assert_array_equal(acc_g, acc_o)
+        assert 300 < acc_o.sum() < 1500
+        # minPosCount = 0 switches to the ratio rule (C/bloom/FastqBloomFilter.java:122)
+        _, acc_o2 = oflt.accept_reads_mt(K, b_h, o_h, 4, min_pos_count=0, pos_ratio=0.5)
+        fs = native.FilterSession(flt, K, 0, 0.5)
+        acc_g2 = fs.collect(fs.submit(b_h, o_h))
+        fs.close()
+        np.testing.assert_array_equal(acc_g2, acc_o2)
+    finally:
+        flt.close()
+        oflt.free()
+
+
+def test_bacterial_scale_store_against_the_oracle(native, oracle, gpu_ctx):
+    """BASELINE.json configs[2] at its own size: 2e9 k-mers (59 GB on the device: 34 GB probe table, 512 MB unique-k-mer bitset,
+    64-bit minimizer order), 20 000 reads, every per-read and per-taxon integer incl. the unique k-mer counts against the oracle
+    holding the same 2e9-key store in host memory.  Needs ~50 GB of host RAM and ~110 GB of device memory."""
+    import psutil
+    import torch
+    import bench
+    import util
+    avail = psutil.virtual_memory().available / 1e9
+    free_dev = torch.cuda.mem_get_info(0)[0] / 1e9
+    if avail < 56 or free_dev < 120:
+        pytest.skip("SKIPPED LOUDLY: the 2e9-key spot check needs 56 GB of host RAM and 120 GB of device memory (have %.0f / %.0f)" % (avail, free_dev))
+    dev = torch.device("cuda:0")
+    wl = dict(bench.WORKLOADS["bacterial"])
+    keys, vals_raw, parent, codes = bench.make_database(torch, dev, bench.DATABASES["bacterial"], seed=43)
+    n_db, V = int(keys.numel()), len(parent)
+    assert n_db > 1_900_000_000
+    n = 20_000
+    bases, offsets = bench.make_reads(torch, dev, wl, codes, n, seed=4444)
+    del codes
+    b_h = bases[: n * 150].cpu().numpy()
+    o_h = offsets.cpu().numpy().astype(np.uint64)
+    del bases, offsets
+    torch.cuda.empty_cache()   # the library allocates with cudaMalloc: give torch's cached blocks back first
+    db = native.Database.from_pointers(gpu_ctx, K, keys.data_ptr(), vals_raw.data_ptr(), n_db, V, parent, build_bloom=True)
+    try:
+        keys_h, vals_h = keys.cpu().numpy(), vals_raw.cpu().numpy()
+        del keys, vals_raw
+        torch.cuda.empty_cache()
+        odb = oracle.OracleDb.from_arrays(K, keys_h, vals_h, V, parent, build_bloom=True)
+        try:
+            # lookups: stored keys come back with their position and value, the probe table agrees with the sorted array on all
+            idx = np.random.default_rng(3).integers(0, n_db, size=100_000)
+            v, p = db.lookup(keys_h[idx])
+            np.testing.assert_array_equal(p, idx)
+            np.testing.assert_array_equal(v, vals_h[idx].astype(np.int32) + 32768)
+            del keys_h, vals_h
+            orun = odb.match_files(oracle.match_cfg(k=K, count_unique=True), [_fastq(b_h, o_h, n)])
+            res, c = _run(native, db, b_h, o_h, splits=(0, 7_001, None))
+            util.assert_match_parity(native, orun, res, c)
+            assert 0.05 < c["kmers"].sum() / (n * 120.0) < 0.1 and c["unique_kmers"].sum() > 0.9 * c["kmers"].sum()
+            # the reference's own structures on the device (Bloom filter + binary search over 2e9 keys) give the same answers
+            res_c, c_c = _run(native, db, b_h, o_h, layout=native.GS_LAYOUT_CLASSIC)
+            np.testing.assert_array_equal(res_c, res)
+            for f in FIELDS + ("unique_kmers", "max_contig_len", "max_contig_read_no"):
+                np.testing.assert_array_equal(c_c[f], c[f], err_msg=f)
+        finally:
+            odb.free()
+    finally:
+        db.close()
