@@ -7,6 +7,8 @@ its sample data, not outputs of its code:
   taxtree_nodes.dmp / names.dmp     <- core/src/test/resources/taxtree/{nodes,names}.dmp      (T/match/FastqKMerMatcherTest.java:322-412)
   dengue1.fasta / dengue1_test.fastq <- core/src/test/resources/projects/dengue1/{dengue1.fasta,test.fastq} (same test)
   sample_fastq_read_lengths.txt.gz  <- read lengths of data/projects/human_virus/fastq/sample.fastq.gz (README.md:169 totals)
+  human_virus_sample.fastq.gz       <- data/projects/human_virus/fastq/sample.fastq.gz itself (6565 real reads, variable length,
+                                       real headers and qualities; README.md:169: 6565 reads / 658 255 bps / 461 305 k-mers)
 """
 import gzip
 import os
@@ -23,6 +25,7 @@ if __name__ == "__main__":
     shutil.copy(os.path.join(res, "taxtree/names.dmp"), os.path.join(HERE, "taxtree_names.dmp"))
     shutil.copy(os.path.join(res, "projects/dengue1/dengue1.fasta"), os.path.join(HERE, "dengue1.fasta"))
     shutil.copy(os.path.join(res, "projects/dengue1/test.fastq"), os.path.join(HERE, "dengue1_test.fastq"))
+    shutil.copy(os.path.join(REF, "data/projects/human_virus/fastq/sample.fastq.gz"), os.path.join(HERE, "human_virus_sample.fastq.gz"))
     lens = []
     with gzip.open(os.path.join(REF, "data/projects/human_virus/fastq/sample.fastq.gz"), "rb") as f:
         lines = f.read().split(b"\n")

@@ -392,3 +392,53 @@ def test_fastq_feeder_fuzz_against_reference_parser(project, oracle, host):
         n_refused += res.text_chunks_refused
         n_gpu += res.text_chunks - res.text_chunks_refused
     assert n_gpu > 20 and n_refused > 5   # both paths were exercised
+
+
+def test_match_goal_on_the_reference_sample_reads(oracle, native, gpu_ctx, host, tmp_path):
+    """Real data: the reference's own sample (data/projects/human_virus/fastq/sample.fastq.gz -- 6565 Illumina reads of variable
+    length with real headers, qualities and N runs) through the whole `match` goal: as the gzip file it ships as (zlib's
+    sequential reader), re-packed as block gzip (device inflater + GPU record splitter) and as plain text, against the oracle on
+    a database built from a third of those reads.  The totals row must be the one the reference's README prints
+    (README.md:169: 6565 reads, 658 255 bps, 461 305 k-mers)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    gz_path = os.path.join(here, "golden", "human_virus_sample.fastq.gz")
+    text = gzip.decompress(open(gz_path, "rb").read())
+    lines = text.split(b"\n")
+    seqs = [lines[i] for i in range(1, len(lines), 4) if i < len(lines) - 1]
+    assert len(seqs) == 6565
+    nodes, names, genomes = util.small_project(genome_len=1000, seed=3)
+    leaves = [t for t, _ in genomes]
+    # every third read (upper-case letters only survive the store's k-mer window) becomes "genome" text of one of the leaf taxa
+    parts = {t: [] for t in leaves}
+    for i in range(0, len(seqs), 3):
+        parts[leaves[(i // 3) % len(leaves)]].append(seqs[i])
+    genomes = [(t, b"N".join(parts[t])) for t in leaves]
+    odb, gdb = util.build_pair(oracle, native, gpu_ctx, K, nodes, names, genomes)
+    meta = util.host_meta(host, odb)
+    try:
+        ocfg = oracle.match_cfg(k=K, write_filtered=True, write_kraken=True, with_probs=True)
+        orun = odb.match_files(ocfg, [text])
+        assert (orun.total_reads, orun.total_bps, orun.total_kmers) == (6565, 658255, 461305)
+        plain = str(tmp_path / "sample.fastq")
+        open(plain, "wb").write(text)
+        bgzf = str(tmp_path / "sample.bgzf.fastq.gz")
+        open(bgzf, "wb").write(util.bgzf_bytes(text, block=30000))
+        hit_rows = 0
+        for src, chunk in ((gz_path, 1 << 20), (bgzf, 200000), (plain, 150000), (text, 1 << 22)):
+            res = host.match_goal(gdb, meta, [src], write_filtered=True, write_kraken=True, with_probs=1, text_chunk_bytes=chunk)
+            assert (res.total_reads, res.total_bps, res.total_kmers) == (6565, 658255, 461305)
+            assert res.filtered == orun.filtered
+            assert res.kraken == orun.kraken
+            for i in range(4):
+                np.testing.assert_array_equal(res.dsums[i], orun.dstats[i])
+            _assert_csv_equal(res.csv, orun.csv)
+            hit_rows = len(res.csv.split(b"\n"))
+        assert hit_rows > 5 and len(orun.filtered) > 100000   # a third of the reads are in the database: plenty of hits
+        # and with the sequential host parser instead of the GPU feeder
+        res0 = host.match_goal(gdb, meta, [gz_path], write_filtered=True, write_kraken=True, with_probs=1, gpu_parse=False)
+        assert res0.filtered == orun.filtered and res0.kraken == orun.kraken
+        _assert_csv_equal(res0.csv, orun.csv)
+    finally:
+        meta.free()
+        gdb.close()
+        odb.free()

@@ -97,6 +97,19 @@ def test_sample_fastq_totals(oracle):
     assert (run.total_reads, run.total_bps, run.total_kmers) == (6565, 658255, 461305)
 
 
+def test_sample_fastq_itself_through_the_oracle_parser(oracle):
+    """The same totals from the reference's sample file itself (real headers, qualities, N runs): the oracle's restatement of
+    AbstractFastqReader.doReadFastq + BufferedLineReader on real data, and the product's host parser on the same bytes."""
+    import gzip
+    text = gzip.decompress(open(os.path.join(HERE, "golden", "human_virus_sample.fastq.gz"), "rb").read())
+    flt = oracle.Bloom(kind=0)
+    flt.ensure(10)
+    run = oracle.filter_files(flt, 31, [text], with_probs=True)
+    flt.free()
+    assert (run.total_reads, run.total_bps, run.total_kmers) == (6565, 658255, 461305)
+    assert run.rest == text   # nothing accepted: every record is rewritten, byte for byte, to the rest stream
+
+
 def test_kraken_line_shape(oracle):
     """R/projects/dengue1/test.out: `C\\ttest\\t1\\t41\\t0:2 1:7 0:2` -- shape of writeMatchDetails + printKrakenStyleOut."""
     golden = open(os.path.join(HERE, "golden", "dengue1_test.out"), "rb").read()
