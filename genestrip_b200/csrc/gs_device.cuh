@@ -270,24 +270,24 @@ __device__ __forceinline__ int gs_table_match(int rbits, u64 h, const GsBucket& 
         if ((bk.e[jj] & cmpMask) == want) { j = jj; e = bk.e[jj]; }
     return j;
 }
-// (scalars instead of the view: a reference to the kernel parameter block would force a local copy of it)
-static __device__ __noinline__ u32 gs_table_chain(const u64* tab, int rbits, u64 h, u64 b, u64* posOut, u32* seenOut) {
-    u32 lab = GS_LABEL_MISS;
+// (scalars instead of the view: a reference to the kernel parameter block would force a local copy of it; the result comes back
+// in registers -- x = slot id, y = label | seen bit << 32 -- so that the caller keeps nothing in local memory for the call)
+static __device__ __noinline__ ulonglong2 gs_table_chain(const u64* tab, int rbits, u64 h, u64 b) {
+    ulonglong2 r = make_ulonglong2(0ULL, (u64)GS_LABEL_MISS);
     for (int t = 1; t <= GS_TAB_DISP_MAX; t++) {
         b = b + 1;
         const GsBucket bk = gs_load_bucket(tab, b);
         u64 e;
         const int j = gs_table_match(rbits, h, bk, e, t);
         if (j >= 0) {
-            *posOut = b * GS_TAB_SLOT_STRIDE + (u64)j;
-            *seenOut = (u32)(e & GS_TAB_SEEN);
             const u32 v = (u32)(e >> GS_TAB_VAL_SHIFT) & 0xFFFFu;
-            lab = v == GS_VAL_NONODE ? GS_LABEL_MISS : v;
+            r.x = b * GS_TAB_SLOT_STRIDE + (u64)j;
+            r.y = (u64)(v == GS_VAL_NONODE ? GS_LABEL_MISS : v) | ((e & GS_TAB_SEEN) << 32);
             break;
         }
         if (!(bk.e[0] & GS_TAB_SPILL)) break;
     }
-    return lab;
+    return r;
 }
 
 __device__ __forceinline__ u32 gs_lookup_table(const GsDbView& db, u64 key, u64& pos) {

@@ -115,24 +115,40 @@ __global__ void gs_mark_starts_kernel(const u64* __restrict__ offsets, u32 nRead
 // one position: forward / reverse-complement k-mer in registers, minimizer prefilter (L2-resident bit filter, shared by
 // neighbouring lanes), one 256-bit probe-table load for the k-mers that pass, seen bit / hit counter for the hits.
 // The k-mer and m-mer hash of chunk c+1 are computed while chunk c is finished (the sliding minimum needs them anyway).
-template <int LAYOUT, bool DUMP, bool WIDE>
+// KT = k as a compile-time constant (31, the reference's default: masks and shift counts become immediates) or 0 = run time.
+// Instruction diet of round 2 (same results; ncu: 373 -> see profiles/r02 warp instructions per 32 k-mers): the three staged
+// streams of a warp sit in ONE shared-memory struct (one base register, immediate offsets), the code stream is kept as 32-bit
+// big-endian words (no index swizzle per load), label / mask stores run on incremented pointers, the first-bucket match is
+// computed once (the chain into following buckets is a cold call) in both lookup shapes.
+struct __align__(16) GsSegStage {
+    u32 code[2 * GS_SEG_WORDS];   // 2-bit codes, word j = bases 16j .. 16j+15 of the segment, first base in the top pair
+    u32 valid[GS_SEG_WORDS];      // bit b of word w = base 32w + b is one of CGAT
+    u32 start[GS_SEG_WORDS];      // bit b of word w = a read starts at base 32w + b
+};
+
+// forward k-mer of the window whose first base sits in word cp[0] at bit offset sh = 2 * (position & 15) from the top
+__device__ __forceinline__ u64 gs_extract_w(const u32* cp, u32 sh, int k) {
+    const u32 w0 = cp[0], w1 = cp[1], w2 = cp[2];
+    const u32 x1 = __funnelshift_l(w1, w0, sh), x0 = __funnelshift_l(w2, w1, sh);
+    return (((u64)x1 << 32) | x0) >> (64 - 2 * k);
+}
+
+template <int LAYOUT, bool DUMP, bool WIDE, int KT>
 __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_BLOCKS_WIDE : GS_LABEL_MIN_BLOCKS) gs_label_kernel(const GsMatchParams P) {
     typedef typename std::conditional<WIDE, u64, u32>::type MzT;  // the minimizer order: 32-bit hash, or 64 bits for large stores
-    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
-    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
-    __shared__ u32 s_start[GS_WARPS_PER_BLOCK][GS_SEG_WORDS];
+    __shared__ GsSegStage s_stage[GS_WARPS_PER_BLOCK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GsDbView& db = P.db;
-    const int k = db.k;
+    const int k = KT > 0 ? KT : db.k;
     const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
     const u32 k1mask = (1u << (k - 1)) - 1u;   // read starts inside (f, f + k - 1] = the window crosses a read boundary
     const bool useBloom = P.useBloom && db.hasBloom;
     const bool mz = LAYOUT == GS_LAYOUT_TABLE && db.mzFilter != nullptr;
     const int m = k - GS_MZ_S;
     const u64 mmask = (1ULL << (2 * (m > 0 ? m : 1))) - 1;
-    u64* cw = s_code[warp];
-    u32* vw = s_valid[warp];
-    u32* sw = s_start[warp];
+    GsSegStage& S = s_stage[warp];
+    const u32* cp = S.code + (lane >> 4);      // this lane's window of chunk c starts in word cp[2c]
+    const u32 csh = (u32)(lane & 15) * 2;
     const uint8_t* fb = P.bases + P.off0 - P.lead;  // 16-byte aligned start of the flat array
     const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
     for (;;) {
@@ -142,55 +158,60 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
         if (seg >= nSeg) break;
         const u64 f0 = (u64)seg * GS_SEG_POS;
         const int nb = (int)min((u64)GS_SEG_BASES, P.flatLen - f0);
+        const u64 w0 = (u64)seg * GS_SEG_CHUNKS;   // first mask word of the segment (validBits / startBits / bmask / packed words)
         __syncwarp();
         // ---- stage: ASCII -> packed 2-bit codes + validity bits (C/util/CGAT.java:60-69)
-        const uint4* ap = (const uint4*)(fb + f0);
         if (seg < P.packSegs) {  // the host packed this part of the batch: the two streams arrive ready-made, one coalesced load each
-            cw[lane] = __ldg(P.packCodes + (u64)seg * GS_SEG_CHUNKS + lane);
-            vw[lane] = __ldg(P.packValid + (u64)seg * GS_SEG_CHUNKS + lane);
-        } else
+            const u64 cwd = __ldg(P.packCodes + w0 + lane);
+            ((uint2*)S.code)[lane] = make_uint2((u32)(cwd >> 32), (u32)cwd);
+            S.valid[lane] = __ldg(P.packValid + w0 + lane);
+        } else {
+            const uint4* ap = (const uint4*)(fb + f0);
 #pragma unroll
-        for (int j = lane; j < GS_SEG_BASES / 16; j += 32) {
-            u32 code = 0, valid = 0;
-            const int rem = nb - j * 16;
-            if (rem > 0) {
-                const uint4 A = __ldg(ap + j);
-                u32 c0, c1, c2, c3, v0, v1, v2, v3;
-                gs_conv4(A.x, c0, v0); gs_conv4(A.y, c1, v1); gs_conv4(A.z, c2, v2); gs_conv4(A.w, c3, v3);
-                code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-                valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
-                if (rem < 16) valid &= (1u << rem) - 1u;
-                if (seg == 0) {  // alignment bytes in front of the first read are not bases
-                    const int lo = (int)P.lead - j * 16;
-                    if (lo > 0) valid &= lo >= 16 ? 0u : ~((1u << lo) - 1u);
+            for (int j = lane; j < GS_SEG_BASES / 16; j += 32) {
+                u32 code = 0, valid = 0;
+                const int rem = nb - j * 16;
+                if (rem > 0) {
+                    const uint4 A = __ldg(ap + j);
+                    u32 c0, c1, c2, c3, v0, v1, v2, v3;
+                    gs_conv4(A.x, c0, v0); gs_conv4(A.y, c1, v1); gs_conv4(A.z, c2, v2); gs_conv4(A.w, c3, v3);
+                    code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+                    valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+                    if (rem < 16) valid &= (1u << rem) - 1u;
+                    if (seg == 0) {  // alignment bytes in front of the first read are not bases
+                        const int lo = (int)P.lead - j * 16;
+                        if (lo > 0) valid &= lo >= 16 ? 0u : ~((1u << lo) - 1u);
+                    }
                 }
+                S.code[j] = code;
+                ((uint16_t*)S.valid)[j] = (uint16_t)valid;
             }
-            ((u32*)cw)[j ^ 1] = code;
-            ((uint16_t*)vw)[j] = (uint16_t)valid;
         }
-        sw[lane] = __ldg(P.startBits + (u64)seg * GS_SEG_CHUNKS + lane);
-        if (lane < 2) { cw[32 + lane] = 0; vw[32 + lane] = 0; sw[32 + lane] = lane == 0 ? __ldg(P.startBits + (u64)seg * GS_SEG_CHUNKS + 32) : 0u; }
+        S.start[lane] = __ldg(P.startBits + w0 + lane);
+        if (lane < 2) { ((uint2*)S.code)[32 + lane] = make_uint2(0u, 0u); S.valid[32 + lane] = 0; S.start[32 + lane] = lane == 0 ? __ldg(P.startBits + w0 + 32) : 0u; }
         __syncwarp();
-        if (lane < GS_SEG_CHUNKS) P.validBits[(u64)seg * GS_SEG_CHUNKS + lane] = vw[lane];  // for the reduce kernel's INVALID count
+        if (lane < GS_SEG_CHUNKS) P.validBits[w0 + lane] = S.valid[lane];  // for the reduce kernel's INVALID count
 
         // ---- chunks
-        u64 fwdN = gs_extract(cw, lane, k), rcN = gs_revcomp(fwdN, k);
+        // only the forward k-mer is carried from chunk to chunk: the reverse complement is needed in full by the lanes that reach
+        // the table (computed there) and otherwise only for the m-mer hash (its low 2m bits)
+        u64 fwdN = gs_extract_w(cp, csh, k);
         u32 carryLab = 0;  // label of the last position of the previous chunk (run-boundary masks)
         MzT hN = 0, preN = 0;
-        if (mz) { hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcN & mmask) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask); preN = gs_seg_prefix_min(hN, lane); }
+        if (mz) { const u64 rcm = gs_revcomp(fwdN, k) & mmask; hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcm) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcm); preN = gs_seg_prefix_min(hN, lane); }
+        u32* labP = P.labels + f0 + lane;                       // this lane's label of chunk c goes to labP[32c]
+        int left = (int)min((u64)GS_SEG_POS, P.flatLen - f0) - lane;   // positions of the segment from this lane's on: store while > 0
 #pragma unroll 1
         for (int c = 0; c < GS_SEG_CHUNKS; c++) {
-            const int prel = c * 32 + lane;
-            const u64 f = f0 + (u64)prel;
-            const u64 fwd = fwdN, rc = rcN;
+            const u64 fwd = fwdN;
             const MzT hC = hN, preC = preN;
-            fwdN = gs_extract(cw, prel + 32, k);
-            rcN = gs_revcomp(fwdN, k);
-            const u32 vbits = __funnelshift_r(vw[c], vw[c + 1], lane);
-            const u32 sbits = __funnelshift_rc(sw[c], sw[c + 1], lane + 1);
+            fwdN = gs_extract_w(cp + 2 * c + 2, csh, k);
+            const u32 vbits = __funnelshift_r(S.valid[c], S.valid[c + 1], lane);
+            const u32 sbits = __funnelshift_rc(S.start[c], S.start[c + 1], lane + 1);
             u32 lab = (sbits & k1mask) ? GS_LABEL_END : ((vbits & kmask) != kmask ? GS_LABEL_INVALID : GS_LABEL_PENDING);
             if (mz) {
-                hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcN & mmask) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcN & mmask);
+                const u64 rcm = gs_revcomp(fwdN, k) & mmask;
+                hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcm) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcm);
                 preN = gs_seg_prefix_min(hN, lane);
                 const u32 mzv = gs_mz_index((u32)gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane), db.mzMask);
                 if (lab == GS_LABEL_PENDING && !((__ldg(db.mzFilter + (mzv >> 6)) >> (mzv & 63)) & 1ULL)) lab = GS_LABEL_MISS;
@@ -203,14 +224,14 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                 //    31 % more warp instructions and 7.70 instead of 6.58 ms with the divergent shape);
                 //  * otherwise only the pending lanes probe (fewer instructions when most chunks are either all pending or all
                 //    rejected by the prefilter: 6.53 instead of 6.69 ms on the viral workload).
+                // Either way the first bucket is matched in straight-line code; the rare walk into following buckets is a call.
                 const bool pend = lab == GS_LABEL_PENDING;
-                const u64 key = fwd > rc ? fwd : rc;  // standardKMer (CGAT.java:145-147)
                 u64 pos = 0;
                 bool seen = false;
-                if (LAYOUT == GS_LAYOUT_TABLE && WIDE) {
-                    if (__any_sync(FULL, pend)) {
-                        const u64 h = gs_mix62(key);
-                        const u64 b0 = pend ? (h >> db.rbits) : 0ULL;
+                if (LAYOUT == GS_LAYOUT_TABLE) {
+                    if (WIDE ? __any_sync(FULL, pend) : pend) {
+                        const u64 h = gs_mix62(gs_canonical(fwd, k));  // standardKMer (CGAT.java:145-147)
+                        const u64 b0 = (WIDE && !pend) ? 0ULL : (h >> db.rbits);
                         const GsBucket bk = gs_load_bucket(db.tab, b0);
                         u64 e;
                         const int j = gs_table_match(db.rbits, h, bk, e);
@@ -220,18 +241,12 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                         pos = b0 * GS_TAB_SLOT_STRIDE + (u64)(j >= 0 ? j : 0);
                         seen = e & GS_TAB_SEEN;
                         if (more) {  // rare: the key was pushed to a following bucket
-                            u32 sn = 0;
-                            lab = gs_table_chain(db.tab, db.rbits, h, b0, &pos, &sn);
-                            seen = sn != 0;
+                            const ulonglong2 r = gs_table_chain(db.tab, db.rbits, h, b0);
+                            pos = r.x; lab = (u32)r.y; seen = (r.y >> 32) != 0;
                         }
                     }
                 } else if (pend) {
-                    if (LAYOUT == GS_LAYOUT_TABLE) {
-                        const u64 h = gs_mix62(key);
-                        lab = gs_table_resolve(db, h, gs_load_bucket(db.tab, h >> db.rbits), pos, seen);
-                    } else {
-                        lab = gs_lookup(db, key, useBloom, pos);
-                    }
+                    lab = gs_lookup(db, gs_canonical(fwd, k), useBloom, pos);
                 }
                 if (pend && lab < GS_LABEL_INVALID) {
                     // unique k-mer bit / hit counter (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143)
@@ -241,11 +256,13 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                         if (!(*(volatile u64*)(P.bitset + (pos >> 6)) & bit)) atomicOr(P.bitset + (pos >> 6), bit);
                     }
                     if (P.hitCounts) gs_hit_count_inc(P.hitCounts, pos);
-                    if (DUMP) P.flatPos[f] = (long long)pos;
+                    if (DUMP) P.flatPos[f0 + (u64)(c * 32 + lane)] = (long long)pos;
                 }
             }
             __syncwarp();  // reconverge here, not at the compiler's leisure: the shuffles of the next chunk need the full warp
-            if (f < P.flatLen) P.labels[f] = lab;
+            if (left > 0) *labP = lab;
+            labP += 32;
+            left -= 32;
             if (P.bmask) {
                 // run-boundary mask for the warp-per-read reduce kernel: bit = this position's label differs from its
                 // predecessor's.  The predecessor of a segment's first position belongs to another warp: that bit is set
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                 u32 pv = __shfl_up_sync(FULL, lab, 1);
                 if (lane == 0) pv = carryLab;
                 const u32 bm = __ballot_sync(FULL, lab != pv || (c == 0 && lane == 0));
-                if (lane == 0) P.bmask[(u64)seg * GS_SEG_CHUNKS + c] = bm;
+                if (lane == 0) P.bmask[w0 + c] = bm;
                 carryLab = __shfl_sync(FULL, lab, 31);
             }
         }
@@ -895,11 +912,13 @@ void gs_launch_label(const GsMatchParams& P, bool dump, int blocks, cudaStream_t
     const int threads = GS_WARPS_PER_BLOCK * 32;
     if (P.layout == GS_LAYOUT_TABLE) {
         const bool wide = P.db.mzFilter != nullptr && P.db.mzWide;
-        if (dump) { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, true, true><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, true, false><<<blocks, threads, 0, st>>>(P); }
-        else { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, false, true><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, false, false><<<blocks, threads, 0, st>>>(P); }
+        if (dump) { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, true, true, 0><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, true, false, 0><<<blocks, threads, 0, st>>>(P); }
+        else if (P.db.k == 31) {  // the reference's default k (C/GSConfigKey.java KMER_SIZE): masks and shift counts compiled in
+            if (wide) gs_label_kernel<GS_LAYOUT_TABLE, false, true, 31><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, false, false, 31><<<blocks, threads, 0, st>>>(P);
+        } else { if (wide) gs_label_kernel<GS_LAYOUT_TABLE, false, true, 0><<<blocks, threads, 0, st>>>(P); else gs_label_kernel<GS_LAYOUT_TABLE, false, false, 0><<<blocks, threads, 0, st>>>(P); }
     } else {
-        if (dump) gs_label_kernel<GS_LAYOUT_CLASSIC, true, false><<<blocks, threads, 0, st>>>(P);
-        else gs_label_kernel<GS_LAYOUT_CLASSIC, false, false><<<blocks, threads, 0, st>>>(P);
+        if (dump) gs_label_kernel<GS_LAYOUT_CLASSIC, true, false, 0><<<blocks, threads, 0, st>>>(P);
+        else gs_label_kernel<GS_LAYOUT_CLASSIC, false, false, 0><<<blocks, threads, 0, st>>>(P);
     }
 }
 void gs_launch_reduce(const GsMatchParams& P, int mode, bool dump, int blocks, cudaStream_t st) {
@@ -1368,8 +1387,8 @@ int gs_match_kernel_occupancy(int mode) {
     int nb = 0;
     if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<0, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
-    else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false, false, 31>, GS_WARPS_PER_BLOCK * 32, 0);
+    else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false, false, 0>, GS_WARPS_PER_BLOCK * 32, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
     return nb;
 }
