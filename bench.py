@@ -410,6 +410,8 @@ def run_match(E, name, wl, want_fastq, want_cpu):
     cfg.host_pack_percent = args.pack_percent
     native_options = {"layout": args.layout, "minimizer_prefilter": bool(cfg.prefilter) and args.layout == "table", "host_pack_threads": int(cfg.host_pack_threads)}
     sess = capi.MatchSession(db, cfg)
+    l2w = sess.l2_window()
+    native_options["l2_persisting_window"] = ({"what": "minimizer prefilter", "window_bytes": l2w[0], "persisting_bytes": l2w[1], "hit_ratio": l2w[2]} if l2w[0] else None)
     if E.comm:
         sess.prepare_merge(E.comm)   # set-up, not part of the job: peer mappings of the bitsets, merge kernel loaded
     stream = torch.cuda.ExternalStream(sess.stream, device=dev)
@@ -685,13 +687,14 @@ def run_filter(E, name, wl, want_cpu):
 
     def step(i):
         b, o = batches[i % n_batches]
-        sess.run_device(b.data_ptr(), o.data_ptr(), R, d_acc.data_ptr())
+        sess.run_device(b.data_ptr(), o.data_ptr(), R, R * READ_LEN, d_acc.data_ptr())
 
     for i in range(args.warmup):
         step(i)
     sess.sync()
     sampler = ClockSampler(E.local)
     sampler.start()
+    launches0 = sess.kernel_launches
     E.barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with torch.cuda.stream(stream):
@@ -701,6 +704,7 @@ def run_filter(E, name, wl, want_cpu):
             ev[i + 1].record(stream)
     sess.sync()
     E.barrier()
+    launches = sess.kernel_launches - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     clocks = sampler.result()
     accepted = int(d_acc.sum().item())
@@ -756,9 +760,9 @@ def run_filter(E, name, wl, want_cpu):
                "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                "reads_per_s": value / (READ_LEN - K + 1), "config": config, "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": nb + (R + 1) * 8, "d2h_bytes_per_step": R},
-               "gpu_launches": args.steps,
+               "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                            "kernel": "gs_filter_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk, "peak_source": peak_src,
+                            "kernel": "gs_filter_flat_kernel (+ gs_mark_starts_kernel, gs_filter_accept_kernel)", "kernel_ms": kernel_ms, "algorithmic_bytes_per_kmer": bpk, "peak_source": peak_src,
                             "dram": dram, "request_roofline": reqroof},
                "accepted_read_fraction": hfrac, "index": {"kind": "xor", "keys": n_index, "bits": bits, "hashes": hashes}}
     if rank == 0 and world == 1 and want_cpu:

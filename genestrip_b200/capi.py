@@ -10,7 +10,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GS_ABI_VERSION = 7
+GS_ABI_VERSION = 8
 GS_MAX_INFLIGHT = 3
 GS_READ_FOUND, GS_READ_ACCEPTED, GS_READ_SLOWPATH = 1, 2, 4
 GS_RUN_MISS, GS_RUN_INVALID = 0xFFFFFFFE, 0xFFFFFFFD
@@ -94,6 +94,7 @@ _SIGS = {
     "gs_pack_bases": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int]),
     "gs_pack_isa": (C.c_char_p, []),
     "gs_match_pack_fraction": (C.c_double, [_P]),
+    "gs_match_l2_window": (C.c_int, [_P, _P, _P, _P]),
     "gs_match_pack_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gs_match_merge_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "gs_match_close": (None, [_P]),
@@ -115,7 +116,8 @@ _SIGS = {
     "gs_filter_collect": (C.c_int, [_P, C.c_uint64, _P]),
     "gs_filter_submit_fastq": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(FastqInfo), C.POINTER(C.c_uint64)]),
     "gs_filter_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P)]),
-    "gs_filter_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
+    "gs_filter_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _P]),
+    "gs_filter_kernel_launches": (C.c_uint64, [_P]),
     "gs_filter_sync": (C.c_int, [_P]),
     "gs_filter_stream": (_P, [_P]),
     "gs_filter_close": (None, [_P]),
@@ -502,6 +504,12 @@ class MatchSession:
     def pack_fraction(self):
         return lib().gs_match_pack_fraction(self.h)
 
+    def l2_window(self):
+        """(window bytes, persisting carve-out bytes, hit ratio) of the L2 access policy window on the compute stream."""
+        w, c, r = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        _check(lib().gs_match_l2_window(self.h, C.byref(w), C.byref(c), C.byref(r)))
+        return int(w.value), int(c.value), float(r.value)
+
     def pack_stats(self):
         """(threads, host seconds spent packing, bases packed, base bytes put on the link) of this session's submits."""
         t, sec, n, b = C.c_int(0), C.c_double(0), C.c_uint64(0), C.c_uint64(0)
@@ -620,8 +628,12 @@ class FilterSession:
         r = np.ctypeslib.as_array(C.cast(rc, C.POINTER(C.c_uint8)), shape=((n.value + 1) * 16,)).view(FASTQ_REC_DTYPE)
         return a, r
 
-    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr):
-        _check(lib().gs_filter_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, d_accept_ptr))
+    def run_device(self, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_accept_ptr):
+        _check(lib().gs_filter_run_device(self.h, d_bases_ptr, d_offsets_ptr, n_reads, n_bases, d_accept_ptr))
+
+    @property
+    def kernel_launches(self):
+        return int(lib().gs_filter_kernel_launches(self.h))
 
     def sync(self):
         _check(lib().gs_filter_sync(self.h))

@@ -869,6 +869,8 @@ struct MatchSlot {
 struct DevSess {
     int dev = 0, devIndex = 0, sms = 148;
     cudaStream_t sCopyIn = nullptr, sCompute = nullptr, sCopyOut = nullptr;
+    size_t l2WindowBytes = 0, l2CarveBytes = 0;   // access policy window on sCompute (minimizer prefilter), 0 = none
+    float l2HitRatio = 0.f;
     long long* counters = nullptr;  // [7][V]
     u64* maxcontig = nullptr;       // [V]
     u64* bitset = nullptr; u64 bitsetWords = 0;
@@ -970,6 +972,35 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
     D.labelBlocks = D.sms * std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
     if (const char* e = getenv("GS_DEBUG_LABEL_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0) D.labelBlocks = D.sms * v; }  // tuning experiments
     D.slowBlocks = std::max(1, D.sms / 4);
+    // L2-persisting access window over the minimizer prefilter: the one structure every k-mer of every batch reads, next to
+    // 600 MB of bases and 2 GB of labels per batch that stream through the same L2.  Set when the whole filter fits the
+    // device's persisting carve-out (79 MB on B200).  GS_L2_PERSIST=0 switches the window off (A/B).
+    {
+        const gs_db* db = s->db;
+        const char* e = getenv("GS_L2_PERSIST");
+        const bool want = !(e && atoi(e) == 0);
+        cudaDeviceProp prop;
+        if (want && s->layout == GS_LAYOUT_TABLE && s->cfg.prefilter && db->mzBits && db->d[D.devIndex].mzFilter &&
+            cudaGetDeviceProperties(&prop, D.dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t fBytes = (size_t)1 << (db->mzBits - 3);
+            const size_t carve = fBytes;
+            // measured (profiles/r02/bench_l_*.json): a filter that fits (32 MB at 1e8 k-mers) gains 3-4 %; of the 512 MB filter of
+            // the 2e9-k-mer store only 79 MB can be pinned and the kernel gets 2.6 % slower -- no window then
+            if (fBytes <= (size_t)prop.persistingL2CacheMaxSize && fBytes <= (size_t)prop.accessPolicyMaxWindowSize && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = (void*)db->d[D.devIndex].mzFilter;
+                av.accessPolicyWindow.num_bytes = std::min<size_t>(fBytes, (size_t)prop.accessPolicyMaxWindowSize);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(D.sCompute, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) {
+                    D.l2WindowBytes = av.accessPolicyWindow.num_bytes; D.l2CarveBytes = carve; D.l2HitRatio = av.accessPolicyWindow.hitRatio;
+                }
+            }
+            cudaGetLastError();  // a refused window is not an error of the session
+        }
+    }
     CU(dmalloc(&D.slowTable, (size_t)D.slowBlocks * GS_WARPS_PER_BLOCK * 2 * std::max(V, 1)));
     for (MatchSlot& sl : D.slots) {
         CU(cudaEventCreateWithFlags(&sl.evH2D, cudaEventDisableTiming));
@@ -989,6 +1020,7 @@ extern "C" void gs_match_close(gs_sess* s) {
     for (DevSess& D : s->devs) {
         cudaSetDevice(D.dev);
         cudaDeviceSynchronize();
+        if (D.l2WindowBytes) cudaCtxResetPersistingL2Cache();   // hand the carve-out back: nothing of this session stays pinned in the L2
         for (MatchSlot& sl : D.slots) {
             cudaFree(sl.dBases); cudaFree(sl.dOffsets); cudaFree(sl.dOut); cudaFree(sl.dEv); cudaFree(sl.dNEv);
             cudaFree(sl.dKmerOff); cudaFree(sl.dRuns); cudaFree(sl.dRunCounts);
@@ -2109,6 +2141,14 @@ extern "C" int gs_pack_bases(const uint8_t* bases, uint64_t n, uint64_t* codes, 
 }
 extern "C" const char* gs_pack_isa(void) { return gsp::pack_isa(); }
 
+extern "C" int gs_match_l2_window(const gs_sess* s, uint64_t* window_bytes, uint64_t* persisting_bytes, double* hit_ratio) {
+    if (!s || s->devs.empty()) return gs_fail(GS_ERR_ARG, "gs_match_l2_window: no session");
+    const DevSess& D = s->devs[0];
+    if (window_bytes) *window_bytes = D.l2WindowBytes;
+    if (persisting_bytes) *persisting_bytes = D.l2CarveBytes;
+    if (hit_ratio) *hit_ratio = D.l2HitRatio;
+    return GS_OK;
+}
 extern "C" double gs_match_pack_fraction(const gs_sess* s) { return s ? (s->cfg.host_pack_threads == 0 ? 0.0 : s->cfg.host_pack_percent >= 0 ? s->cfg.host_pack_percent / 100.0 : s->packFrac) : 0.0; }
 extern "C" int gs_match_pack_stats(const gs_sess* s, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes) {
     if (!s) return gs_fail(GS_ERR_ARG, "null session");
@@ -2228,6 +2268,10 @@ struct DevFsess {
     int dev = 0, devIndex = 0, blocks = 0;
     cudaStream_t sCopyIn = nullptr, sCompute = nullptr, sCopyOut = nullptr;
     FilterSlot slots[GS_MAX_INFLIGHT];
+    // scratch of the flat filter kernels (kernels of one device run back to back on sCompute: one set is enough)
+    u32* startBits = nullptr; u32* hitBits = nullptr; size_t bitsCap = 0;
+    u32* segCounter = nullptr;
+    u64 launches = 0;
 };
 struct gs_fsess {
     gs_filter* f = nullptr;
@@ -2251,6 +2295,7 @@ extern "C" void gs_filter_close(gs_fsess* s) {
             if (sl.evCompute) cudaEventDestroy(sl.evCompute);
             if (sl.evDone) cudaEventDestroy(sl.evDone);
         }
+        cudaFree(D.startBits); cudaFree(D.hitBits); cudaFree(D.segCounter);
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
         if (D.sCompute) cudaStreamDestroy(D.sCompute);
         if (D.sCopyOut) cudaStreamDestroy(D.sCopyOut);
@@ -2278,14 +2323,43 @@ extern "C" gs_fsess* gs_filter_open(gs_filter* f, int k, int min_pos_count, doub
                  dmalloc(&sl.dErr, 1) == cudaSuccess && cudaMallocHost((void**)&sl.hErr, sizeof(u32)) == cudaSuccess;
         if (!ok) { gs_fail(GS_ERR_CUDA, "filter session setup failed: %s", cudaGetErrorString(cudaGetLastError())); gs_filter_close(s); return nullptr; }
         D.blocks = f->ctx->sms[i] * std::max(1, gs_match_kernel_occupancy(2));
+        ok = dmalloc(&D.segCounter, 2) == cudaSuccess;
+        if (!ok) { gs_fail(GS_ERR_CUDA, "filter session setup failed: %s", cudaGetErrorString(cudaGetLastError())); gs_filter_close(s); return nullptr; }
     }
     cudaSetDevice(f->d[0].dev);
     return s;
 }
 
 static void fill_fparams(gs_fsess* s, DevFsess& D, GsFilterParams& P) {
+    memset(&P, 0, sizeof(P));
     P.f = s->f->d[D.devIndex].view;
     P.k = s->k; P.minPosCount = s->minPosCount; P.posRatio = s->posRatio;
+}
+
+// The three kernels of a filter batch on the device's compute stream: read-start bitmap, hit bit per k-mer position, accept
+// byte per read.  `bases + off0` = first base of the batch, nBytes = its length (reads back to back).
+static int filter_launch(DevFsess& D, GsFilterParams& P, u64 off0, u64 nBytes) {
+    if (!P.nReads) return GS_OK;
+    P.off0 = off0;
+    P.lead = (u32)((uintptr_t)(P.bases + off0) & 15);
+    P.flatLen = nBytes + P.lead;
+    const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+    const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
+    if (words > D.bitsCap) {
+        CU(cudaStreamSynchronize(D.sCompute));
+        cudaFree(D.startBits); cudaFree(D.hitBits); D.startBits = D.hitBits = nullptr; D.bitsCap = 0;
+        CU(dmalloc(&D.startBits, words + words / 4));
+        CU(dmalloc(&D.hitBits, words + words / 4));
+        D.bitsCap = words + words / 4;
+    }
+    P.startBits = D.startBits; P.hitBits = D.hitBits; P.segCounter = D.segCounter;
+    CU(cudaMemsetAsync(D.startBits, 0, words * sizeof(u32), D.sCompute));
+    CU(cudaMemsetAsync(D.segCounter, 0, 2 * sizeof(u32), D.sCompute));
+    const int blocks = (int)std::max<u64>(1, std::min<u64>((u64)D.blocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
+    gs_launch_filter(P, blocks, D.sCompute);
+    CU(cudaGetLastError());
+    D.launches += 3;
+    return GS_OK;
 }
 
 extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, gs_ticket* ticket) {
@@ -2312,11 +2386,7 @@ extern "C" int gs_filter_submit(gs_fsess* s, const uint8_t* bases, const uint64_
     fill_fparams(s, D, P);
     P.bases = sl.dBases - base0; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept; P.errFlag = sl.dErr;
     CU(cudaMemsetAsync(sl.dErr, 0, sizeof(u32), D.sCompute));
-    if (n_reads) {
-        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
-        gs_launch_filter(P, blocks, D.sCompute);
-        CU(cudaGetLastError());
-    }
+    { const int rcl = filter_launch(D, P, base0, nBytes); if (rcl) return rcl; }
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
@@ -2355,11 +2425,7 @@ extern "C" int gs_filter_submit_fastq(gs_fsess* s, const uint8_t* text, uint64_t
     fill_fparams(s, D, P);
     P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.accept = sl.dAccept; P.errFlag = sl.dErr;
     CU(cudaMemsetAsync(sl.dErr, 0, sizeof(u32), D.sCompute));
-    if (n_reads) {
-        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
-        gs_launch_filter(P, blocks, D.sCompute);
-        CU(cudaGetLastError());
-    }
+    { const int rcl = filter_launch(D, P, 0, info->total_bps); if (rcl) return rcl; }
     CU(cudaEventRecord(sl.evCompute, D.sCompute));
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hAccept, sl.dAccept, n_reads, cudaMemcpyDeviceToHost, D.sCopyOut));
@@ -2403,7 +2469,7 @@ extern "C" int gs_filter_collect(gs_fsess* s, gs_ticket t, uint8_t* accept) {
     return GS_OK;
 }
 
-extern "C" int gs_filter_run_device(gs_fsess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint8_t* d_accept) {
+extern "C" int gs_filter_run_device(gs_fsess* s, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases, uint8_t* d_accept) {
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     if (((uintptr_t)d_bases & 15) != 0) return gs_fail(GS_ERR_ARG, "d_bases must be 16-byte aligned");
     DevFsess& D = s->devs[0];
@@ -2411,13 +2477,15 @@ extern "C" int gs_filter_run_device(gs_fsess* s, const uint8_t* d_bases, const u
     GsFilterParams P;
     fill_fparams(s, D, P);
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.accept = d_accept; P.errFlag = nullptr;
-    if (n_reads) {
-        const int blocks = (int)std::min<u64>((u64)D.blocks, ((u64)n_reads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
-        gs_launch_filter(P, blocks, D.sCompute);
-        CU(cudaGetLastError());
-    }
-    return GS_OK;
+    return filter_launch(D, P, 0, n_bases);
 }
+
+extern "C" uint64_t gs_filter_kernel_launches(const gs_fsess* s) {
+    u64 n = 0;
+    if (s) for (const DevFsess& D : s->devs) n += D.launches;
+    return n;
+}
+
 
 extern "C" int gs_filter_sync(gs_fsess* s) {
     if (!s) return gs_fail(GS_ERR_STATE, "null session");

@@ -1336,51 +1336,146 @@ void gs_launch_filter_contains(const GsFilterView& f, const u64* kmers, u64 n, u
 }
 
 // FastqBloomFilter.isAcceptRead (C/bloom/FastqBloomFilter.java:120-161).  The two early exits are mutually
-// exclusive (hits + misses <= max), so the decision is  hits_total >= max(1, posThreshold); the scan stops as soon
-// as that many hits were seen (warp-wide, chunk granularity).
-__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32) gs_filter_kernel(const GsFilterParams P) {
-    __shared__ u64 s_code[GS_WARPS_PER_BLOCK][GS_CODE_WORDS];
-    __shared__ u32 s_valid[GS_WARPS_PER_BLOCK][GS_VALID_WORDS];
+// exclusive (hits + misses <= max), so the decision is  hits_total >= max(1, posThreshold).
+//
+// Shape (round 2; the warp-per-read kernel of round 1 sat on the DRAM line-request cap with 1.70 lines per k-mer): the same
+// flat decomposition as the match path.  gs_filter_flat_kernel walks the batch's bases as ONE array (segments of GS_SEG_POS
+// positions claimed by atomic counter, staged like the label kernel), every lane tests one k-mer and the warp writes one hit bit
+// per position; gs_filter_accept_kernel counts a read's bits (one thread per read).
+//
+// What was measured on the way (profiles/experiments/README.md "filter kernel"): the flat kernel runs at the same speed as the
+// warp-per-read one (18.6 vs 18.2 ms per 4 M reads) -- both sit on the DRAM line-request cap, an absent k-mer costs two
+// probes = two DRAM lines of a filter that is half full and four times the L2 -- and a pass that first looked for a clear
+// bit among the hash functions landing in an L2-pinned part of the filter cost more issue slots than it saved requests.
+#ifndef GS_FILTER_MIN_BLOCKS
+#define GS_FILTER_MIN_BLOCKS 6
+#endif
+
+template <int KIND>
+__device__ __forceinline__ u64 gs_filter_index(const GsFilterView& f, long long fac, u64 key) {
+    const long long h = KIND == GS_BLOOM_XOR ? (long long)((u64)fac ^ key) : (long long)gs_murmur64(key, (u64)fac);
+    return gs_absmod(h, (u64)f.p0, f.magic);
+}
+
+// AbstractKMerBloomFilter.containsLong (C/bloom/AbstractKMerBloomFilter.java:209-216): the reference's order, stop at the first 0 bit
+template <int KIND>
+__device__ __forceinline__ bool gs_filter_contains_hashed(const GsFilterView& f, const long long* fac, u64 key) {
+    const int H = (int)f.p1;
+    for (int i = 0; i < H; i++) {
+        const u64 idx = gs_filter_index<KIND>(f, fac[i], key);
+        if (!((__ldg(f.words + (idx >> 6)) >> (idx & 63)) & 1ULL)) return false;
+    }
+    return true;
+}
+
+#define GS_FILTER_MAX_FACTORS 64   // hash factors staged in shared memory (27 at fpp 1e-8); filters with more use the global array
+
+template <int KIND, int KT>
+__global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, GS_FILTER_MIN_BLOCKS) gs_filter_flat_kernel(const GsFilterParams P) {
+    __shared__ GsSegStage s_stage[GS_WARPS_PER_BLOCK];
+    __shared__ long long s_fac[GS_FILTER_MAX_FACTORS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 gw = blockIdx.x * GS_WARPS_PER_BLOCK + warp, nw = gridDim.x * GS_WARPS_PER_BLOCK;
-    const int k = P.k;
+    const int k = KT > 0 ? KT : P.k;
     const u32 kmask = (k >= 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
-    u64* cw = s_code[warp];
-    u32* vw = s_valid[warp];
-    for (u32 r = gw; r < P.nReads; r += nw) {
-        const u64 start = P.offsets[r];
-        const u64 end = P.offsets[r + 1];
-        int L = (int)(end - start);
-        if (end < start || end - start > 0x7FFFFFF0ULL) {
-            if (lane == 0 && P.errFlag) atomicOr(P.errFlag, 1u);
-            L = 0;
-        }
-        const int max = L - k + 1;
-        int posThreshold = P.minPosCount > 0 ? P.minPosCount : (int)((double)max * P.posRatio);  // :122
-        const int need = posThreshold < 1 ? 1 : posThreshold;
-        int hits = 0;
-        for (int t0 = 0; t0 < max && hits < need; t0 += GS_TILE_POS) {
-            const int nb = min(L - t0, GS_TILE_BASES);
-            int d0 = 0, d1 = 0;
-            __syncwarp();
-            gs_stage_tile(P.bases + start + t0, nb, lane, (u32*)cw, (uint16_t*)vw, 0, 0, d0, d1);
-            __syncwarp();
-            const int lim = min(max - t0, GS_TILE_POS);
-            for (int c = 0; c * 32 < lim && hits < need; c++) {
-                const int prel = c * 32 + lane;
-                bool hit = false;
-                if (prel < lim) {
-                    u32 vbits = __funnelshift_r(vw[prel >> 5], vw[(prel >> 5) + 1], prel & 31);
-                    if ((vbits & kmask) == kmask) hit = gs_filter_contains(P.f, gs_canonical(gs_extract(cw, prel, k), k));
+    const u32 k1mask = (1u << (k - 1)) - 1u;
+    const long long* fac = P.f.factors;
+    if (KIND != GS_BLOOM_BLOCKED && (int)P.f.p1 <= GS_FILTER_MAX_FACTORS) {
+        if ((int)threadIdx.x < (int)P.f.p1) s_fac[threadIdx.x] = __ldg(P.f.factors + threadIdx.x);
+        fac = s_fac;
+    }
+    __syncthreads();
+    GsSegStage& S = s_stage[warp];
+    const u32* cp = S.code + (lane >> 4);
+    const u32 csh = (u32)(lane & 15) * 2;
+    const uint8_t* fb = P.bases + P.off0 - P.lead;  // 16-byte aligned start of the flat array
+    const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
+    for (;;) {
+        u32 seg = 0;
+        if (lane == 0) seg = atomicAdd(P.segCounter, 1u);
+        seg = __shfl_sync(FULL, seg, 0);
+        if (seg >= nSeg) break;
+        const u64 f0 = (u64)seg * GS_SEG_POS;
+        const int nb = (int)min((u64)GS_SEG_BASES, P.flatLen - f0);
+        const u64 w0 = (u64)seg * GS_SEG_CHUNKS;
+        __syncwarp();
+        const uint4* ap = (const uint4*)(fb + f0);
+#pragma unroll
+        for (int j = lane; j < GS_SEG_BASES / 16; j += 32) {
+            u32 code = 0, valid = 0;
+            const int rem = nb - j * 16;
+            if (rem > 0) {
+                const uint4 A = __ldg(ap + j);
+                u32 c0, c1, c2, c3, v0, v1, v2, v3;
+                gs_conv4(A.x, c0, v0); gs_conv4(A.y, c1, v1); gs_conv4(A.z, c2, v2); gs_conv4(A.w, c3, v3);
+                code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+                valid = v0 | (v1 << 4) | (v2 << 8) | (v3 << 12);
+                if (rem < 16) valid &= (1u << rem) - 1u;
+                if (seg == 0) {  // alignment bytes in front of the first read are not bases
+                    const int lo = (int)P.lead - j * 16;
+                    if (lo > 0) valid &= lo >= 16 ? 0u : ~((1u << lo) - 1u);
                 }
-                hits += __popc(__ballot_sync(FULL, hit));
             }
+            S.code[j] = code;
+            ((uint16_t*)S.valid)[j] = (uint16_t)valid;
         }
-        if (lane == 0) P.accept[r] = hits >= need ? 1 : 0;
+        S.start[lane] = __ldg(P.startBits + w0 + lane);
+        if (lane < 2) { ((uint2*)S.code)[32 + lane] = make_uint2(0u, 0u); S.valid[32 + lane] = 0; S.start[32 + lane] = lane == 0 ? __ldg(P.startBits + w0 + 32) : 0u; }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < GS_SEG_CHUNKS; c++) {
+            const u32 vbits = __funnelshift_r(S.valid[c], S.valid[c + 1], lane);
+            const u32 sbits = __funnelshift_rc(S.start[c], S.start[c + 1], lane + 1);
+            // a window that crosses a read boundary is no k-mer of any read; one that holds a non-CGAT byte counts as a miss
+            // (FastqBloomFilter.java:133-141)
+            const bool valid = !(sbits & k1mask) && (vbits & kmask) == kmask;
+            bool hit = false;
+            if (valid) {
+                const u64 key = gs_canonical(gs_extract_w(cp + 2 * c, csh, k), k);
+                if (KIND == GS_BLOOM_BLOCKED) hit = gs_bloom_blocked(P.f.words, (u64)P.f.p1, P.f.magic, P.f.p0, key);
+                else hit = gs_filter_contains_hashed<KIND>(P.f, fac, key);
+            }
+            __syncwarp();
+            const u32 hb = __ballot_sync(FULL, hit);
+            if (lane == 0) P.hitBits[w0 + c] = hb;
+        }
     }
 }
+
+// one thread per read: hits = set bits of the read's k-mer positions, accept = hits >= max(1, posThreshold) (:122, :143-158)
+__global__ void gs_filter_accept_kernel(const GsFilterParams P) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < P.nReads; r += stride) {
+        const u64 start = P.offsets[r], end = P.offsets[r + 1];
+        long long L = (long long)(end - start);
+        const u64 f = start - P.off0 + P.lead;
+        if (end < start || end - start > 0x7FFFFFF0ULL || start < P.off0 || f + (u64)L > P.flatLen) {
+            if (P.errFlag) atomicOr(P.errFlag, 1u);
+            L = 0;
+        }
+        const int max = (int)L - P.k + 1;
+        const int posThreshold = P.minPosCount > 0 ? P.minPosCount : (int)((double)max * P.posRatio);  // :122
+        const int need = posThreshold < 1 ? 1 : posThreshold;
+        int hits = 0;
+        if (max > 0) {
+            const u64 e = f + (u64)max;   // bits [f, e)
+            for (u64 w = f >> 5; w <= ((e - 1) >> 5); w++) {
+                u32 m = __ldg(P.hitBits + w);
+                if (w == (f >> 5)) m &= 0xFFFFFFFFu << (f & 31);
+                if (w == ((e - 1) >> 5)) m &= 0xFFFFFFFFu >> (31 - (u32)((e - 1) & 31));
+                hits += __popc(m);
+            }
+        }
+        P.accept[r] = hits >= need ? 1 : 0;
+    }
+}
+
 void gs_launch_filter(const GsFilterParams& P, int blocks, cudaStream_t st) {
-    gs_filter_kernel<<<blocks, GS_WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    const int threads = GS_WARPS_PER_BLOCK * 32;
+    gs_mark_starts_kernel<<<148 * 4, 256, 0, st>>>(P.offsets, P.nReads, P.off0, P.lead, P.flatLen, P.startBits);
+    if (P.f.kind == GS_BLOOM_XOR) { if (P.k == 31) gs_filter_flat_kernel<GS_BLOOM_XOR, 31><<<blocks, threads, 0, st>>>(P); else gs_filter_flat_kernel<GS_BLOOM_XOR, 0><<<blocks, threads, 0, st>>>(P); }
+    else if (P.f.kind == GS_BLOOM_MURMUR) gs_filter_flat_kernel<GS_BLOOM_MURMUR, 0><<<blocks, threads, 0, st>>>(P);
+    else gs_filter_flat_kernel<GS_BLOOM_BLOCKED, 0><<<blocks, threads, 0, st>>>(P);
+    gs_filter_accept_kernel<<<148 * 4, 256, 0, st>>>(P);
 }
 
 int gs_match_kernel_occupancy(int mode) {
@@ -1389,7 +1484,7 @@ int gs_match_kernel_occupancy(int mode) {
     else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_reduce_kernel<1, false, false>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_TABLE, false, false, 31>, GS_WARPS_PER_BLOCK * 32, 0);
     else if (mode == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_label_kernel<GS_LAYOUT_CLASSIC, false, false, 0>, GS_WARPS_PER_BLOCK * 32, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_kernel, GS_WARPS_PER_BLOCK * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_filter_flat_kernel<GS_BLOOM_XOR, 31>, GS_WARPS_PER_BLOCK * 32, 0);
     return nb;
 }
 

@@ -61,6 +61,12 @@ struct GsFilterParams {
     double posRatio;
     uint8_t* accept;
     u32* errFlag;
+    // flat geometry of the batch, as in GsMatchParams: flat position f = byte offset - off0 + lead
+    u64 off0, flatLen;
+    u32 lead;
+    u32* startBits;         // [segments * 31 (+pad)] bit f = a read starts at f (zeroed by the caller, set by gs_mark_starts_kernel)
+    u32* hitBits;           // same size: bit f = the k-mer that starts at f is a k-mer of a read and is contained in the filter
+    u32* segCounter;        // next unclaimed segment (zeroed by the caller)
 };
 
 void gs_launch_mark_starts(const GsMatchParams& P, cudaStream_t st);

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 7
+#define GS_ABI_VERSION 8
 
 typedef enum gs_status {
     GS_OK = 0,
@@ -263,6 +263,10 @@ double gs_match_pack_fraction(const gs_sess*); /* the share of a batch that is p
 /* Measurement of the last merge of this session: CUDA-event time of the whole merge and of its bitset part (ms, on the
  * session's compute stream), bitset bytes this rank read from the other ranks, path (1 = peer mappings, 2 = NCCL exchange). */
 int gs_match_merge_stats(const gs_sess*, double* total_ms, double* bitset_ms, uint64_t* bytes_from_peers, int* path);
+/* L2-persisting access window of this session's compute stream on its first device (north_star: "L2-persisting access
+ * windows"): bytes of the window (the minimizer prefilter), bytes of the persisting carve-out, hit ratio; all 0 = no window
+ * (classic layout, prefilter off, GS_L2_PERSIST=0, or refused by the device). */
+int gs_match_l2_window(const gs_sess*, uint64_t* window_bytes, uint64_t* persisting_bytes, double* hit_ratio);
 
 /* Device-resident variants (inputs already in HBM; used by bench.py's kernel-only number and by a host that
  * decodes on the GPU).  d_bases must be 16-byte aligned and readable 32 bytes past the last base; d_offsets[0] == 0 and
@@ -315,8 +319,11 @@ int gs_filter_collect(gs_fsess*, gs_ticket, uint8_t* accept);
  * staging, valid until GS_MAX_INFLIGHT further batches were submitted to the same device. */
 int gs_filter_submit_fastq(gs_fsess*, const uint8_t* text, uint64_t n_bytes, gs_fastq_info* info, gs_ticket* ticket);
 int gs_filter_collect_fastq(gs_fsess*, gs_ticket, const uint8_t** accept, uint32_t* n_reads, const gs_fastq_rec** recs);
-int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+/* Device-resident variant (inputs already in HBM): d_bases 16-byte aligned and readable 32 bytes past the last base,
+ * d_offsets[0] == 0 and d_offsets[n_reads] == n_bases; asynchronous on the session's compute stream (gs_filter_stream). */
+int gs_filter_run_device(gs_fsess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads, uint64_t n_bases,
                          uint8_t* d_accept);
+uint64_t gs_filter_kernel_launches(const gs_fsess*); /* kernels this session has launched so far */
 int gs_filter_sync(gs_fsess*);
 void* gs_filter_stream(gs_fsess*);
 void gs_filter_close(gs_fsess*);

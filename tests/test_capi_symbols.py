@@ -22,7 +22,7 @@ def test_header_symbols_are_exported(native):
     for name in declared:
         assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
     assert set(native.EXPORTED_SYMBOLS) == set(declared)
-    assert lib.gs_abi_version() == native.GS_ABI_VERSION == 7
+    assert lib.gs_abi_version() == native.GS_ABI_VERSION == 8
 
 
 def test_struct_layouts(native):
