@@ -209,12 +209,18 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
             const u32 vbits = __funnelshift_r(S.valid[c], S.valid[c + 1], lane);
             const u32 sbits = __funnelshift_rc(S.start[c], S.start[c + 1], lane + 1);
             u32 lab = (sbits & k1mask) ? GS_LABEL_END : ((vbits & kmask) != kmask ? GS_LABEL_INVALID : GS_LABEL_PENDING);
+#ifdef GS_EXP_FAKE_LOCAL
+            u32 expLine = 0;   // timing experiment only (wrong results): address the table by minimizer, as a line-addressed table would
+#endif
             if (mz) {
                 const u64 rcm = gs_revcomp(fwdN, k) & mmask;
                 hN = WIDE ? (MzT)gs_mmer_hash2w(fwdN >> (2 * GS_MZ_S), rcm) : (MzT)gs_mmer_hash2(fwdN >> (2 * GS_MZ_S), rcm);
                 preN = gs_seg_prefix_min(hN, lane);
                 const u32 mzv = gs_mz_index((u32)gs_window_min(gs_seg_suffix_min(hC, lane), preC, preN, lane), db.mzMask);
                 if (lab == GS_LABEL_PENDING && !((__ldg(db.mzFilter + (mzv >> 6)) >> (mzv & 63)) & 1ULL)) lab = GS_LABEL_MISS;
+#ifdef GS_EXP_FAKE_LOCAL
+                expLine = mzv;
+#endif
             }
             {
                 // The lookup.  Two shapes of the same probe (template parameter, same results):
@@ -231,7 +237,11 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                 if (LAYOUT == GS_LAYOUT_TABLE) {
                     if (WIDE ? __any_sync(FULL, pend) : pend) {
                         const u64 h = gs_mix62(gs_canonical(fwd, k));  // standardKMer (CGAT.java:145-147)
+#ifdef GS_EXP_FAKE_LOCAL
+                        const u64 b0 = (WIDE && !pend) ? 0ULL : ((((u64)(expLine * 0x85EBCA77u) & ((1ULL << (db.tbits - 2)) - 1)) << 2) | (h & 3));
+#else
                         const u64 b0 = (WIDE && !pend) ? 0ULL : (h >> db.rbits);
+#endif
                         const GsBucket bk = gs_load_bucket(db.tab, b0);
                         u64 e;
                         const int j = gs_table_match(db.rbits, h, bk, e);
