@@ -118,6 +118,8 @@ _SIGS = {
     "gs_filter_collect_fastq": (C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     "gs_filter_run_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _P]),
     "gs_filter_kernel_launches": (C.c_uint64, [_P]),
+    "gs_filter_save_file": (C.c_int, [_P, C.c_char_p]),
+    "gs_filter_load_file": (_P, [_P, C.c_char_p]),
     "gs_filter_sync": (C.c_int, [_P]),
     "gs_filter_stream": (_P, [_P]),
     "gs_filter_close": (None, [_P]),
@@ -579,6 +581,19 @@ class Filter:
         out = np.empty(len(kmers), dtype=np.uint8)
         _check(lib().gs_filter_contains(self.h, _ptr(kmers), len(kmers), _ptr(out)))
         return out
+
+    def save_file(self, path):
+        """Flat GSF1 index file (gs_filter_save_file)."""
+        _check(lib().gs_filter_save_file(self.h, os.fsencode(path)))
+
+    @classmethod
+    def load_file(cls, ctx, path):
+        """gs_filter_load_file: the index KMerProbFilter.load would deserialize, without a JVM."""
+        self = cls.__new__(cls)
+        self.h = lib().gs_filter_load_file(ctx.h, os.fsencode(path))
+        if not self.h:
+            raise GenestripError(-1, lib().gs_last_error().decode())
+        return self
 
     def close(self):
         if self.h:

@@ -2180,6 +2180,10 @@ struct DevFilter {
 struct gs_filter {
     gs_ctx* ctx = nullptr;
     std::vector<DevFilter> d;
+    int kind = 0;
+    long long p0 = 0, p1 = 0;
+    u64 nWords = 0;
+    std::vector<long long> factors;   // host copy (hashed kinds): what gs_filter_save_file writes
 };
 
 extern "C" void gs_filter_destroy(gs_filter* f) {
@@ -2205,6 +2209,8 @@ extern "C" gs_filter* gs_filter_create(gs_ctx* ctx, int kind, int64_t p0, int64_
     } else { gs_fail(GS_ERR_ARG, "unknown filter kind %d", kind); return nullptr; }
     gs_filter* f = new gs_filter();
     f->ctx = ctx;
+    f->kind = kind; f->p0 = p0; f->p1 = p1; f->nWords = n_words;
+    if (kind != GS_BLOOM_BLOCKED) f->factors.assign(factors, factors + p1);
     f->d.resize(ctx->devs.size());
     for (size_t i = 0; i < ctx->devs.size(); i++) {
         DevFilter& d = f->d[i];
@@ -2226,6 +2232,64 @@ extern "C" gs_filter* gs_filter_create(gs_ctx* ctx, int kind, int64_t p0, int64_
     }
     cudaSetDevice(ctx->devs[0]);
     return f;
+}
+
+// Flat little-endian filter index file "GSF1": what KMerProbFilter.save / load move as a Java object stream
+// (C/bloom/KMerProbFilter.java, C/goals/LoadIndexGoal.java:92-104), as plain arrays.
+//   header (48 bytes): magic "GSF1\0\0\0\0", i32 version = 1, i32 kind (GS_BLOOM_*), i64 p0, i64 p1, u64 n_factors, u64 n_words
+//   i64 factors[n_factors]   (hashed kinds: hashFactors, AbstractKMerBloomFilter.java:104-110; blocked: none)
+//   i64 words[n_words]       (the bit array: long[] or the segments of the large array, in order)
+struct GsfHeader { char magic[8]; int32_t version; int32_t kind; int64_t p0, p1; uint64_t n_factors, n_words; };
+static_assert(sizeof(GsfHeader) == 48, "GSF1 header layout");
+
+extern "C" int gs_filter_save_file(gs_filter* f, const char* path) {
+    if (!f || !path) return gs_fail(GS_ERR_ARG, "null argument");
+    try {
+        std::vector<int64_t> words((size_t)f->nWords);
+        CU(cudaSetDevice(f->d[0].dev));
+        CU(cudaMemcpy(words.data(), f->d[0].words, (size_t)f->nWords * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        FILE* o = fopen(path, "wb");
+        if (!o) return gs_fail(GS_ERR_ARG, "cannot create %s", path);
+        GsfHeader h;
+        memset(&h, 0, sizeof(h));
+        memcpy(h.magic, "GSF1\0\0\0\0", 8);
+        h.version = 1; h.kind = f->kind; h.p0 = f->p0; h.p1 = f->p1; h.n_factors = f->factors.size(); h.n_words = f->nWords;
+        bool ok = fwrite(&h, sizeof(h), 1, o) == 1;
+        ok = ok && (f->factors.empty() || fwrite(f->factors.data(), sizeof(long long), f->factors.size(), o) == f->factors.size());
+        ok = ok && (words.empty() || fwrite(words.data(), sizeof(int64_t), words.size(), o) == words.size());
+        ok = (fclose(o) == 0) && ok;
+        if (!ok) return gs_fail(GS_ERR_ARG, "short write to %s", path);
+        return GS_OK;
+    } catch (const std::exception& e) {
+        return gs_fail(GS_ERR_ARG, "%s: %s", path, e.what());
+    }
+}
+
+extern "C" gs_filter* gs_filter_load_file(gs_ctx* ctx, const char* path) {
+    if (!ctx || !path) { gs_fail(GS_ERR_ARG, "null argument"); return nullptr; }
+    try {
+        FILE* in = fopen(path, "rb");
+        if (!in) { gs_fail(GS_ERR_ARG, "cannot open %s", path); return nullptr; }
+        struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{in};
+        GsfHeader h;
+        if (fread(&h, sizeof(h), 1, in) != 1 || memcmp(h.magic, "GSF1\0\0\0\0", 8) != 0 || h.version != 1) { gs_fail(GS_ERR_ARG, "%s is not a GSF1 filter file", path); return nullptr; }
+        if (fseek(in, 0, SEEK_END) != 0) { gs_fail(GS_ERR_ARG, "%s: cannot seek", path); return nullptr; }
+        const u64 fileBytes = (u64)ftell(in);
+        fseek(in, (long)sizeof(h), SEEK_SET);
+        // the header's sizes must add up to the file's size before anything is allocated from them
+        const bool hashed = h.kind == GS_BLOOM_XOR || h.kind == GS_BLOOM_MURMUR;
+        const bool sane = (hashed || h.kind == GS_BLOOM_BLOCKED) && h.n_words <= fileBytes / 8 && h.n_factors <= 4096 &&
+                          (hashed ? (h.p1 > 0 && (u64)h.p1 == h.n_factors) : h.n_factors == 0);
+        if (!sane || sizeof(h) + h.n_factors * 8 + h.n_words * 8 != fileBytes) { gs_fail(GS_ERR_ARG, "%s: header does not match the file (%llu bytes)", path, (unsigned long long)fileBytes); return nullptr; }
+        std::vector<int64_t> factors((size_t)h.n_factors), words((size_t)h.n_words);
+        if ((h.n_factors && fread(factors.data(), 8, factors.size(), in) != factors.size()) || (h.n_words && fread(words.data(), 8, words.size(), in) != words.size())) {
+            gs_fail(GS_ERR_ARG, "%s: truncated", path); return nullptr;
+        }
+        return gs_filter_create(ctx, h.kind, h.p0, h.p1, hashed ? factors.data() : nullptr, words.data(), h.n_words);   // validates bits / buckets against n_words
+    } catch (const std::exception& e) {
+        gs_fail(GS_ERR_ARG, "%s: %s", path, e.what());
+        return nullptr;
+    }
 }
 
 extern "C" int gs_filter_contains(gs_filter* f, const int64_t* kmers, uint64_t n, uint8_t* out) {

@@ -307,6 +307,12 @@ int gs_match_dump_labels(gs_sess*, const uint8_t* d_bases, const uint64_t* d_off
  * factors[hashes] = hashFactors (C/bloom/AbstractKMerBloomFilter.java:104-110). */
 gs_filter* gs_filter_create(gs_ctx*, int kind, int64_t p0, int64_t p1, const int64_t* factors,
                             const int64_t* words, uint64_t n_words);
+/* Flat little-endian filter index file "GSF1" (layout in gs_capi.cu): what KMerProbFilter.save / KMerProbFilter.load move as
+ * a Java object stream (`*_index.ser.gz`, C/goals/LoadIndexGoal.java:92-104, C/goals/refseq/BloomIndexGoal.java:66-111), as plain
+ * arrays: kind, bits / hashes (or seed / buckets), hash factors, words.  Written by gs_filter_save_file or by the Java-side
+ * exporter (integration/java/.../bloom/GsfExporter.java); gs_filter_load_file = read + gs_filter_create, no JVM needed. */
+int gs_filter_save_file(gs_filter*, const char* path);
+gs_filter* gs_filter_load_file(gs_ctx*, const char* path);
 void gs_filter_destroy(gs_filter*);
 int gs_filter_n_devices(const gs_filter*);
 /* KMerProbFilter.containsLong (C/bloom/KMerProbFilter.java:66) for tests. */

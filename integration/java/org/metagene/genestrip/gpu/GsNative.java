@@ -39,6 +39,8 @@ public final class GsNative {
     public static native ByteBuffer[] matchCollectFastq(long sess, long ticket);
     // filter
     public static native long filterCreate(long ctx, int kind, long p0, long p1, long[] factors, long[] words);
+    public static native long filterLoadFile(long ctx, String path);   // flat GSF1 index file (GsfExporter), no Java object stream
+    public static native void filterSaveFile(long filter, String path);
     public static native long filterOpen(long filter, int k, int minPosCount, double posRatio);
     public static native long filterSubmit(long fsess, ByteBuffer bases, ByteBuffer offsets, int nReads);
     public static native void filterCollect(long fsess, long ticket, ByteBuffer accept);

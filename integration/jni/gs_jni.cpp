@@ -147,6 +147,19 @@ JNIEXPORT jlong JNICALL J(filterCreate)(JNIEnv* env, jclass, jlong ctx, jint kin
     if (!flt) throwLast(env);
     return (jlong)flt;
 }
+JNIEXPORT jlong JNICALL J(filterLoadFile)(JNIEnv* env, jclass, jlong ctx, jstring path) {
+    const char* p = env->GetStringUTFChars(path, nullptr);
+    gs_filter* flt = gs_filter_load_file((gs_ctx*)ctx, p);
+    env->ReleaseStringUTFChars(path, p);
+    if (!flt) throwLast(env);
+    return (jlong)flt;
+}
+JNIEXPORT void JNICALL J(filterSaveFile)(JNIEnv* env, jclass, jlong flt, jstring path) {
+    const char* p = env->GetStringUTFChars(path, nullptr);
+    const int rc = gs_filter_save_file((gs_filter*)flt, p);
+    env->ReleaseStringUTFChars(path, p);
+    if (rc) throwLast(env);
+}
 JNIEXPORT jlong JNICALL J(filterOpen)(JNIEnv* env, jclass, jlong flt, jint k, jint minPosCount, jdouble posRatio) {
     gs_fsess* s = gs_filter_open((gs_filter*)flt, k, minPosCount, posRatio);
     if (!s) throwLast(env);

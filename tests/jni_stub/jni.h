@@ -26,6 +26,7 @@ class _jintArray : public _jarray {};
 class _jlongArray : public _jarray {};
 class _jshortArray : public _jarray {};
 class _jobjectArray : public _jarray {};
+class _jstring : public _jobject {};
 typedef _jobject* jobject;
 typedef _jclass* jclass;
 typedef _jarray* jarray;
@@ -33,6 +34,7 @@ typedef _jintArray* jintArray;
 typedef _jlongArray* jlongArray;
 typedef _jshortArray* jshortArray;
 typedef _jobjectArray* jobjectArray;
+typedef _jstring* jstring;
 struct _jmethodID;
 typedef _jmethodID* jmethodID;
 
@@ -54,5 +56,7 @@ struct JNIEnv {
     void SetLongArrayRegion(jlongArray array, jsize start, jsize len, const jlong* buf);
     jmethodID GetStaticMethodID(jclass clazz, const char* name, const char* sig);
     jobject CallStaticObjectMethod(jclass clazz, jmethodID methodID, ...);
+    const char* GetStringUTFChars(jstring str, jboolean* isCopy);
+    void ReleaseStringUTFChars(jstring str, const char* chars);
 };
 #endif

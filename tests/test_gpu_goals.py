@@ -177,6 +177,58 @@ def test_filter_goal(project, oracle, native, gpu_ctx, host, kind):
             flt_o.free()
 
 
+@pytest.mark.parametrize("kind", ["xor", "murmur", "blocked"])
+def test_filter_index_file_round_trip(project, oracle, native, gpu_ctx, host, tmp_path, kind):
+    """gs_filter_save_file / gs_filter_load_file: the flat GSF1 file that stands in for KMerProbFilter.save / load
+    (`*_index.ser.gz`, C/goals/LoadIndexGoal.java:92-104).  A loaded index answers containsLong and runs the `filter` goal
+    exactly like the uploaded one; the file is also written field by field here (what the Java-side GsfExporter writes)
+    and loads to the same answers; truncated, foreign and lying files are refused."""
+    import struct
+    odb, gdb, meta, genomes = project
+    if kind == "xor":
+        flt_o = odb.index_filter()
+    else:
+        keys, vals = odb.export()
+        flt_o = oracle.Bloom(kind=2 if kind == "murmur" else 0, fpp=1e-5)
+        flt_o.ensure(len(keys[::3]))
+        flt_o.put(keys[::3])
+    okind, p0, p1, factors, words = flt_o.params()
+    g1 = native.Filter(gpu_ctx, okind, p0, p1, factors, words)
+    path, path2 = str(tmp_path / "index.gsf"), str(tmp_path / "index_by_hand.gsf")
+    try:
+        g1.save_file(path)
+    finally:
+        g1.close()
+    fac = np.zeros(0, np.int64) if okind == 0 else np.asarray(factors, dtype=np.int64)
+    w = np.asarray(words, dtype=np.int64)
+    blob = b"GSF1\0\0\0\0" + struct.pack("<iiqqQQ", 1, okind, int(p0), int(p1), len(fac), len(w)) + fac.tobytes() + w.tobytes()
+    open(path2, "wb").write(blob)
+    assert open(path, "rb").read() == blob
+    keys, _ = odb.export()
+    rng = np.random.default_rng(21)
+    q = np.concatenate([keys[:3000], rng.integers(0, 1 << 62, size=3000, dtype=np.int64), np.array([0, -1, -(1 << 63)], dtype=np.int64)])
+    b, o, s_ = _reads(genomes, 2000, 31, frac_db=0.3)
+    fq = synth.fastq_bytes(b, o, s_)
+    orun = oracle.filter_files(flt_o, K, [fq], min_pos_count=1, pos_ratio=0.2)
+    for pth in (path, path2):
+        g2 = native.Filter.load_file(gpu_ctx, pth)
+        try:
+            np.testing.assert_array_equal(g2.contains(q), flt_o.contains(q))
+            res = host.filter_goal(g2, K, [fq], min_pos_count=1, pos_ratio=0.2, batch_reads=700)
+            np.testing.assert_array_equal(res.accept, orun.accept)
+            assert res.filtered == orun.filtered and res.rest == orun.rest
+        finally:
+            g2.close()
+    bad = str(tmp_path / "bad.gsf")
+    for data in (blob[:100], b"not an index", blob[:8] + struct.pack("<iiqqQQ", 1, okind, int(p0), int(p1), len(fac), len(w) + (1 << 40)) + blob[48:],
+                 blob[:8] + struct.pack("<iiqqQQ", 1, 7, int(p0), int(p1), len(fac), len(w)) + blob[48:]):
+        open(bad, "wb").write(data)
+        with pytest.raises(native.GenestripError):
+            native.Filter.load_file(gpu_ctx, bad)
+    if kind != "xor":
+        flt_o.free()
+
+
 @pytest.mark.parametrize("with_probs", [False, True], ids=["noprobs", "probs"])
 def test_match_goal_gpu_fastq_feeder(project, oracle, host, tmp_path, with_probs):
     """`match` with the GPU FASTQ feeder (text chunks split on the device) == the oracle (sequential parser + matchRead):
