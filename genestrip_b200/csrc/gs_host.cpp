@@ -570,6 +570,13 @@ private:
 // then parks the batch and cur() yields the next one), false if it refused (not strict 4-line
 // FASTQ); from the first refusal on, the rest of the input -- the refused chunk included -- goes through the sequential
 // parser (`sequential(LineReader&)`), so the results never depend on this fast path.
+// GS_HOST_TIMING=1: where the goal driver's wall time goes (seconds per phase on stderr at the end of runMatcher)
+struct HostTimers {
+    double submit = 0, collectWait = 0, process = 0, readerJoin = 0, open = 0, finish = 0;
+    bool on = getenv("GS_HOST_TIMING") != nullptr;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+static HostTimers g_timers;
 template <typename CurFn, typename NextFn, typename SubmitFn, typename SeqFn>
 static void feedFastqText(gs_ctx* ctx, const Input& in, size_t chunkBytes, CurFn&& cur, NextFn&& next, SubmitFn&& submit, SeqFn&& sequential) {
     gzFile gz = nullptr;
@@ -705,7 +712,7 @@ static void feedFastqText(gs_ctx* ctx, const Input& in, size_t chunkBytes, CurFn
             b->textLen = cut;
             try { taken = submit(b, cut); } catch (const std::exception& e) { submitErr = e.what(); }
         }
-        if (reader.joinable()) reader.join();
+        { const double t0 = HostTimers::now(); if (reader.joinable()) reader.join(); g_timers.readerJoin += HostTimers::now() - t0; }
         if (!submitErr.empty()) fail(submitErr);
         if (!readErr.empty()) fail(readErr);
         if (!taken) {
@@ -779,6 +786,28 @@ void FastqKMerMatcher::writeKrakenLine(OutputSink& krakenOut, const gs_read_resu
     krakenOut.write(line.data(), line.size());
 }
 
+// ---- the four double sums of the classified reads (FastqKMerMatcher.java:511-526) --------------------------------------------
+// errorSum, errorSquaredSum, classErrorSum and classErrorSquaredSum are floating-point sums, i.e. order dependent: they are
+// added on this thread in read order.  (Measured, GS_HOST_TIMING=1, 32 M reads: 0.19 s = 6 ns per read; a pool of threads that
+// each own a residue class of taxa -- every taxon still sees its reads in order, so the doubles stay bit-identical -- was tried
+// and was slower, 0.27 s: eight threads each stream the whole result table of the batch out of pinned memory.)
+// maxOf(i) = L - k + 1 of read i of the batch
+template <typename MaxFn>
+static void classifiedReadSums(const gs_read_result* res, uint32_t n, std::vector<CountsPerTaxid>& stats, MaxFn&& maxOf) {
+    for (uint32_t i = 0; i < n; i++) {
+        const gs_read_result& r = res[i];
+        if (!(r.flags & GS_READ_ACCEPTED)) continue;
+        const int64_t max = maxOf(i);
+        CountsPerTaxid& st = stats[(size_t)r.class_vidx];
+        const double err = ((double)(int32_t)r.tax_err) / (double)max;
+        const double classErr = ((double)(int32_t)(max - (int64_t)r.read_kmers)) / (double)max;
+        st.errorSum += err;
+        st.errorSquaredSum += err * err;
+        st.classErrorSum += classErr;
+        st.classErrorSquaredSum += classErr * classErr;
+    }
+}
+
 void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, OutputSink* krakenOut, std::vector<CountsPerTaxid>& stats,
                                     std::vector<uint64_t>& bestKey) {
     const int V = meta_.nValues;
@@ -809,7 +838,6 @@ void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, 
         const gs_read_result& r = res[i];
         const uint64_t a = b.offsets[i], e = b.offsets[i + 1];
         const int64_t L = (int64_t)(e - a);
-        const int64_t max = L - k + 1;
         size_t dl, pl;
         const uint8_t* d = b.desc(i, dl);
         // afterMatch (:304-315)
@@ -818,17 +846,9 @@ void FastqKMerMatcher::processBatch(gs_sess* s, Batch& b, OutputSink* filtered, 
             writeRead(*filtered, d, dl, b.bases + a, (size_t)L, p, pl, b.hasProbs[i] != 0, scratch);
         }
         if (krakenOut) writeKrakenLine(*krakenOut, r, d, dl, L, runs.data() + runOff[i], (size_t)(runOff[i + 1] - runOff[i]), b.entry[i], line);
-        // classified-read statistics: the four double sums in read order (:511-526)
-        if (r.flags & GS_READ_ACCEPTED) {
-            CountsPerTaxid& st = stats[(size_t)r.class_vidx];
-            const double err = ((double)(int32_t)r.tax_err) / (double)max;
-            const double classErr = ((double)(int32_t)(max - (int64_t)r.read_kmers)) / (double)max;
-            st.errorSum += err;
-            st.errorSquaredSum += err * err;
-            st.classErrorSum += classErr;
-            st.classErrorSquaredSum += classErr * classErr;
-        }
     }
+    // classified-read statistics: the four double sums, per taxon in read order (:511-526)
+    classifiedReadSums(res.data(), b.n, stats, [&](uint32_t i) { return (int64_t)(b.offsets[i + 1] - b.offsets[i]) - k + 1; });
 }
 
 // A batch that went to the device as raw FASTQ text: descriptors, bases and qualities are read from the (pinned) text through
@@ -840,8 +860,12 @@ void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filter
     std::vector<uint64_t> runOff;
     std::vector<gs_run> runs;
     if (krakenOut) { runOff.assign((size_t)b.n + 1, 0); runs.resize((size_t)std::max<uint64_t>(b.totalKmers, 1)); }
+    const double tc0 = HostTimers::now();
     check(gs_match_collect_fastq(s, b.ticket, &res, &n, &ev, &evHdr, &nEv, &recs, krakenOut ? runOff.data() : nullptr,
                                  krakenOut ? runs.data() : nullptr, b.totalKmers), "gs_match_collect_fastq");
+    const double tc1 = HostTimers::now();
+    g_timers.collectWait += tc1 - tc0;
+    struct ProcT { double t0; ~ProcT() { g_timers.process += HostTimers::now() - t0; } } procT{tc1};
     for (uint32_t e = 0; e < nEv; e++) {  // maxContigDescriptor (FastqKMerMatcher.java:402-409)
         const gs_maxcontig_event& x = ev[e];
         const uint64_t key = ((uint64_t)x.contig_len << 40) | ((((uint64_t)1 << 40) - 1) - x.read_no);
@@ -856,27 +880,20 @@ void FastqKMerMatcher::processTextBatch(gs_sess* s, Batch& b, OutputSink* filter
     }
     std::string scratch, line;
     const int k = meta_.k;
-    for (uint32_t i = 0; i < n; i++) {
-        const gs_read_result& r = res[i];
-        const gs_fastq_rec& rc = recs[i];
-        const int64_t L = (int64_t)rc.seq_len;
-        const int64_t max = L - k + 1;
-        if ((r.flags & GS_READ_FOUND) && filtered)  // afterMatch (:304-315)
-            writeRead(*filtered, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), b.text + rc.seq_start, (size_t)L,
-                      b.text + rc.qual_start, (size_t)(recs[i + 1].hdr_start - 1 - rc.qual_start), cfg_.withProbs, scratch);
-        if (krakenOut)  // FASTQ records always travel in the first pooled ReadEntry at threads = 0 (AbstractFastqReader.java:447-455)
-            writeKrakenLine(*krakenOut, r, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), L, runs.data() + runOff[i],
-                            (size_t)(runOff[i + 1] - runOff[i]), 0, line);
-        if (r.flags & GS_READ_ACCEPTED) {  // the four double sums in read order (:511-526)
-            CountsPerTaxid& st = stats[(size_t)r.class_vidx];
-            const double err = ((double)(int32_t)r.tax_err) / (double)max;
-            const double classErr = ((double)(int32_t)(max - (int64_t)r.read_kmers)) / (double)max;
-            st.errorSum += err;
-            st.errorSquaredSum += err * err;
-            st.classErrorSum += classErr;
-            st.classErrorSquaredSum += classErr * classErr;
+    if (filtered || krakenOut)   // the outputs are written in read order by this thread
+        for (uint32_t i = 0; i < n; i++) {
+            const gs_read_result& r = res[i];
+            const gs_fastq_rec& rc = recs[i];
+            const int64_t L = (int64_t)rc.seq_len;
+            if ((r.flags & GS_READ_FOUND) && filtered)  // afterMatch (:304-315)
+                writeRead(*filtered, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), b.text + rc.seq_start, (size_t)L,
+                          b.text + rc.qual_start, (size_t)(recs[i + 1].hdr_start - 1 - rc.qual_start), cfg_.withProbs, scratch);
+            if (krakenOut)  // FASTQ records always travel in the first pooled ReadEntry at threads = 0 (AbstractFastqReader.java:447-455)
+                writeKrakenLine(*krakenOut, r, b.text + rc.hdr_start, (size_t)(rc.seq_start - 1 - rc.hdr_start), L, runs.data() + runOff[i],
+                                (size_t)(runOff[i + 1] - runOff[i]), 0, line);
         }
-    }
+    // the four double sums, per taxon in read order (:511-526)
+    classifiedReadSums(res, n, stats, [&](uint32_t i) { return (int64_t)recs[i].seq_len - k + 1; });
 }
 
 MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, OutputSink* filtered, OutputSink* krakenOut) {
@@ -887,8 +904,11 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
     c.use_bloom_filter = cfg_.useBloomFilterForMatch; c.max_classification_paths = cfg_.maxClassificationPaths;
     c.min_kmers_for_class = cfg_.minKMersForClass; c.max_read_tax_error_count = cfg_.maxReadTaxErrorCount;
     c.max_read_class_error_count = cfg_.maxReadClassErrorCount; c.want_runs = krakenOut ? 1 : 0; c.layout = cfg_.layout;
+    const double tOpen0 = HostTimers::now();
+    g_timers = HostTimers();
     gs_sess* s = gs_match_open(db_, &c);
     if (!s) fail(std::string("gs_match_open: ") + gs_last_error());
+    g_timers.open = HostTimers::now() - tOpen0;
     struct Closer { gs_sess* s; ~Closer() { gs_match_close(s); } } closer{s};
     if (filtered && !filtered->open()) fail("cannot open filtered output");
     if (krakenOut && !krakenOut->open()) fail("cannot open kraken output");
@@ -943,7 +963,7 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
             [&](HostBatch* b, size_t cut) -> bool {
                 gs_fastq_info info;
                 gs_ticket t = 0;
-                check(gs_match_submit_fastq(s, b->text, cut, ordinal, &info, &t), "gs_match_submit_fastq");
+                { const double t0 = HostTimers::now(); check(gs_match_submit_fastq(s, b->text, cut, ordinal, &info, &t), "gs_match_submit_fastq"); g_timers.submit += HostTimers::now() - t0; }
                 textChunks++;
                 if (info.status) return false;
                 b->ticket = t; b->n = info.n_reads; b->firstOrdinal = ordinal; b->totalKmers = info.total_kmers;
@@ -972,8 +992,12 @@ MatchingResult FastqKMerMatcher::runMatcher(const std::vector<Input>& fastqs, Ou
     std::vector<int16_t> top;
     const bool withCounts = cfg_.countUniqueKMers && cfg_.maxKMerResCounts > 0;
     if (withCounts) top.assign((size_t)(V + 1) * (size_t)cfg_.maxKMerResCounts, 0);
-    check(gs_match_finish(s, counts.data(), withCounts ? top.data() : nullptr), "gs_match_finish");
+    { const double t0 = HostTimers::now(); check(gs_match_finish(s, counts.data(), withCounts ? top.data() : nullptr), "gs_match_finish"); g_timers.finish = HostTimers::now() - t0; }
     launches_ += gs_match_kernel_launches(s);
+    if (g_timers.on)
+        fprintf(stderr, "gs_host timing: total %.3f s since open | open %.3f submit %.3f collect-wait %.3f process %.3f reader-join %.3f finish %.3f (text chunks %llu)\n",
+                HostTimers::now() - tOpen0, g_timers.open, g_timers.submit, g_timers.collectWait, g_timers.process, g_timers.readerJoin, g_timers.finish,
+                (unsigned long long)textChunks);
 
     // runMatcher tail (:199-234)
     MatchingResult res;

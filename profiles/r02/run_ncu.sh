@@ -4,7 +4,7 @@
 mkdir -p gpurun_out/r02
 WLS=${@:-viral bacterial longread filter}
 for W in $WLS; do
-  K="gs_label"; [ $W = filter ] && K="gs_filter"
+  K="gs_label"; [ $W = filter ] && K="gs_filter_flat"
   # plain run first (exit 0 without ncu), then the launch list, then the full capture of the dominant kernel
   python bench.py --workload $W --also none --steps 2 --warmup 3 --no-cpu-baseline --no-fastq > gpurun_out/r02/plain_$W.json 2> gpurun_out/r02/plain_$W.err || { echo "$W plain run failed"; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gs_" --launch-skip 12 -c 24 --csv --log-file gpurun_out/r02/launches_$W.csv \
