@@ -901,6 +901,9 @@ struct gs_sess {
     bool timing = false;
     int layout = GS_LAYOUT_TABLE;
     bool inlineSeen = false;  // unique k-mer bits are kept in the probe-table lines (leased from the database)
+    bool dualBits = false;    // ... and mirrored into the compact bitset as they are set (gs_match_prepare_merge before the first batch):
+                              // the merge then starts from a current bitset instead of streaming the whole table for its seen bits
+    u64 batchesLaunched = 0;
     u64 nPos = 0;  // "storage positions" addressed by the unique-k-mer bitset: table slot ids or sorted-array indices
     // end-of-run merge across GPUs (merge_state)
     bool merged = false;
@@ -1085,7 +1088,7 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     P.db = s->db->d[D.devIndex].view;
     if (!s->cfg.prefilter) P.db.mzFilter = nullptr;
     P.counters = D.counters; P.maxcontig = D.maxcontig; P.hitCounts = D.hitCounts;
-    if (s->inlineSeen) { P.bitset = nullptr; P.seenTab = (u32*)s->db->d[D.devIndex].tab; }
+    if (s->inlineSeen) { P.bitset = s->dualBits ? D.bitset : nullptr; P.seenTab = (u32*)s->db->d[D.devIndex].tab; }
     else { P.bitset = D.bitset; P.seenTab = nullptr; }
     P.classify = s->cfg.classify_reads ? 1 : 0;
     P.useBloom = s->cfg.use_bloom_filter ? 1 : 0;
@@ -1122,6 +1125,7 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
         CU(dgrow(&D.overflowList, &D.ovCap, (size_t)P.nReads));
     }
     P.overflowList = D.overflowList;
+    s->batchesLaunched++;
     int rc = prepare_flat(D, P, off0, nBytes);
     if (rc) return rc;
     CU(cudaMemsetAsync(D.overflowCount, 0, 8 * sizeof(u32), D.sCompute));
@@ -1539,7 +1543,7 @@ extern "C" int gs_match_sync(gs_sess* s) {
 
 // In-line seen bits -> the session's compact bitset (same addressing as the external one: slot id = bucket * 16 + j)
 static int materialize_bitset(gs_sess* s, DevSess& D) {
-    if (!s->inlineSeen) return GS_OK;
+    if (!s->inlineSeen || s->dualBits) return GS_OK;   // dual mode: the label kernel has kept the compact bitset current
     CU(cudaSetDevice(D.dev));
     if (!D.bitset) CU(dmalloc(&D.bitset, D.bitsetWords));
     gs_launch_table_extract_seen(s->db->d[D.devIndex].tab, s->nPos, D.bitset, D.sCompute);
@@ -1841,6 +1845,11 @@ extern "C" int gs_match_prepare_merge(gs_sess* s, gs_comm* cm) {
         if (!D.bitset) {   // in-line seen bits: the compact bitset only exists from the end of the run on, but its address can be handed out now
             CU(dmalloc(&D.bitset, D.bitsetWords));
             CU(cudaMemsetAsync(D.bitset, 0, std::max<u64>(D.bitsetWords, 1) * sizeof(u64), D.sCompute));
+            // no batch has run yet: from here on every first-time seen bit also goes into the compact bitset (one more RED per
+            // distinct k-mer of the run), and the merge needs no pass over the table (5.5 ms for the 34 GB table of the 2e9-k-mer
+            // store).  GS_MERGE_DUAL_BITS=0: extract at the end as before (A/B).
+            const char* e = getenv("GS_MERGE_DUAL_BITS");
+            if (s->inlineSeen && s->batchesLaunched == 0 && !(e && atoi(e) == 0)) s->dualBits = true;
         }
         const char* force = getenv("GS_MERGE_PATH");
         if (!(force && strcmp(force, "nccl") == 0)) {
@@ -1860,6 +1869,22 @@ extern "C" int gs_match_prepare_merge(gs_sess* s, gs_comm* cm) {
         gs_launch_merge_or_popcount(none, 0, D.bitset, 0, 0, s->db->d[D.devIndex].view, s->layout, D.unique, D.popPartial, 1, D.sCompute);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(D.sCompute));
+    }
+    {   // the merge's collectives once at their own sizes, types and operators on scratch: NCCL sets up the protocol and the
+        // channels a message size needs the first time it sees it (measured on 8 GPUs: 20 ms inside the first merge of the
+        // 2e9-k-mer store's 54 k value indices after two workloads with 11 k), and that belongs in front of the run
+        const int V = s->db->V;
+        long long* scratch = nullptr;
+        CU(dmalloc(&scratch, (size_t)7 * std::max(V, 1)));
+        CU(cudaMemsetAsync(scratch, 0, (size_t)7 * std::max(V, 1) * sizeof(long long), D.sCompute));
+        int rcn = GS_OK;
+        auto nc = [&](ncclResult_t r) { if (r != ncclSuccess && rcn == GS_OK) rcn = gs_fail(GS_ERR_CUDA, "NCCL warm-up: %s", N->GetErrorString(r)); };
+        nc(N->AllReduce(scratch, scratch, (size_t)7 * V, ncclInt64, ncclSum, cm->comms[0], D.sCompute));
+        nc(N->AllReduce(scratch, scratch, (size_t)V, ncclUint64, ncclMax, cm->comms[0], D.sCompute));
+        nc(N->AllReduce(scratch, scratch, (size_t)V, ncclInt64, ncclSum, cm->comms[0], D.sCompute));
+        cudaStreamSynchronize(D.sCompute);
+        cudaFree(scratch);
+        if (rcn) return rcn;
     }
     s->prepComm = cm;
     return GS_OK;

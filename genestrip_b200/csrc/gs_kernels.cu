@@ -260,7 +260,12 @@ __global__ void __launch_bounds__(GS_WARPS_PER_BLOCK * 32, WIDE ? GS_LABEL_MIN_B
                 }
                 if (pend && lab < GS_LABEL_INVALID) {
                     // unique k-mer bit / hit counter (KMerUniqueCounterBits.putInlined, C/store/KMerUniqueCounterBits.java:117-143)
-                    if (P.seenTab) { if (!seen) atomicOr(P.seenTab + pos * 2, (u32)GS_TAB_SEEN); }  // seen bit came with the bucket
+                    if (P.seenTab) {   // the seen bit came with the bucket
+                        if (!seen) {
+                            atomicOr(P.seenTab + pos * 2, (u32)GS_TAB_SEEN);
+                            if (P.bitset) atomicOr(P.bitset + (pos >> 6), 1ULL << (pos & 63));   // dual mode: compact bitset kept current for the merge
+                        }
+                    }
                     else if (P.bitset) {
                         const u64 bit = 1ULL << (pos & 63);
                         if (!(*(volatile u64*)(P.bitset + (pos >> 6)) & bit)) atomicOr(P.bitset + (pos >> 6), bit);
