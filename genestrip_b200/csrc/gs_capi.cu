@@ -209,12 +209,26 @@ extern "C" int gs_inflate_blocks(gs_ctx* c, const uint8_t* comp, uint64_t comp_b
         if (b.in_off > comp_bytes || b.in_len > comp_bytes - b.in_off || b.out_off > out_bytes || b.out_len > out_bytes - b.out_off)
             return gs_fail(GS_ERR_ARG, "deflate block %u lies outside the buffers", i);
     }
+    // the output ranges must not overlap (the blocks are inflated concurrently: an overlap would make text and CRC depend on
+    // the order of the warps); they normally tile [0, out_bytes) -- if they leave gaps, the gaps come back as zero bytes, not
+    // as whatever an earlier call left in the device buffer
+    bool gaps = false;
+    {
+        uint64_t end = 0;
+        for (uint32_t i = 0; i < n_blocks; i++) {
+            if (blocks[i].out_off < end) return gs_fail(GS_ERR_ARG, "deflate block %u: output ranges must be ascending and must not overlap", i);
+            gaps = gaps || blocks[i].out_off > end;
+            end = blocks[i].out_off + blocks[i].out_len;
+        }
+        gaps = gaps || end < out_bytes;
+    }
     std::lock_guard<std::mutex> lock(c->infMutex);
     CU(cudaSetDevice(c->devs[0]));
     if (!c->infStream) CU(cudaStreamCreateWithFlags(&c->infStream, cudaStreamNonBlocking));
     CU(dgrow(&c->infComp, &c->infCompCap, (size_t)comp_bytes + 16));
     CU(dgrow(&c->infText, &c->infTextCap, (size_t)out_bytes + 16));
     CU(dgrow(&c->infBlocks, &c->infBlocksCap, (size_t)n_blocks));
+    if (gaps) CU(cudaMemsetAsync(c->infText, 0, (size_t)out_bytes, c->infStream));
     CU(cudaMemcpyAsync(c->infComp, comp, comp_bytes, cudaMemcpyHostToDevice, c->infStream));
     CU(cudaMemcpyAsync(c->infBlocks, blocks, (size_t)n_blocks * sizeof(gs_deflate_block), cudaMemcpyHostToDevice, c->infStream));
     gs_launch_inflate_blocks(c->infComp, c->infText, c->infBlocks, n_blocks, c->infStream);

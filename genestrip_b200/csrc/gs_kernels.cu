@@ -767,7 +767,12 @@ __global__ void __launch_bounds__(GS_T_THREADS, MASKED ? 8 : GS_T_BLOCKS) gs_red
                     if (prev < GS_LABEL_INVALID && len > 0) {  // a contig of taxon `prev` ends (:396-410, 458-471)
                         int j = 0;
                         while (j < nTab && s_vi[j][t] != prev) j++;
-                        if (j < nTab) {
+                        if (j < nTab && ((s_pk[j][t] >> 11) & 0x3FFu) == 0x3FFu) {
+                            // the taxon's contig count would leave its 10-bit field (a taxon alternating with misses in a read of
+                            // ~2000 bases): hand the read to the warp kernel, like a table overflow
+                            overflow = true;
+                            break;
+                        } else if (j < nTab) {
                             const u32 pk = s_pk[j][t];
                             const u32 ml = pk & 0x7FFu;
                             s_pk[j][t] = (((pk >> 21) + (u32)len) << 21) | ((((pk >> 11) & 0x3FFu) + 1u) << 11) | ((u32)len > ml ? (u32)len : ml);

@@ -71,3 +71,18 @@ def test_inflate_blocks_detects_corruption(native, gpu_ctx):
         b2["in_off"][0] = len(comp)
         gpu_ctx.inflate_blocks(comp, b2, n)
     assert e.value.code == -1
+    # output ranges that overlap are refused (the blocks are inflated concurrently); ranges that leave gaps are accepted and
+    # the gaps come back as zero bytes, whatever an earlier call left in the device buffer
+    if len(blocks) >= 3:
+        b2 = blocks.copy()
+        b2["out_off"][1] = int(b2["out_off"][1]) - 1
+        with pytest.raises(native.GenestripError) as e:
+            gpu_ctx.inflate_blocks(comp, b2, n)
+        assert e.value.code == -1
+        gpu_ctx.inflate_blocks(comp, blocks, n)                         # fills the device buffer with text
+        b3 = blocks.copy()
+        shift = 64
+        b3["out_off"][1:] = b3["out_off"][1:] + shift                   # a hole of 64 bytes behind the first block
+        out, _ = gpu_ctx.inflate_blocks(comp, b3, n + shift)
+        e0 = int(blocks["out_off"][1])
+        assert out[:e0].tobytes() == data[:e0] and not out[e0:e0 + shift].any() and out[e0 + shift:].tobytes() == data[e0:]
