@@ -831,7 +831,9 @@ def reference_arm(args, emit):
     odb = gs_oracle.OracleDb.from_arrays(K, keys.cpu().numpy(), vals_raw.cpu().numpy(), V, parent, build_bloom=True)
     del keys, vals_raw, codes, bases
     torch.cuda.empty_cache()
-    n, kmers, per, times = cpu_match(gs_oracle, odb, b0_h, off_h, threads, args.cpu_seconds, steps=max(1, args.steps + args.warmup))
+    # every step is a bounded sample of the workload, sized so that the whole --steps K --warmup W run ends within a few minutes
+    per_step_s = min(args.cpu_seconds, max(1.0, 150.0 / max(1, args.steps + args.warmup)))
+    n, kmers, per, times = cpu_match(gs_oracle, odb, b0_h, off_h, threads, per_step_s, steps=max(1, args.steps + args.warmup))
     odb.free()
     times = times[args.warmup:] if len(times) > args.warmup else times
     dt = float(np.mean(times))
