@@ -435,6 +435,8 @@ def run_match(E, name, wl, want_fastq, want_cpu):
         ev[0].record(stream)
         for i in range(args.steps):
             device_step(sess, args.warmup + i)
+            if i == args.steps - 1:
+                sess.join()   # the last batch's reduce kernels run on the session's second stream: the closing event waits for them
             ev[i + 1].record(stream)
     sess.sync()
     E.barrier()

@@ -95,6 +95,7 @@ _SIGS = {
     "gs_pack_isa": (C.c_char_p, []),
     "gs_match_pack_fraction": (C.c_double, [_P]),
     "gs_match_l2_window": (C.c_int, [_P, _P, _P, _P]),
+    "gs_match_join": (C.c_int, [_P]),
     "gs_match_pack_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gs_match_merge_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "gs_match_close": (None, [_P]),
@@ -505,6 +506,10 @@ class MatchSession:
     @property
     def pack_fraction(self):
         return lib().gs_match_pack_fraction(self.h)
+
+    def join(self):
+        """Orders the compute stream behind everything submitted so far (no host wait): before an event of one's own."""
+        _check(lib().gs_match_join(self.h))
 
     def l2_window(self):
         """(window bytes, persisting carve-out bytes, hit ratio) of the L2 access policy window on the compute stream."""

@@ -891,19 +891,42 @@ struct DevSess {
     uint16_t* hitCounts = nullptr;
     long long* unique = nullptr;    // [V]
     u32* popPartial = nullptr; size_t popPartialCap = 0;   // per-CTA count tables of the popcount kernel
-    u32* overflowList = nullptr; size_t ovCap = 0;
-    u32* overflowCount = nullptr;
     u32* slowTable = nullptr;
-    int fastBlocks = 0, slowBlocks = 0, labelBlocks = 0;
-    // label kernel -> reduce kernel hand-over (one set per device: the kernels of successive batches run in stream order)
-    u32* labels = nullptr; size_t labelsCap = 0;
-    u32* validBits = nullptr; size_t validCap = 0;
-    u32* startBits = nullptr; size_t startCap = 0;
-    u32* bmask = nullptr; size_t bmaskCap = 0;
-    u32* redoList = nullptr; size_t redoCap = 0;
-    std::vector<cudaEvent_t> timingEv;  // gs_match_set_timing: 3 events per batch (before label, after label, after reduce)
+    int fastBlocks = 0, slowBlocks = 0, labelBlocks = 0, labelBlocksOverlap = 0;
+    // label kernel -> reduce kernels hand-over.  Two sets per device, used by alternate batches: the reduce kernels of batch i
+    // run on their own stream (sReduce) while the label kernel of batch i + 1 already fills the other set -- the thread-per-read
+    // reduce is a latency-bound kernel of 0.3-0.4 ms that hides behind the label kernel when that leaves it one CTA slot per SM.
+    // GS_OVERLAP_REDUCE=0: sReduce is the compute stream itself and everything runs in stream order as before (A/B).
+    struct HandOver {
+        u32* labels = nullptr; size_t labelsCap = 0;
+        u32* validBits = nullptr; size_t validCap = 0;
+        u32* startBits = nullptr; size_t startCap = 0;
+        u32* bmask = nullptr; size_t bmaskCap = 0;
+        u32* redoList = nullptr; size_t redoCap = 0;
+        u32* overflowList = nullptr; size_t ovCap = 0;
+        u32* overflowCount = nullptr;   // [0] overflow list length, [1] read claim counter, [2] segment claim counter, [3] redo list length, [4] read-group claim counter
+        cudaEvent_t evLabel = nullptr, evReduce = nullptr;
+        bool reduceRecorded = false;
+    } ho[2];
+    cudaStream_t sReduce = nullptr;     // == sCompute when the overlap is off
+    bool overlap = false;
+    u64 batchNo = 0;
+    std::vector<cudaEvent_t> timingEv;  // gs_match_set_timing: 4 events per batch (before / after the label kernel, before / after the reduce kernels)
     MatchSlot slots[GS_MAX_INFLIGHT];
 };
+
+// The compute stream waits for the reduce kernels still in flight on sReduce (no host wait): whatever is launched on sCompute
+// next -- merge, popcount, a dump, the caller's own event -- is ordered behind all the work of the batches submitted so far.
+static int join_reduce(DevSess& D) {
+    if (!D.overlap) return GS_OK;
+    for (DevSess::HandOver& H : D.ho) if (H.reduceRecorded) CU(cudaStreamWaitEvent(D.sCompute, H.evReduce, 0));
+    return GS_OK;
+}
+static int sync_compute(DevSess& D) {
+    CU(cudaStreamSynchronize(D.sCompute));
+    if (D.overlap) CU(cudaStreamSynchronize(D.sReduce));
+    return GS_OK;
+}
 
 struct gs_sess {
     gs_db* db = nullptr;
@@ -931,10 +954,8 @@ struct gs_sess {
     std::vector<void*> prepOpened;           // mappings to close (cudaIpcCloseMemHandle)
     gsp::Packer* packer = nullptr;           // host_pack_threads != 0: made on the first gs_match_submit
     double packFrac = 0.7;                   // share of a batch's bases that goes over the link packed (the rest as ASCII)
-    bool packSeeded = false;                 // packFrac was set once from the first batch's measured costs
-    int packDir = 1, packAcc = 0;            // hill climbing on the time per byte between submits
-    double packAccSec = 0, packAccBytes = 0, packLastCost = 0, packPrevBytes = 0;
-    std::chrono::steady_clock::time_point packPrevSubmit;
+    bool packSeeded = false;                 // the smoothed route costs hold a first measurement
+    double packP = 0, packA = 0;             // smoothed seconds per byte: packing on the host's cores, ASCII on the link
     double packSeconds = 0;                  // host time spent packing (gs_match_pack_stats)
     u64 packBytes = 0, h2dBytes = 0;         // bases packed / bytes of base data put on the link
 };
@@ -961,7 +982,17 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
     const int V = s->db->V;
     CU(cudaSetDevice(D.dev));
     CU(cudaStreamCreateWithFlags(&D.sCopyIn, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&D.sCompute, cudaStreamNonBlocking));
+    {   // the label kernel's stream gets the greater priority: its CTAs are placed first and the reduce kernels of the batch
+        // before take the slot per SM it leaves free (the other way round the reduce kernel fills the SMs for its 0.4 ms and the
+        // label kernel waits: measured, no overlap at all)
+        const char* e = getenv("GS_OVERLAP_REDUCE");
+        D.overlap = !(e && atoi(e) == 0);
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
+        CU(cudaStreamCreateWithPriority(&D.sCompute, cudaStreamNonBlocking, D.overlap ? hi : lo));
+        if (D.overlap) CU(cudaStreamCreateWithPriority(&D.sReduce, cudaStreamNonBlocking, lo));
+        else D.sReduce = D.sCompute;
+    }
     CU(cudaStreamCreateWithFlags(&D.sCopyOut, cudaStreamNonBlocking));
     CU(dmalloc(&D.counters, (size_t)7 * V));
     CU(cudaMemset(D.counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
@@ -983,11 +1014,20 @@ static int sess_alloc_dev(gs_sess* s, DevSess& D) {
             CU(cudaMemset(D.hitCounts, 0, (s->nPos + 2) * sizeof(uint16_t)));
         }
     }
-    CU(dmalloc(&D.overflowCount, 8));  // [0] overflow list length, [1] read claim counter, [2] segment claim counter, [3] redo list length, [4] read-group claim counter
+    {
+        for (DevSess::HandOver& H : D.ho) {
+            CU(dmalloc(&H.overflowCount, 8));
+            CU(cudaEventCreateWithFlags(&H.evLabel, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&H.evReduce, cudaEventDisableTiming));
+        }
+    }
     const int occ0 = std::max(1, gs_match_kernel_occupancy(0));
     D.fastBlocks = D.sms * occ0;
-    D.labelBlocks = D.sms * std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
+    const int labelOcc = std::max(1, gs_match_kernel_occupancy(s->layout == GS_LAYOUT_TABLE ? 3 : 4));
+    D.labelBlocks = D.sms * labelOcc;
     if (const char* e = getenv("GS_DEBUG_LABEL_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0) D.labelBlocks = D.sms * v; }  // tuning experiments
+    D.labelBlocksOverlap = D.labelBlocks;   // GS_OVERLAP_SHORT=1 experiments: CTAs per SM the label kernel of a short-read batch gets
+    if (const char* e = getenv("GS_OVERLAP_LABEL_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0) D.labelBlocksOverlap = D.sms * v; }
     D.slowBlocks = std::max(1, D.sms / 4);
     // L2-persisting access window over the minimizer prefilter: the one structure every k-mer of every batch reads, next to
     // 600 MB of bases and 2 GB of labels per batch that stream through the same L2.  Set when the whole filter fits the
@@ -1057,8 +1097,14 @@ extern "C" void gs_match_close(gs_sess* s) {
             if (sl.evAscii1) cudaEventDestroy(sl.evAscii1);
         }
         cudaFree(D.counters); cudaFree(D.maxcontig); cudaFree(D.bitset); cudaFree(D.hitCounts); cudaFree(D.unique); cudaFree(D.popPartial);
-        cudaFree(D.overflowList); cudaFree(D.overflowCount); cudaFree(D.slowTable);
-        cudaFree(D.labels); cudaFree(D.validBits); cudaFree(D.startBits); cudaFree(D.redoList); cudaFree(D.bmask);
+        cudaFree(D.slowTable);
+        for (DevSess::HandOver& H : D.ho) {
+            cudaFree(H.overflowList); cudaFree(H.overflowCount);
+            cudaFree(H.labels); cudaFree(H.validBits); cudaFree(H.startBits); cudaFree(H.redoList); cudaFree(H.bmask);
+            if (H.evLabel) cudaEventDestroy(H.evLabel);
+            if (H.evReduce) cudaEventDestroy(H.evReduce);
+        }
+        if (D.overlap && D.sReduce) cudaStreamDestroy(D.sReduce);
         for (cudaEvent_t e : D.timingEv) cudaEventDestroy(e);
         D.timingEv.clear();
         if (D.sCopyIn) cudaStreamDestroy(D.sCopyIn);
@@ -1111,43 +1157,58 @@ static void fill_params(gs_sess* s, DevSess& D, GsMatchParams& P) {
     P.layout = s->layout;
     P.maxTaxErr = s->cfg.max_read_tax_error_count;
     P.maxClassErr = s->cfg.max_read_class_error_count;
-    P.overflowList = D.overflowList; P.overflowCount = D.overflowCount; P.workCounter = D.overflowCount + 1; P.slowTable = D.slowTable;
+    P.slowTable = D.slowTable;   // (the per-batch hand-over pointers are set by prepare_flat / launch_batch from the batch's set)
 }
 
-// flat geometry of a batch whose bases cover byte offsets [off0, off0 + nBytes) of P.bases; grows the hand-over buffers
-static int prepare_flat(DevSess& D, GsMatchParams& P, u64 off0, u64 nBytes) {
+// flat geometry of a batch whose bases cover byte offsets [off0, off0 + nBytes) of P.bases; grows the hand-over buffers of set H
+static int prepare_flat(DevSess& D, DevSess::HandOver& H, GsMatchParams& P, u64 off0, u64 nBytes) {
     P.off0 = off0;
     P.lead = P.packCodes ? 0u : (u32)((uintptr_t)(P.bases + off0) & 15);   // packed words start at the batch's first base
     P.flatLen = (u64)P.lead + nBytes;
     const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
     const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
-    if (P.flatLen + 32 > D.labelsCap || words > D.validCap || words > D.startCap) {
-        CU(cudaStreamSynchronize(D.sCompute));
-        CU(dgrow(&D.labels, &D.labelsCap, (size_t)P.flatLen + 32));
-        CU(dgrow(&D.validBits, &D.validCap, words));
-        CU(dgrow(&D.startBits, &D.startCap, words));
+    if (P.flatLen + 32 > H.labelsCap || words > H.validCap || words > H.startCap) {
+        int rc = sync_compute(D);
+        if (rc) return rc;
+        CU(dgrow(&H.labels, &H.labelsCap, (size_t)P.flatLen + 32));
+        CU(dgrow(&H.validBits, &H.validCap, words));
+        CU(dgrow(&H.startBits, &H.startCap, words));
     }
-    P.labels = D.labels; P.validBits = D.validBits; P.startBits = D.startBits; P.segCounter = D.overflowCount + 2;
+    P.labels = H.labels; P.validBits = H.validBits; P.startBits = H.startBits;
+    P.overflowCount = H.overflowCount; P.workCounter = H.overflowCount + 1; P.segCounter = H.overflowCount + 2;
     return GS_OK;
 }
 
-// kernels of one batch on the compute stream: read-start bitmap, label kernel, reduce kernel (fast path, then the slow path
-// over the overflow list), max-contig events
-static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv, u64 off0, u64 nBytes) {
-    if (P.nReads > D.ovCap || !D.overflowList) {
-        CU(cudaStreamSynchronize(D.sCompute));
-        CU(dgrow(&D.overflowList, &D.ovCap, (size_t)P.nReads));
-    }
-    P.overflowList = D.overflowList;
+// Kernels of one batch.  Compute stream: read-start bitmap, label kernel.  Reduce stream (the compute stream itself when the
+// overlap is off): reduce kernels (thread per read / warp per read, then the slow path over the overflow list), max-contig
+// events, and whatever the caller appends through `tail` (it runs on the reduce stream behind them).  The batch uses one of the
+// device's two hand-over sets; the set's previous user is two batches back, and the compute stream waits for that batch's
+// reduce kernels before the label kernel overwrites the labels.
+template <typename Tail>
+static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv, u64 off0, u64 nBytes, Tail&& tail) {
+    DevSess::HandOver& H = D.ho[D.overlap ? (D.batchNo & 1) : 0];
+    D.batchNo++;
     s->batchesLaunched++;
-    int rc = prepare_flat(D, P, off0, nBytes);
+    if (D.overlap && H.reduceRecorded) CU(cudaStreamWaitEvent(D.sCompute, H.evReduce, 0));
+    if (P.nReads > H.ovCap || !H.overflowList) {
+        int rcs = sync_compute(D);
+        if (rcs) return rcs;
+        CU(dgrow(&H.overflowList, &H.ovCap, (size_t)P.nReads));
+    }
+    P.overflowList = H.overflowList;
+    int rc = prepare_flat(D, H, P, off0, nBytes);
     if (rc) return rc;
-    CU(cudaMemsetAsync(D.overflowCount, 0, 8 * sizeof(u32), D.sCompute));
+    CU(cudaMemsetAsync(H.overflowCount, 0, 8 * sizeof(u32), D.sCompute));
     if (dNEv) CU(cudaMemsetAsync(dNEv, 0, 2 * sizeof(u32), D.sCompute));
     P.errFlag = dNEv ? dNEv + 1 : nullptr;
-    if (P.nReads == 0) return GS_OK;
+    if (P.nReads == 0) {
+        rc = tail(D.sCompute);
+        if (rc) return rc;
+        if (D.overlap) { CU(cudaEventRecord(H.evReduce, D.sCompute)); H.reduceRecorded = true; }
+        return GS_OK;
+    }
     const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
-    CU(cudaMemsetAsync(D.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
+    CU(cudaMemsetAsync(H.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
     gs_launch_mark_starts(P, D.sCompute);
     CU(cudaGetLastError());
     // short reads: one thread per read; reads it cannot take (too many taxa / too long) go to the warp-per-read kernel
@@ -1155,44 +1216,66 @@ static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_e
     static const bool noMask = getenv("GS_DEBUG_NO_BMASK") != nullptr;   // A/B: reduce kernels that walk every label
     if (!noMask) {  // the label kernel also marks the run boundaries: the reduce kernels visit boundaries, not labels
         const size_t words = (size_t)nSeg * GS_SEG_CHUNKS + 64;
-        if (words > D.bmaskCap) {
-            CU(cudaStreamSynchronize(D.sCompute));
-            CU(dgrow(&D.bmask, &D.bmaskCap, words));
+        if (words > H.bmaskCap) {
+            int rcs = sync_compute(D);
+            if (rcs) return rcs;
+            CU(dgrow(&H.bmask, &H.bmaskCap, words));
         }
-        P.bmask = D.bmask;
+        P.bmask = H.bmask;
     }
-    const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)D.labelBlocks, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
-    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
+    if (threadPath && P.nReads > H.redoCap) {
+        int rcs = sync_compute(D);
+        if (rcs) return rcs;
+        CU(dgrow(&H.redoList, &H.redoCap, (size_t)P.nReads));
+    }
+    // Which batches overlap (measured, profiles/r02/ab/bench_overlap_*.json): the warp-per-read reduce of long reads fills the
+    // tail of the next label kernel -- the SMs whose persistent CTAs have run out of segments -- and the step gets 3.8 % shorter.
+    // The thread-per-read reduce of short reads gains nothing there (its 0.38 ms just move), and leaving it a CTA slot per SM
+    // costs the label kernel more (6.08 -> 6.50 ms) than it hides: short-read batches keep the stream order.
+    // GS_OVERLAP_SHORT=1 overlaps them too (label kernel at GS_OVERLAP_LABEL_BLOCKS_PER_SM CTAs per SM, default all).
+    static const bool overlapShort = [] { const char* e = getenv("GS_OVERLAP_SHORT"); return e && atoi(e) != 0; }();
+    const bool ov = D.overlap && (!threadPath || overlapShort);
+    const cudaStream_t sR = ov ? D.sReduce : D.sCompute;
+    const int gridCap = (threadPath && ov) ? D.labelBlocksOverlap : D.labelBlocks;
+    const int labelBlocks = (int)std::max<u64>(1, std::min<u64>((u64)gridCap, (nSeg + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK));
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (s->timing) {
-        for (int i = 0; i < 3; i++) { CU(cudaEventCreate(&tev[i])); D.timingEv.push_back(tev[i]); }
+        for (int i = 0; i < 4; i++) { CU(cudaEventCreate(&tev[i])); D.timingEv.push_back(tev[i]); }
         CU(cudaEventRecord(tev[0], D.sCompute));
     }
     gs_launch_label(P, false, labelBlocks, D.sCompute);
     CU(cudaGetLastError());
     if (s->timing) CU(cudaEventRecord(tev[1], D.sCompute));
+    if (ov) {
+        CU(cudaEventRecord(H.evLabel, D.sCompute));
+        CU(cudaStreamWaitEvent(sR, H.evLabel, 0));
+    }
+    if (s->timing) CU(cudaEventRecord(tev[2], sR));
     if (threadPath) {
-        if (P.nReads > D.redoCap) {
-            CU(cudaStreamSynchronize(D.sCompute));
-            CU(dgrow(&D.redoList, &D.redoCap, (size_t)P.nReads));
-        }
-        P.redoList = D.redoList; P.redoCount = D.overflowCount + 3; P.groupCounter = D.overflowCount + 4;
-        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 8, ((u64)P.nReads + 127) / 128), D.sCompute);
+        P.redoList = H.redoList; P.redoCount = H.overflowCount + 3; P.groupCounter = H.overflowCount + 4;
+        gs_launch_reduce_thread(P, (int)std::min<u64>((u64)D.sms * 8, ((u64)P.nReads + 127) / 128), sR);
         CU(cudaGetLastError());
         s->launches += 1;
     }
     const int fastBlocks = threadPath ? D.slowBlocks : (int)std::min<u64>((u64)D.fastBlocks, ((u64)P.nReads + GS_WARPS_PER_BLOCK - 1) / GS_WARPS_PER_BLOCK);
-    gs_launch_reduce(P, 0, false, fastBlocks, D.sCompute);
+    gs_launch_reduce(P, 0, false, fastBlocks, sR);
     CU(cudaGetLastError());
-    gs_launch_reduce(P, 1, false, D.slowBlocks, D.sCompute);
+    gs_launch_reduce(P, 1, false, D.slowBlocks, sR);
     CU(cudaGetLastError());
-    if (s->timing) CU(cudaEventRecord(tev[2], D.sCompute));
+    if (s->timing) CU(cudaEventRecord(tev[3], sR));
     s->launches += 4;
     if (dEv) {
-        gs_launch_maxcontig_events(D.maxcontig, s->db->V, P.firstReadNo, P.nReads, dEv, dNEv, D.sCompute);
+        gs_launch_maxcontig_events(D.maxcontig, s->db->V, P.firstReadNo, P.nReads, dEv, dNEv, sR);
         CU(cudaGetLastError());
         s->launches += 1;
     }
+    rc = tail(sR);
+    if (rc) return rc;
+    if (D.overlap) { CU(cudaEventRecord(H.evReduce, sR)); H.reduceRecorded = true; }
     return GS_OK;
+}
+static int launch_batch(gs_sess* s, DevSess& D, GsMatchParams& P, gs_maxcontig_event* dEv, u32* dNEv, u64 off0, u64 nBytes) {
+    return launch_batch(s, D, P, dEv, dNEv, off0, nBytes, [](cudaStream_t) { return GS_OK; });
 }
 
 extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
@@ -1227,28 +1310,8 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     // bases to 0.375 bytes each, gs_pack.hpp).  Either alone is the bottleneck somewhere -- the link with one GPU, the cores
     // (host memory bandwidth, really) with eight -- so a batch is split at a segment boundary: the tail goes out as ASCII
     // first, its copy runs while the pool packs the head, then the packed words follow.  The label kernel stages a segment
-    // from whichever form holds it.  The split follows the measured cost per byte of the two routes (adaptive unless
-    // host_pack_percent fixes it); results do not depend on it.
-    if (s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && nBytes >= (1u << 22)) {
-        // time per byte from one submit to the next = what the caller sees; every second batch the split takes one step, and
-        // turns round when the last step made things worse.  (A caller that is slower than both routes sees a flat cost: the
-        // split then wanders, harmlessly.)
-        const auto now = std::chrono::steady_clock::now();
-        if (s->packPrevBytes > 0) {
-            s->packAccSec += std::chrono::duration<double>(now - s->packPrevSubmit).count();
-            s->packAccBytes += s->packPrevBytes;
-            if (++s->packAcc == 2) {
-                const double cost = s->packAccSec / s->packAccBytes;
-                if (s->packSeeded) {
-                    if (s->packLastCost > 0 && cost > s->packLastCost * 1.01) s->packDir = -s->packDir;
-                    s->packFrac = std::min(1.0, std::max(0.0, s->packFrac + 0.05 * s->packDir));
-                }
-                s->packLastCost = cost;
-                s->packAcc = 0; s->packAccSec = 0; s->packAccBytes = 0;
-            }
-        }
-        s->packPrevSubmit = now; s->packPrevBytes = (double)nBytes;
-    }
+    // from whichever form holds it.  The split follows the measured cost per byte of the two routes (gs_match_collect*: adaptive
+    // unless host_pack_percent fixes it); results do not depend on it.
     const u64 nSegAll = (nBytes + GS_SEG_POS - 1) / GS_SEG_POS;
     u64 packSegs = 0;
     if (s->cfg.host_pack_threads != 0 && nBytes > 0) {
@@ -1311,9 +1374,8 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     // offsets are relative to bases + offsets[0] on the device: the kernel subtracts nothing, so rebase here
     // (the device copy of the base stream starts at host offset base0)
     if (!P.bases) P.bases = (const uint8_t*)nullptr - base0;   // nothing travels as ASCII: only the alignment of P.bases + base0 is looked at
-    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, base0, nBytes);
+    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, base0, nBytes, [&](cudaStream_t st) -> int { CU(cudaEventRecord(sl.evCompute, st)); return GS_OK; });
     if (rc) return rc;
-    CU(cudaEventRecord(sl.evCompute, D.sCompute));
     // results: device -> pinned host on the copy-out stream
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hOut, sl.dOut, (size_t)n_reads * sizeof(gs_read_result), cudaMemcpyDeviceToHost, D.sCopyOut));
@@ -1421,12 +1483,14 @@ extern "C" int gs_match_submit_fastq(gs_sess* s, const uint8_t* text, uint64_t n
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evH2D, 0));
     CU(cudaMemcpyAsync(sl.hRecs, sl.dRecs, ((size_t)n_reads + 1) * sizeof(gs_fastq_rec), cudaMemcpyDeviceToHost, D.sCopyOut));
     P.bases = sl.dBases; P.offsets = sl.dOffsets; P.nReads = n_reads; P.firstReadNo = first_read_no; P.out = sl.dOut;
-    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, 0, nBytes);
+    int rc = launch_batch(s, D, P, sl.dEv, sl.dNEv, 0, nBytes, [&](cudaStream_t st) -> int {
+        gs_launch_text_event_headers(sl.dEv, sl.dNEv, (u32)std::max(V, 1), sl.dRecs, first_read_no, n_reads, sl.dEvHdr, st);
+        CU(cudaGetLastError());
+        s->launches += 1;
+        CU(cudaEventRecord(sl.evCompute, st));
+        return GS_OK;
+    });
     if (rc) return rc;
-    gs_launch_text_event_headers(sl.dEv, sl.dNEv, (u32)std::max(V, 1), sl.dRecs, first_read_no, n_reads, sl.dEvHdr, D.sCompute);
-    CU(cudaGetLastError());
-    s->launches += 1;
-    CU(cudaEventRecord(sl.evCompute, D.sCompute));
     CU(cudaStreamWaitEvent(D.sCopyOut, sl.evCompute, 0));
     if (n_reads) CU(cudaMemcpyAsync(sl.hOut, sl.dOut, (size_t)n_reads * sizeof(gs_read_result), cudaMemcpyDeviceToHost, D.sCopyOut));
     CU(cudaMemcpyAsync(sl.hNEv, sl.dNEv, 2 * sizeof(u32), cudaMemcpyDeviceToHost, D.sCopyOut));
@@ -1451,15 +1515,20 @@ static int wait_ticket(gs_sess* s, gs_ticket t, DevSess** Dout, MatchSlot** slOu
     CU(cudaEventSynchronize(sl.evDone));
     sl.pending = false;
     *Dout = &D; *slOut = &sl;
-    if (!sl.isText && s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && !s->packSeeded && sl.packedBases >= (1u << 22) && sl.asciiBytes >= (1u << 22)) {
-        // first estimate of the split from the first batch's own costs: packing time p per byte on the cores, copy time a per
-        // byte on the link; cores and link are busy equally long when  p x = a (1 - x) + 0.375 a x.  From there on the split
-        // climbs along the measured time per batch (pack_split_step in gs_match_submit).
+    if (!sl.isText && s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && sl.packedBases >= (1u << 22) && sl.asciiBytes >= (1u << 22)) {
+        // The split from the two routes' own costs, measured on every batch inside the pipeline: packing time p per byte on the
+        // cores (next to the DMA traffic it competes with), copy time a per byte on the link.  Cores and link are busy equally
+        // long when  p x = a (1 - x) + 0.375 a x,  i.e.  x = a / (p + 0.625 a);  p itself falls as x rises (less ASCII traffic
+        // through the same DRAM), so the split is iterated on smoothed measurements until it stops moving.  (Round 2, first
+        // version: seeded once from the first -- cold -- batch and then a blind hill-climb on the time per batch, which stayed
+        // at 0.36 as often as it found 0.6-0.7: e2e 57 vs 61 G k-mers/s on the same box.)
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, sl.evAscii0, sl.evAscii1) == cudaSuccess && ms > 0) {
+        if (cudaEventElapsedTime(&ms, sl.evAscii0, sl.evAscii1) == cudaSuccess && ms > 0 && sl.packSec > 0) {
             const double pB = sl.packSec / (double)sl.packedBases, aB = ms * 1e-3 / (double)sl.asciiBytes;
-            s->packFrac = std::min(0.9, std::max(0.1, aB / (pB + 0.625 * aB)));
-            s->packSeeded = true;
+            if (!s->packSeeded) { s->packP = pB; s->packA = aB; s->packSeeded = true; }
+            else { s->packP += 0.3 * (pB - s->packP); s->packA += 0.3 * (aB - s->packA); }
+            const double target = s->packA / (s->packP + 0.625 * s->packA);
+            s->packFrac = std::min(0.92, std::max(0.08, s->packFrac + 0.5 * (target - s->packFrac)));
         } else {
             cudaGetLastError();
         }
@@ -1549,9 +1618,17 @@ extern "C" int gs_match_sync(gs_sess* s) {
     for (DevSess& D : s->devs) {
         CU(cudaSetDevice(D.dev));
         CU(cudaStreamSynchronize(D.sCopyIn));
-        CU(cudaStreamSynchronize(D.sCompute));
+        { int rc = sync_compute(D); if (rc) return rc; }
         CU(cudaStreamSynchronize(D.sCopyOut));
     }
+    return GS_OK;
+}
+
+// Orders the compute stream (gs_match_stream) behind everything submitted so far, without a host wait: a caller that times or
+// chains device work on that stream (bench.py's CUDA events, a host that decodes on the GPU) calls this before its own event.
+extern "C" int gs_match_join(gs_sess* s) {
+    if (!s) return gs_fail(GS_ERR_STATE, "null session");
+    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); int rc = join_reduce(D); if (rc) return rc; }
     return GS_OK;
 }
 
@@ -1559,6 +1636,7 @@ extern "C" int gs_match_sync(gs_sess* s) {
 static int materialize_bitset(gs_sess* s, DevSess& D) {
     if (!s->inlineSeen || s->dualBits) return GS_OK;   // dual mode: the label kernel has kept the compact bitset current
     CU(cudaSetDevice(D.dev));
+    { int rc = join_reduce(D); if (rc) return rc; }
     if (!D.bitset) CU(dmalloc(&D.bitset, D.bitsetWords));
     gs_launch_table_extract_seen(s->db->d[D.devIndex].tab, s->nPos, D.bitset, D.sCompute);
     CU(cudaGetLastError());
@@ -1587,6 +1665,7 @@ extern "C" int gs_match_unique_popcount(gs_sess* s, const uint64_t* d_bitset, ui
     if (!s) return gs_fail(GS_ERR_STATE, "null session");
     DevSess& D = s->devs[0];
     CU(cudaSetDevice(D.dev));
+    { int rc = join_reduce(D); if (rc) return rc; }
     CU(dgrow(&D.popPartial, &D.popPartialCap, (size_t)gs_popcount_scratch_words(D.sms, s->db->V)));
     gs_launch_unique_popcount((const u64*)d_bitset, word_begin, word_end, s->db->d[0].view, s->layout, (long long*)d_unique, D.popPartial, D.sms, D.sCompute);
     CU(cudaGetLastError());
@@ -1603,7 +1682,7 @@ static void timing_clear(DevSess& D) {
 }
 extern "C" int gs_match_set_timing(gs_sess* s, int on) {
     if (!s) return gs_fail(GS_ERR_ARG, "null session");
-    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); CU(cudaStreamSynchronize(D.sCompute)); timing_clear(D); }
+    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); int rc = sync_compute(D); if (rc) return rc; timing_clear(D); }
     s->timing = on != 0;
     return GS_OK;
 }
@@ -1612,11 +1691,11 @@ extern "C" int gs_match_kernel_times(gs_sess* s, double* label_ms, double* reduc
     double lab = 0, red = 0; u64 n = 0;
     for (DevSess& D : s->devs) {
         CU(cudaSetDevice(D.dev));
-        CU(cudaStreamSynchronize(D.sCompute));
-        for (size_t i = 0; i + 2 < D.timingEv.size(); i += 3) {
+        { int rc = sync_compute(D); if (rc) return rc; }
+        for (size_t i = 0; i + 3 < D.timingEv.size(); i += 4) {   // reduce: on its own stream, next to the following batch's label kernel when the overlap is on
             float a = 0, b = 0;
             CU(cudaEventElapsedTime(&a, D.timingEv[i], D.timingEv[i + 1]));
-            CU(cudaEventElapsedTime(&b, D.timingEv[i + 1], D.timingEv[i + 2]));
+            CU(cudaEventElapsedTime(&b, D.timingEv[i + 2], D.timingEv[i + 3]));
             lab += a; red += b; n++;
         }
     }
@@ -1645,20 +1724,20 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     P.overflowList = ovList; P.overflowCount = ovCount; P.workCounter = ovCount + 1;
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
     P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
-    CU(cudaStreamSynchronize(D.sCompute));
+    { int rc = sync_compute(D); if (rc) return rc; }
     long long* flatPos = nullptr;
     if (n_reads) {
         u64 ends[2] = {0, 0};
         CU(cudaMemcpy(&ends[0], d_offsets, sizeof(u64), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&ends[1], d_offsets + n_reads, sizeof(u64), cudaMemcpyDeviceToHost));
         if (ends[1] < ends[0]) return gs_fail(GS_ERR_ARG, "offsets not ascending");
-        int rc = prepare_flat(D, P, ends[0], ends[1] - ends[0]);
+        int rc = prepare_flat(D, D.ho[0], P, ends[0], ends[1] - ends[0]);
         if (rc) return rc;
-        P.segCounter = ovCount + 2;
+        P.overflowCount = ovCount; P.workCounter = ovCount + 1; P.segCounter = ovCount + 2;
         const u64 nSeg = (P.flatLen + GS_SEG_POS - 1) / GS_SEG_POS;
         CU(dmalloc(&flatPos, (size_t)P.flatLen + 32));
         P.flatPos = flatPos;
-        CU(cudaMemsetAsync(D.startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
+        CU(cudaMemsetAsync(D.ho[0].startBits, 0, ((size_t)nSeg * GS_SEG_CHUNKS + 64) * sizeof(u32), D.sCompute));
         gs_launch_mark_starts(P, D.sCompute);
         gs_launch_label(P, true, D.labelBlocks, D.sCompute);
         gs_launch_reduce(P, 0, true, D.fastBlocks, D.sCompute);
@@ -1912,6 +1991,7 @@ static int merge_state(gs_sess* s, gs_comm* cm) {
     const bool uniq = s->cfg.count_unique_kmers != 0;
     int rc;
     DevSess& D0 = s->devs[0];
+    for (DevSess& D : s->devs) { CU(cudaSetDevice(D.dev)); int rcj = join_reduce(D); if (rcj) return rcj; }   // the merge follows every batch's reduce kernels
     CU(cudaSetDevice(D0.dev));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));

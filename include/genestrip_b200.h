@@ -274,6 +274,11 @@ int gs_match_l2_window(const gs_sess*, uint64_t* window_bytes, uint64_t* persist
  * stream; gs_match_sync waits. */
 int gs_match_run_device(gs_sess*, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                         uint64_t n_bases, uint64_t first_read_no, gs_read_result* d_out);
+/* The kernels of a batch run on two streams of the session: the label kernel on the compute stream (gs_match_stream), the
+ * reduce kernels on a second one, so that they overlap the next batch's label kernel.  gs_match_join orders the compute stream
+ * behind everything submitted so far without a host wait -- call it before recording an event of your own on gs_match_stream
+ * or before chaining your own device work there.  gs_match_sync / collect / finish need no join. */
+int gs_match_join(gs_sess*);
 int gs_match_sync(gs_sess*);
 /* Raw device state (tests; before ABI 5 also the hook for a reduction outside the library -- see gs_match_finish_comm):
  * counters = int64[7][n_values] (kmers, contigs, sqsum, reads1, reads, readsKmers, readsBPs),
