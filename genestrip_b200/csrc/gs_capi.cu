@@ -250,6 +250,16 @@ extern "C" void* gs_alloc_pinned(size_t bytes) {
 }
 extern "C" void gs_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
+// Frees the device temporaries of an entry point when its scope is left, early CU() returns included (the watched variables
+// are read at that moment, so buffers grown or allocated later in the function are covered as well).
+struct DevTemps {
+    std::vector<void**> p;
+    void watch(void** q) { p.push_back(q); }
+    template <typename T> void watch(T** q) { p.push_back((void**)q); }
+    void release() { for (void** q : p) if (*q) { cudaFree(*q); *q = nullptr; } }
+    ~DevTemps() { release(); }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // database
 // ---------------------------------------------------------------------------------------------------------
@@ -734,9 +744,12 @@ extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, con
     const u64 kGroup = 64ULL << 20;  // bases per pass (labels + positions take 12 bytes per base)
     unsigned long long* dChanged = nullptr;
     u32* dCtr = nullptr;
+    uint8_t* dSeq = nullptr; u64* dOff = nullptr; int* dNode = nullptr; u32* dLab = nullptr; long long* dPos = nullptr; u32* dValid = nullptr; u32* dStart = nullptr;
+    DevTemps temps;
+    temps.watch(&dChanged); temps.watch(&dCtr); temps.watch(&dSeq); temps.watch(&dOff); temps.watch(&dNode); temps.watch(&dLab); temps.watch(&dPos);
+    temps.watch(&dValid); temps.watch(&dStart);
     CU(dmalloc(&dChanged, 1)); CU(cudaMemset(dChanged, 0, sizeof(unsigned long long)));
     CU(dmalloc(&dCtr, 8));
-    uint8_t* dSeq = nullptr; u64* dOff = nullptr; int* dNode = nullptr; u32* dLab = nullptr; long long* dPos = nullptr; u32* dValid = nullptr; u32* dStart = nullptr;
     size_t seqCap = 0, offCap = 0, nodeCap = 0, labCap = 0, posCap = 0, validCap = 0, startCap = 0;
     int rc = GS_OK;
     std::vector<u64> rel;
@@ -775,7 +788,7 @@ extern "C" int gs_db_update(gs_db* db, const uint8_t* seq, uint64_t n_bytes, con
     unsigned long long changed = 0;
     CU(cudaMemcpy(&changed, dChanged, sizeof(changed), cudaMemcpyDeviceToHost));
     if (n_changed) *n_changed = changed;
-    cudaFree(dSeq); cudaFree(dOff); cudaFree(dNode); cudaFree(dLab); cudaFree(dPos); cudaFree(dValid); cudaFree(dStart); cudaFree(dChanged); cudaFree(dCtr);
+    temps.release();   // before the table is rebuilt (early returns above are covered by the guard's destructor)
     if (changed) {  // the probe table carries the values in its entries: rebuild it, then refresh the replicas
         int rcb = build_table(db);
         if (rcb) return rcb;
@@ -824,13 +837,13 @@ extern "C" int gs_db_lookup(gs_db* db, const int64_t* kmers, uint64_t n, int use
     if (!db || !db->finalized) return gs_fail(GS_ERR_STATE, "database not finalized");
     CU(cudaSetDevice(db->d[0].dev));
     u64* dK = nullptr; int* dV = nullptr; long long* dP = nullptr;
+    DevTemps temps; temps.watch(&dK); temps.watch(&dV); temps.watch(&dP);
     CU(dmalloc(&dK, n)); CU(dmalloc(&dV, n)); CU(dmalloc(&dP, n));
     CU(cudaMemcpy(dK, kmers, n * sizeof(u64), cudaMemcpyHostToDevice));
     if (n) gs_launch_lookup(db->d[0].view, dK, n, use_bloom, dV, dP, 0);
     CU(cudaGetLastError());
     CU(cudaMemcpy(vidx_out, dV, n * sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(pos_out, dP, n * sizeof(long long), cudaMemcpyDeviceToHost));
-    CU(cudaFree(dK)); CU(cudaFree(dV)); CU(cudaFree(dP));
     return GS_OK;
 }
 
@@ -1713,6 +1726,9 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     // side-effect free apart from the dump: private scratch accumulators
     const int V = s->db->V;
     long long* counters = nullptr; u64* maxcontig = nullptr; gs_read_result* out = nullptr; u32* ovList = nullptr; u32* ovCount = nullptr;
+    long long* flatPos = nullptr;
+    DevTemps temps;
+    temps.watch(&counters); temps.watch(&maxcontig); temps.watch(&out); temps.watch(&ovList); temps.watch(&ovCount); temps.watch(&flatPos);
     CU(dmalloc(&counters, (size_t)7 * V)); CU(dmalloc(&maxcontig, (size_t)V)); CU(dmalloc(&out, (size_t)n_reads));
     CU(dmalloc(&ovList, (size_t)n_reads)); CU(dmalloc(&ovCount, 4));
     CU(cudaMemset(counters, 0, std::max<size_t>((size_t)7 * V, 1) * sizeof(long long)));
@@ -1725,7 +1741,6 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     P.bases = d_bases; P.offsets = (const u64*)d_offsets; P.nReads = n_reads; P.firstReadNo = 0; P.out = out;
     P.kmerOffsets = (const u64*)d_kmer_offsets; P.dumpLabels = d_labels; P.dumpPos = (long long*)d_pos;
     { int rc = sync_compute(D); if (rc) return rc; }
-    long long* flatPos = nullptr;
     if (n_reads) {
         u64 ends[2] = {0, 0};
         CU(cudaMemcpy(&ends[0], d_offsets, sizeof(u64), cudaMemcpyDeviceToHost));
@@ -1744,7 +1759,6 @@ extern "C" int gs_match_dump_labels(gs_sess* s, const uint8_t* d_bases, const ui
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(D.sCompute));
-    CU(cudaFree(counters)); CU(cudaFree(maxcontig)); CU(cudaFree(out)); CU(cudaFree(ovList)); CU(cudaFree(ovCount)); CU(cudaFree(flatPos));
     return GS_OK;
 }
 
