@@ -1351,14 +1351,23 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
         CU(hgrow(&sl.hValid, &sl.hValidCap, (size_t)wordsAll));
         CU(dgrow(&sl.dCodes, &sl.dCodesCap, (size_t)wordsAll + 64));
         CU(dgrow(&sl.dValid, &sl.dValidCap, (size_t)wordsAll + 64));
+        // packed in a few pieces, each handed to the link as soon as it is ready: the copy of the packed words runs under the
+        // packing of the next piece instead of behind all of it (2-3 ms less latency per batch, which counts with three
+        // batches in flight)
         const auto t0 = std::chrono::steady_clock::now();
-        s->packer->pack(bases + base0, packBases, (uint64_t*)sl.hCodes, sl.hValid);
+        const size_t nPieces = words >= ((size_t)1 << 20) ? 4 : 1;
+        for (size_t pc = 0; pc < nPieces; pc++) {
+            const size_t w0 = (words * pc / nPieces) & ~(size_t)1023, w1 = pc + 1 == nPieces ? words : ((words * (pc + 1) / nPieces) & ~(size_t)1023);
+            if (w1 <= w0) continue;
+            const u64 b0 = (u64)w0 * 32, b1 = std::min<u64>(packBases, (u64)w1 * 32);
+            s->packer->pack(bases + base0 + b0, b1 > b0 ? b1 - b0 : 0, (uint64_t*)sl.hCodes + w0, sl.hValid + w0);
+            CU(cudaMemcpyAsync(sl.dCodes + w0, sl.hCodes + w0, (w1 - w0) * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
+            CU(cudaMemcpyAsync(sl.dValid + w0, sl.hValid + w0, (w1 - w0) * sizeof(u32), cudaMemcpyHostToDevice, D.sCopyIn));
+        }
         sl.packSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         sl.packedBases = packBases;
         s->packSeconds += sl.packSec;
         s->packBytes += packBases; s->h2dBytes += words * 12;
-        CU(cudaMemcpyAsync(sl.dCodes, sl.hCodes, words * sizeof(u64), cudaMemcpyHostToDevice, D.sCopyIn));
-        CU(cudaMemcpyAsync(sl.dValid, sl.hValid, words * sizeof(u32), cudaMemcpyHostToDevice, D.sCopyIn));
         CU(cudaMemsetAsync(sl.dCodes + words, 0, 64 * sizeof(u64), D.sCopyIn));
         CU(cudaMemsetAsync(sl.dValid + words, 0, 64 * sizeof(u32), D.sCopyIn));
         P.packCodes = sl.dCodes; P.packValid = sl.dValid; P.packSegs = (u32)std::min<u64>(packSegs, 0xFFFFFFFFu);
