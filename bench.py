@@ -406,7 +406,11 @@ def run_match(E, name, wl, want_fastq, want_cpu):
     log("rank %d: %s: database on device: %.2f GB, %d reads/step" % (rank, name, db.device_bytes / 1e9, R))
     cfg = capi.default_match_cfg(layout=capi.GS_LAYOUT_CLASSIC if args.layout == "classic" else capi.GS_LAYOUT_TABLE)
     cfg.prefilter = 0 if args.no_prefilter else 1
-    cfg.host_pack_threads = args.pack_threads if args.pack_threads >= 0 else max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    cores_per_rank = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    # two cores stay free for the submitting thread's own work and the driver's threads when the rank has eight or more: every
+    # pack() is a barrier over the pool, and a pool as wide as the machine waits for whichever thread was descheduled
+    # (measured: 14 threads 64.9-65.6 G k-mers/s e2e, 16 threads 63.5-63.7 G on the 16-core box)
+    cfg.host_pack_threads = args.pack_threads if args.pack_threads >= 0 else (cores_per_rank - 2 if cores_per_rank >= 8 else cores_per_rank)
     cfg.host_pack_percent = args.pack_percent
     native_options = {"layout": args.layout, "minimizer_prefilter": bool(cfg.prefilter) and args.layout == "table", "host_pack_threads": int(cfg.host_pack_threads)}
     sess = capi.MatchSession(db, cfg)
