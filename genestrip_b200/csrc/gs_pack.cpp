@@ -183,6 +183,7 @@ Packer::Packer(int threads) : p(new Impl()) {
         cpu_set_t set;
         CPU_ZERO(&set);
         threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        if (threads >= 8) threads -= 2;   // every pack() is a barrier over the pool: leave room for the caller's and the driver's other threads
         threads = std::max(1, std::min(threads, 32));
     }
     for (int i = 1; i < threads; i++) p->workers.emplace_back([this] { p->loop(); });

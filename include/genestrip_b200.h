@@ -127,7 +127,7 @@ typedef struct gs_match_cfg {
     int host_pack_threads;             /* how gs_match_submit moves the bases to the device.  0: as they are, 1 byte per base.
                                           n > 0: n host threads (the caller included) first pack them to 2-bit codes + a
                                           validity bit, 0.375 bytes per base on the link; -1 (default): n = the CPUs this
-                                          process may run on, at most 32.  Same results either way.                      */
+                                          process may run on (two fewer from eight on), at most 32.  Same results either way. */
     int host_pack_percent;             /* with host_pack_threads != 0: the share of every batch that is packed, the rest crosses
                                           the link as ASCII while the pool packs (link and cores work side by side).
                                           -1 (default): follows the measured cost of the two routes; 0..100: fixed.       */
