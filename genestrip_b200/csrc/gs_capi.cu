@@ -969,6 +969,10 @@ struct gs_sess {
     double packFrac = 0.7;                   // share of a batch's bases that goes over the link packed (the rest as ASCII)
     bool packSeeded = false;                 // the smoothed route costs hold a first measurement
     double packP = 0, packA = 0;             // smoothed seconds per byte: packing on the host's cores, ASCII on the link
+    // search on the time per batch around the model's split (GS_PACK_SEARCH=0 switches it off): phases of four batches below / above it
+    double packBias = 0, probeSum[2] = {0, 0}, probePrevBytes = 0;
+    int probeN[2] = {0, 0}, probePhase = 0, probeIdx = -1;
+    std::chrono::steady_clock::time_point probePrev;
     double packSeconds = 0;                  // host time spent packing (gs_match_pack_stats)
     u64 packBytes = 0, h2dBytes = 0;         // bases packed / bytes of base data put on the link
 };
@@ -1327,8 +1331,39 @@ extern "C" int gs_match_submit(gs_sess* s, const uint8_t* bases, const uint64_t*
     // unless host_pack_percent fixes it); results do not depend on it.
     const u64 nSegAll = (nBytes + GS_SEG_POS - 1) / GS_SEG_POS;
     u64 packSegs = 0;
+    double probeOffset = 0;
+    // The model balances this rank's cores against this rank's link.  When several ranks share one host's memory system that is
+    // not the whole picture (the packed route costs 2.1 bytes of host memory traffic per base, the ASCII route 1.0), so the split
+    // is also searched on what the caller sees, the time per byte from one submit to the next: phases of four batches a step
+    // below and a step above the model's split, the last two of each phase counted, and a bias that moves towards the cheaper
+    // side when the two differ by more than 1.5 %.  A caller that is slower than both routes sees no difference: the bias stays.
+    // Measured: one GPU 64.7-64.8 G k-mers/s with the search, 64.5 G without (the bias ends at the upper clamp); four ranks on one
+    // 32-core host 100.6 G with it, 74.5 G without (share 0.47 and still moving after 66 batches).  GS_PACK_SEARCH=0: model only.
+    static const bool packSearch = [] { const char* e = getenv("GS_PACK_SEARCH"); return !(e && atoi(e) == 0); }();
+    if (packSearch && s->cfg.host_pack_threads != 0 && s->cfg.host_pack_percent < 0 && nBytes >= (1u << 22)) {
+        const double step = 0.08;
+        const auto now = std::chrono::steady_clock::now();
+        if (s->probeIdx >= 0 && s->probePrevBytes > 0 && s->probeIdx >= 2) {
+            s->probeSum[s->probePhase] += std::chrono::duration<double>(now - s->probePrev).count() / s->probePrevBytes;
+            s->probeN[s->probePhase]++;
+        }
+        if (++s->probeIdx == 4) {
+            s->probeIdx = 0;
+            s->probePhase ^= 1;
+            if (s->probePhase == 0 && s->probeN[0] > 0 && s->probeN[1] > 0) {   // a low and a high phase are complete
+                const double lo = s->probeSum[0] / s->probeN[0], hi = s->probeSum[1] / s->probeN[1];
+                if (hi < lo * 0.985) s->packBias += step;
+                else if (lo < hi * 0.985) s->packBias -= step;
+                s->packBias = std::min(0.15, std::max(-0.9, s->packBias));
+                s->probeSum[0] = s->probeSum[1] = 0; s->probeN[0] = s->probeN[1] = 0;
+            }
+        }
+        s->probePrev = now; s->probePrevBytes = (double)nBytes;
+        probeOffset = s->packBias + (s->probePhase ? step : -step);
+    }
     if (s->cfg.host_pack_threads != 0 && nBytes > 0) {
-        const double frac = s->cfg.host_pack_percent >= 0 ? std::min(100, s->cfg.host_pack_percent) / 100.0 : s->packFrac;
+        const double frac = s->cfg.host_pack_percent >= 0 ? std::min(100, s->cfg.host_pack_percent) / 100.0
+                                                           : std::min(0.95, std::max(0.05, s->packFrac + probeOffset));
         packSegs = std::min<u64>(nSegAll, (u64)llround(frac * (double)nSegAll));
     }
     const u64 asciiFrom = std::min<u64>(nBytes, packSegs * GS_SEG_POS);   // first byte that travels as ASCII (a multiple of 16)
@@ -2291,7 +2326,7 @@ extern "C" int gs_match_l2_window(const gs_sess* s, uint64_t* window_bytes, uint
     if (hit_ratio) *hit_ratio = D.l2HitRatio;
     return GS_OK;
 }
-extern "C" double gs_match_pack_fraction(const gs_sess* s) { return s ? (s->cfg.host_pack_threads == 0 ? 0.0 : s->cfg.host_pack_percent >= 0 ? s->cfg.host_pack_percent / 100.0 : s->packFrac) : 0.0; }
+extern "C" double gs_match_pack_fraction(const gs_sess* s) { return s ? (s->cfg.host_pack_threads == 0 ? 0.0 : s->cfg.host_pack_percent >= 0 ? s->cfg.host_pack_percent / 100.0 : std::min(0.95, std::max(0.05, s->packFrac + s->packBias))) : 0.0; }
 extern "C" int gs_match_pack_stats(const gs_sess* s, int* threads, double* pack_seconds, uint64_t* bases_packed, uint64_t* h2d_base_bytes) {
     if (!s) return gs_fail(GS_ERR_ARG, "null session");
     if (threads) *threads = s->packer ? s->packer->threads() : 0;
